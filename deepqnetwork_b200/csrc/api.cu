@@ -1,0 +1,883 @@
+// C ABI of libdqn_b200 (see include/dqn_b200.h): handle lifecycle, host<->device plumbing and the
+// orchestration of one training step (DeepQAgent._train_run_train, rl/deep_q_agent.py:326-349).
+#include "learner.h"
+#include <string.h>
+#include <algorithm>
+
+static std::string g_create_error;
+
+// launchers living in other translation units
+void launch_tree_stats(dqn_learner* h, double per_b_override);
+void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
+
+long long* tree_size_ptr(dqn_learner* h) { return &h->d_dev->tree_size; }
+
+#define API_BEGIN(h)                        \
+    if (!(h)) return 2;                     \
+    try {                                   \
+        DQN_CUDA_OK(cudaSetDevice((h)->device));
+#define API_END(h)                          \
+    } catch (const std::string& e) {        \
+        (h)->err = e;                       \
+        return 1;                           \
+    }                                       \
+    return 0;
+
+template <class T>
+static void dmalloc(T*& p, size_t count) {
+    void* q = nullptr;
+    DQN_CUDA_OK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    p = static_cast<T*>(q);
+}
+
+__global__ void set_ll_kernel(long long* p, long long v) { *p = v; }
+__global__ void set_f2_kernel(float* a, float va, float* b, float vb) { *a = va; *b = vb; }
+static void set_ll(dqn_learner* h, long long* p, long long v) {
+    set_ll_kernel<<<1, 1, 0, h->stream>>>(p, v);
+    DQN_CUDA_OK(cudaGetLastError());
+}
+static void push_sizes(dqn_learner* h) {
+    set_ll(h, &h->d_dev->tree_size, h->tree_size);
+    set_ll(h, &h->d_dev->ring_len, h->ring_size);
+}
+static void read_scalars(dqn_learner* h) {
+    DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(dqn_learner::Scalars), cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+
+static void alloc_tower(dqn_learner* h, TowerActs& t, int rows) {
+    const NetDesc& net = h->net;
+    for (int l = 0; l < 3; ++l) dmalloc(t.act[l], (size_t)rows * net.conv[l].oh * net.conv[l].ow * net.conv[l].cout);
+    dmalloc(t.fc_part, (size_t)h->fc_splits * rows * net.NH);
+    dmalloc(t.hid, (size_t)rows * net.NH);
+    dmalloc(t.q, (size_t)rows * net.A);
+}
+
+extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return 2; }
+    dqn_learner* h = nullptr;
+    try {
+        DQN_REQUIRE(cfg->struct_size == (int32_t)sizeof(dqn_config), "dqn_config size mismatch (ABI drift)");
+        DQN_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= 32, "num_actions must be in [1,32]");
+        DQN_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= 4096, "batch_size out of range");
+        DQN_REQUIRE(cfg->replay_capacity >= 2, "replay_capacity must be >= 2");
+        DQN_REQUIRE(cfg->math_mode == DQN_MATH_FP32, "only DQN_MATH_FP32 is built in this revision");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw std::string("no CUDA device: libdqn_b200 has no CPU fallback");
+        DQN_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+        DQN_CUDA_OK(cudaSetDevice(cfg->device));
+        h = new dqn_learner();
+        h->cfg = *cfg;
+        h->device = cfg->device;
+        cudaDeviceProp prop;
+        DQN_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+        h->sm_count = prop.multiProcessorCount;
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        net_describe(h->net, h->cfg);
+        const NetDesc& net = h->net;
+        h->state_bytes = (size_t)net.H * net.W * net.C;
+        DQN_REQUIRE(h->state_bytes % 16 == 0, "H*W*C must be a multiple of 16 bytes");
+        DQN_REQUIRE(net.C == 4, "input_channels must be 4 (NUM_FRAMES_PER_STATE)");
+        h->B = cfg->batch_size;
+        h->max_rows = cfg->max_rows > 0 ? cfg->max_rows : std::max(2 * h->B, 256);
+        if (h->max_rows < h->B) h->max_rows = h->B;
+        h->fc_splits = ceil_div(net.flat, 256);
+
+        // parameters + optimizer slots + gradient slab
+        const size_t P = (size_t)net.slab;
+        dmalloc(h->online, P); dmalloc(h->target, P); dmalloc(h->slot_m, P); dmalloc(h->slot_v, P); dmalloc(h->grads, P);
+        for (float* p : {h->online, h->target, h->slot_m, h->slot_v, h->grads}) DQN_CUDA_OK(cudaMemsetAsync(p, 0, P * 4, h->stream));
+        dmalloc(h->d_sc, 1); dmalloc(h->d_dev, 1);
+        DQN_CUDA_OK(cudaMemsetAsync(h->d_sc, 0, sizeof(dqn_learner::Scalars), h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(h->d_dev, 0, sizeof(dqn_learner::DevSizes), h->stream));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, sizeof(dqn_learner::Scalars), cudaHostAllocDefault));
+        set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, 0.9f, &h->d_sc->b2p, 0.999f);
+
+        // replay ring + tree
+        h->cap = cfg->replay_capacity;
+        const size_t N = (size_t)h->cap;
+        dmalloc(h->r_states, N * h->state_bytes); dmalloc(h->r_next, N * h->state_bytes);
+        dmalloc(h->r_actions, N); dmalloc(h->r_rewards, N); dmalloc(h->r_cont, N); dmalloc(h->r_losses, N);
+        DQN_CUDA_OK(cudaMemsetAsync(h->r_losses, 0, N * sizeof(__half), h->stream));
+        dmalloc(h->tree, 2 * N - 1); dmalloc(h->tree_data, N);
+        DQN_CUDA_OK(cudaMemsetAsync(h->tree, 0, (2 * N - 1) * 4, h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(h->tree_data, 0, N * 4, h->stream));
+
+        // batches
+        const size_t R = (size_t)h->max_rows;
+        dmalloc(h->b_states, 2 * R * h->state_bytes); dmalloc(h->in_states, 2 * R * h->state_bytes);
+        dmalloc(h->b_actions, R); dmalloc(h->b_rewards, R); dmalloc(h->b_cont, R); dmalloc(h->b_losses, R);
+        dmalloc(h->in_actions, R); dmalloc(h->in_rewards, R); dmalloc(h->in_cont, R); dmalloc(h->in_isw, R);
+        dmalloc(h->b_tree_idx, R); dmalloc(h->b_data_idx, R); dmalloc(h->b_mem_idx, R);
+        dmalloc(h->b_prio, R); dmalloc(h->b_isw64, R); dmalloc(h->b_isw, R); dmalloc(h->b_u, R);
+        dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_losses_out, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
+        dmalloc(h->b_rows, R);
+
+        // activations
+        alloc_tower(h, h->acts_on, 2 * h->max_rows);
+        alloc_tower(h, h->acts_tg, h->max_rows);
+        dmalloc(h->d_hid, R * net.NH);
+        for (int l = 0; l < 3; ++l) dmalloc(h->d_act[l], R * net.conv[l].oh * net.conv[l].ow * net.conv[l].cout);
+        h->wg_part_floats = 0;
+        for (int l = 0; l < 3; ++l) {
+            const ConvGeom& g = net.conv[l];
+            h->wg_part_floats = std::max<int64_t>(h->wg_part_floats, (int64_t)64 * (g.k * g.k * g.cin + 4) * g.cout);
+        }
+        dmalloc(h->wg_part, (size_t)h->wg_part_floats);
+        h->dev_stage_bytes = 8u << 20;
+        dmalloc(h->dev_stage, h->dev_stage_bytes);
+        dmalloc(h->stats_scratch, 8192);
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    } catch (const std::string& e) {
+        g_create_error = e;
+        if (h) { cudaDeviceSynchronize(); delete h; }
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int dqn_destroy(dqn_learner* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
+                    h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
+                    h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions, h->in_rewards, h->in_cont, h->in_isw,
+                    h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
+                    h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
+                    h->wg_part, h->dev_stage, h->stats_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
+        for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
+        cudaFree(t->fc_part); cudaFree(t->hid); cudaFree(t->q);
+    }
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    for (auto& ev : h->prof_events) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* dqn_last_error(const dqn_learner* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int dqn_sync(dqn_learner* h) {
+    API_BEGIN(h)
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_set_stream(dqn_learner* h, void* s) {
+    API_BEGIN(h)
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->graph_valid = false;
+    API_END(h)
+}
+
+// ---- parameters ---------------------------------------------------------------------------------------
+extern "C" int dqn_num_params(const dqn_learner* h, int32_t* n_tensors, int64_t* n_floats) {
+    if (!h) return 2;
+    int64_t tot = 0;
+    for (auto& t : h->net.tensors) tot += t.count;
+    if (n_tensors) *n_tensors = (int32_t)h->net.tensors.size();
+    if (n_floats) *n_floats = tot;
+    return 0;
+}
+
+extern "C" int dqn_param_info(const dqn_learner* h, int32_t i, const char** name, int64_t* count, int64_t* offset) {
+    if (!h || i < 0 || i >= (int)h->net.tensors.size()) return 2;
+    const TensorInfo& t = h->net.tensors[i];
+    if (name) *name = t.name.c_str();
+    if (count) *count = t.count;
+    if (offset) *offset = t.offset;
+    return 0;
+}
+
+static float* slab_of(dqn_learner* h, int tower, int slot) {
+    if (slot == 0) return tower == 0 ? h->online : h->target;
+    DQN_REQUIRE(tower == 0, "optimizer slots exist for the online tower only");
+    if (slot == 1) return h->slot_m;
+    if (slot == 2) return h->slot_v;
+    if (slot == 3) return h->grads;
+    throw std::string("bad slot");
+}
+static const TensorInfo& find_tensor(dqn_learner* h, const char* name) {
+    for (auto& t : h->net.tensors) if (t.name == name) return t;
+    throw std::string("unknown parameter name: ") + name;
+}
+
+extern "C" int dqn_get_param(dqn_learner* h, int32_t tower, int32_t slot, const char* name, float* out, int64_t count) {
+    API_BEGIN(h)
+    const TensorInfo& t = find_tensor(h, name);
+    DQN_REQUIRE(count == t.count, "parameter element count mismatch");
+    DQN_CUDA_OK(cudaMemcpyAsync(out, slab_of(h, tower, slot) + t.offset, count * 4, cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_set_param(dqn_learner* h, int32_t tower, int32_t slot, const char* name, const float* in, int64_t count) {
+    API_BEGIN(h)
+    const TensorInfo& t = find_tensor(h, name);
+    DQN_REQUIRE(count == t.count, "parameter element count mismatch");
+    DQN_CUDA_OK(cudaMemcpyAsync(slab_of(h, tower, slot) + t.offset, in, count * 4, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_device_ptr(dqn_learner* h, const char* what, void** ptr, int64_t* bytes) {
+    API_BEGIN(h)
+    const std::string w = what;
+    const int64_t P4 = h->net.slab * 4;
+    void* p = nullptr; int64_t b = 0;
+    if (w == "grads") { p = h->grads; b = P4; }
+    else if (w == "online") { p = h->online; b = P4; }
+    else if (w == "target") { p = h->target; b = P4; }
+    else if (w == "adam_m") { p = h->slot_m; b = P4; }
+    else if (w == "adam_v") { p = h->slot_v; b = P4; }
+    else if (w == "tree") { p = h->tree; b = (2 * h->cap - 1) * 4; }
+    else if (w == "replay_states") { p = h->r_states; b = h->cap * (int64_t)h->state_bytes; }
+    else if (w == "replay_next_states") { p = h->r_next; b = h->cap * (int64_t)h->state_bytes; }
+    else if (w == "batch_states") { p = h->b_states; b = 2 * (int64_t)h->max_rows * h->state_bytes; }
+    else if (w == "scalars") { p = h->d_sc; b = sizeof(dqn_learner::Scalars); }
+    else throw std::string("unknown device buffer: ") + w;
+    if (ptr) *ptr = p;
+    if (bytes) *bytes = b;
+    API_END(h)
+}
+
+extern "C" int dqn_get_step(dqn_learner* h, int64_t* step) {
+    API_BEGIN(h)
+    read_scalars(h);
+    h->host_step = h->h_sc->step;
+    if (step) *step = h->h_sc->step;
+    API_END(h)
+}
+extern "C" int dqn_set_step(dqn_learner* h, int64_t step) {
+    API_BEGIN(h)
+    set_ll(h, &h->d_sc->step, step);
+    h->host_step = step;
+    API_END(h)
+}
+extern "C" int dqn_get_game_count(dqn_learner* h, int64_t* n) {
+    API_BEGIN(h)
+    read_scalars(h);
+    if (n) *n = h->h_sc->game_count;
+    API_END(h)
+}
+extern "C" int dqn_set_game_count(dqn_learner* h, int64_t n) {
+    API_BEGIN(h)
+    set_ll(h, &h->d_sc->game_count, n);
+    API_END(h)
+}
+extern "C" int dqn_get_beta_powers(dqn_learner* h, float* b1p, float* b2p) {
+    API_BEGIN(h)
+    read_scalars(h);
+    if (b1p) *b1p = h->h_sc->b1p;
+    if (b2p) *b2p = h->h_sc->b2p;
+    API_END(h)
+}
+extern "C" int dqn_set_beta_powers(dqn_learner* h, float b1p, float b2p) {
+    API_BEGIN(h)
+    set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, b1p, &h->d_sc->b2p, b2p);
+    DQN_CUDA_OK(cudaGetLastError());
+    API_END(h)
+}
+extern "C" int dqn_copy_network(dqn_learner* h) {
+    API_BEGIN(h)
+    launch_copy_network(h);
+    API_END(h)
+}
+extern "C" int dqn_get_stats(dqn_learner* h, float* out8) {
+    API_BEGIN(h)
+    read_scalars(h);
+    const dqn_learner::Scalars& s = *h->h_sc;
+    const float v[8] = {s.stat_min, s.stat_max, s.stat_avg, s.stat_total, s.last_max_weight, s.per_b, s.loss, s.loss_sum};
+    memcpy(out8, v, sizeof(v));
+    API_END(h)
+}
+
+// ---- replay ring ------------------------------------------------------------------------------------------
+__global__ void store_losses_kernel(__half* losses, long long cap, long long cur, long long n, const float* __restrict__ src) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < n) losses[(cur + j) % cap] = __float2half_rn(src[j]);  // replay_memory.py:109-110: f16 store
+}
+
+static void ring_copy(dqn_learner* h, uint8_t* ring, const uint8_t* src, int64_t cur, int64_t n, size_t elt) {
+    const int64_t first = std::min<int64_t>(n, h->cap - cur);
+    DQN_CUDA_OK(cudaMemcpyAsync(ring + (size_t)cur * elt, src, (size_t)first * elt, cudaMemcpyHostToDevice, h->stream));
+    if (n > first)
+        DQN_CUDA_OK(cudaMemcpyAsync(ring, src + (size_t)first * elt, (size_t)(n - first) * elt, cudaMemcpyHostToDevice, h->stream));
+}
+
+extern "C" int dqn_replay_append(dqn_learner* h, int64_t n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw,
+                                 const uint8_t* ns, const uint8_t* ct, const float* losses) {
+    API_BEGIN(h)
+    DQN_REQUIRE(!(h->cfg.use_per && !losses), "use_per: losses (priorities) are required on append");
+    int64_t done = 0;
+    const int64_t max_chunk = std::min<int64_t>(h->cap, (int64_t)(h->dev_stage_bytes / 4));
+    while (done < n) {
+        const int64_t m = std::min(n - done, max_chunk);
+        const int64_t cur = h->ring_cur;
+        if (losses) {
+            float* d_sc = (float*)h->dev_stage;
+            DQN_CUDA_OK(cudaMemcpyAsync(d_sc, losses + done, m * 4, cudaMemcpyHostToDevice, h->stream));
+            if (h->cfg.use_per) {
+                // ReplaySamplerPriority.append: sum_tree.add(loss, replay_memory.cur_idx) then replay append
+                // (replay_sampler_priority.py:22-24); the tree write pointer moves in lock-step with the ring
+                DQN_REQUIRE(h->tree_write == cur, "sum tree write pointer out of step with the ring");
+                launch_tree_add(h, m, d_sc, nullptr, h->tree_write);
+                if (h->tree_write + m >= h->cap) h->tree_max_reached = true;
+                h->tree_size = h->tree_max_reached ? h->cap : h->tree_write + m;
+                h->tree_write = (h->tree_write + m) % h->cap;
+            }
+            store_losses_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, h->stream>>>(h->r_losses, h->cap, cur, m, d_sc);
+            DQN_CUDA_OK(cudaGetLastError());
+        }
+        ring_copy(h, h->r_states, st + (size_t)done * h->state_bytes, cur, m, h->state_bytes);
+        ring_copy(h, h->r_next, ns + (size_t)done * h->state_bytes, cur, m, h->state_bytes);
+        ring_copy(h, h->r_actions, ac + done, cur, m, 1);
+        ring_copy(h, h->r_rewards, rw + done, cur, m, 1);
+        ring_copy(h, h->r_cont, ct + done, cur, m, 1);
+        if (cur + m >= h->cap) h->ring_full = true;
+        h->ring_cur = (cur + m) % h->cap;
+        h->ring_size = h->ring_full ? h->cap : h->ring_cur;
+        done += m;
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));  // staging buffer and caller memory are reusable on return
+    }
+    push_sizes(h);
+    API_END(h)
+}
+
+extern "C" int dqn_replay_read(dqn_learner* h, int64_t n, const int64_t* rows, uint8_t* st, uint8_t* ac, uint8_t* rw,
+                               uint8_t* ns, uint8_t* ct, uint16_t* ls) {
+    API_BEGIN(h)
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t r = rows[j];
+        DQN_REQUIRE(r >= 0 && r < h->cap, "row out of range");
+        const size_t S = h->state_bytes;
+        if (st) DQN_CUDA_OK(cudaMemcpyAsync(st + j * S, h->r_states + r * S, S, cudaMemcpyDeviceToHost, h->stream));
+        if (ns) DQN_CUDA_OK(cudaMemcpyAsync(ns + j * S, h->r_next + r * S, S, cudaMemcpyDeviceToHost, h->stream));
+        if (ac) DQN_CUDA_OK(cudaMemcpyAsync(ac + j, h->r_actions + r, 1, cudaMemcpyDeviceToHost, h->stream));
+        if (rw) DQN_CUDA_OK(cudaMemcpyAsync(rw + j, h->r_rewards + r, 1, cudaMemcpyDeviceToHost, h->stream));
+        if (ct) DQN_CUDA_OK(cudaMemcpyAsync(ct + j, h->r_cont + r, 1, cudaMemcpyDeviceToHost, h->stream));
+        if (ls) DQN_CUDA_OK(cudaMemcpyAsync(ls + j, h->r_losses + r, 2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_replay_info(dqn_learner* h, int64_t* size, int64_t* cur, int32_t* full) {
+    if (!h) return 2;
+    if (size) *size = h->ring_size;
+    if (cur) *cur = h->ring_cur;
+    if (full) *full = h->ring_full ? 1 : 0;
+    return 0;
+}
+
+extern "C" int dqn_replay_clear(dqn_learner* h) {
+    API_BEGIN(h)
+    h->ring_cur = 0; h->ring_full = false; h->ring_size = 0;
+    push_sizes(h);
+    API_END(h)
+}
+
+extern "C" int dqn_replay_fill_synthetic(dqn_learner* h, int64_t n, uint64_t seed) {
+    API_BEGIN(h)
+    DQN_REQUIRE(n >= 1 && n <= h->cap && h->ring_size == 0, "synthetic fill needs an empty ring and n <= capacity");
+    const int64_t chunk = (int64_t)(h->dev_stage_bytes / 4);
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+        const int64_t m = std::min(chunk, n - s0);
+        float* d_prio = (float*)h->dev_stage;
+        launch_fill_synthetic(h, s0, m, seed, d_prio);
+        if (h->cfg.use_per) {
+            launch_tree_add(h, m, d_prio, nullptr, s0);
+            h->tree_size = s0 + m;
+            h->tree_write = (s0 + m) % h->cap;
+            if (s0 + m >= h->cap) h->tree_max_reached = true;
+        }
+    }
+    h->ring_cur = n % h->cap; h->ring_full = n >= h->cap; h->ring_size = n;
+    push_sizes(h);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+// ---- sum tree ------------------------------------------------------------------------------------------------
+extern "C" int dqn_tree_add(dqn_learner* h, int64_t n, const float* scores, const uint32_t* data) {
+    API_BEGIN(h)
+    const int64_t max_chunk = std::min<int64_t>(h->cap, (int64_t)(h->dev_stage_bytes / 8));
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min(n - done, max_chunk);
+        float* d_s = (float*)h->dev_stage;
+        uint32_t* d_d = (uint32_t*)(h->dev_stage + h->dev_stage_bytes / 2);
+        DQN_CUDA_OK(cudaMemcpyAsync(d_s, scores + done, m * 4, cudaMemcpyHostToDevice, h->stream));
+        if (data) DQN_CUDA_OK(cudaMemcpyAsync(d_d, data + done, m * 4, cudaMemcpyHostToDevice, h->stream));
+        launch_tree_add(h, m, d_s, data ? d_d : nullptr, h->tree_write);
+        if (h->tree_write + m >= h->cap) h->tree_max_reached = true;
+        h->tree_size = h->tree_max_reached ? h->cap : h->tree_write + m;
+        h->tree_write = (h->tree_write + m) % h->cap;
+        done += m;
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    push_sizes(h);
+    API_END(h)
+}
+
+extern "C" int dqn_tree_update(dqn_learner* h, int64_t n, const int64_t* idx, const float* scores, int32_t store_losses) {
+    API_BEGIN(h)
+    const int64_t max_chunk = (int64_t)(h->dev_stage_bytes / 16);
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min(n - done, max_chunk);
+        long long* d_i = (long long*)h->dev_stage;
+        float* d_s = (float*)(h->dev_stage + h->dev_stage_bytes / 2);
+        for (int64_t j = 0; j < m; ++j) DQN_REQUIRE(idx[done + j] >= h->cap - 1 && idx[done + j] < 2 * h->cap - 1, "tree_idx is not a leaf");
+        DQN_CUDA_OK(cudaMemcpyAsync(d_i, idx + done, m * 8, cudaMemcpyHostToDevice, h->stream));
+        DQN_CUDA_OK(cudaMemcpyAsync(d_s, scores + done, m * 4, cudaMemcpyHostToDevice, h->stream));
+        launch_tree_update(h, (int)m, d_i, d_s, store_losses);
+        done += m;
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    API_END(h)
+}
+
+template <class T>
+static void d2h(dqn_learner* h, T* dst, const T* src, size_t n) {
+    if (dst) DQN_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+}
+
+extern "C" int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* u, int64_t* t_idx, int64_t* d_idx,
+                               double* prio, int64_t* m_idx) {
+    API_BEGIN(h)
+    DQN_REQUIRE(batch >= 1 && batch <= h->max_rows, "batch exceeds max_rows");
+    DQN_REQUIRE(u != nullptr, "uniform draws are required");
+    DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, batch * 8, cudaMemcpyHostToDevice, h->stream));
+    const int saved = h->cfg.use_per;
+    h->cfg.use_per = 0;  // indices only: no IS weights
+    launch_tree_sample(h, batch, 0, -1.0);
+    h->cfg.use_per = saved;
+    d2h(h, (long long*)t_idx, h->b_tree_idx, batch); d2h(h, (long long*)d_idx, h->b_data_idx, batch);
+    d2h(h, prio, h->b_prio, batch); d2h(h, (long long*)m_idx, h->b_mem_idx, batch);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_tree_stats(dqn_learner* h, float* mn, float* mx, float* avg, float* total) {
+    API_BEGIN(h)
+    launch_tree_stats(h, -1.0);
+    read_scalars(h);
+    if (mn) *mn = h->h_sc->stat_min;
+    if (mx) *mx = h->h_sc->stat_max;
+    if (avg) *avg = h->h_sc->stat_avg;
+    if (total) *total = h->h_sc->stat_total;
+    API_END(h)
+}
+
+extern "C" int dqn_tree_read(dqn_learner* h, float* tree, uint32_t* data, int64_t* size, int64_t* write) {
+    API_BEGIN(h)
+    d2h(h, tree, h->tree, (size_t)(2 * h->cap - 1));
+    d2h(h, data, h->tree_data, (size_t)h->cap);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (size) *size = h->tree_size;
+    if (write) *write = h->tree_write;
+    API_END(h)
+}
+
+// ---- samplers --------------------------------------------------------------------------------------------------
+extern "C" int dqn_per_sample(dqn_learner* h, const double* u, int32_t refresh, double per_b, int64_t* t_idx,
+                              double* prio, double* isw) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->cfg.use_per, "handle was created without use_per");
+    DQN_REQUIRE(u != nullptr, "uniform draws are required");
+    if (refresh) launch_tree_stats(h, per_b);
+    DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_tree_sample(h, h->B, 0, per_b);
+    launch_gather(h, h->b_mem_idx, h->B);
+    d2h(h, (long long*)t_idx, h->b_tree_idx, h->B); d2h(h, prio, h->b_prio, h->B); d2h(h, isw, h->b_isw64, h->B);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_uniform_sample(dqn_learner* h, const int64_t* rows) {
+    API_BEGIN(h)
+    for (int i = 0; i < h->B; ++i) DQN_REQUIRE(rows[i] >= 0 && rows[i] < h->cap, "row out of range");
+    DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows, h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_gather(h, h->b_rows, h->B);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t* rw, uint8_t* ns, uint8_t* ct, uint16_t* ls) {
+    API_BEGIN(h)
+    const size_t S = h->state_bytes, B = h->B;
+    d2h(h, st, h->b_states, B * S); d2h(h, ns, h->b_states + B * S, B * S);
+    d2h(h, ac, h->b_actions, B); d2h(h, rw, h->b_rewards, B); d2h(h, ct, h->b_cont, B);
+    d2h(h, (__half*)ls, h->b_losses, B);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+// ---- the training step ---------------------------------------------------------------------------------------
+static void prof_mark(dqn_learner* h, const char* name) {
+    if (!h->profile) return;
+    if (h->prof_used >= h->prof_events.size()) {
+        cudaEvent_t e; DQN_CUDA_OK(cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+    }
+    DQN_CUDA_OK(cudaEventRecord(h->prof_events[h->prof_used], h->stream));
+    h->prof_marks.push_back(name);
+    h->prof_used++;
+}
+
+// forward both towers, TD epilogue and (train) backward on a [2n,S] batch laid out as rows [0,n)=s, [n,2n)=s'
+static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8_t* actions, const uint8_t* rewards,
+                      const uint8_t* cont, const float* isw, int train, double grad_scale) {
+    const size_t S = h->state_bytes;
+    const int A = h->net.A;
+    prof_mark(h, "forward_online");
+    if (h->cfg.use_double) tower_forward(h, h->online, states2, 2 * n, h->acts_on);  // s and s' share one pass
+    else tower_forward(h, h->online, states2, n, h->acts_on);
+    prof_mark(h, "forward_target");
+    tower_forward(h, h->target, states2 + (size_t)n * S, n, h->acts_tg);
+    prof_mark(h, "td_epilogue");
+    launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
+                       grad_scale);
+    if (train) {
+        prof_mark(h, "backward");
+        launch_head_backward(h, n, actions);
+        tower_backward(h, states2, n);
+    }
+}
+
+static void finish_step(dqn_learner* h, int per_update) {
+    prof_mark(h, "optimizer");
+    launch_optimizer(h);
+    prof_mark(h, "post_step");
+    launch_post_step(h, per_update);
+    prof_mark(h, "end");
+    h->host_step++;
+}
+
+static void maybe_refresh_stats(dqn_learner* h) {
+    // deep_q_agent.py:505: step % per_calculate_steps == 0 or last_max_weight is None
+    if (h->cfg.use_per && (!h->has_max_weight || h->host_step % h->cfg.per_calculate_steps == 0)) {
+        launch_tree_stats(h, -1.0);
+        h->has_max_weight = true;
+    }
+}
+
+__global__ void uniform_rows_kernel(int batch, const long long* p_len, uint64_t seed, dqn_learner::Scalars* sc,
+                                    long long* rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    // replay_sampler.py:27-30: size = len/B ; randint(int(i*size), int((i+1)*size - 1)) inclusive
+    const double size = (double)(*p_len) / (double)batch;
+    const long long lo = (long long)((double)i * size), hi = (long long)((double)(i + 1) * size - 1.0);
+    uint32_t r[4];
+    const unsigned long long ctr = sc->rng_counter;
+    philox4x32((uint32_t)i, 1u, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    long long span = hi - lo + 1;
+    if (span < 1) span = 1;
+    long long off = (long long)(u53(r[0], r[1]) * (double)span);
+    if (off >= span) off = span - 1;
+    rows[i] = lo + off;
+}
+
+// sample + gather into the device batch. u / rows: host-provided draws for parity, NULL -> device Philox.
+static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* rows) {
+    prof_mark(h, "sample");
+    if (h->cfg.use_per) {
+        if (u) DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, h->B * 8, cudaMemcpyHostToDevice, h->stream));
+        launch_tree_sample(h, h->B, u ? 0 : 1, -1.0);
+        prof_mark(h, "gather");
+        launch_gather(h, h->b_mem_idx, h->B);
+    } else {
+        if (rows) DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows, h->B * 8, cudaMemcpyHostToDevice, h->stream));
+        else {
+            uniform_rows_kernel<<<ceil_div(h->B, 128), 128, 0, h->stream>>>(h->B, &h->d_dev->ring_len, h->cfg.seed, h->d_sc, h->b_rows);
+            DQN_CUDA_OK(cudaGetLastError());
+            h->launches++;
+        }
+        prof_mark(h, "gather");
+        launch_gather(h, h->b_rows, h->B);
+    }
+}
+
+static void fused_step_launches(dqn_learner* h, const double* u, const int64_t* rows, double grad_scale, int phases) {
+    if (phases & 1) {
+        sample_into_batch(h, u, rows);
+        step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1, grad_scale);
+    }
+    if (phases & 2) finish_step(h, h->cfg.use_per);
+}
+
+static void after_step_host(dqn_learner* h) {
+    // deep_q_agent.py:358-360: copy online -> target every copy_network_steps (step is the post-increment value)
+    if (h->cfg.copy_network_steps > 0 && h->host_step % h->cfg.copy_network_steps == 0) launch_copy_network(h);
+}
+
+extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* rows, int64_t* step, float* losses, float* loss) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+    h->prof_used = 0; h->prof_marks.clear();
+    maybe_refresh_stats(h);
+    fused_step_launches(h, u, rows, 1.0, 3);
+    after_step_host(h);
+    if (step || losses || loss) {
+        d2h(h, losses, h->b_losses_out, h->B);
+        read_scalars(h);
+        if (step) *step = h->h_sc->step;
+        if (loss) *loss = h->h_sc->loss;
+    }
+    API_END(h)
+}
+
+extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+    if (h->profile) {
+        for (int64_t i = 0; i < n; ++i) {
+            h->prof_used = 0; h->prof_marks.clear();
+            maybe_refresh_stats(h);
+            fused_step_launches(h, nullptr, nullptr, 1.0, 3);
+            after_step_host(h);
+            // accumulate segment times
+            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+            for (size_t s = 0; s + 1 < h->prof_used; ++s) {
+                float ms = 0.f;
+                DQN_CUDA_OK(cudaEventElapsedTime(&ms, h->prof_events[s], h->prof_events[s + 1]));
+                bool found = false;
+                for (auto& kv : h->prof_acc) if (kv.first == h->prof_marks[s]) { kv.second += ms; found = true; }
+                if (!found) h->prof_acc.push_back({h->prof_marks[s], ms});
+            }
+            h->prof_steps++;
+        }
+        return 0;
+    }
+    if (!h->graph_valid) {
+        // capture one fused step (device RNG) into a graph: ~30 short kernels replayed with a single launch
+        cudaGraph_t g = nullptr;
+        const int64_t l0 = h->launches, s0 = h->host_step;
+        DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            fused_step_launches(h, nullptr, nullptr, 1.0, 3);
+        } catch (...) {
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+        h->graph_launches = h->launches - l0;
+        h->launches = l0; h->host_step = s0;
+        if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+        DQN_CUDA_OK(cudaGraphInstantiate(&h->step_graph, g, 0));
+        DQN_CUDA_OK(cudaGraphDestroy(g));
+        h->graph_valid = true;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        maybe_refresh_stats(h);
+        DQN_CUDA_OK(cudaGraphLaunch(h->step_graph, h->stream));
+        h->launches += h->graph_launches;
+        h->host_step++;
+        after_step_host(h);
+    }
+    API_END(h)
+}
+
+extern "C" int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale) {
+    API_BEGIN(h)
+    h->prof_used = 0; h->prof_marks.clear();
+    if (phase == 0) {
+        DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+        maybe_refresh_stats(h);
+        fused_step_launches(h, nullptr, nullptr, grad_scale, 1);
+    } else {
+        fused_step_launches(h, nullptr, nullptr, grad_scale, 2);
+        after_step_host(h);
+    }
+    API_END(h)
+}
+
+static void upload_batch(dqn_learner* h, int n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw, const uint8_t* ct,
+                         const uint8_t* ns, const float* isw) {
+    const size_t S = h->state_bytes;
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st, n * S, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_states + n * S, ns, n * S, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_actions, ac, n, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_rewards, rw, n, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_cont, ct, n, cudaMemcpyHostToDevice, h->stream));
+    if (isw) DQN_CUDA_OK(cudaMemcpyAsync(h->in_isw, isw, n * 4, cudaMemcpyHostToDevice, h->stream));
+}
+
+extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw,
+                               const uint8_t* ct, const uint8_t* ns, const float* isw, int64_t* step, float* losses, float* loss) {
+    API_BEGIN(h)
+    DQN_REQUIRE(n >= 1 && n <= h->max_rows, "n exceeds max_rows");
+    DQN_REQUIRE(!h->cfg.use_per || isw, "use_per: is_weights are required");
+    h->prof_used = 0; h->prof_marks.clear();
+    upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
+    step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
+    finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
+    d2h(h, losses, h->b_losses_out, n);
+    read_scalars(h);
+    if (step) *step = h->h_sc->step;
+    if (loss) *loss = h->h_sc->loss;
+    API_END(h)
+}
+
+extern "C" int dqn_get_losses(dqn_learner* h, int32_t n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw,
+                              const uint8_t* ct, const uint8_t* ns, float* losses) {
+    API_BEGIN(h)
+    DQN_REQUIRE(n >= 1 && n <= h->max_rows, "n exceeds max_rows");
+    upload_batch(h, n, st, ac, rw, ct, ns, nullptr);
+    // the losses tensor does not depend on is_weights (deep_q_model.py:150-157 feeds none)
+    const int saved_profile = h->profile; h->profile = 0;
+    static_cast<void>(saved_profile);
+    if (h->cfg.use_per) {
+        DQN_CUDA_OK(cudaMemsetAsync(h->in_isw, 0, n * 4, h->stream));
+    }
+    step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 0, 1.0);
+    h->profile = saved_profile;
+    d2h(h, losses, h->b_losses_out, n);
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_predict(dqn_learner* h, int32_t n, const uint8_t* st, int32_t use_target, float* q) {
+    API_BEGIN(h)
+    const size_t S = h->state_bytes;
+    const int A = h->net.A;
+    const int saved_profile = h->profile; h->profile = 0;
+    for (int done = 0; done < n;) {
+        const int m = std::min(n - done, h->max_rows);
+        DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st + (size_t)done * S, m * S, cudaMemcpyHostToDevice, h->stream));
+        TowerActs& acts = use_target ? h->acts_tg : h->acts_on;
+        tower_forward(h, use_target ? h->target : h->online, h->in_states, m, acts);
+        DQN_CUDA_OK(cudaMemcpyAsync(q + (size_t)done * A, acts.q, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream));
+        done += m;
+    }
+    h->profile = saved_profile;
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_debug_read(dqn_learner* h, const char* what, float* out, int64_t count) {
+    API_BEGIN(h)
+    const std::string w = what;
+    const float* src = nullptr;
+    if (w == "q_online") src = h->acts_on.q;
+    else if (w == "q_target") src = h->acts_tg.q;
+    else if (w == "y") src = h->b_y;
+    else if (w == "max_q") src = h->b_maxq;
+    else if (w == "losses") src = h->b_losses_out;
+    else if (w == "dq") src = h->b_dq;
+    else if (w == "new_priorities") src = h->b_newprio;
+    else if (w == "is_weights") src = h->b_isw;
+    else if (w == "d_hid") src = h->d_hid;
+    else if (w == "hid_online") src = h->acts_on.hid;
+    else if (w == "act1_online") src = h->acts_on.act[0];
+    else if (w == "act2_online") src = h->acts_on.act[1];
+    else if (w == "act3_online") src = h->acts_on.act[2];
+    else if (w == "d_act1") src = h->d_act[0];
+    else if (w == "d_act2") src = h->d_act[1];
+    else if (w == "d_act3") src = h->d_act[2];
+    else throw std::string("unknown debug buffer: ") + w;
+    DQN_CUDA_OK(cudaMemcpyAsync(out, src, count * 4, cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+extern "C" int dqn_launch_count(const dqn_learner* h, int64_t* n) {
+    if (!h) return 2;
+    if (n) *n = h->launches;
+    return 0;
+}
+
+extern "C" int dqn_set_profile(dqn_learner* h, int32_t enabled) {
+    if (!h) return 2;
+    h->profile = enabled;
+    h->prof_acc.clear();
+    h->prof_steps = 0;
+    return 0;
+}
+
+extern "C" int dqn_get_profile(dqn_learner* h, int32_t* n, const char** names, float* ms, int32_t cap, int64_t* steps) {
+    if (!h) return 2;
+    int k = 0;
+    for (auto& kv : h->prof_acc) {
+        if (k >= cap) break;
+        names[k] = kv.first;
+        ms[k] = kv.second;
+        ++k;
+    }
+    if (n) *n = k;
+    if (steps) *steps = h->prof_steps;
+    return 0;
+}
+
+// ---- persistence -------------------------------------------------------------------------------------------
+struct CkptHeader {
+    char magic[8];
+    int32_t version, n_tensors;
+    int64_t slab, step, game_count;
+    float b1p, b2p;
+    int32_t H, W, C, A, hidden, dueling, variant, pad;
+};
+
+extern "C" int dqn_save(dqn_learner* h, const char* prefix) {
+    API_BEGIN(h)
+    read_scalars(h);
+    const std::string path = std::string(prefix) + ".dqnb200";
+    FILE* f = fopen((path + ".tmp").c_str(), "wb");
+    DQN_REQUIRE(f != nullptr, "cannot open checkpoint for writing");
+    CkptHeader hd; memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "DQNB200", 8); hd.version = 1; hd.n_tensors = (int32_t)h->net.tensors.size();
+    hd.slab = h->net.slab; hd.step = h->h_sc->step; hd.game_count = h->h_sc->game_count;
+    hd.b1p = h->h_sc->b1p; hd.b2p = h->h_sc->b2p;
+    hd.H = h->net.H; hd.W = h->net.W; hd.C = h->net.C; hd.A = h->net.A; hd.hidden = h->net.hidden;
+    hd.dueling = h->net.dueling; hd.variant = h->cfg.conv_variant;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    std::vector<float> buf((size_t)h->net.slab);
+    for (float* slab : {h->online, h->target, h->slot_m, h->slot_v}) {
+        DQN_CUDA_OK(cudaMemcpy(buf.data(), slab, buf.size() * 4, cudaMemcpyDeviceToHost));
+        ok = ok && fwrite(buf.data(), 4, buf.size(), f) == buf.size();
+    }
+    fclose(f);
+    DQN_REQUIRE(ok, "short write on checkpoint");
+    DQN_REQUIRE(rename((path + ".tmp").c_str(), path.c_str()) == 0, "cannot move checkpoint into place");
+    API_END(h)
+}
+
+extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
+    if (!h) return 2;
+    const std::string path = std::string(prefix) + ".dqnb200";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return 3;  // "model does not exist" (rl/model/model.py:76-78)
+    try {
+        DQN_CUDA_OK(cudaSetDevice(h->device));
+        CkptHeader hd;
+        DQN_REQUIRE(fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "DQNB200", 8) == 0, "not a dqn_b200 checkpoint");
+        DQN_REQUIRE(hd.slab == h->net.slab && hd.H == h->net.H && hd.W == h->net.W && hd.A == h->net.A &&
+                        hd.hidden == h->net.hidden && hd.dueling == h->net.dueling && hd.variant == h->cfg.conv_variant,
+                    "checkpoint was written for a different network configuration");
+        std::vector<float> buf((size_t)h->net.slab);
+        for (float* slab : {h->online, h->target, h->slot_m, h->slot_v}) {
+            DQN_REQUIRE(fread(buf.data(), 4, buf.size(), f) == buf.size(), "truncated checkpoint");
+            DQN_CUDA_OK(cudaMemcpy(slab, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+        }
+        fclose(f); f = nullptr;
+        set_ll(h, &h->d_sc->step, hd.step);
+        set_ll(h, &h->d_sc->game_count, hd.game_count);
+        set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, hd.b1p, &h->d_sc->b2p, hd.b2p);
+        h->host_step = hd.step;
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    } catch (const std::string& e) {
+        if (f) fclose(f);
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,358 @@
+// fp32 implicit-GEMM on CUDA cores: C[M,N] = A[M,K] * B[K,N] with operand functors that gather
+// conv windows / transposes on the fly (no im2col buffer is ever materialised) and epilogue functors
+// that fuse bias, ReLU, ReLU-gating and split-K partial stores.
+//
+// This is the DQN_MATH_FP32 path (strict fp32, FFMA): register-blocked TMxTN micro tiles, double-buffered
+// shared memory, 16-byte global loads along whichever dimension the operand is contiguous in.
+#pragma once
+#include "learner.h"
+
+template <int BM_, int BN_, int BK_, int TM_, int TN_>
+struct TileCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, TM = TM_, TN = TN_;
+    static constexpr int THREADS = (BM / TM) * (BN / TN);
+};
+
+// ---------------- operand functors ----------------
+// KCONTIG=true : load4(row, r, k, z) returns elements (r, k..k+3)
+// KCONTIG=false: load4(row, r, k, z) returns elements (r..r+3, k)
+// row(r, z) precomputes whatever depends only on r.
+
+struct OpRowMajorK {  // Op(r,k) = p[r*ld + k]
+    static constexpr bool KCONTIG = true;
+    const float* p; int ld;
+    typedef const float* Row;
+    __device__ __forceinline__ Row row(int r, int) const { return p + (size_t)r * ld; }
+    __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const { return *reinterpret_cast<const float4*>(rw + k); }
+};
+
+struct OpColContig {  // Op(r,k) = p[k*ld + r]
+    static constexpr bool KCONTIG = false;
+    const float* p; int ld;
+    typedef const float* Row;
+    __device__ __forceinline__ Row row(int r, int) const { return p + r; }
+    __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const {
+        return *reinterpret_cast<const float4*>(rw + (size_t)k * ld);
+    }
+};
+
+// hidden-layer weights of the (up to) two streams seen as one [flat, NH] matrix: B(k,n) = W[n/hid][k][n%hid]
+struct OpFcWeightFwd {
+    static constexpr bool KCONTIG = false;
+    const float* w0; const float* w1; int hid;
+    typedef const float* Row;
+    __device__ __forceinline__ Row row(int n, int) const { return n < hid ? w0 + n : w1 + (n - hid); }
+    __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const {
+        return *reinterpret_cast<const float4*>(rw + (size_t)k * hid);
+    }
+};
+
+// transposed view for dgrad: B(k,n) = W[k/hid][n][k%hid]
+struct OpFcWeightBwd {
+    static constexpr bool KCONTIG = true;
+    const float* w0; const float* w1; int hid;
+    typedef size_t Row;
+    __device__ __forceinline__ Row row(int n, int) const { return (size_t)n * hid; }
+    __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const {
+        const float* w = k < hid ? w0 : w1;
+        const int kk = k < hid ? k : k - hid;
+        return *reinterpret_cast<const float4*>(w + rw + kk);
+    }
+};
+
+__device__ __forceinline__ float4 load_px4(const void* in, int is_u8, size_t idx) {
+    if (is_u8) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(in) + idx);
+        return make_float4(u8_to_unit(w & 255u), u8_to_unit((w >> 8) & 255u), u8_to_unit((w >> 16) & 255u),
+                           u8_to_unit(w >> 24));
+    }
+    return *reinterpret_cast<const float4*>(static_cast<const float*>(in) + idx);
+}
+
+// conv forward A: rows m=(n,oy,ox), k=(kh,kw,ci) -- the im2col view of an NHWC tensor (u8 or f32)
+struct OpConvFwdA {
+    static constexpr bool KCONTIG = true;
+    const void* in; ConvGeom g; int is_u8;
+    struct Row { size_t base; int iy0, ix0; };
+    __device__ __forceinline__ Row row(int m, int) const {
+        const int hw = g.oh * g.ow;
+        const int n = m / hw, rem = m - n * hw;
+        const int oy = rem / g.ow, ox = rem - oy * g.ow;
+        Row r; r.base = (size_t)n * g.ih * g.iw * g.cin; r.iy0 = oy * g.s - g.pt; r.ix0 = ox * g.s - g.pl;
+        return r;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
+        const int tap = k >> g.cin_log2, ci = k & (g.cin - 1);
+        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int iy = r.iy0 + kh, ix = r.ix0 + kw;
+        if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return load_px4(in, is_u8, r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci);
+    }
+};
+
+// conv wgrad A^T: rows m=(kh,kw,ci) (4 consecutive ci per load), k=(n,oy,ox)
+struct OpConvWgradA {
+    static constexpr bool KCONTIG = false;
+    const void* in; ConvGeom g; int is_u8;
+    struct Row { int kh, kw, ci; };
+    __device__ __forceinline__ Row row(int m, int) const {
+        const int tap = m >> g.cin_log2;
+        Row r; r.ci = m & (g.cin - 1); r.kh = tap / g.k; r.kw = tap - r.kh * g.k;
+        return r;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
+        const int hw = g.oh * g.ow;
+        const int n = k / hw, rem = k - n * hw;
+        const int oy = rem / g.ow, ox = rem - oy * g.ow;
+        const int iy = oy * g.s - g.pt + r.kh, ix = ox * g.s - g.pl + r.kw;
+        if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return load_px4(in, is_u8, (((size_t)n * g.ih + iy) * g.iw + ix) * g.cin + r.ci);
+    }
+};
+
+// conv dgrad, decomposed by stride-parity class z = ry*s + rx so that only taps that actually reach an
+// input pixel are multiplied: rows m=(n,a,b) with iy = y0(ry)+s*a, ix = x0(rx)+s*b; k=(jh,jw,co), kh = ry+s*jh.
+struct DgradClass {
+    ConvGeom g;
+    __device__ __forceinline__ void cls(int z, int& ry, int& rx, int& y0, int& x0, int& cy, int& cx) const {
+        ry = z / g.s; rx = z - ry * g.s;
+        // smallest iy >= 0 with (iy + pt) % s == ry
+        y0 = ((ry - g.pt) % g.s + g.s) % g.s; x0 = ((rx - g.pl) % g.s + g.s) % g.s;
+        cy = y0 < g.ih ? (g.ih - y0 + g.s - 1) / g.s : 0;
+        cx = x0 < g.iw ? (g.iw - x0 + g.s - 1) / g.s : 0;
+    }
+};
+
+struct OpConvDgradA {
+    static constexpr bool KCONTIG = true;
+    const float* dy; DgradClass c; int cout_log2; int nimg;
+    struct Row { size_t base; int oy0, ox0; int ok; };
+    __device__ __forceinline__ Row row(int m, int z) const {
+        int ry, rx, y0, x0, cy, cx; c.cls(z, ry, rx, y0, x0, cy, cx);
+        Row r; r.ok = 0; r.base = 0; r.oy0 = 0; r.ox0 = 0;
+        const int per = cy * cx;
+        if (per == 0) return r;
+        const int n = m / per, rem = m - n * per;
+        if (n >= nimg) return r;
+        const int a = rem / cx, b = rem - a * cx;
+        const int iy = y0 + c.g.s * a, ix = x0 + c.g.s * b;
+        r.ok = 1; r.base = (size_t)n * c.g.oh * c.g.ow;
+        r.oy0 = (iy + c.g.pt - ry) / c.g.s; r.ox0 = (ix + c.g.pl - rx) / c.g.s;
+        return r;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
+        const int kt = c.g.k / c.g.s;  // taps per axis in one class
+        const int tap = k >> cout_log2, co = k & (c.g.cout - 1);
+        const int jh = tap / kt, jw = tap - jh * kt;
+        const int oy = r.oy0 - jh, ox = r.ox0 - jw;
+        if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow)
+            return make_float4(0.f, 0.f, 0.f, 0.f);
+        return *reinterpret_cast<const float4*>(dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co);
+    }
+};
+
+struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
+    static constexpr bool KCONTIG = true;
+    const float* w; ConvGeom g; int cout_log2;
+    typedef int Row;
+    __device__ __forceinline__ Row row(int n, int) const { return n; }
+    __device__ __forceinline__ float4 load4(Row ci, int, int k, int z) const {
+        const int ry = z / g.s, rx = z - ry * g.s;
+        const int kt = g.k / g.s;
+        const int tap = k >> cout_log2, co = k & (g.cout - 1);
+        const int jh = tap / kt, jw = tap - jh * kt;
+        const int kh = ry + g.s * jh, kw = rx + g.s * jw;
+        return *reinterpret_cast<const float4*>(w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co);
+    }
+};
+
+// ---------------- epilogues ----------------
+struct EpiBiasRelu {  // out[m][n] = relu(acc + bias[n])
+    float* out; const float* bias; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
+        float* o = out + (size_t)m * ldo + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + n + j);
+            float4 r = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f),
+                                   fmaxf(v[j + 3] + b.w, 0.f));
+            *reinterpret_cast<float4*>(o + j) = r;
+        }
+    }
+};
+
+struct EpiPartial {  // part[z][m][n] = acc   (split-K partial sums, reduced by a consumer kernel)
+    float* part; int M; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int z) const {
+        float* o = part + ((size_t)z * M + m) * ldo + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
+struct EpiGateStore {  // out[m][n] = acc * (gate[m][n] > 0)   (ReLU backward fused into dgrad)
+    float* out; const float* gate; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
+        const size_t o = (size_t)m * ldo + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(gate + o + j);
+            *reinterpret_cast<float4*>(out + o + j) = make_float4(g.x > 0.f ? v[j] : 0.f, g.y > 0.f ? v[j + 1] : 0.f,
+                                                                 g.z > 0.f ? v[j + 2] : 0.f, g.w > 0.f ? v[j + 3] : 0.f);
+        }
+    }
+};
+
+struct EpiDgradGate {  // conv dgrad: row m of class z -> pixel (n,iy,ix); out = acc * (gate > 0)
+    float* out; const float* gate; DgradClass c; int nimg;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int z) const {
+        int ry, rx, y0, x0, cy, cx; c.cls(z, ry, rx, y0, x0, cy, cx);
+        const int per = cy * cx;
+        if (per == 0) return;
+        const int img = m / per, rem = m - img * per;
+        if (img >= nimg) return;
+        const int a = rem / cx, b = rem - a * cx;
+        const int iy = y0 + c.g.s * a, ix = x0 + c.g.s * b;
+        const size_t o = (((size_t)img * c.g.ih + iy) * c.g.iw + ix) * c.g.cin + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(gate + o + j);
+            *reinterpret_cast<float4*>(out + o + j) = make_float4(g.x > 0.f ? v[j] : 0.f, g.y > 0.f ? v[j + 1] : 0.f,
+                                                                 g.z > 0.f ? v[j + 2] : 0.f, g.w > 0.f ? v[j + 3] : 0.f);
+        }
+    }
+};
+
+struct EpiFcWgrad {  // dW of the two hidden streams: column n -> stream n/hid, grads laid out like the params
+    float* g0; float* g1; int hid;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
+        float* o = (n < hid ? g0 + n : g1 + (n - hid)) + (size_t)m * hid;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
+// ---------------- the kernel ----------------
+// grid = (ceil(M/BM), ceil(N/BN), Z).  SPLIT: z selects the K range [z*kchunk, min(K,(z+1)*kchunk));
+// otherwise z is a group id handed to the functors (dgrad parity class) and the whole K is reduced.
+template <class Cfg, bool SPLIT, class AOp, class BOp, class Epi>
+__global__ void __launch_bounds__(Cfg::THREADS) igemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
+                                                            int kchunk) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN, T = Cfg::THREADS;
+    constexpr int PAD = 4;
+    constexpr int LA = (BM * BK / 4) / T, LB = (BN * BK / 4) / T;
+    static_assert(LA * T * 4 == BM * BK && LB * T * 4 == BN * BK, "tile/thread mismatch");
+    static_assert(TM % 4 == 0 && TN % 4 == 0, "micro tile must be float4 multiples");
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int z = blockIdx.z;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kbeg = SPLIT ? z * kchunk : 0;
+    const int kend = SPLIT ? min(K, kbeg + kchunk) : K;
+
+    // static (row, k-offset) assignment of this thread's 16-byte loads
+    int a_r[LA], a_k[LA], b_r[LB], b_k[LB];
+    typename AOp::Row a_row[LA];
+    typename BOp::Row b_row[LB];
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+        const int f = tid + i * T;
+        if (AOp::KCONTIG) { a_r[i] = f / (BK / 4); a_k[i] = (f % (BK / 4)) * 4; }
+        else { a_k[i] = f / (BM / 4); a_r[i] = (f % (BM / 4)) * 4; }
+        a_row[i] = a.row(min(m0 + a_r[i], M - 1), z);
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+        const int f = tid + i * T;
+        if (BOp::KCONTIG) { b_r[i] = f / (BK / 4); b_k[i] = (f % (BK / 4)) * 4; }
+        else { b_k[i] = f / (BN / 4); b_r[i] = (f % (BN / 4)) * 4; }
+        b_row[i] = b.row(min(n0 + b_r[i], N - 1), z);
+    }
+
+    float4 a_reg[LA], b_reg[LB];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int r = m0 + a_r[i], k = k0 + a_k[i];
+            a_reg[i] = (r < M && k < kend) ? a.load4(a_row[i], r, k, z) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int r = n0 + b_r[i], k = k0 + b_k[i];
+            b_reg[i] = (r < N && k < kend) ? b.load4(b_row[i], r, k, z) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            if (AOp::KCONTIG) {
+                As[buf][a_k[i] + 0][a_r[i]] = a_reg[i].x; As[buf][a_k[i] + 1][a_r[i]] = a_reg[i].y;
+                As[buf][a_k[i] + 2][a_r[i]] = a_reg[i].z; As[buf][a_k[i] + 3][a_r[i]] = a_reg[i].w;
+            } else {
+                *reinterpret_cast<float4*>(&As[buf][a_k[i]][a_r[i]]) = a_reg[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            if (BOp::KCONTIG) {
+                Bs[buf][b_k[i] + 0][b_r[i]] = b_reg[i].x; Bs[buf][b_k[i] + 1][b_r[i]] = b_reg[i].y;
+                Bs[buf][b_k[i] + 2][b_r[i]] = b_reg[i].z; Bs[buf][b_k[i] + 3][b_r[i]] = b_reg[i].w;
+            } else {
+                *reinterpret_cast<float4*>(&Bs[buf][b_k[i]][b_r[i]]) = b_reg[i];
+            }
+        }
+    };
+
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    if (kbeg < kend) {
+        gload(kbeg);
+        sstore(0);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        const bool more = k0 + BK < kend;
+        if (more) gload(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) *reinterpret_cast<float4*>(&av[i]) = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + i]);
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(&bv[j]) = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) sstore(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i, n = n0 + tx * TN;
+        if (m < M && n < N) epi.store(m, n, acc[i], z);
+    }
+}
+
+template <class Cfg, bool SPLIT, class AOp, class BOp, class Epi>
+static void launch_igemm(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+    dim3 grid(ceil_div(M, Cfg::BM), ceil_div(N, Cfg::BN), Z);
+    igemm_kernel<Cfg, SPLIT, AOp, BOp, Epi><<<grid, Cfg::THREADS, 0, h->stream>>>(a, b, e, M, N, K, kchunk);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
+}

@@ -1,0 +1,155 @@
+// Internal state of a dqn_learner handle.
+#pragma once
+#include "common.cuh"
+#include "../../include/dqn_b200.h"
+#include <vector>
+#include <string>
+#include <utility>
+
+struct ConvGeom {
+    int ih, iw, cin, oh, ow, cout, k, s, pt, pl;
+    int cin_log2;
+};
+
+struct TensorInfo {
+    std::string name;
+    int64_t offset;  // floats from slab base (16-byte aligned)
+    int64_t count;
+};
+
+struct NetDesc {
+    int H, W, C, A, hidden, dueling, NH;  // NH = hidden * (dueling ? 2 : 1)
+    ConvGeom conv[3];
+    int flat;
+    int64_t off_cw[3], off_cb[3];
+    int64_t off_fc_w[2], off_fc_b[2];  // hidden layers: [0]=advantage (or the only) stream, [1]=value stream
+    int64_t off_hd_w[2], off_hd_b[2];  // heads: [0]=advantage/Q head [hidden,A], [1]=value head [hidden,1]
+    int64_t slab;                      // padded float count of one tower
+    std::vector<TensorInfo> tensors;   // TF creation order
+};
+
+// activations of one tower forward over `rows` samples
+struct TowerActs {
+    float* act[3];   // post-ReLU conv outputs, NHWC
+    float* fc_part;  // split-K partials [splits][rows][NH]
+    float* hid;      // post-ReLU hidden [rows][NH]
+    float* q;        // [rows][A]
+};
+
+struct dqn_learner {
+    dqn_config cfg;
+    NetDesc net;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // parameters
+    float *online = nullptr, *target = nullptr, *slot_m = nullptr, *slot_v = nullptr, *grads = nullptr;
+    // device scalars: [0]=step (int64), game_count, beta powers, PER stats
+    struct Scalars {
+        long long step;
+        long long game_count;
+        float b1p, b2p;
+        float stat_min, stat_max, stat_avg, stat_total;  // raw leaf stats (SumTree.get_*)
+        float last_max_weight;                            // deep_q_agent.py:510
+        float per_b;                                      // beta used by the last sample
+        float loss;                                       // scalar loss of the last step
+        float loss_sum;                                   // running sum for the report line
+        int has_max_weight;
+        unsigned long long rng_counter;
+    };
+    Scalars* d_sc = nullptr;
+    Scalars* h_sc = nullptr;  // pinned mirror for reads
+    // host-owned sizes mirrored on the device so that captured graphs see current values
+    struct DevSizes { long long tree_size; long long ring_len; };
+    DevSizes* d_dev = nullptr;
+    int64_t host_step = 0;     // host mirror of Scalars::step (cadence decisions without a device read)
+    bool has_max_weight = false;
+
+    // replay ring (SoA, HBM)
+    int64_t cap = 0, ring_size = 0, ring_cur = 0;
+    bool ring_full = false;
+    size_t state_bytes = 0;
+    uint8_t *r_states = nullptr, *r_next = nullptr, *r_actions = nullptr, *r_rewards = nullptr, *r_cont = nullptr;
+    __half* r_losses = nullptr;
+
+    // sum tree
+    float* tree = nullptr;       // 2*cap-1
+    uint32_t* tree_data = nullptr;  // cap
+    int64_t tree_size = 0, tree_write = 0;
+    bool tree_max_reached = false;
+
+    // train batch (device): rows [0,B) = s, [B,2B) = s'
+    int B = 0, max_rows = 0;
+    uint8_t* b_states = nullptr;  // sampled batch [2*max_rows][S]
+    uint8_t *b_actions = nullptr, *b_rewards = nullptr, *b_cont = nullptr;
+    // host-fed batch (train_batch / predict / get_losses), kept apart from the sampled one
+    uint8_t* in_states = nullptr;
+    uint8_t *in_actions = nullptr, *in_rewards = nullptr, *in_cont = nullptr;
+    float* in_isw = nullptr;
+    long long* b_rows = nullptr;       // uniform-sampler rows
+    __half* b_losses = nullptr;
+    long long* b_tree_idx = nullptr;   // [B]
+    long long* b_data_idx = nullptr;
+    long long* b_mem_idx = nullptr;
+    double* b_prio = nullptr;          // f32 tree values widened, as the reference's float array holds them
+    double* b_isw64 = nullptr;
+    float* b_isw = nullptr;            // fed as f32
+    double* b_u = nullptr;             // uniforms
+    float *b_y = nullptr, *b_maxq = nullptr, *b_losses_out = nullptr, *b_dq = nullptr, *b_newprio = nullptr;
+
+    // activations / workspaces
+    TowerActs acts_on, acts_tg;
+    float *d_hid = nullptr, *d_act[3] = {nullptr, nullptr, nullptr};
+    float* wg_part = nullptr;  // split-K partials for conv wgrad
+    int64_t wg_part_floats = 0;
+    int fc_splits = 1;
+
+    // staging
+    uint8_t* dev_stage = nullptr;
+    size_t dev_stage_bytes = 0;
+    uint8_t* stats_scratch = nullptr;
+
+    // graph for the fused step
+    cudaGraphExec_t step_graph = nullptr;
+    bool graph_valid = false;
+    int64_t graph_launches = 0;
+
+    // per-segment CUDA-event timing (dqn_set_profile)
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<const char*> prof_marks;
+    size_t prof_used = 0;
+    std::vector<std::pair<const char*, float>> prof_acc;
+    int64_t prof_steps = 0;
+};
+
+// ---- kernels / launchers (defined across the .cu files) ----
+void net_describe(NetDesc& net, const dqn_config& cfg);
+
+// replay.cu
+void launch_gather(dqn_learner* h, const long long* d_rows, int n);
+void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
+
+// sumtree.cu
+void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b);
+void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
+void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uint32_t* d_data, int64_t write0);
+void launch_tree_stats(dqn_learner* h, double per_b_override);
+
+// nn.cu
+void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, int rows, TowerActs& acts);
+void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows);
+
+// heads.cu
+void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q_on_next, const float* q_tg_next,
+                        const uint8_t* actions, const uint8_t* rewards, const uint8_t* cont, const float* isw,
+                        int train, double grad_scale);
+void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions);
+
+// optim.cu
+void launch_optimizer(dqn_learner* h);
+void launch_post_step(dqn_learner* h, int per_update);
+void launch_copy_network(dqn_learner* h);

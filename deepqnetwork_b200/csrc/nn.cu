@@ -1,0 +1,255 @@
+// Q-network tower forward and backward (fp32 implicit-GEMM path).
+//
+// Replaces the TF graph built by rl/deep_q_model.py:266-354 (_make_q_network: 3x conv 'same'+ReLU, NHWC flatten,
+// dense 512 ReLU, optional dueling streams) and its autodiff backward (rl/deep_q_model.py:391 optimizer.minimize).
+// Layout: activations NHWC f32, conv kernels HWIO (== row-major [KH*KW*Cin, Cout]), dense kernels [in,out] --
+// the TF layouts, so tensors copy 1:1 to/from checkpoints.
+#include "igemm.cuh"
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+void net_describe(NetDesc& net, const dqn_config& cfg) {
+    net.H = cfg.input_height; net.W = cfg.input_width; net.C = cfg.input_channels;
+    net.A = cfg.num_actions; net.hidden = cfg.num_hidden; net.dueling = cfg.use_dueling ? 1 : 0;
+    net.NH = net.hidden * (net.dueling ? 2 : 1);
+    const int maps[3] = {32, 64, 64};
+    const int ks_ref[3] = {8, 4, 4}, ks_nat[3] = {8, 4, 3};
+    const int st[3] = {4, 2, 1};
+    const bool same = cfg.conv_variant == DQN_CONV_REFERENCE;
+    int ih = net.H, iw = net.W, cin = net.C;
+    for (int l = 0; l < 3; ++l) {
+        ConvGeom& g = net.conv[l];
+        g.ih = ih; g.iw = iw; g.cin = cin; g.cout = maps[l]; g.s = st[l];
+        g.k = same ? ks_ref[l] : ks_nat[l];
+        if (same) {  // TF 'SAME': out = ceil(in/s); pad_total = max((out-1)*s + k - in, 0); before = pad_total/2
+            g.oh = (ih + g.s - 1) / g.s; g.ow = (iw + g.s - 1) / g.s;
+            int ph = (g.oh - 1) * g.s + g.k - ih; if (ph < 0) ph = 0;
+            int pw = (g.ow - 1) * g.s + g.k - iw; if (pw < 0) pw = 0;
+            g.pt = ph / 2; g.pl = pw / 2;
+        } else {
+            g.oh = (ih - g.k) / g.s + 1; g.ow = (iw - g.k) / g.s + 1; g.pt = g.pl = 0;
+        }
+        g.cin_log2 = ilog2(cin);
+        DQN_REQUIRE((1 << g.cin_log2) == cin && cin % 4 == 0, "channel counts must be powers of two >= 4");
+        DQN_REQUIRE(g.k % g.s == 0, "kernel size must be a multiple of the stride");
+        ih = g.oh; iw = g.ow; cin = g.cout;
+    }
+    net.flat = ih * iw * cin;
+    DQN_REQUIRE(net.hidden % 8 == 0 && net.flat % 16 == 0, "hidden/flat alignment");
+    int64_t off = 0;
+    auto add = [&](const std::string& name, int64_t count) {
+        TensorInfo t; t.name = name; t.offset = off; t.count = count;
+        net.tensors.push_back(t);
+        int64_t o = off;
+        off += (count + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+        return o;
+    };
+    net.tensors.clear();
+    for (int l = 0; l < 3; ++l) {
+        const ConvGeom& g = net.conv[l];
+        std::string nm = l == 0 ? "conv2d" : ("conv2d_" + std::to_string(l));
+        net.off_cw[l] = add(nm + "/kernel", (int64_t)g.k * g.k * g.cin * g.cout);
+        net.off_cb[l] = add(nm + "/bias", g.cout);
+    }
+    // creation order of rl/deep_q_model.py:312-343: dense (adv hidden), dense_1 (adv), dense_2 (val hidden), dense_3 (val)
+    const int streams = net.dueling ? 2 : 1;
+    for (int s = 0; s < streams; ++s) {
+        const int outs = s == 0 ? net.A : 1;
+        std::string n0 = (2 * s) == 0 ? "dense" : ("dense_" + std::to_string(2 * s));
+        std::string n1 = "dense_" + std::to_string(2 * s + 1);
+        net.off_fc_w[s] = add(n0 + "/kernel", (int64_t)net.flat * net.hidden);
+        net.off_fc_b[s] = add(n0 + "/bias", net.hidden);
+        net.off_hd_w[s] = add(n1 + "/kernel", (int64_t)net.hidden * outs);
+        net.off_hd_b[s] = add(n1 + "/bias", outs);
+    }
+    if (!net.dueling) { net.off_fc_w[1] = net.off_fc_w[0]; net.off_fc_b[1] = net.off_fc_b[0]; net.off_hd_w[1] = net.off_hd_w[0]; net.off_hd_b[1] = net.off_hd_b[0]; }
+    net.slab = off;
+}
+
+// ---- tile selection: largest tile that still yields >= one CTA per SM --------------------------------
+template <bool SPLIT, class AOp, class BOp, class Epi>
+static void igemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+    const int sms = h->sm_count;
+    auto tiles = [&](int bm, int bn) { return (int64_t)ceil_div(M, bm) * ceil_div(N, bn) * Z; };
+    if (N % 64 == 0) {
+        if (M > 64 && tiles(128, 64) >= sms) return launch_igemm<TileCfg<128, 64, 16, 8, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+        if (M > 32 && tiles(64, 64) >= sms) return launch_igemm<TileCfg<64, 64, 16, 4, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+        return launch_igemm<TileCfg<32, 64, 16, 4, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    }
+    if (M > 64 && tiles(128, 32) >= sms) return launch_igemm<TileCfg<128, 32, 16, 8, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (M > 32 && tiles(64, 32) >= sms) return launch_igemm<TileCfg<64, 32, 16, 4, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    return launch_igemm<TileCfg<32, 32, 16, 4, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+}
+
+// ---- dense hidden layer: reduce split-K partials, bias, ReLU, then the head dot products and dueling combine
+#define MAX_ACTIONS 32
+__global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __restrict__ part, int splits, int rows, int NH,
+                                                              int hidden, int A, int dueling,
+                                                              const float* __restrict__ b0, const float* __restrict__ b1,
+                                                              const float* __restrict__ hw0, const float* __restrict__ hb0,
+                                                              const float* __restrict__ hw1, const float* __restrict__ hb1,
+                                                              float* __restrict__ hid, float* __restrict__ q) {
+    const int row = blockIdx.x;
+    float acc[MAX_ACTIONS + 1];
+#pragma unroll
+    for (int a = 0; a <= MAX_ACTIONS; ++a) acc[a] = 0.f;
+    for (int col = threadIdx.x; col < NH; col += blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[((size_t)z * rows + row) * NH + col];
+        const int st = col >= hidden, j = st ? col - hidden : col;
+        s += st ? b1[j] : b0[j];
+        const float hv = fmaxf(s, 0.f);  // tf.nn.relu (deep_q_model.py:316,325,339)
+        hid[(size_t)row * NH + col] = hv;
+        if (!st) {
+#pragma unroll
+            for (int a = 0; a < MAX_ACTIONS; ++a)
+                if (a < A) acc[a] = fmaf(hv, hw0[j * A + a], acc[a]);
+        } else {
+            acc[MAX_ACTIONS] = fmaf(hv, hw1[j], acc[MAX_ACTIONS]);
+        }
+    }
+    __shared__ float red[8][MAX_ACTIONS + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a <= MAX_ACTIONS; ++a) {
+        if (a < A || a == MAX_ACTIONS) {
+            float v = acc[a];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[w][a] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float adv[MAX_ACTIONS];
+        float mean = 0.f;
+        for (int a = 0; a < A; ++a) {
+            float v = 0.f;
+            for (int ww = 0; ww < 8; ++ww) v += red[ww][a];
+            adv[a] = v + hb0[a];
+            mean += adv[a];
+        }
+        if (dueling) {
+            float val = 0.f;
+            for (int ww = 0; ww < 8; ++ww) val += red[ww][MAX_ACTIONS];
+            val += hb1[0];
+            mean /= (float)A;  // tf.reduce_mean(advantage, axis=1) (deep_q_model.py:332-334)
+            for (int a = 0; a < A; ++a) q[(size_t)row * A + a] = val + (adv[a] - mean);
+        } else {
+            for (int a = 0; a < A; ++a) q[(size_t)row * A + a] = adv[a];
+        }
+    }
+}
+
+static int fc_kchunk() { return 256; }
+
+void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, int rows, TowerActs& acts) {
+    const NetDesc& net = h->net;
+    const void* in = d_states;
+    for (int l = 0; l < 3; ++l) {
+        const ConvGeom& g = net.conv[l];
+        OpConvFwdA a{in, g, l == 0 ? 1 : 0};
+        OpColContig b{P + net.off_cw[l], g.cout};
+        EpiBiasRelu e{acts.act[l], P + net.off_cb[l], g.cout};
+        igemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
+        in = acts.act[l];
+    }
+    const int kchunk = fc_kchunk();
+    const int splits = ceil_div(net.flat, kchunk);
+    DQN_REQUIRE(splits <= h->fc_splits, "fc split workspace too small");
+    OpRowMajorK a{acts.act[2], net.flat};
+    OpFcWeightFwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+    EpiPartial e{acts.fc_part, rows, net.NH};
+    igemm_auto<true>(h, a, b, e, rows, net.NH, net.flat, splits, kchunk);
+    fc_reduce_heads_kernel<<<rows, 256, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, net.dueling,
+                                                        P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0],
+                                                        P + net.off_hd_b[0], P + net.off_hd_w[1], P + net.off_hd_b[1],
+                                                        acts.hid, acts.q);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
+}
+
+// ---- backward ------------------------------------------------------------------------------------------
+// conv wgrad with an extra all-ones row appended to A^T so the same GEMM also yields the bias gradient
+struct OpConvWgradABias {
+    static constexpr bool KCONTIG = false;
+    OpConvWgradA base; int mreal;
+    typedef OpConvWgradA::Row Row;
+    __device__ __forceinline__ Row row(int m, int z) const { return base.row(m < mreal ? m : 0, z); }
+    __device__ __forceinline__ float4 load4(const Row& r, int m, int k, int z) const {
+        if (m >= mreal) return make_float4(m == mreal ? 1.f : 0.f, 0.f, 0.f, 0.f);
+        return base.load4(r, m, k, z);
+    }
+};
+
+// grads[w_off + i] = sum_z part[z][i] for i < mreal*N ; grads[b_off + n] = sum_z part[z][mreal][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int Z, int mreal, int N, float* __restrict__ gw,
+                                    float* __restrict__ gb) {
+    const int total4 = (mreal + 1) * N / 4;
+    const size_t zstride = (size_t)(mreal + 4) * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < Z; ++z) {
+            const float4 v = *reinterpret_cast<const float4*>(part + z * zstride + (size_t)i * 4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const int e = i * 4;
+        if (e < mreal * N) *reinterpret_cast<float4*>(gw + e) = s;
+        else *reinterpret_cast<float4*>(gb + (e - mreal * N)) = s;
+    }
+}
+
+void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
+    const NetDesc& net = h->net;
+    const float* P = h->online;
+    float* G = h->grads;
+    TowerActs& acts = h->acts_on;
+    // dense hidden: dW = X^T dH (K = batch), written straight into the gradient slab
+    {
+        OpColContig a{acts.act[2], net.flat};
+        OpColContig b{h->d_hid, net.NH};
+        EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
+        igemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+    }
+    // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
+    {
+        OpRowMajorK a{h->d_hid, net.NH};
+        OpFcWeightBwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+        EpiGateStore e{h->d_act[2], acts.act[2], net.flat};
+        igemm_auto<false>(h, a, b, e, rows, net.flat, net.NH, 1, 0);
+    }
+    float* part = h->wg_part;
+    for (int l = 2; l >= 0; --l) {
+        const ConvGeom& g = net.conv[l];
+        const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
+        // wgrad (+bias) split over the pixel dimension
+        {
+            const int mt = ceil_div(mreal + 4, 64);
+            int Z = (2 * h->sm_count) / (mt * ceil_div(N, 64));
+            if (Z < 1) Z = 1; if (Z > 64) Z = 64;
+            int kchunk = ceil_div(ceil_div(K, Z), 16) * 16;
+            Z = ceil_div(K, kchunk);
+            DQN_REQUIRE((int64_t)Z * (mreal + 4) * N <= h->wg_part_floats, "wgrad workspace too small");
+            OpConvWgradABias a{OpConvWgradA{l == 0 ? (const void*)d_states : (const void*)acts.act[l - 1], g, l == 0 ? 1 : 0}, mreal};
+            OpColContig b{h->d_act[l], N};
+            EpiPartial e{part, mreal + 4, N};
+            igemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
+            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 256), 256, 0, h->stream>>>(part, Z, mreal, N,
+                                                                                          G + net.off_cw[l], G + net.off_cb[l]);
+            DQN_CUDA_OK(cudaGetLastError());
+            h->launches++;
+        }
+        if (l == 0) break;  // no gradient flows into the input image
+        // dgrad into the previous activation, gated by its ReLU
+        {
+            const int cl2 = ilog2(g.cout);
+            DgradClass c{g};
+            const int Zc = g.s * g.s;
+            const int cy = ceil_div(g.ih, g.s), cx = ceil_div(g.iw, g.s);
+            const int Mc = rows * cy * cx;  // upper bound over classes
+            OpConvDgradA a{h->d_act[l], c, cl2, rows};
+            OpConvDgradB b{P + net.off_cw[l], g, cl2};
+            EpiDgradGate e{h->d_act[l - 1], acts.act[l - 1], c, rows};
+            igemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
+        }
+    }
+}

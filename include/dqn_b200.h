@@ -1,0 +1,171 @@
+/*
+ * dqn_b200.h -- C ABI of the B200-native DQN learner (libdqn_b200.so).
+ *
+ * Drop-in boundary for the training-step hot path of reynkun/DeepQNetwork.
+ * Every entry point cites the reference interface it replaces (file:line into
+ * the reference tree).  Plain pointers and sizes only; all functions return 0
+ * on success and a non-zero status on failure, with the message available from
+ * dqn_last_error().  CUDA errors are fatal for the handle: there is no CPU
+ * fallback anywhere behind this interface.
+ *
+ * Pointers named h_* are HOST pointers (pageable or pinned); the library does
+ * the host<->device copies on the handle's stream.  One handle = one CUDA
+ * device + one stream; a handle is not thread-safe.
+ */
+#ifndef DQN_B200_H
+#define DQN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dqn_learner dqn_learner;
+
+/* conv stack variants */
+#define DQN_CONV_REFERENCE 0 /* rl/deep_q_model.py:278-283: k 8/4/4, s 4/2/1, padding 'same' */
+#define DQN_CONV_NATURE    1 /* labelled extra: k 8/4/3, s 4/2/1, 'valid'       */
+
+/* matmul arithmetic modes */
+#define DQN_MATH_FP32  0 /* FFMA fp32 on CUDA cores                                   */
+#define DQN_MATH_TC3X  1 /* tcgen05 kind::tf32, 3-term split (fp32-grade accuracy)    */
+#define DQN_MATH_TC1X  2 /* tcgen05 kind::tf32 single pass (reported separately)      */
+
+typedef struct dqn_config {
+    int32_t struct_size;      /* = sizeof(dqn_config); guards ABI drift */
+    int32_t device;           /* CUDA ordinal */
+    /* model: rl/deep_q_model.py:42-59 class attrs + :24-37 DEFAULT_OPTIONS */
+    int32_t input_height, input_width, input_channels;
+    int32_t num_actions;      /* conf['action_space'], deep_q_model.py:71 */
+    int32_t num_hidden;       /* NUM_HIDDEN = 512 */
+    int32_t conv_variant;     /* DQN_CONV_* */
+    int32_t use_dueling, use_double, use_per, use_momentum;
+    double  learning_rate;    /* 0.00025 */
+    double  momentum;         /* 0.95, nesterov */
+    double  discount_rate;    /* 0.99 */
+    /* agent: rl/deep_q_agent.py:33-72 */
+    int32_t batch_size;       /* 32 */
+    int64_t replay_capacity;  /* replay_max_memory_length */
+    double  per_a, per_b_start, per_b_end;
+    int64_t per_anneal_steps;
+    int32_t use_per_annealing;
+    int64_t per_calculate_steps;  /* 5000 */
+    int64_t copy_network_steps;   /* 10000 */
+    int32_t max_rows;         /* largest n for predict/get_losses/train_batch (0 -> max(2*batch,256)) */
+    int32_t math_mode;        /* DQN_MATH_* */
+    uint64_t seed;            /* device Philox seed for throughput-mode sampling */
+} dqn_config;
+
+/* ---- lifecycle ------------------------------------------------------- */
+/* replaces DeepQModel(conf)+Model.open (rl/deep_q_model.py:62-72, rl/model/model.py:86-99)
+ * and DeepQAgent._train_init_memory (rl/deep_q_agent.py:197-237): allocates params
+ * (online, target, optimizer slots), the replay ring, the sum tree and workspaces in HBM. */
+int dqn_create(const dqn_config* cfg, dqn_learner** out);
+int dqn_destroy(dqn_learner* h);
+const char* dqn_last_error(const dqn_learner* h); /* h may be NULL: last create error */
+int dqn_sync(dqn_learner* h);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the private stream */
+int dqn_set_stream(dqn_learner* h, void* cuda_stream);
+
+/* ---- parameters: names are the TF variable names of rl/deep_q_model.py:292-343
+ * relative to the tower scope ("conv2d/kernel", "dense_1/bias", ...). tower: 0 online, 1 target.
+ * slot: 0 value, 1 Adam m / Momentum accumulator, 2 Adam v.  Replaces tf.train.Saver access
+ * (rl/model/model.py:60-83) at tensor granularity. */
+int dqn_num_params(const dqn_learner* h, int32_t* n_tensors, int64_t* n_floats);
+int dqn_param_info(const dqn_learner* h, int32_t i, const char** name, int64_t* count, int64_t* offset);
+int dqn_get_param(dqn_learner* h, int32_t tower, int32_t slot, const char* name, float* h_out, int64_t count);
+int dqn_set_param(dqn_learner* h, int32_t tower, int32_t slot, const char* name, const float* h_in, int64_t count);
+/* raw device pointers, for torch.distributed all-reduce of the gradient slab and zero-copy views */
+int dqn_device_ptr(dqn_learner* h, const char* what, void** ptr, int64_t* bytes);
+int dqn_get_step(dqn_learner* h, int64_t* step);          /* DeepQModel.get_training_step, deep_q_model.py:168 */
+int dqn_set_step(dqn_learner* h, int64_t step);
+int dqn_get_game_count(dqn_learner* h, int64_t* n);        /* deep_q_model.py:176-188 */
+int dqn_set_game_count(dqn_learner* h, int64_t n);
+int dqn_get_beta_powers(dqn_learner* h, float* b1p, float* b2p);
+int dqn_set_beta_powers(dqn_learner* h, float b1p, float b2p);
+int dqn_copy_network(dqn_learner* h);                      /* DeepQModel.copy_network, deep_q_model.py:160-165 */
+/* {min, max, avg, total, last_max_weight, per_b, last loss, running loss sum}: the PER fields of the
+ * [train] report line (rl/deep_q_agent.py:386-392) */
+int dqn_get_stats(dqn_learner* h, float* out8);
+
+/* ---- replay ring: rl/data/replay_memory.py -------------------------- */
+/* ReplayMemory.append x n (replay_memory.py:54-67). When use_per, also SumTree.add(loss, cur_idx)
+ * per row first, as ReplaySamplerPriority.append does (replay_sampler_priority.py:22-24).
+ * h_losses may be NULL (no PER / uniform sampler). states are [n,H,W,C] u8. */
+int dqn_replay_append(dqn_learner* h, int64_t n, const uint8_t* h_states, const uint8_t* h_actions,
+                      const uint8_t* h_rewards, const uint8_t* h_next_states, const uint8_t* h_continues,
+                      const float* h_losses);
+/* ReplayMemory.get for a list of rows (replay_memory.py:78-91); any out pointer may be NULL */
+int dqn_replay_read(dqn_learner* h, int64_t n, const int64_t* h_rows, uint8_t* h_states, uint8_t* h_actions,
+                    uint8_t* h_rewards, uint8_t* h_next_states, uint8_t* h_continues, uint16_t* h_losses_f16);
+int dqn_replay_info(dqn_learner* h, int64_t* size, int64_t* cur_idx, int32_t* is_full); /* __len__, cur_idx, is_full */
+int dqn_replay_clear(dqn_learner* h);                                                    /* replay_memory.py:46-52 */
+/* bench/test fill on the device (SURVEY.md 8d "synthetic inputs"): n rows from Philox(seed);
+ * when use_per the tree is built with the semantics of n sequential SumTree.add calls. */
+int dqn_replay_fill_synthetic(dqn_learner* h, int64_t n, uint64_t seed);
+
+/* ---- sum tree: rl/data/sum_tree.py ---------------------------------- */
+int dqn_tree_add(dqn_learner* h, int64_t n, const float* h_scores, const uint32_t* h_data);       /* SumTree.add :23-42 */
+int dqn_tree_update(dqn_learner* h, int64_t n, const int64_t* h_tree_idx, const float* h_scores,   /* update_score :45-52, in order */
+                    int32_t store_losses);                                                         /* + replay.losses[mem]=p (replay_sampler_priority.py:46-50) */
+/* SumTree.get_with_info for the B stratified probes of ReplaySamplerPriority.sample_memories
+ * (replay_sampler_priority.py:30-35); u are the B uniform draws (random.random()). Outputs may be NULL. */
+int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* h_u, int64_t* h_tree_idx, int64_t* h_data_idx,
+                    double* h_priorities, int64_t* h_mem_idx);
+int dqn_tree_stats(dqn_learner* h, float* mn, float* mx, float* avg, float* total);               /* :139-165 */
+int dqn_tree_read(dqn_learner* h, float* h_tree /*2N-1*/, uint32_t* h_data /*N*/, int64_t* size, int64_t* write);
+
+/* ---- samplers (seam 3): fill the device-resident train batch --------- */
+/* ReplaySamplerPriority.sample_memories (replay_sampler_priority.py:27-43) + the IS-weight maths of
+ * DeepQAgent._sample_memories (deep_q_agent.py:500-524). refresh_stats!=0 recomputes avg/min/max and
+ * last_max_weight first. */
+int dqn_per_sample(dqn_learner* h, const double* h_u, int32_t refresh_stats, double per_b,
+                   int64_t* h_tree_idx, double* h_priorities, double* h_is_weights);
+/* ReplaySampler.sample_memories (replay_sampler.py:21-32) with the caller's randint draws */
+int dqn_uniform_sample(dqn_learner* h, const int64_t* h_rows);
+/* read back the device train batch (parity/debug only); any pointer may be NULL */
+int dqn_batch_read(dqn_learner* h, uint8_t* h_states, uint8_t* h_actions, uint8_t* h_rewards,
+                   uint8_t* h_next_states, uint8_t* h_continues, uint16_t* h_losses_f16);
+
+/* ---- model (seam 2): host-buffer calls ------------------------------- */
+/* DeepQModel.train (deep_q_model.py:75-103). h_is_weights NULL unless use_per. */
+int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* h_states, const uint8_t* h_actions,
+                    const uint8_t* h_rewards, const uint8_t* h_continues, const uint8_t* h_next_states,
+                    const float* h_is_weights, int64_t* step, float* h_losses, float* loss);
+/* DeepQModel.predict (deep_q_model.py:118-131) */
+int dqn_predict(dqn_learner* h, int32_t n, const uint8_t* h_states, int32_t use_target, float* h_q);
+/* DeepQModel.get_losses (deep_q_model.py:144-157) */
+int dqn_get_losses(dqn_learner* h, int32_t n, const uint8_t* h_states, const uint8_t* h_actions,
+                   const uint8_t* h_rewards, const uint8_t* h_continues, const uint8_t* h_next_states,
+                   float* h_losses);
+/* debug: Q-values/targets of the last train step (q_online[B,A], y[B], max_q[B]); grads when kept */
+int dqn_debug_read(dqn_learner* h, const char* what, float* h_out, int64_t count);
+
+/* ---- fused step: DeepQAgent._train_run_train (deep_q_agent.py:326-349) ------------------------
+ * sample -> gather -> target -> forward/backward -> optimizer -> priority write-back, all on device.
+ * Parity runs hand in the reference's draws: h_u = B random.random() values (PER) or h_rows = B randint rows
+ * (uniform sampler); both NULL -> device Philox. Outputs may be NULL (then there is no D2H and no sync). */
+int dqn_train_step(dqn_learner* h, const double* h_u, const int64_t* h_rows, int64_t* step, float* h_losses, float* loss);
+/* n back-to-back fused steps (device RNG), target sync every copy_network_steps and PER stats
+ * refresh every per_calculate_steps included; returns after enqueueing (call dqn_sync). */
+int dqn_train_steps(dqn_learner* h, int64_t n);
+/* data-parallel split step (new capability): phase 0 = sample..backward (gradient left
+ * in the "grads" slab for an external all-reduce), phase 1 = optimizer + priority write-back.
+ * grad_scale multiplies dL/dq (1/world_size for a global mean). */
+int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale);
+/* per-kernel launch counter since creation (bench.py reports gpu_launches from this) */
+int dqn_launch_count(const dqn_learner* h, int64_t* n);
+/* CUDA-event time per step segment (sample, gather, forward_online, forward_target, td_epilogue, backward,
+ * optimizer, post_step), accumulated over dqn_train_steps calls while enabled (steps run un-graphed) */
+int dqn_set_profile(dqn_learner* h, int32_t enabled);
+int dqn_get_profile(dqn_learner* h, int32_t* n, const char** names, float* ms, int32_t cap, int64_t* steps);
+
+/* ---- persistence (own container format; TF-bundle compatibility is SURVEY.md 8f-3) -- */
+int dqn_save(dqn_learner* h, const char* prefix);     /* Model.save, rl/model/model.py:60-68 */
+int dqn_restore(dqn_learner* h, const char* prefix);  /* Model.restore :71-83; returns 1 if absent */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQN_B200_H */

@@ -1,0 +1,236 @@
+"""-m gpu parity: Q-network forward / TD target / loss / backward / optimizer through the C ABI vs the torch-CPU
+fp64 restatement of rl/deep_q_model.py (oracle/nn_ref.py).  Tolerance: 1e-4 relative per tensor
+(||a-b||inf / ||b||inf) for Q-values, losses, loss, gradients, updated weights and optimizer
+slots in the fp32 mode; argmax actions bit-exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_ref
+from tests.gpu_util import need_gpu, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    need_gpu()
+
+
+CONFIGS = {
+    'c1_vanilla': dict(h=89, w=80, a=4, dueling=False, double=False, per=False),
+    'c2_breakout_ddp': dict(h=89, w=80, a=4, dueling=True, double=True, per=True),
+    'c3_mspacman_ddp': dict(h=86, w=80, a=9, dueling=True, double=True, per=True),
+    'double_only_momentum': dict(h=89, w=80, a=6, dueling=False, double=True, per=False, momentum=True),
+    'dueling_only': dict(h=86, w=80, a=9, dueling=True, double=False, per=False),
+    'nature84': dict(h=84, w=84, a=4, dueling=False, double=False, per=False, variant='nature'),
+    'nature84_ddp': dict(h=84, w=84, a=4, dueling=True, double=True, per=True, variant='nature'),
+}
+
+
+def make(cfg, batch=32, capacity=256, seed=0):
+    from deepqnetwork_b200.learner import Learner
+    from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
+    variant = cfg.get('variant', 'reference')
+    L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
+                use_per=cfg['per'], use_momentum=cfg.get('momentum', False), batch_size=batch, replay_capacity=capacity,
+                conv_variant=variant)
+    spec = nn_ref.NetSpec(cfg['h'], cfg['w'], 4, cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
+                          use_per=cfg['per'], use_momentum=cfg.get('momentum', False), variant=variant)
+    shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], variant)
+    assert {k: tuple(v) for k, v in shapes.items()} == {k: tuple(v) for k, v in spec.param_shapes().items()}
+    assert [t[0] for t in L.tensors()] == list(shapes)
+    assert L.num_params == spec.num_params()
+    on = init_tower_params(shapes, seed + 1); tg = init_tower_params(shapes, seed + 2)
+    # non-zero biases so bias handling is exercised
+    rng = np.random.default_rng(seed)
+    for p in (on, tg):
+        for k in p:
+            if k.endswith('/bias'):
+                p[k] = (rng.normal(0, 0.05, p[k].shape)).astype(np.float32)
+    L.set_tower(on, 0); L.set_tower(tg, 1)
+    return L, spec, shapes, on, tg
+
+
+def rand_batch(cfg, n, seed):
+    rng = np.random.default_rng(seed)
+    shp = (n, cfg['h'], cfg['w'], 4)
+    # image-like: large constant regions plus noise, so ReLU gates are a mix of on/off
+    st = (rng.integers(0, 256, shp) * (rng.random(shp) < 0.5)).astype(np.uint8)
+    ns = (rng.integers(0, 256, shp) * (rng.random(shp) < 0.5)).astype(np.uint8)
+    return dict(states=st, next_states=ns, actions=rng.integers(0, cfg['a'], n).astype(np.uint8),
+                rewards=rng.choice([0, 1, 4, 7, 200], n).astype(np.uint8), continues=rng.random(n) < 0.8)
+
+
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_predict_matches_oracle(name):
+    cfg = CONFIGS[name]
+    L, spec, shapes, on, tg = make(cfg)
+    for n in (1, 32, 77):
+        x = rand_batch(cfg, n, n)['states']
+        for tower, params in ((False, on), (True, tg)):
+            q = L.predict(x, use_target=tower)
+            ref = nn_ref.forward(nn_ref.to_torch(params, torch.float64), x, spec, torch.float64).numpy()
+            assert q.shape == ref.shape and rel_err(q, ref) < TOL, (name, n, rel_err(q, ref))
+            assert np.array_equal(np.argmax(q, 1), np.argmax(ref, 1))  # argmax actions bit-exact
+    L.close()
+
+
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_train_batch_matches_oracle(name):
+    """DeepQModel.train (two runs + host target) for three consecutive steps on fresh batches."""
+    cfg = CONFIGS[name]
+    L, spec, shapes, on, tg = make(cfg)
+    o = nn_ref.to_torch(on, torch.float64); t = nn_ref.to_torch(tg, torch.float64)
+    opt = nn_ref.OptState(o, spec, torch.float64)
+    for it in range(3):
+        b = rand_batch(cfg, 32, 100 + it)
+        w = np.random.default_rng(it).random(32).astype(np.float32) + 0.1 if cfg['per'] else None
+        step, losses, loss = L.train_batch(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'], w)
+        rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, b, w, spec, torch.float64)
+        assert step == rstep == it + 1
+        A = cfg['a']
+        assert rel_err(L.debug_read('q_online', (32, A)), aux['q']) < TOL
+        assert rel_err(L.debug_read('max_q', (32,)), aux['max_q']) < TOL
+        assert rel_err(L.debug_read('y', (32,)), aux['y']) < TOL
+        assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
+        for k in shapes:
+            g = L.get_param(k, slot=3)
+            assert rel_err(g, aux['grads'][k].reshape(-1)) < TOL, (name, it, 'grad', k, rel_err(g, aux['grads'][k].reshape(-1)))
+        for k in shapes:
+            assert rel_err(L.get_param(k), o[k].numpy().reshape(-1)) < TOL, (name, it, 'weight', k)
+            assert rel_err(L.get_param(k, slot=1), opt.m[k].numpy().reshape(-1)) < TOL, (name, it, 'm', k)
+            if not cfg.get('momentum'):
+                assert rel_err(L.get_param(k, slot=2), opt.v[k].numpy().reshape(-1)) < 2 * TOL, (name, it, 'v', k)
+            # the target tower only changes through copy_network
+            assert np.array_equal(L.get_param(k, tower=1), tg[k].reshape(-1))
+    L.copy_network()
+    for k in shapes:
+        assert np.array_equal(L.get_param(k, tower=1), L.get_param(k, tower=0))
+    L.close()
+
+
+def test_double_dqn_masked_max_clamps_negative_targets():
+    """D6: reduce_max(target_q * one_hot(argmax online_q)) clamps a negative selected Q to 0 (deep_q_model.py:247-252)."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    L, spec, shapes, on, tg = make(cfg)
+    tg = dict(tg); tg['dense_3/bias'] = np.array([-50.0], np.float32)  # value stream bias: all target Q << 0
+    L.set_tower(tg, 1)
+    b = rand_batch(cfg, 32, 5)
+    w = np.ones(32, np.float32)
+    L.train_batch(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'], w)
+    mq = L.debug_read('max_q', (32,)); y = L.debug_read('y', (32,))
+    assert np.all(mq == 0.0) and np.array_equal(y, b['rewards'].astype(np.float32))
+    ref = nn_ref.max_q_values(nn_ref.to_torch(on, torch.float64), nn_ref.to_torch(tg, torch.float64), b['next_states'], spec, torch.float64)
+    assert np.all(ref.numpy() == 0.0)
+    L.close()
+
+
+@pytest.mark.parametrize('name', ['c1_vanilla', 'c2_breakout_ddp'])
+def test_get_losses_matches_oracle(name):
+    """DeepQModel.get_losses on the 128-row PER insert batch (deep_q_agent.py:481-485)."""
+    cfg = CONFIGS[name]
+    L, spec, shapes, on, tg = make(cfg)
+    b = rand_batch(cfg, 128, 9)
+    got = L.get_losses(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'])
+    ref = nn_ref.losses_only(nn_ref.to_torch(on, torch.float64), nn_ref.to_torch(tg, torch.float64), b, spec, torch.float64)
+    assert rel_err(got, ref) < TOL
+    assert L.get_step() == 0  # no optimizer step
+    L.close()
+
+
+@pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c1_vanilla', 'c3_mspacman_ddp'])
+def test_fused_train_steps_match_reference_loop(name):
+    """DeepQAgent._train_run_train for 4 consecutive steps, fully on device, vs the oracle loop fed the same
+    random.random()/randint draws: sampled indices and gathered rows bit-exact, IS weights / losses / weights
+    within tolerance, priority write-back bit-exact given the device priorities."""
+    from oracle.sumtree_c import SumTreeC
+    from oracle.sumtree_ref import uniform_rows
+    cfg = CONFIGS[name]
+    N, B = 2000, 32
+    L, spec, shapes, on, tg = make(cfg, capacity=N)
+    L.replay_fill_synthetic(N, seed=77)
+    o = nn_ref.to_torch(on, torch.float64); t = nn_ref.to_torch(tg, torch.float64)
+    opt = nn_ref.OptState(o, spec, torch.float64)
+    ref_tree = SumTreeC(N)
+    rnd = random.Random(0)
+    max_w = None
+    for it in range(4):
+        if cfg['per']:
+            tree, data, size, write = L.tree_read()
+            ref_tree.load(tree, data, size, write)
+            u = np.array([rnd.random() for _ in range(B)])
+            step, losses, loss = L.train_step(uniforms=u)
+            ti, di, p, mi = ref_tree.sample(u)
+            if max_w is None:  # step % per_calculate_steps == 0 or first (deep_q_agent.py:505-510)
+                leaves = tree[N - 1:N - 1 + size]
+                max_w = nn_ref.max_weight(leaves.min(), tree[0], B, 0.4)
+            isw = nn_ref.is_weights(p, tree[0], B, 0.4, max_w)
+            assert rel_err(L.debug_read('is_weights', (B,)), isw) < 1e-6
+        else:
+            mi = uniform_rows(N, B, rnd)
+            step, losses, loss = L.train_step(rows=mi)
+            isw = None
+        got = L.batch_read(); rows = L.replay_read(mi)
+        for k in ('states', 'next_states', 'actions', 'rewards', 'continues'):
+            assert np.array_equal(got[k], rows[k]), k
+        rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, rows, isw, spec, torch.float64)
+        assert step == rstep
+        assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
+        for k in shapes:
+            assert rel_err(L.get_param(k), o[k].numpy().reshape(-1)) < TOL, (name, it, k)
+        if cfg['per']:
+            newp = L.debug_read('new_priorities', (B,))
+            assert rel_err(newp, nn_ref.make_priority(losses)) < 1e-6  # powf vs np.power, float tolerance
+            ref_tree.update(ti, newp)
+            assert np.array_equal(L.tree_read()[0], ref_tree.tree)  # order-preserving scatter, bit-exact
+            last = {}
+            for r, v in zip(mi.tolist(), newp.astype(np.float16)):
+                last[r] = v  # later duplicates win, as the sequential loop does
+            assert all(L.replay_read([r], ('losses',))['losses'][0] == v for r, v in last.items())
+    L.close()
+
+
+def test_graph_replay_equals_eager_steps():
+    """dqn_train_steps (CUDA-graph replay, device Philox) == the same steps launched one by one."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    res = []
+    for mode in ('eager', 'graph'):
+        L, spec, shapes, on, tg = make(cfg, capacity=4096)
+        L.replay_fill_synthetic(4096, seed=5)
+        if mode == 'eager':
+            for _ in range(6):
+                L.train_step(fetch=False)
+        else:
+            L.train_steps(6)
+        L.sync()
+        assert L.get_step() == 6
+        res.append((L.get_tower(0), L.tree_read()[0], L.launch_count()))
+        L.close()
+    for k in res[0][0]:
+        assert np.array_equal(res[0][0][k], res[1][0][k]), k
+    assert np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2] > 6 * 20
+
+
+def test_save_restore_roundtrip(tmp_path):
+    cfg = CONFIGS['c2_breakout_ddp']
+    L, spec, shapes, on, tg = make(cfg, capacity=512)
+    L.replay_fill_synthetic(512, seed=5)
+    L.train_steps(3); L.set_game_count(17); L.sync()
+    prefix = str(tmp_path / 'rl.game_environment.BreakoutEnvironment')
+    L.save(prefix)
+    before = (L.get_tower(0), L.get_tower(1), L.get_tower(0, slot=1), L.get_tower(0, slot=2), L.get_beta_powers())
+    L.close()
+    L2, *_ = make(cfg, capacity=512, seed=9)
+    assert L2.restore(str(tmp_path / 'missing')) is False
+    assert L2.restore(prefix) is True
+    assert L2.get_step() == 3 and L2.get_game_count() == 17 and L2.get_beta_powers() == before[4]
+    after = (L2.get_tower(0), L2.get_tower(1), L2.get_tower(0, slot=1), L2.get_tower(0, slot=2))
+    for a, b in zip(before[:4], after):
+        for k in a:
+            assert np.array_equal(a[k], b[k])
+    L2.close()

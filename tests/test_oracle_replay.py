@@ -126,3 +126,22 @@ def test_ring_gather_and_wrap():
     b = r.gather([0, 1, 2, 3])
     assert b['states'][:, 0, 0, 0].tolist() == [4, 5, 2, 3]
     assert b['rewards'].tolist() == [160, 200, 80, 120]
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(G, 'per_trace_*.npz'))))
+def test_c_restatement_matches_reference_traces(path):
+    """oracle/sumtree_ref.c (used for full-size parity runs) against the same reference executions."""
+    from oracle.sumtree_c import SumTreeC
+    g = np.load(path)
+    cap, n_add, bsz, rounds, seed = g['meta'].tolist()
+    t = SumTreeC(cap)
+    t.add(g['add_scores'], (np.arange(n_add) % cap).astype(np.uint32))
+    assert np.array_equal(t.tree, g['tree_after_add']) and np.array_equal(t.data, g['data_after_add'])
+    assert [t.size, t.write] == g['size_write'][:2].tolist()
+    for r in range(rounds):
+        ti, di, p, mi = t.sample(g['uniforms'][r])
+        assert np.array_equal(ti, g['tree_idx'][r]) and np.array_equal(di, g['data_idx'][r])
+        assert np.array_equal(p, g['prio'][r]) and np.array_equal(mi, g['mem_idx'][r])
+        t.update(ti, g['new_scores'][r])
+        assert t.total == g['roots'][r]
+    assert np.array_equal(t.tree, g['tree_final'])
