@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Throughput benchmark: DQN train steps/sec (batch 32, PER, reference Q-network) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c1|c2|c3|nature] [--capacity R]
+
+A *step* is one DeepQAgent._train_run_train equivalent (rl/deep_q_agent.py:326-349): PER sum-tree sample ->
+replay gather -> target/online forward -> TD loss -> backward -> Adam -> priority write-back, with the
+target sync every copy_network_steps and the PER stats refresh every per_calculate_steps included.
+
+N=1 workload = BASELINE.json configs[1] (C2): Breakout double+dueling+PER, 89x80x4 uint8, batch 32, 1M-transition
+replay resident in HBM, synthetic data.  N>1 (torchrun, one rank per GPU) = configs[3] (C4):
+N independent learners, no data-path collective, value = total steps of all ranks / max-over-ranks time.
+
+Printed JSON (one line, rank 0): the driver contract keys plus
+  roofline     -- the dominant kernel (largest CUDA-event time in a per-kernel profile pass of the same step),
+                  algorithmic bytes per launch (DESIGN.md "kernels" table) / its average launch time, vs the measured
+                  HBM peak of MEASURED_PEAKS.json;
+  cpu_baseline -- the oracle's CPU restatement of the reference step (NumPy/Python replay+PER exactly as the
+                  reference structures it, torch-CPU fp32 network) timed on this box's host cores;
+  e2e          -- the same step driven through the reference-facing seams with HOST buffers: tree sample (seam 3),
+                  DeepQModel.train with pinned host states/next_states (seam 2, H2D inside the timed region),
+                  priority write-back, losses read back every step.
+`--impl reference` times the CPU restatement of the reference alone (TensorFlow cannot be installed here; see
+DESIGN.md) and prints the same line shape with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    'c1': dict(name='C1 Breakout vanilla DQN', h=89, w=80, a=4, dueling=False, double=False, per=False, variant='reference'),
+    'c2': dict(name='C2 Breakout double+dueling+PER', h=89, w=80, a=4, dueling=True, double=True, per=True, variant='reference'),
+    'c3': dict(name='C3 MsPacman double+dueling+PER', h=86, w=80, a=9, dueling=True, double=True, per=True, variant='reference'),
+    'nature': dict(name='canonical Nature-84 vanilla (labelled extra)', h=84, w=84, a=4, dueling=False, double=False, per=False, variant='nature'),
+}
+METRIC = 'DQN train steps/sec (batch 32, PER, Nature CNN) per B200 and at 1/2/4/8 GPUs'
+UNIT = 'train steps/s'
+BATCH = 32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic work: P params, F fwd MACs/sample, per-kernel bytes
+def net_numbers(cfg):
+    from deepqnetwork_b200.deep_q_model import conv_geometry, tower_param_shapes
+    geo = conv_geometry(cfg['h'], cfg['w'], 4, cfg['variant'])
+    shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
+    P = sum(int(np.prod(s)) for s in shapes.values())
+    conv_macs = [g['oh'] * g['ow'] * g['cout'] * g['k'] * g['k'] * g['cin'] for g in geo]
+    flat = geo[-1]['oh'] * geo[-1]['ow'] * geo[-1]['cout']
+    streams = 2 if cfg['dueling'] else 1
+    fc_macs = flat * 512 * streams + 512 * cfg['a'] + (512 if cfg['dueling'] else 0)
+    F = sum(conv_macs) + fc_macs
+    n_fwd = 3 if cfg['double'] else 2
+    flops = 2 * BATCH * (n_fwd * F + F + (F - conv_macs[0]))
+    S = cfg['h'] * cfg['w'] * 4
+    step_bytes = 8 * 4 * P + 2 * BATCH * S + 15 * BATCH
+    return dict(P=P, F=F, flops=flops, step_bytes=step_bytes, S=S, flat=flat, geo=geo, streams=streams, n_fwd=n_fwd)
+
+
+def kernel_bytes(name, cfg, nn):
+    """Algorithmic HBM bytes of one launch of the named profile segment (unique reads + writes, fp32)."""
+    geo, flat, st, B = nn['geo'], nn['flat'], nn['streams'], BATCH
+    rows_on = 2 * B if cfg['double'] else B
+    base = name[3:] if name[:3] in ('on_', 'tg_') else name
+    rows = rows_on if name.startswith('on_') else B
+    acts = [g['oh'] * g['ow'] * g['cout'] for g in geo]
+    wts = [g['k'] * g['k'] * g['cin'] * g['cout'] for g in geo]
+    ins = [nn['S'] // 4 * 1, acts[0], acts[1]]  # elements per sample feeding conv l (conv1 input counted as bytes below)
+    if base.startswith('conv') and base.endswith('_fwd'):
+        l = int(base[4]) - 1
+        in_b = rows * nn['S'] if l == 0 else rows * acts[l - 1] * 4
+        return in_b + wts[l] * 4 + rows * acts[l] * 4
+    if base == 'fc_fwd':
+        return rows * flat * 4 + flat * 512 * st * 4 + rows * 512 * st * 4
+    if base == 'fc_reduce_heads':
+        return rows * 512 * st * 4 * 2
+    if base == 'fc_wgrad':
+        return B * flat * 4 + B * 512 * st * 4 + flat * 512 * st * 4
+    if base == 'fc_dgrad':
+        return B * 512 * st * 4 + flat * 512 * st * 4 + 2 * B * flat * 4
+    if base.endswith('_wgrad'):
+        l = int(base[4]) - 1
+        in_b = B * nn['S'] if l == 0 else B * acts[l - 1] * 4
+        return in_b + B * acts[l] * 4 + wts[l] * 4
+    if base.endswith('_wgrad_reduce'):
+        l = int(base[4]) - 1
+        return 2 * wts[l] * 4
+    if base.endswith('_dgrad'):
+        l = int(base[4]) - 1
+        return B * acts[l] * 4 + wts[l] * 4 + 2 * B * acts[l - 1] * 4
+    if base == 'optimizer':
+        return 7 * 4 * nn['P']      # read g,p,m,v ; write p,m,v (un-fused optimizer of this revision)
+    if base == 'gather':
+        return 2 * 2 * B * nn['S']
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+def clocks_sampler_start():
+    path = tempfile.mktemp(prefix='clocks_', suffix='.csv')
+    q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    try:
+        f = open(path, 'w')
+        p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+                             stdout=f, stderr=subprocess.DEVNULL)
+        return p, f, path
+    except OSError:
+        return None, None, path
+
+
+def clocks_sampler_stop(handle, device_index):
+    p, f, path = handle
+    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+    if p is None:
+        return out
+    p.terminate()
+    try:
+        p.wait(timeout=5)
+    except Exception:
+        p.kill()
+    f.close()
+    sm, mx, reasons = [], [], set()
+    try:
+        for line in open(path):
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9 or c[0] != str(device_index):
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(path)
+    except OSError:
+        pass
+    if sm:
+        out['sm_mhz'] = statistics.median(sm); out['sm_max_mhz'] = max(mx); out['samples'] = len(sm)
+    out['reasons'] = sorted(reasons)
+    return out
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, steps, warmup, replay_rows, time_budget_s, threads=None):
+    """The reference's CPU path, restated (oracle/): NumPy/Python replay ring + sum tree structured exactly like
+    rl/data/*.py, torch-CPU fp32 network + TF-formula Adam like rl/deep_q_model.py, driven like
+    DeepQAgent._train_run_train.  Returns (steps_per_s, steps_timed, threads)."""
+    import random
+    import torch
+    from oracle import nn_ref
+    from oracle.sumtree_ref import ReplayRingRef, SumTreeRef, per_sample, per_update, uniform_rows
+    from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec = nn_ref.NetSpec(cfg['h'], cfg['w'], 4, cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
+                          use_per=cfg['per'], variant=cfg['variant'])
+    shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
+    o = nn_ref.to_torch(init_tower_params(shapes, 42), torch.float32)
+    t = nn_ref.to_torch(init_tower_params(shapes, 43), torch.float32)
+    opt = nn_ref.OptState(o, spec, torch.float32)
+    rng = np.random.default_rng(1234)
+    ring = ReplayRingRef(cfg['h'], cfg['w'], 4, replay_rows)
+    ring.states[:] = rng.integers(0, 256, ring.states.shape, dtype=np.uint8)
+    ring.next_states[:] = rng.integers(0, 256, ring.states.shape, dtype=np.uint8)
+    ring.actions[:] = rng.integers(0, cfg['a'], replay_rows); ring.rewards[:] = rng.choice([0, 1, 4, 7], replay_rows, p=[.9, .06, .03, .01])
+    ring.continues[:] = rng.random(replay_rows) < 0.99
+    ring.cur_idx, ring.is_full = 0, True
+    tree = SumTreeRef(replay_rows)
+    pr = nn_ref.make_priority(np.abs(rng.normal(0, 0.3, replay_rows)).astype(np.float32))
+    if cfg['per']:
+        # first fill: leaves + bottom-up sums (timing only; the bit-exact add path is exercised in tests)
+        tree.tree[replay_rows - 1:] = pr
+        for i in range(replay_rows - 2, -1, -1):
+            tree.tree[i] = tree.tree[2 * i + 1] + tree.tree[2 * i + 2]
+        tree.data[:] = np.arange(replay_rows); tree.size = replay_rows
+    random.seed(0)
+    per_b, max_w = 0.4, None
+
+    def one_step():
+        nonlocal max_w
+        if cfg['per']:
+            if max_w is None:
+                max_w = nn_ref.max_weight(tree.get_min(), tree.total, BATCH, per_b)
+            u = [random.random() for _ in range(BATCH)]
+            ti, di, p, mi = per_sample(tree, BATCH, u)
+            isw = nn_ref.is_weights(p, tree.total, BATCH, per_b, max_w)
+        else:
+            mi = uniform_rows(replay_rows, BATCH, random); isw = None
+        batch = ring.gather(mi)
+        step, losses, loss, _ = nn_ref.train_step(o, t, opt, batch, isw, spec, torch.float32)
+        if cfg['per']:
+            per_update(tree, ti, nn_ref.make_priority(losses), ring.losses)
+        return loss
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        one_step()
+        done += 1
+        if time.perf_counter() - t0 > time_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, threads
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='c2', choices=list(CONFIGS))
+    ap.add_argument('--capacity', type=int, default=1000000, help='replay transitions resident in HBM')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg = CONFIGS[args.config]
+    nn = net_numbers(cfg)
+    workload = '%s, %dx%dx4 uint8, batch %d, %d-transition replay in HBM' % (cfg['name'], cfg['h'], cfg['w'], BATCH, args.capacity)
+    if world > 1:
+        workload = 'C4 %d independent learners (one per GPU, no collectives), each: ' % world + workload
+    config = dict(workload=workload, batch=BATCH, replay_transitions=args.capacity, parallelism='replicas x%d' % world,
+                  params=nn['P'], gflop_per_step=round(nn['flops'] / 1e9, 3), algorithmic_mb_per_step=round(nn['step_bytes'] / 1e6, 1),
+                  l2='no flush: steady-state step; per-step working set (5 parameter-sized slabs = %.0f MB + random replay rows '
+                     'out of %.1f GB) exceeds the 126 MB L2' % (5 * 4 * nn['P'] / 1e6, 2 * args.capacity * nn['S'] / 1e9),
+                  math='fp32 FFMA (DQN_MATH_FP32)')
+
+    # ---- reference arm: the CPU restatement of the reference, rank 0 only -------------------------------------
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, done, threads = cpu_reference_run(cfg, args.steps, min(args.warmup, 5), 20000, 150.0)
+        line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=done, warmup=min(args.warmup, 5),
+                    ms_per_step=1000.0 / v, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    data='synthetic', impl='reference', config=config, gpu_launches=0,
+                    cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind='port',
+                                      sample='%d consecutive train steps, 20000-row host replay (sampler cost is O(log N))' % done),
+                    e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    # ---- B200 arm ---------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: deepqnetwork_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from deepqnetwork_b200.learner import Learner
+    from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
+
+    L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
+                use_per=cfg['per'], batch_size=BATCH, replay_capacity=args.capacity, conv_variant=cfg['variant'],
+                seed=7 + rank, device=local_rank)
+    stream = torch.cuda.Stream()      # a real (non-default) stream: stream capture is illegal on the legacy stream
+    torch.cuda.set_stream(stream)
+    L.set_stream(stream.cuda_stream)  # so that torch.cuda.Event brackets exactly the learner's work
+    shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
+    L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)
+    L.set_tower(init_tower_params(shapes, 43 + 2 * rank), 1)
+    L.replay_fill_synthetic(args.capacity, seed=1234 + rank)
+    L.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also captures the CUDA graph of the fused step)
+    L.train_steps(args.warmup)
+    barrier()
+    clk = clocks_sampler_start() if rank == 0 else None
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    L.train_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count() - l0
+    clocks = clocks_sampler_stop(clk, local_rank) if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        lsum = torch.tensor([launches], device='cuda', dtype=torch.int64)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+        launches = int(lsum.item())
+    value = world * args.steps / (ms / 1000.0)
+    step_now = L.get_step()
+    assert step_now == args.warmup + args.steps, 'step counter does not match the steps requested'
+
+    # ---- per-kernel profile pass (CUDA events around every launch, un-graphed) -> roofline of the dominant kernel
+    roofline = None
+    if rank == 0:
+        prof_steps = max(20, min(200, args.steps // 10))
+        L.set_profile(True)
+        L.train_steps(prof_steps)
+        L.sync()
+        prof, n = L.get_profile()
+        L.set_profile(False)
+        per_kernel = {k: v / n * 1000.0 for k, v in prof.items()}  # us per step
+        total_us = sum(per_kernel.values())
+        dom = max(per_kernel, key=per_kernel.get)
+        kb = kernel_bytes(dom, cfg, nn)
+        peak, how = measured_peak_hbm()
+        achieved = kb / (per_kernel[dom] * 1e-6) / 1e9 if kb else None
+        roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s',
+                        frac=(achieved / peak) if achieved else None, traffic=None, peak_source=how,
+                        algorithmic_bytes_per_launch=kb, us_per_launch=per_kernel[dom],
+                        kernel_share_of_step=per_kernel[dom] / total_us,
+                        step_frac_of_hbm_roofline=(nn['step_bytes'] / (ms / args.steps * 1e-3) / 1e9) / peak,
+                        per_kernel_us={k: round(v, 2) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])})
+
+    # ---- e2e: through the reference-facing seams with pinned HOST buffers -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        S = nn['S']
+        pool = 8
+        hs = [torch.randint(0, 256, (BATCH, cfg['h'], cfg['w'], 4), dtype=torch.uint8).pin_memory() for _ in range(2 * pool)]
+        ha = np.random.default_rng(0).integers(0, cfg['a'], BATCH).astype(np.uint8)
+        hr = np.zeros(BATCH, np.uint8); hc = np.ones(BATCH, np.uint8)
+        from deepqnetwork_b200.deep_q_agent import make_priority as host_make_priority
+        e2e_steps = max(50, min(args.steps, 500))
+        rs = np.random.default_rng(5)
+
+        def e2e_step(i):
+            st, ns = hs[2 * (i % pool)].numpy(), hs[2 * (i % pool) + 1].numpy()
+            if cfg['per']:
+                t, p, w = L.per_sample(rs.random(BATCH), i % 5000 == 0, 0.4)        # seam 3: H2D u, D2H idx/prio/is_w
+                step, losses, loss = L.train_batch(st, ha, hr, hc, ns, w)           # seam 2: H2D batch, D2H losses/loss
+                L.tree_update(t, host_make_priority(losses), store_losses=True)    # seam 3: H2D idx/prio
+            else:
+                step, losses, loss = L.train_batch(st, ha, hr, hc, ns, None)
+            return loss
+
+        for i in range(10):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tm = torch.tensor([dt], device='cuda', dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        h2d = 2 * BATCH * S + 3 * BATCH + (BATCH * (8 + 4 + 8 + 4) if cfg['per'] else 0)
+        d2h = BATCH * 4 + 12 + (BATCH * 32 if cfg['per'] else 0)
+        e2e = dict(value=world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                   path='seam 3 dqn_per_sample -> seam 2 dqn_train_batch (pinned host batch) -> seam 3 dqn_tree_update')
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, done, threads = cpu_reference_run(cfg, 10 ** 9, 3, 20000, args.cpu_seconds)
+        cpu = dict(value=v, unit=UNIT, cores=threads, kind='port',
+                   sample='%d consecutive train steps (%.0f s), 20000-row host replay; NumPy/Python replay+PER as in '
+                          'rl/data/*.py, torch-CPU fp32 network (stand-in for TF 1.x CPU)' % (done, args.cpu_seconds))
+
+    L.close()
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
+                    cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -144,6 +144,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    if (h->prof_graph) cudaGraphExecDestroy(h->prof_graph);
     void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions, h->in_rewards, h->in_cont, h->in_isw,
@@ -175,6 +176,7 @@ extern "C" int dqn_set_stream(dqn_learner* h, void* s) {
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     h->graph_valid = false;
+    if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }
 
@@ -521,13 +523,16 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 }
 
 // ---- the training step ---------------------------------------------------------------------------------------
-static void prof_mark(dqn_learner* h, const char* name) {
+void prof_mark(dqn_learner* h, const char* name) {
     if (!h->profile) return;
     if (h->prof_used >= h->prof_events.size()) {
         cudaEvent_t e; DQN_CUDA_OK(cudaEventCreate(&e));
         h->prof_events.push_back(e);
     }
-    DQN_CUDA_OK(cudaEventRecord(h->prof_events[h->prof_used], h->stream));
+    // inside the profiled graph the marks become event-record nodes, so the intervals are device-side times
+    // between kernels with no host launch latency in them
+    DQN_CUDA_OK(cudaEventRecordWithFlags(h->prof_events[h->prof_used], h->stream,
+                                         h->prof_capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     h->prof_marks.push_back(name);
     h->prof_used++;
 }
@@ -537,16 +542,16 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
                       const uint8_t* cont, const float* isw, int train, double grad_scale) {
     const size_t S = h->state_bytes;
     const int A = h->net.A;
-    prof_mark(h, "forward_online");
+    h->prof_tag = "on_";
     if (h->cfg.use_double) tower_forward(h, h->online, states2, 2 * n, h->acts_on);  // s and s' share one pass
     else tower_forward(h, h->online, states2, n, h->acts_on);
-    prof_mark(h, "forward_target");
+    h->prof_tag = "tg_";
     tower_forward(h, h->target, states2 + (size_t)n * S, n, h->acts_tg);
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
                        grad_scale);
     if (train) {
-        prof_mark(h, "backward");
+        prof_mark(h, "head_backward");
         launch_head_backward(h, n, actions);
         tower_backward(h, states2, n);
     }
@@ -561,6 +566,12 @@ static void finish_step(dqn_learner* h, int per_update) {
     h->host_step++;
 }
 
+static void maybe_refresh_stats(dqn_learner* h);
+static void maybe_refresh_stats_noprof(dqn_learner* h) {
+    const int p = h->profile; h->profile = 0;
+    maybe_refresh_stats(h);
+    h->profile = p;
+}
 static void maybe_refresh_stats(dqn_learner* h) {
     // deep_q_agent.py:505: step % per_calculate_steps == 0 or last_max_weight is None
     if (h->cfg.use_per && (!h->has_max_weight || h->host_step % h->cfg.per_calculate_steps == 0)) {
@@ -639,12 +650,33 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
     API_BEGIN(h)
     DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
     if (h->profile) {
-        for (int64_t i = 0; i < n; ++i) {
+        if (!h->prof_graph) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = h->launches, s0 = h->host_step;
             h->prof_used = 0; h->prof_marks.clear();
-            maybe_refresh_stats(h);
-            fused_step_launches(h, nullptr, nullptr, 1.0, 3);
+            h->prof_capturing = true;
+            DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                fused_step_launches(h, nullptr, nullptr, 1.0, 3);
+            } catch (...) {
+                h->prof_capturing = false;
+                cudaStreamEndCapture(h->stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            h->prof_capturing = false;
+            DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+            h->graph_launches = h->launches - l0;
+            h->launches = l0; h->host_step = s0;
+            DQN_CUDA_OK(cudaGraphInstantiate(&h->prof_graph, g, 0));
+            DQN_CUDA_OK(cudaGraphDestroy(g));
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            maybe_refresh_stats_noprof(h);
+            DQN_CUDA_OK(cudaGraphLaunch(h->prof_graph, h->stream));
+            h->launches += h->graph_launches;
+            h->host_step++;
             after_step_host(h);
-            // accumulate segment times
             DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
             for (size_t s = 0; s + 1 < h->prof_used; ++s) {
                 float ms = 0.f;

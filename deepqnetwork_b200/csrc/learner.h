@@ -119,6 +119,9 @@ struct dqn_learner {
 
     // per-segment CUDA-event timing (dqn_set_profile)
     int profile = 0;
+    bool prof_capturing = false;
+    cudaGraphExec_t prof_graph = nullptr;
+    const char* prof_tag = "";  // "on_" / "tg_": which tower the forward marks belong to
     std::vector<cudaEvent_t> prof_events;
     std::vector<const char*> prof_marks;
     size_t prof_used = 0;
@@ -127,6 +130,7 @@ struct dqn_learner {
 };
 
 // ---- kernels / launchers (defined across the .cu files) ----
+void prof_mark(dqn_learner* h, const char* name);  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);
 
 // replay.cu

@@ -145,8 +145,11 @@ static int fc_kchunk() { return 256; }
 void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, int rows, TowerActs& acts) {
     const NetDesc& net = h->net;
     const void* in = d_states;
+    const bool tg = h->prof_tag[0] == 't';
+    static const char* kConvName[2][3] = {{"on_conv1_fwd", "on_conv2_fwd", "on_conv3_fwd"}, {"tg_conv1_fwd", "tg_conv2_fwd", "tg_conv3_fwd"}};
     for (int l = 0; l < 3; ++l) {
         const ConvGeom& g = net.conv[l];
+        prof_mark(h, kConvName[tg][l]);
         OpConvFwdA a{in, g, l == 0 ? 1 : 0};
         OpColContig b{P + net.off_cw[l], g.cout};
         EpiBiasRelu e{acts.act[l], P + net.off_cb[l], g.cout};
@@ -159,7 +162,9 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, int 
     OpRowMajorK a{acts.act[2], net.flat};
     OpFcWeightFwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
     EpiPartial e{acts.fc_part, rows, net.NH};
+    prof_mark(h, tg ? "tg_fc_fwd" : "on_fc_fwd");
     igemm_auto<true>(h, a, b, e, rows, net.NH, net.flat, splits, kchunk);
+    prof_mark(h, tg ? "tg_fc_reduce_heads" : "on_fc_reduce_heads");
     fc_reduce_heads_kernel<<<rows, 256, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, net.dueling,
                                                         P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0],
                                                         P + net.off_hd_b[0], P + net.off_hd_w[1], P + net.off_hd_b[1],
@@ -205,6 +210,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
     TowerActs& acts = h->acts_on;
     // dense hidden: dW = X^T dH (K = batch), written straight into the gradient slab
     {
+        prof_mark(h, "fc_wgrad");
         OpColContig a{acts.act[2], net.flat};
         OpColContig b{h->d_hid, net.NH};
         EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
@@ -212,6 +218,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
     }
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
+        prof_mark(h, "fc_dgrad");
         OpRowMajorK a{h->d_hid, net.NH};
         OpFcWeightBwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
         EpiGateStore e{h->d_act[2], acts.act[2], net.flat};
@@ -229,10 +236,14 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
             int kchunk = ceil_div(ceil_div(K, Z), 16) * 16;
             Z = ceil_div(K, kchunk);
             DQN_REQUIRE((int64_t)Z * (mreal + 4) * N <= h->wg_part_floats, "wgrad workspace too small");
+            static const char* kW[3] = {"conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
+            prof_mark(h, kW[l]);
             OpConvWgradABias a{OpConvWgradA{l == 0 ? (const void*)d_states : (const void*)acts.act[l - 1], g, l == 0 ? 1 : 0}, mreal};
             OpColContig b{h->d_act[l], N};
             EpiPartial e{part, mreal + 4, N};
             igemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
+            static const char* kR[3] = {"conv1_wgrad_reduce", "conv2_wgrad_reduce", "conv3_wgrad_reduce"};
+            prof_mark(h, kR[l]);
             wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 256), 256, 0, h->stream>>>(part, Z, mreal, N,
                                                                                           G + net.off_cw[l], G + net.off_cb[l]);
             DQN_CUDA_OK(cudaGetLastError());
@@ -241,6 +252,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
         if (l == 0) break;  // no gradient flows into the input image
         // dgrad into the previous activation, gated by its ReLU
         {
+            prof_mark(h, l == 2 ? "conv3_dgrad" : "conv2_dgrad");
             const int cl2 = ilog2(g.cout);
             DgradClass c{g};
             const int Zc = g.s * g.s;

@@ -91,7 +91,7 @@ class NetSpec:
         return sum(int(np.prod(s)) for s in self.param_shapes().values())
 
 
-def forward(params, x_u8, spec, dtype=torch.float32, return_hidden=False):
+def forward(params, x_u8, spec, dtype=torch.float32, acts=None):
     """One tower.  params: name -> torch tensor (HWIO / [in,out]).  x_u8: [n,H,W,C] uint8 (numpy or torch)."""
     x = torch.as_tensor(np.asarray(x_u8)) if not torch.is_tensor(x_u8) else x_u8
     x = x.to(dtype) / 255
@@ -101,17 +101,25 @@ def forward(params, x_u8, spec, dtype=torch.float32, return_hidden=False):
         w = params[name + '/kernel'].to(dtype).permute(3, 2, 0, 1)  # HWIO -> OIHW
         x = F.pad(x, (l['pl'], l['pr'], l['pt'], l['pb']))
         x = F.relu(F.conv2d(x, w, params[name + '/bias'].to(dtype), stride=l['s']))
+        if acts is not None:
+            acts.append(x.permute(0, 2, 3, 1).detach().numpy())  # NHWC, post-ReLU
     flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # tf.layers.flatten on NHWC
     def dense(i, inp, relu):
         name = 'dense' if i == 0 else 'dense_%d' % i
         y = inp @ params[name + '/kernel'].to(dtype) + params[name + '/bias'].to(dtype)
         return F.relu(y) if relu else y
     if spec.use_dueling:
-        adv = dense(1, dense(0, flat, True), False)
-        val = dense(3, dense(2, flat, True), False)
+        ha, hv = dense(0, flat, True), dense(2, flat, True)
+        adv = dense(1, ha, False)
+        val = dense(3, hv, False)
         q = val + (adv - adv.mean(dim=1, keepdim=True))
+        if acts is not None:
+            acts.append(torch.cat([ha, hv], dim=1).detach().numpy())
     else:
-        q = dense(1, dense(0, flat, True), False)
+        hh = dense(0, flat, True)
+        q = dense(1, hh, False)
+        if acts is not None:
+            acts.append(hh.detach().numpy())
     return q
 
 
@@ -155,16 +163,19 @@ class OptState:
     def __init__(self, params, spec, dtype=torch.float32):
         self.m = {k: torch.zeros_like(v, dtype=dtype) for k, v in params.items()}
         self.v = {k: torch.zeros_like(v, dtype=dtype) for k, v in params.items()}
-        self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-8
+        # TF converts the python-float hyper-parameters to tensors of the variable dtype (float32) before ApplyAdam
+        # uses them, so the true constants are the f32 roundings (1 - f32(0.999) differs from 0.001 by 1.3e-5)
+        f32 = lambda x: float(np.float32(x))
+        self.beta1, self.beta2, self.eps = f32(0.9), f32(0.999), f32(1e-8)
         self.beta1_power = torch.tensor(self.beta1, dtype=dtype)
         self.beta2_power = torch.tensor(self.beta2, dtype=dtype)
         self.step = 0
 
 
 def apply_optimizer(params, grads, opt, spec, dtype):
-    lr = torch.tensor(spec.learning_rate, dtype=dtype)
+    lr = torch.tensor(float(np.float32(spec.learning_rate)), dtype=dtype)
     if spec.use_momentum:
-        mom = torch.tensor(spec.momentum, dtype=dtype)
+        mom = torch.tensor(float(np.float32(spec.momentum)), dtype=dtype)
         for k in params:
             g = grads[k]
             opt.m[k] = opt.m[k] * mom + g
@@ -194,7 +205,8 @@ def train_step(online, target, opt, batch, is_weights, spec, dtype=torch.float32
     # fed through a tf.float32 placeholder; the fp64 truth keeps full precision
     y = torch.as_tensor(y64.astype(np.float32)).to(dtype) if dtype == torch.float32 else torch.as_tensor(y64)
     leaf = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in online.items())
-    q = forward(leaf, batch['states'], spec, dtype)
+    acts = []
+    q = forward(leaf, batch['states'], spec, dtype, acts=acts)
     onehot = F.one_hot(torch.as_tensor(np.asarray(batch['actions'])).long(), spec.num_actions).to(dtype)
     qa = (q * onehot).sum(1)
     abs_l = (y - qa).abs()
@@ -212,7 +224,7 @@ def train_step(online, target, opt, batch, is_weights, spec, dtype=torch.float32
         apply_optimizer(online, grads, opt, spec, dtype)
     return opt.step, losses.detach().numpy(), float(loss.detach()), dict(q=q.detach().numpy(), y=y.numpy(),
                                                                         grads={k: g.numpy() for k, g in grads.items()},
-                                                                        max_q=mq.numpy())
+                                                                        max_q=mq.numpy(), acts=acts)
 
 
 def to_torch(params_np, dtype=torch.float32):

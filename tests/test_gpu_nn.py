@@ -55,6 +55,20 @@ def make(cfg, batch=32, capacity=256, seed=0):
     return L, spec, shapes, on, tg
 
 
+def gate_flips(L, aux, n=32):
+    """Number of ReLU units whose on/off state differs between the device step and the fp64 truth (and check the
+    activations themselves at TOL).  A pre-activation below fp32 resolution can land on either side of zero; the
+    forward is unaffected but that unit's gradient path is switched, and Adam's first steps (update ~ lr*sign(g))
+    amplify it.  Parity of gradients / optimizer slots / weights at 1e-4 is therefore asserted for runs whose gates
+    all agree; after a flipped gate those tensors are held to 2e-2 instead (Q-values, targets, losses stay at 1e-4)."""
+    flips = 0
+    for nm, a_ref in zip(('act1_online', 'act2_online', 'act3_online', 'hid_online'), aux['acts']):
+        a_gpu = L.debug_read(nm, (2 * n,) + a_ref.shape[1:] if L.cfg.use_double else a_ref.shape)[:n]
+        flips += int(np.sum((a_gpu > 0) != (a_ref > 0)))
+        assert rel_err(a_gpu, a_ref) < TOL, nm
+    return flips
+
+
 def rand_batch(cfg, n, seed):
     rng = np.random.default_rng(seed)
     shp = (n, cfg['h'], cfg['w'], 4)
@@ -79,33 +93,73 @@ def test_predict_matches_oracle(name):
     L.close()
 
 
+def oracle_state_from_gpu(L, shapes, spec):
+    """fp64 oracle state (weights, optimizer slots, beta powers, step) equal to the device's current state, so that
+    every step is compared from identical inputs instead of letting two chaotic trajectories drift apart."""
+    o = nn_ref.to_torch({k: L.get_param(k).reshape(shapes[k]) for k in shapes}, torch.float64)
+    t = nn_ref.to_torch({k: L.get_param(k, tower=1).reshape(shapes[k]) for k in shapes}, torch.float64)
+    opt = nn_ref.OptState(o, spec, torch.float64)
+    opt.m = nn_ref.to_torch({k: L.get_param(k, slot=1).reshape(shapes[k]) for k in shapes}, torch.float64)
+    opt.v = nn_ref.to_torch({k: L.get_param(k, slot=2).reshape(shapes[k]) for k in shapes}, torch.float64)
+    b1p, b2p = L.get_beta_powers()
+    opt.beta1_power = torch.tensor(b1p, dtype=torch.float64); opt.beta2_power = torch.tensor(b2p, dtype=torch.float64)
+    opt.step = L.get_step()
+    return o, t, opt
+
+
+def check_optimizer_given_grads(L, shapes, spec, o_before, opt_before):
+    """Optimizer parity in isolation: apply the oracle's Adam/Momentum to the DEVICE's gradient and compare weights
+    and slots tightly.  (End-to-end, Adam's early steps behave like lr*sign(g), so an element whose gradient is
+    within fp32 noise of zero legitimately moves by up to ~2*lr in either direction; that is bounded separately.)"""
+    g = {k: torch.as_tensor(L.get_param(k, slot=3).reshape(shapes[k])).to(torch.float64) for k in shapes}
+    nn_ref.apply_optimizer(o_before, g, opt_before, spec, torch.float64)
+    for k in shapes:
+        assert rel_err(L.get_param(k), o_before[k].numpy().reshape(-1)) < 2e-6, ('opt weight', k)
+        assert rel_err(L.get_param(k, slot=1), opt_before.m[k].numpy().reshape(-1)) < 2e-6, ('opt m', k)
+        if not spec.use_momentum:
+            assert rel_err(L.get_param(k, slot=2), opt_before.v[k].numpy().reshape(-1)) < 2e-6, ('opt v', k)
+
+
+def check_weights_end_to_end(L, shapes, spec, o_after, flipped):
+    """Updated weights vs the fp64 truth: 1e-4 relative per tensor, except for elements whose update sign is decided
+    by a gradient inside fp32 noise (|dw| then differs by at most ~2*lr); those must be rare."""
+    lr = spec.learning_rate
+    for k in shapes:
+        got = L.get_param(k).astype(np.float64); ref = o_after[k].numpy().reshape(-1)
+        scale = max(np.max(np.abs(ref)), 1e-30)
+        bad = np.abs(got - ref) > TOL * scale
+        assert np.max(np.abs(got - ref)) <= TOL * scale + 2.5 * lr, ('e2e weight bound', k)
+        assert bad.mean() <= (1e-3 if not flipped else 5e-2), ('e2e weight outliers', k, float(bad.mean()))
+
+
 @pytest.mark.parametrize('name', list(CONFIGS))
 def test_train_batch_matches_oracle(name):
-    """DeepQModel.train (two runs + host target) for three consecutive steps on fresh batches."""
+    """DeepQModel.train (two runs + host target) for three consecutive steps on fresh batches.  Each step starts
+    the fp64 oracle from the device's own state."""
+    import copy
     cfg = CONFIGS[name]
     L, spec, shapes, on, tg = make(cfg)
-    o = nn_ref.to_torch(on, torch.float64); t = nn_ref.to_torch(tg, torch.float64)
-    opt = nn_ref.OptState(o, spec, torch.float64)
     for it in range(3):
         b = rand_batch(cfg, 32, 100 + it)
         w = np.random.default_rng(it).random(32).astype(np.float32) + 0.1 if cfg['per'] else None
+        o, t, opt = oracle_state_from_gpu(L, shapes, spec)
+        o2, opt2 = copy.deepcopy(o), copy.deepcopy(opt)
         step, losses, loss = L.train_batch(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'], w)
         rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, b, w, spec, torch.float64)
         assert step == rstep == it + 1
         A = cfg['a']
+        flipped = gate_flips(L, aux) > 0
+        gtol = TOL if not flipped else 2e-2
         assert rel_err(L.debug_read('q_online', (32, A)), aux['q']) < TOL
         assert rel_err(L.debug_read('max_q', (32,)), aux['max_q']) < TOL
         assert rel_err(L.debug_read('y', (32,)), aux['y']) < TOL
         assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
         for k in shapes:
             g = L.get_param(k, slot=3)
-            assert rel_err(g, aux['grads'][k].reshape(-1)) < TOL, (name, it, 'grad', k, rel_err(g, aux['grads'][k].reshape(-1)))
-        for k in shapes:
-            assert rel_err(L.get_param(k), o[k].numpy().reshape(-1)) < TOL, (name, it, 'weight', k)
-            assert rel_err(L.get_param(k, slot=1), opt.m[k].numpy().reshape(-1)) < TOL, (name, it, 'm', k)
-            if not cfg.get('momentum'):
-                assert rel_err(L.get_param(k, slot=2), opt.v[k].numpy().reshape(-1)) < 2 * TOL, (name, it, 'v', k)
-            # the target tower only changes through copy_network (SURVEY Q8)
+            assert rel_err(g, aux['grads'][k].reshape(-1)) < gtol, (name, it, 'grad', k, flipped, rel_err(g, aux['grads'][k].reshape(-1)))
+        check_optimizer_given_grads(L, shapes, spec, o2, opt2)
+        check_weights_end_to_end(L, shapes, spec, o, flipped)
+        for k in shapes:  # the target tower only changes through copy_network (SURVEY Q8)
             assert np.array_equal(L.get_param(k, tower=1), tg[k].reshape(-1))
     L.copy_network()
     for k in shapes:
@@ -153,12 +207,12 @@ def test_fused_train_steps_match_reference_loop(name):
     N, B = 2000, 32
     L, spec, shapes, on, tg = make(cfg, capacity=N)
     L.replay_fill_synthetic(N, seed=77)
-    o = nn_ref.to_torch(on, torch.float64); t = nn_ref.to_torch(tg, torch.float64)
-    opt = nn_ref.OptState(o, spec, torch.float64)
     ref_tree = SumTreeC(N)
     rnd = random.Random(0)
     max_w = None
+    ever_flipped = False
     for it in range(4):
+        o, t, opt = oracle_state_from_gpu(L, shapes, spec)
         if cfg['per']:
             tree, data, size, write = L.tree_read()
             ref_tree.load(tree, data, size, write)
@@ -180,8 +234,7 @@ def test_fused_train_steps_match_reference_loop(name):
         rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, rows, isw, spec, torch.float64)
         assert step == rstep
         assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
-        for k in shapes:
-            assert rel_err(L.get_param(k), o[k].numpy().reshape(-1)) < TOL, (name, it, k)
+        check_weights_end_to_end(L, shapes, spec, o, gate_flips(L, aux) > 0)
         if cfg['per']:
             newp = L.debug_read('new_priorities', (B,))
             assert rel_err(newp, nn_ref.make_priority(losses)) < 1e-6  # powf vs np.power, float tolerance
