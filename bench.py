@@ -234,6 +234,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c2', choices=list(CONFIGS))
     ap.add_argument('--capacity', type=int, default=1000000, help='replay transitions resident in HBM')
+    ap.add_argument('--math', default='tc3x', choices=['fp32', 'tc3x', 'tc1x'],
+                    help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
@@ -253,7 +255,8 @@ def main():
                   params=nn['P'], gflop_per_step=round(nn['flops'] / 1e9, 3), algorithmic_mb_per_step=round(nn['step_bytes'] / 1e6, 1),
                   l2='no flush: steady-state step; per-step working set (5 parameter-sized slabs = %.0f MB + random replay rows '
                      'out of %.1f GB) exceeds the 126 MB L2' % (5 * 4 * nn['P'] / 1e6, 2 * args.capacity * nn['S'] / 1e9),
-                  math='fp32 FFMA (DQN_MATH_FP32)')
+                  math={'fp32': 'fp32 FFMA (DQN_MATH_FP32)', 'tc3x': 'tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (DQN_MATH_TC3X; parity-tested at 1e-4 like fp32)',
+                        'tc1x': 'tcgen05 kind::tf32 single pass (DQN_MATH_TC1X; NOT fp32-grade, ~1e-3)'}[args.math])
 
     # ---- reference arm: the CPU restatement of the reference, rank 0 only -------------------------------------
     if args.impl == 'reference':
@@ -287,7 +290,7 @@ def main():
 
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
                 use_per=cfg['per'], batch_size=BATCH, replay_capacity=args.capacity, conv_variant=cfg['variant'],
-                seed=7 + rank, device=local_rank)
+                math_mode=args.math, seed=7 + rank, device=local_rank)
     stream = torch.cuda.Stream()      # a real (non-default) stream: stream capture is illegal on the legacy stream
     torch.cuda.set_stream(stream)
     L.set_stream(stream.cuda_stream)  # so that torch.cuda.Event brackets exactly the learner's work
@@ -399,7 +402,8 @@ def main():
     L.close()
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype={'fp32': 'f32', 'tc3x': 'f32 (tf32x3 on tcgen05)', 'tc1x': 'tf32'}[args.math],
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
                     cpu_baseline=cpu)
         print(json.dumps(line))

@@ -61,7 +61,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         DQN_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= 32, "num_actions must be in [1,32]");
         DQN_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= 4096, "batch_size out of range");
         DQN_REQUIRE(cfg->replay_capacity >= 2, "replay_capacity must be >= 2");
-        DQN_REQUIRE(cfg->math_mode == DQN_MATH_FP32, "only DQN_MATH_FP32 is built in this revision");
+        DQN_REQUIRE(cfg->math_mode >= DQN_MATH_FP32 && cfg->math_mode <= DQN_MATH_TC1X, "bad math_mode");
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0) throw std::string("no CUDA device: libdqn_b200 has no CPU fallback");
@@ -83,7 +83,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         h->B = cfg->batch_size;
         h->max_rows = cfg->max_rows > 0 ? cfg->max_rows : std::max(2 * h->B, 256);
         if (h->max_rows < h->B) h->max_rows = h->B;
-        h->fc_splits = ceil_div(net.flat, 256);
+        h->fc_splits = std::max(ceil_div(net.flat, 256), 40);
 
         // parameters + optimizer slots + gradient slab
         const size_t P = (size_t)net.slab;
@@ -126,6 +126,14 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             h->wg_part_floats = std::max<int64_t>(h->wg_part_floats, (int64_t)64 * (g.k * g.k * g.cin + 4) * g.cout);
         }
         dmalloc(h->wg_part, (size_t)h->wg_part_floats);
+        dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4);
+        DQN_CUDA_OK(cudaMemsetAsync(h->zeros16, 0, 16, h->stream));
+        {
+            const float one[4] = {1.f, 0.f, 0.f, 0.f};
+            DQN_CUDA_OK(cudaMemcpyAsync(h->ones_row, one, 16, cudaMemcpyHostToDevice, h->stream));
+            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        }
+        dmalloc(h->x_f32, 2 * R * h->state_bytes);
         h->dev_stage_bytes = 8u << 20;
         dmalloc(h->dev_stage, h->dev_stage_bytes);
         dmalloc(h->stats_scratch, 8192);
@@ -150,7 +158,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions, h->in_rewards, h->in_cont, h->in_isw,
                     h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
@@ -542,18 +550,24 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
                       const uint8_t* cont, const float* isw, int train, double grad_scale) {
     const size_t S = h->state_bytes;
     const int A = h->net.A;
+    const float* xf = nullptr;
+    if (h->cfg.math_mode != DQN_MATH_FP32) {
+        prof_mark(h, "u8_to_f32");
+        launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S);
+        xf = h->x_f32;
+    }
     h->prof_tag = "on_";
-    if (h->cfg.use_double) tower_forward(h, h->online, states2, 2 * n, h->acts_on);  // s and s' share one pass
-    else tower_forward(h, h->online, states2, n, h->acts_on);
+    if (h->cfg.use_double) tower_forward(h, h->online, states2, xf, 2 * n, h->acts_on);  // s and s' share one pass
+    else tower_forward(h, h->online, states2, xf, n, h->acts_on);
     h->prof_tag = "tg_";
-    tower_forward(h, h->target, states2 + (size_t)n * S, n, h->acts_tg);
+    tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
                        grad_scale);
     if (train) {
         prof_mark(h, "head_backward");
         launch_head_backward(h, n, actions);
-        tower_backward(h, states2, n);
+        tower_backward(h, states2, xf, n);
     }
 }
 
@@ -787,7 +801,9 @@ extern "C" int dqn_predict(dqn_learner* h, int32_t n, const uint8_t* st, int32_t
         const int m = std::min(n - done, h->max_rows);
         DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st + (size_t)done * S, m * S, cudaMemcpyHostToDevice, h->stream));
         TowerActs& acts = use_target ? h->acts_tg : h->acts_on;
-        tower_forward(h, use_target ? h->target : h->online, h->in_states, m, acts);
+        const float* xf = nullptr;
+        if (h->cfg.math_mode != DQN_MATH_FP32) { launch_u8_to_f32(h, h->in_states, h->x_f32, (size_t)m * S); xf = h->x_f32; }
+        tower_forward(h, use_target ? h->target : h->online, h->in_states, xf, m, acts);
         DQN_CUDA_OK(cudaMemcpyAsync(q + (size_t)done * A, acts.q, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream));
         done += m;
     }
@@ -912,4 +928,27 @@ extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
         return 1;
     }
     return 0;
+}
+
+
+// GEMM engine self-test (tests/test_gpu_tcgemm.py): C[M,N] = A * B with host matrices, through the FFMA kernel
+// (mode 0) or the tcgen05 kernel (mode 1: TF32 x3, mode 2: TF32 x1)
+extern "C" int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,
+                                 int32_t b_kcontig, const float* hA, const float* hB, float* hC) {
+    API_BEGIN(h)
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    dmalloc(dA, (size_t)M * K); dmalloc(dB, (size_t)N * K); dmalloc(dC, (size_t)M * N);
+    try {
+        DQN_CUDA_OK(cudaMemcpyAsync(dA, hA, (size_t)M * K * 4, cudaMemcpyHostToDevice, h->stream));
+        DQN_CUDA_OK(cudaMemcpyAsync(dB, hB, (size_t)N * K * 4, cudaMemcpyHostToDevice, h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(dC, 0xFF, (size_t)M * N * 4, h->stream));
+        selftest_gemm(h, mode, M, N, K, a_kcontig, b_kcontig, dA, dB, dC);
+        DQN_CUDA_OK(cudaMemcpyAsync(hC, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    } catch (...) {
+        cudaFree(dA); cudaFree(dB); cudaFree(dC);
+        throw;
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    API_END(h)
 }

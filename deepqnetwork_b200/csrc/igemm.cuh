@@ -24,6 +24,7 @@ struct OpRowMajorK {  // Op(r,k) = p[r*ld + k]
     typedef const float* Row;
     __device__ __forceinline__ Row row(int r, int) const { return p + (size_t)r * ld; }
     __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const { return *reinterpret_cast<const float4*>(rw + k); }
+    __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + k; }
 };
 
 struct OpColContig {  // Op(r,k) = p[k*ld + r]
@@ -34,6 +35,7 @@ struct OpColContig {  // Op(r,k) = p[k*ld + r]
     __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const {
         return *reinterpret_cast<const float4*>(rw + (size_t)k * ld);
     }
+    __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * ld; }
 };
 
 // hidden-layer weights of the (up to) two streams seen as one [flat, NH] matrix: B(k,n) = W[n/hid][k][n%hid]
@@ -45,6 +47,7 @@ struct OpFcWeightFwd {
     __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const {
         return *reinterpret_cast<const float4*>(rw + (size_t)k * hid);
     }
+    __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * hid; }
 };
 
 // transposed view for dgrad: B(k,n) = W[k/hid][n][k%hid]
@@ -57,6 +60,9 @@ struct OpFcWeightBwd {
         const float* w = k < hid ? w0 : w1;
         const int kk = k < hid ? k : k - hid;
         return *reinterpret_cast<const float4*>(w + rw + kk);
+    }
+    __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const {
+        return (k < hid ? w0 : w1) + rw + (k < hid ? k : k - hid);
     }
 };
 
@@ -88,6 +94,13 @@ struct OpConvFwdA {
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
         return load_px4(in, is_u8, r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci);
     }
+    __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {  // f32 input only
+        const int tap = k >> g.cin_log2, ci = k & (g.cin - 1);
+        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int iy = r.iy0 + kh, ix = r.ix0 + kw;
+        if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
+        return static_cast<const float*>(in) + r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci;
+    }
 };
 
 // conv wgrad A^T: rows m=(kh,kw,ci) (4 consecutive ci per load), k=(n,oy,ox)
@@ -107,6 +120,14 @@ struct OpConvWgradA {
         const int iy = oy * g.s - g.pt + r.kh, ix = ox * g.s - g.pl + r.kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
         return load_px4(in, is_u8, (((size_t)n * g.ih + iy) * g.iw + ix) * g.cin + r.ci);
+    }
+    __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {  // f32 input only
+        const int hw = g.oh * g.ow;
+        const int n = k / hw, rem = k - n * hw;
+        const int oy = rem / g.ow, ox = rem - oy * g.ow;
+        const int iy = oy * g.s - g.pt + r.kh, ix = ox * g.s - g.pl + r.kw;
+        if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
+        return static_cast<const float*>(in) + (((size_t)n * g.ih + iy) * g.iw + ix) * g.cin + r.ci;
     }
 };
 
@@ -149,6 +170,14 @@ struct OpConvDgradA {
             return make_float4(0.f, 0.f, 0.f, 0.f);
         return *reinterpret_cast<const float4*>(dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co);
     }
+    __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {
+        const int kt = c.g.k / c.g.s;
+        const int tap = k >> cout_log2, co = k & (c.g.cout - 1);
+        const int jh = tap / kt, jw = tap - jh * kt;
+        const int oy = r.oy0 - jh, ox = r.ox0 - jw;
+        if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow) return nullptr;
+        return dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co;
+    }
 };
 
 struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
@@ -163,6 +192,14 @@ struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
         const int jh = tap / kt, jw = tap - jh * kt;
         const int kh = ry + g.s * jh, kw = rx + g.s * jw;
         return *reinterpret_cast<const float4*>(w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co);
+    }
+    __device__ __forceinline__ const float* addr4(Row ci, int, int k, int z) const {
+        const int ry = z / g.s, rx = z - ry * g.s;
+        const int kt = g.k / g.s;
+        const int tap = k >> cout_log2, co = k & (g.cout - 1);
+        const int jh = tap / kt, jw = tap - jh * kt;
+        const int kh = ry + g.s * jh, kw = rx + g.s * jw;
+        return w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co;
     }
 };
 
@@ -234,6 +271,40 @@ struct EpiFcWgrad {  // dW of the two hidden streams: column n -> stream n/hid, 
         float* o = (n < hid ? g0 + n : g1 + (n - hid)) + (size_t)m * hid;
 #pragma unroll
         for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
+// transposed variants for swap-AB launches (rows of the GEMM = output columns): thread holds TN consecutive n'
+struct EpiPartialT {  // part[z][n][m]
+    float* part; int rows; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int z) const {
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+            if (n + j < rows) part[((size_t)z * rows + n + j) * ldo + m] = v[j];
+    }
+};
+
+struct EpiGateStoreT {  // out[n][m] = acc * (gate[n][m] > 0)
+    float* out; const float* gate; int rows; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            if (n + j < rows) {
+                const size_t o = (size_t)(n + j) * ldo + m;
+                out[o] = gate[o] > 0.f ? v[j] : 0.f;
+            }
+        }
+    }
+};
+
+struct EpiStore {  // out[m][n] = acc (self-test)
+    float* out; int ldo;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) out[(size_t)m * ldo + n + j] = v[j];
     }
 };
 

@@ -107,6 +107,10 @@ struct dqn_learner {
     int64_t wg_part_floats = 0;
     int fc_splits = 1;
 
+    // tcgen05 path helpers
+    float* zeros16 = nullptr;   // 16 zero bytes (cp.async dummy source)
+    float* ones_row = nullptr;  // {1,0,0,0}: the bias row appended to conv wgrad A^T
+    float* x_f32 = nullptr;     // u8 batch converted to f32 (x/255) for cp.async loaders: [2*max_rows][S]
     // staging
     uint8_t* dev_stage = nullptr;
     size_t dev_stage_bytes = 0;
@@ -144,8 +148,11 @@ void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uin
 void launch_tree_stats(dqn_learner* h, double per_b_override);
 
 // nn.cu
-void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, int rows, TowerActs& acts);
-void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows);
+// x_f32: the same rows as d_states already converted to f32 (used by the tcgen05 path; may be null in FP32 mode)
+void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts);
+void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows);
+void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n);
+int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, int b_kcontig, const float* dA, const float* dB, float* dC);
 
 // heads.cu
 void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q_on_next, const float* q_tg_next,

@@ -4,7 +4,8 @@
 // dense 512 ReLU, optional dueling streams) and its autodiff backward (rl/deep_q_model.py:391 optimizer.minimize).
 // Layout: activations NHWC f32, conv kernels HWIO (== row-major [KH*KW*Cin, Cout]), dense kernels [in,out] --
 // the TF layouts, so tensors copy 1:1 to/from checkpoints.
-#include "igemm.cuh"
+#include "tcgemm.cuh"
+#include <algorithm>
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -81,6 +82,39 @@ static void igemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e,
     return launch_igemm<TileCfg<32, 32, 16, 4, 4>, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
 }
 
+// ---- math-mode dispatch: tcgen05 tensor cores (TF32 x1 / x3) or the FFMA kernel ------------------------------------
+template <int BN, bool SPLIT, class AOp, class BOp, class Epi>
+static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+    if (h->cfg.math_mode == DQN_MATH_TC3X) tc::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    else tc::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+}
+
+template <bool SPLIT, class AOp, class BOp, class Epi>
+static void gemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+    if (h->cfg.math_mode == DQN_MATH_FP32 || (N % 32) != 0) return igemm_auto<SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    const int64_t mt = (int64_t)ceil_div(M, tc::BM) * Z;
+    // widest N tile that still gives about one CTA per SM; narrower tiles re-read A from L2 but fill the chip
+    if (N % 128 == 0 && mt * (N / 128) >= h->sm_count) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (N % 64 == 0 && mt * (N / 64) >= h->sm_count) return tc_go<64, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    return tc_go<32, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+}
+
+__global__ void u8_to_f32_kernel(const uint32_t* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w = src[i];
+        dst[i] = make_float4(u8_to_unit(w & 255u), u8_to_unit((w >> 8) & 255u), u8_to_unit((w >> 16) & 255u), u8_to_unit(w >> 24));
+    }
+}
+
+// cast + divide by 255 (rl/deep_q_model.py:226-227) once per batch for the cp.async loaders of the tcgen05 path
+void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n) {
+    const size_t n4 = n / 4;
+    int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
+    u8_to_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<float4*>(dst), n4);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
+}
+
 // ---- dense hidden layer: reduce split-K partials, bias, ReLU, then the head dot products and dueling combine
 #define MAX_ACTIONS 32
 __global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __restrict__ part, int splits, int rows, int NH,
@@ -142,28 +176,43 @@ __global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __res
 
 static int fc_kchunk() { return 256; }
 
-void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, int rows, TowerActs& acts) {
+void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts) {
     const NetDesc& net = h->net;
-    const void* in = d_states;
+    const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
+    DQN_REQUIRE(!tcm || x_f32 != nullptr, "tensor-core path needs the f32 input batch");
+    const void* in = tcm ? (const void*)x_f32 : (const void*)d_states;
     const bool tg = h->prof_tag[0] == 't';
     static const char* kConvName[2][3] = {{"on_conv1_fwd", "on_conv2_fwd", "on_conv3_fwd"}, {"tg_conv1_fwd", "tg_conv2_fwd", "tg_conv3_fwd"}};
     for (int l = 0; l < 3; ++l) {
         const ConvGeom& g = net.conv[l];
         prof_mark(h, kConvName[tg][l]);
-        OpConvFwdA a{in, g, l == 0 ? 1 : 0};
+        OpConvFwdA a{in, g, (l == 0 && !tcm) ? 1 : 0};
         OpColContig b{P + net.off_cw[l], g.cout};
         EpiBiasRelu e{acts.act[l], P + net.off_cb[l], g.cout};
-        igemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
+        gemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
         in = acts.act[l];
     }
-    const int kchunk = fc_kchunk();
-    const int splits = ceil_div(net.flat, kchunk);
-    DQN_REQUIRE(splits <= h->fc_splits, "fc split workspace too small");
-    OpRowMajorK a{acts.act[2], net.flat};
-    OpFcWeightFwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
-    EpiPartial e{acts.fc_part, rows, net.NH};
+    int kchunk = fc_kchunk();
+    int splits = ceil_div(net.flat, kchunk);
     prof_mark(h, tg ? "tg_fc_fwd" : "on_fc_fwd");
-    igemm_auto<true>(h, a, b, e, rows, net.NH, net.flat, splits, kchunk);
+    if (tcm && rows % 32 == 0) {
+        // swap-AB: the 128-row MMA tile spans hidden units (weights stream as the A operand), the batch is N
+        const int mt = ceil_div(net.NH, tc::BM);
+        int want = std::min(std::max(1, h->sm_count / mt), h->fc_splits);
+        kchunk = ceil_div(ceil_div(net.flat, want), tc::BK) * tc::BK;
+        splits = ceil_div(net.flat, kchunk);
+        DQN_REQUIRE(splits <= h->fc_splits, "fc split workspace too small");
+        OpFcWeightFwd a{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+        OpRowMajorK b{acts.act[2], net.flat};
+        EpiPartialT e{acts.fc_part, rows, net.NH};
+        gemm_auto<true>(h, a, b, e, net.NH, rows, net.flat, splits, kchunk);
+    } else {
+        DQN_REQUIRE(splits <= h->fc_splits, "fc split workspace too small");
+        OpRowMajorK a{acts.act[2], net.flat};
+        OpFcWeightFwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+        EpiPartial e{acts.fc_part, rows, net.NH};
+        igemm_auto<true>(h, a, b, e, rows, net.NH, net.flat, splits, kchunk);
+    }
     prof_mark(h, tg ? "tg_fc_reduce_heads" : "on_fc_reduce_heads");
     fc_reduce_heads_kernel<<<rows, 256, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, net.dueling,
                                                         P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0],
@@ -177,12 +226,16 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, int 
 // conv wgrad with an extra all-ones row appended to A^T so the same GEMM also yields the bias gradient
 struct OpConvWgradABias {
     static constexpr bool KCONTIG = false;
-    OpConvWgradA base; int mreal;
+    OpConvWgradA base; int mreal; const float* ones;  // ones -> {1,0,0,0}
     typedef OpConvWgradA::Row Row;
     __device__ __forceinline__ Row row(int m, int z) const { return base.row(m < mreal ? m : 0, z); }
     __device__ __forceinline__ float4 load4(const Row& r, int m, int k, int z) const {
         if (m >= mreal) return make_float4(m == mreal ? 1.f : 0.f, 0.f, 0.f, 0.f);
         return base.load4(r, m, k, z);
+    }
+    __device__ __forceinline__ const float* addr4(const Row& r, int m, int k, int z) const {
+        if (m >= mreal) return m == mreal ? ones : nullptr;
+        return base.addr4(r, m, k, z);
     }
 };
 
@@ -203,8 +256,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int Z, int m
     }
 }
 
-void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
+void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows) {
     const NetDesc& net = h->net;
+    const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
     const float* P = h->online;
     float* G = h->grads;
     TowerActs& acts = h->acts_on;
@@ -214,15 +268,22 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
         OpColContig a{acts.act[2], net.flat};
         OpColContig b{h->d_hid, net.NH};
         EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
-        igemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+        gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
     }
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
-        OpRowMajorK a{h->d_hid, net.NH};
-        OpFcWeightBwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
-        EpiGateStore e{h->d_act[2], acts.act[2], net.flat};
-        igemm_auto<false>(h, a, b, e, rows, net.flat, net.NH, 1, 0);
+        if (tcm && rows % 32 == 0) {  // swap-AB: weights are the 128-row operand, K-major as stored
+            OpFcWeightBwd a{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+            OpRowMajorK b{h->d_hid, net.NH};
+            EpiGateStoreT e{h->d_act[2], acts.act[2], rows, net.flat};
+            gemm_auto<false>(h, a, b, e, net.flat, rows, net.NH, 1, 0);
+        } else {
+            OpRowMajorK a{h->d_hid, net.NH};
+            OpFcWeightBwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
+            EpiGateStore e{h->d_act[2], acts.act[2], net.flat};
+            igemm_auto<false>(h, a, b, e, rows, net.flat, net.NH, 1, 0);
+        }
     }
     float* part = h->wg_part;
     for (int l = 2; l >= 0; --l) {
@@ -230,18 +291,19 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
         const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
         // wgrad (+bias) split over the pixel dimension
         {
-            const int mt = ceil_div(mreal + 4, 64);
-            int Z = (2 * h->sm_count) / (mt * ceil_div(N, 64));
+            const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
+            int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
-            int kchunk = ceil_div(ceil_div(K, Z), 16) * 16;
+            int kchunk = ceil_div(ceil_div(K, Z), 32) * 32;
             Z = ceil_div(K, kchunk);
             DQN_REQUIRE((int64_t)Z * (mreal + 4) * N <= h->wg_part_floats, "wgrad workspace too small");
             static const char* kW[3] = {"conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
             prof_mark(h, kW[l]);
-            OpConvWgradABias a{OpConvWgradA{l == 0 ? (const void*)d_states : (const void*)acts.act[l - 1], g, l == 0 ? 1 : 0}, mreal};
+            const void* in0 = tcm ? (const void*)x_f32 : (const void*)d_states;
+            OpConvWgradABias a{OpConvWgradA{l == 0 ? in0 : (const void*)acts.act[l - 1], g, (l == 0 && !tcm) ? 1 : 0}, mreal, h->ones_row};
             OpColContig b{h->d_act[l], N};
             EpiPartial e{part, mreal + 4, N};
-            igemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
+            gemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
             static const char* kR[3] = {"conv1_wgrad_reduce", "conv2_wgrad_reduce", "conv3_wgrad_reduce"};
             prof_mark(h, kR[l]);
             wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 256), 256, 0, h->stream>>>(part, Z, mreal, N,
@@ -261,7 +323,28 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, int rows) {
             OpConvDgradA a{h->d_act[l], c, cl2, rows};
             OpConvDgradB b{P + net.off_cw[l], g, cl2};
             EpiDgradGate e{h->d_act[l - 1], acts.act[l - 1], c, rows};
-            igemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
+            gemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
         }
     }
+}
+
+
+// ---- GEMM self-test: plain matrices through either engine (dqn_selftest_gemm) ----------------------------------------
+// A is [M][K] (a_kcontig) or [K][M]; B is [N][K] (b_kcontig) or [K][N]; C is [M][N].
+int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, int b_kcontig, const float* dA,
+                  const float* dB, float* dC) {
+    const int saved = h->cfg.math_mode;
+    h->cfg.math_mode = mode;
+    EpiStore e{dC, N};
+    try {
+        if (a_kcontig && b_kcontig) gemm_auto<false>(h, OpRowMajorK{dA, K}, OpRowMajorK{dB, K}, e, M, N, K, 1, 0);
+        else if (a_kcontig && !b_kcontig) gemm_auto<false>(h, OpRowMajorK{dA, K}, OpColContig{dB, N}, e, M, N, K, 1, 0);
+        else if (!a_kcontig && b_kcontig) gemm_auto<false>(h, OpColContig{dA, M}, OpRowMajorK{dB, K}, e, M, N, K, 1, 0);
+        else gemm_auto<false>(h, OpColContig{dA, M}, OpColContig{dB, N}, e, M, N, K, 1, 0);
+    } catch (...) {
+        h->cfg.math_mode = saved;
+        throw;
+    }
+    h->cfg.math_mode = saved;
+    return 0;
 }

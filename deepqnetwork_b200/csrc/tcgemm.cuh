@@ -4,11 +4,15 @@
 // layer (conv im2col forward, dgrad, wgrad, dense layers, transposed operands) runs on it unchanged.
 //
 // Structure of one CTA (one 128 x BN output tile, 288 threads):
-//   warps 0-7  producers, then epilogue.  Operand tiles are gathered straight from global/L2 into shared memory with
-//              16-byte cp.async (zero-fill for padding / ragged edges), S stages deep.  A 16-byte global chunk is
-//              exactly one row of a UMMA core matrix in either canonical no-swizzle layout: K-major for operands
-//              that are contiguous along K, MN-major for operands contiguous along M/N, so no transposes are needed.
-//              For NTERMS=3 each thread then rewrites its own chunks' low parts (x - tf32(x)) into the *_lo tiles.
+//   warps 0-7  producers, then epilogue.  Both operands are staged K-major in the canonical no-swizzle UMMA layout
+//              (8-row x 16-byte core matrices; LBO padded to 144 bytes so every store pattern below is bank-conflict
+//              free).  Operands that are contiguous along K in global memory are gathered with 16-byte cp.async
+//              (zero-fill for padding / ragged edges), S stages deep: one global chunk is exactly one core-matrix
+//              row.  Operands contiguous along M/N (TF-layout weights [in,out], transposed activations) are loaded
+//              16 bytes at a time into registers two k-blocks ahead and transposed by 4-byte shared stores
+//              (kind::tf32 has no 16-byte-granular MN-major layout).  For NTERMS=3 the low parts (x - tf32(x)) go
+//              into the *_lo tiles: from registers for the transposed operands, by re-reading its own chunks for
+//              the cp.async ones.
 //   warp 8     allocates TMEM, and one elected lane issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per k-step,
 //              releasing smem stages with tcgen05.commit -> mbarrier.
 //   epilogue   tcgen05.ld 32x32b.x16: thread (warp%4, lane) owns accumulator row 32*(warp%4)+lane, warps 4-7 take the
@@ -103,45 +107,48 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// byte offset of 16-byte chunk inside a tile
-//   K-major  tile [R rows x 32 k]: chunk (r, c=k/4)   -> (r/8)*1024 + c*128 + (r%8)*16       LBO=128, SBO=1024
-//   MN-major tile [R mn   x 32 k]: chunk (g=mn/4, k)  -> (k/8)*(R*32) + g*128 + (k%8)*16    LBO=R*32, SBO=128
-template <bool KCONTIG, int R>
-struct TileMap {
-    static constexpr int CHUNKS = R * 8;
-    // chunk f of the tile -> (first row, k offset); consecutive f walk 16-byte pieces of one 128-byte core matrix
-    __device__ static __forceinline__ void rk(int f, int& r, int& k) {
-        if (KCONTIG) { r = f % R; k = (f / R) * 4; }
-        else { k = (f & 7) + 8 * ((f >> 3) / (R / 4)); r = ((f >> 3) % (R / 4)) * 4; }
-    }
+// K-major no-swizzle tile [R rows x 32 k]: element (r,k) at (r/8)*SBO + (k/4)*LBO + (r%8)*16 + (k%4)*4,
+// LBO = 144 (128-byte core matrix + 16 bytes of padding), SBO = 8*LBO.
+constexpr uint32_t LBO = 144, SBO = 8 * LBO;
+template <int R>
+struct Tile {
+    static constexpr int BYTES = (R / 8) * SBO;
+    static constexpr int CHUNKS = R * 8;  // 16-byte pieces
     __device__ static __forceinline__ uint32_t off(int r, int k) {
-        if (KCONTIG) return (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16);
-        return (uint32_t)((k >> 3) * (R * 32) + (r >> 2) * 128 + (k & 7) * 16);
+        return (uint32_t)((r >> 3) * SBO + (k >> 2) * LBO + (r & 7) * 16 + (k & 3) * 4);
     }
-    __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int ks) {
-        if (KCONTIG) return make_desc(tile_addr + ks * 256, 128, 1024);
-        return make_desc(tile_addr + ks * (R * 32), R * 32, 128);
-    }
+    __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int ks) { return make_desc(tile_addr + ks * 2 * LBO, LBO, SBO); }
 };
+// chunk f of a tile -> (first row, first k) of the 16 global bytes it covers
+//   K-contiguous operand : 4 consecutive k of one row; consecutive lanes take consecutive rows
+//   MN-contiguous operand: 4 consecutive rows at one k; consecutive lanes take consecutive k
+template <bool KCONTIG, int R>
+__device__ __forceinline__ void chunk_rk(int f, int& r, int& k) {
+    if (KCONTIG) { r = f % R; k = (f / R) * 4; }
+    else { k = f & 31; r = (f >> 5) * 4; }
+}
 
 template <int BN, int NTERMS>
 struct SmemPlan {
-    static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    static constexpr int A_BYTES = Tile<BM>::BYTES, B_BYTES = Tile<BN>::BYTES;
     static constexpr int STAGE = (A_BYTES + B_BYTES) * (NTERMS == 3 ? 2 : 1);
     static constexpr int MAX_STAGES = (200 * 1024) / STAGE;
     static constexpr int STAGES = MAX_STAGES > 4 ? 4 : (MAX_STAGES < 2 ? 2 : MAX_STAGES);
     static constexpr int BYTES = STAGES * STAGE + 256;
 };
 
+__device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
                                                             int kchunk, const float* __restrict__ zeros16) {
     using Plan = SmemPlan<BN, NTERMS>;
     constexpr int S = Plan::STAGES;
-    using AMap = TileMap<AOp::KCONTIG, BM>;
-    using BMap = TileMap<BOp::KCONTIG, BN>;
-    constexpr int LA = AMap::CHUNKS / PRODUCERS;
-    constexpr int LB = (BMap::CHUNKS + PRODUCERS - 1) / PRODUCERS;
+    using TA = Tile<BM>;
+    using TB = Tile<BN>;
+    constexpr int LA = TA::CHUNKS / PRODUCERS;
+    constexpr int LB = (TB::CHUNKS + PRODUCERS - 1) / PRODUCERS;
+    constexpr int PF = 2;  // register prefetch distance (k-blocks) for MN-contiguous operands
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t bars = sbase + S * Plan::STAGE;  // full[S], empty[S], accum, tmem slot
@@ -186,34 +193,87 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         typename BOp::Row b_row[LB];
 #pragma unroll
         for (int i = 0; i < LA; ++i) {
-            AMap::rk(tid + i * PRODUCERS, a_r[i], a_k[i]);
-            a_off[i] = AMap::off(a_r[i], a_k[i]);
+            chunk_rk<AOp::KCONTIG, BM>(tid + i * PRODUCERS, a_r[i], a_k[i]);
+            a_off[i] = TA::off(a_r[i], a_k[i]);
             a_row[i] = a.row(min(m0 + a_r[i], M - 1), z);
         }
 #pragma unroll
         for (int i = 0; i < LB; ++i) {
             const int f = tid + i * PRODUCERS;
-            if (f < BMap::CHUNKS) {
-                BMap::rk(f, b_r[i], b_k[i]);
-                b_off[i] = BMap::off(b_r[i], b_k[i]);
+            if (f < TB::CHUNKS) {
+                chunk_rk<BOp::KCONTIG, BN>(f, b_r[i], b_k[i]);
+                b_off[i] = TB::off(b_r[i], b_k[i]);
             } else { b_r[i] = -1; b_k[i] = 0; b_off[i] = 0; }
             b_row[i] = b.row(min(n0 + max(b_r[i], 0), N - 1), z);
         }
-        auto issue = [&](int kb) {
+        // K-contiguous operands: asynchronous 16-byte copies straight into the stage
+        auto issue_async = [&](int kb) {
             const int s = kb % S, k0 = kbeg + kb * BK;
-            const uint32_t ta = stage_a(s), tb = stage_b(s);
+            if (AOp::KCONTIG) {
+                const uint32_t ta = stage_a(s);
 #pragma unroll
-            for (int i = 0; i < LA; ++i) {
-                const int r = m0 + a_r[i], k = k0 + a_k[i];
-                const float* src = (r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                cp_async16(ta + a_off[i], src ? src : zeros16, src != nullptr);
+                for (int i = 0; i < LA; ++i) {
+                    const int r = m0 + a_r[i], k = k0 + a_k[i];
+                    const float* src = (r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
+                    cp_async16(ta + a_off[i], src ? src : zeros16, src != nullptr);
+                }
             }
+            if (BOp::KCONTIG) {
+                const uint32_t tb = stage_b(s);
 #pragma unroll
-            for (int i = 0; i < LB; ++i) {
-                if (b_r[i] >= 0) {
+                for (int i = 0; i < LB; ++i) {
+                    if (b_r[i] >= 0) {
+                        const int r = n0 + b_r[i], k = k0 + b_k[i];
+                        const float* src = (r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
+                        cp_async16(tb + b_off[i], src ? src : zeros16, src != nullptr);
+                    }
+                }
+            }
+        };
+        // MN-contiguous operands: 16-byte loads into registers, PF k-blocks ahead
+        float4 a_pf[AOp::KCONTIG ? 1 : PF][AOp::KCONTIG ? 1 : LA];
+        float4 b_pf[BOp::KCONTIG ? 1 : PF][BOp::KCONTIG ? 1 : LB];
+        auto load_regs = [&](int kb, int slot) {
+            const int k0 = kbeg + kb * BK;
+            if (!AOp::KCONTIG) {
+#pragma unroll
+                for (int i = 0; i < LA; ++i) {
+                    const int r = m0 + a_r[i], k = k0 + a_k[i];
+                    const float* src = (kb < nkb && r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
+                    a_pf[slot][i] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (!BOp::KCONTIG) {
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
                     const int r = n0 + b_r[i], k = k0 + b_k[i];
-                    const float* src = (r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                    cp_async16(tb + b_off[i], src ? src : zeros16, src != nullptr);
+                    const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
+                    b_pf[slot][i] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        // transpose store: rows r..r+3 of column k (row stride inside a core matrix is 16 bytes; r%8 is 0 or 4)
+        auto sts_t = [&](uint32_t addr, const float4& v) {
+            asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16], %2;\n\tst.shared.f32 [%0+32], %3;\n\tst.shared.f32 [%0+48], %4;"
+                         ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        };
+        auto store_regs = [&](int s, int slot) {
+            if (!AOp::KCONTIG) {
+#pragma unroll
+                for (int i = 0; i < LA; ++i) {
+                    const float4 v = a_pf[slot][i];
+                    sts_t(stage_a(s) + a_off[i], v);
+                    if (NTERMS == 3) sts_t(stage_alo(s) + a_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
+                }
+            }
+            if (!BOp::KCONTIG) {
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
+                    if (b_r[i] >= 0) {
+                        const float4 v = b_pf[slot][i];
+                        sts_t(stage_b(s) + b_off[i], v);
+                        if (NTERMS == 3) sts_t(stage_blo(s) + b_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
+                    }
                 }
             }
         };
@@ -221,32 +281,39 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
             // the tensor core reads the upper 19 bits of each operand (tf32); what it drops goes into the lo tile
-            v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
+                         "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
         };
         for (int kb = 0; kb < S - 1; ++kb) {
-            if (kb < nkb) issue(kb);
+            if (kb < nkb) issue_async(kb);
             cp_async_commit();
         }
+#pragma unroll
+        for (int p = 0; p < PF; ++p) load_regs(p, p);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
-            cp_async_wait<S - 2>();  // this thread's chunks of block kb have landed
+            // stage s is free: block kb-S (its previous user) was waited for before block kb-1's refill below
+#pragma unroll
+            for (int p = 0; p < PF; ++p)
+                if ((kb % PF) == p) { store_regs(s, p); load_regs(kb + PF, p); }
+            cp_async_wait<S - 2>();  // this thread's cp.async chunks of block kb have landed
             if (NTERMS == 3) {
+                if (AOp::KCONTIG) {
 #pragma unroll
-                for (int i = 0; i < LA; ++i) split_lo(stage_a(s) + a_off[i], stage_alo(s) + a_off[i]);
+                    for (int i = 0; i < LA; ++i) split_lo(stage_a(s) + a_off[i], stage_alo(s) + a_off[i]);
+                }
+                if (BOp::KCONTIG) {
 #pragma unroll
-                for (int i = 0; i < LB; ++i)
-                    if (b_r[i] >= 0) split_lo(stage_b(s) + b_off[i], stage_blo(s) + b_off[i]);
+                    for (int i = 0; i < LB; ++i)
+                        if (b_r[i] >= 0) split_lo(stage_b(s) + b_off[i], stage_blo(s) + b_off[i]);
+                }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
             mbar_arrive(full_bar(s));
-            const int nxt = kb + S - 1;
+            const int nxt = kb + S - 1;  // goes into the stage block kb-1 used
             if (nxt < nkb) {
-                if (kb >= 1) mbar_wait(empty_bar((kb - 1) % S), ((kb - 1) / S) & 1);  // MMAs of block kb-1 are done with the stage
-                issue(nxt);
+                if (kb >= 1) mbar_wait(empty_bar((kb - 1) % S), ((kb - 1) / S) & 1);
+                issue_async(nxt);
             }
             cp_async_commit();
         }
@@ -272,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         tc_fence_before();
     } else {
         // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(BN, !AOp::KCONTIG, !BOp::KCONTIG);
+        const uint32_t idesc = make_idesc(BN, false, false);  // both operands are staged K-major
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             mbar_wait(full_bar(s), (kb / S) & 1);
@@ -280,9 +347,9 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             if (lane == 0) {
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t da = AMap::desc(stage_a(s), ks), db = BMap::desc(stage_b(s), ks);
+                    const uint64_t da = TA::desc(stage_a(s), ks), db = TB::desc(stage_b(s), ks);
                     if (NTERMS == 3) {
-                        const uint64_t dal = AMap::desc(stage_alo(s), ks), dbl = BMap::desc(stage_blo(s), ks);
+                        const uint64_t dal = TA::desc(stage_alo(s), ks), dbl = TB::desc(stage_blo(s), ks);
                         mma_tf32(tmem_base, da, dbl, idesc, (kb | ks) != 0);
                         mma_tf32(tmem_base, dal, db, idesc, 1);
                         mma_tf32(tmem_base, da, db, idesc, 1);

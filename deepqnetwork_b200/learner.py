@@ -293,6 +293,16 @@ class Learner:
         self._c(self._lib.dqn_get_profile(self._h, C.byref(n), names, ms, cap, C.byref(steps)))
         return {names[i].decode(): ms[i] for i in range(n.value)}, steps.value
 
+    def selftest_gemm(self, mode, A, B, a_kcontig=True, b_kcontig=True):
+        """C = A @ B.T-style product through the chosen GEMM engine; A:[M,K], B:[N,K] logical (host float32)."""
+        M, K = A.shape; N = B.shape[0]
+        a = np.ascontiguousarray(A if a_kcontig else A.T, np.float32)
+        b = np.ascontiguousarray(B if b_kcontig else B.T, np.float32)
+        c = np.empty((M, N), np.float32)
+        m = {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
+        self._c(self._lib.dqn_selftest_gemm(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(a), ptr(b), ptr(c)))
+        return c
+
     # -- persistence ---------------------------------------------------------------------------
     def save(self, prefix):
         self._c(self._lib.dqn_save(self._h, str(prefix).encode()))

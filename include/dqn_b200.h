@@ -161,6 +161,12 @@ int dqn_launch_count(const dqn_learner* h, int64_t* n);
 int dqn_set_profile(dqn_learner* h, int32_t enabled);
 int dqn_get_profile(dqn_learner* h, int32_t* n, const char** names, float* ms, int32_t cap, int64_t* steps);
 
+/* GEMM engine self-test: C[M,N] = A*B on host matrices through the FFMA kernel (mode DQN_MATH_FP32) or the
+ * tcgen05 kernel (DQN_MATH_TC3X / DQN_MATH_TC1X). A is [M][K] if a_kcontig else [K][M]; B is [N][K] if b_kcontig
+ * else [K][N]. */
+int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,
+                      int32_t b_kcontig, const float* h_A, const float* h_B, float* h_C);
+
 /* ---- persistence (own container format; TF-bundle compatibility is SURVEY.md 8f-3) -- */
 int dqn_save(dqn_learner* h, const char* prefix);     /* Model.save, rl/model/model.py:60-68 */
 int dqn_restore(dqn_learner* h, const char* prefix);  /* Model.restore :71-83; returns 1 if absent */
