@@ -58,7 +58,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
     dqn_learner* h = nullptr;
     try {
         DQN_REQUIRE(cfg->struct_size == (int32_t)sizeof(dqn_config), "dqn_config size mismatch (ABI drift)");
-        DQN_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= 32, "num_actions must be in [1,32]");
+        DQN_REQUIRE(cfg->num_actions >= 1 && cfg->num_actions <= 31, "num_actions must be in [1,31]");
         DQN_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= 4096, "batch_size out of range");
         DQN_REQUIRE(cfg->replay_capacity >= 2, "replay_capacity must be >= 2");
         DQN_REQUIRE(cfg->math_mode >= DQN_MATH_FP32 && cfg->math_mode <= DQN_MATH_TC1X, "bad math_mode");
@@ -75,6 +75,8 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         h->sm_count = prop.multiProcessorCount;
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        for (auto& e : h->fork_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         net_describe(h->net, h->cfg);
         const NetDesc& net = h->net;
         h->state_bytes = (size_t)net.H * net.W * net.C;
@@ -166,6 +168,8 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     }
     if (h->h_sc) cudaFreeHost(h->h_sc);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
+    for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -531,6 +535,31 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 }
 
 // ---- the training step ---------------------------------------------------------------------------------------
+bool overlap_enabled(const dqn_learner* h) { return h->overlap && !h->profile; }
+
+static cudaEvent_t next_fork_event(dqn_learner* h) {
+    DQN_REQUIRE(h->fork_used < 12, "fork event pool exhausted");
+    return h->fork_ev[h->fork_used++];
+}
+
+void side_begin(dqn_learner* h, cudaStream_t& saved) {
+    saved = h->stream;
+    if (!overlap_enabled(h)) return;
+    cudaEvent_t e = next_fork_event(h);
+    DQN_CUDA_OK(cudaEventRecord(e, saved));
+    DQN_CUDA_OK(cudaStreamWaitEvent(h->side_stream, e, 0));
+    h->stream = h->side_stream;
+}
+
+void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; }
+
+void main_wait_side(dqn_learner* h) {
+    if (!overlap_enabled(h)) return;
+    cudaEvent_t e = next_fork_event(h);
+    DQN_CUDA_OK(cudaEventRecord(e, h->side_stream));
+    DQN_CUDA_OK(cudaStreamWaitEvent(h->stream, e, 0));
+}
+
 void prof_mark(dqn_learner* h, const char* name) {
     if (!h->profile) return;
     if (h->prof_used >= h->prof_events.size()) {
@@ -556,11 +585,17 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S);
         xf = h->x_f32;
     }
+    h->fork_used = 0;
+    // the two towers are independent until the TD epilogue: target tower on the side stream
+    cudaStream_t saved;
+    side_begin(h, saved);
+    h->prof_tag = "tg_";
+    tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
+    side_end(h, saved);
     h->prof_tag = "on_";
     if (h->cfg.use_double) tower_forward(h, h->online, states2, xf, 2 * n, h->acts_on);  // s and s' share one pass
     else tower_forward(h, h->online, states2, xf, n, h->acts_on);
-    h->prof_tag = "tg_";
-    tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
+    main_wait_side(h);
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
                        grad_scale);

@@ -82,8 +82,9 @@ void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q
     h->launches++;
 }
 
-// thread per hidden unit: dH (gated by the hidden ReLU), head weight/bias grads and hidden bias grads
-#define MAX_ACTIONS 32
+// dH (gated by the hidden ReLU), head weight/bias grads and hidden bias grads: thread per hidden column
+// (coalesced across the CTA), a serial walk over the batch with fixed summation order (deterministic).
+template <int AMAX>
 __global__ void __launch_bounds__(128) head_backward_kernel(int n, int NH, int hidden, int A, int dueling,
                                                             const float* __restrict__ hid, const float* __restrict__ dq,
                                                             const uint8_t* __restrict__ actions,
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(128) head_backward_kernel(int n, int NH, int h
                                                             float* __restrict__ g_hb1, float* __restrict__ g_fb0,
                                                             float* __restrict__ g_fb1) {
     extern __shared__ float sm[];
-    float* s_dq = sm;                                   // [n]
+    float* s_dq = sm;                                     // [n]
     uint8_t* s_act = reinterpret_cast<uint8_t*>(sm + n);  // [n]
     for (int i = threadIdx.x; i < n; i += blockDim.x) { s_dq[i] = dq[i]; s_act[i] = actions[i]; }
     __syncthreads();
@@ -103,16 +104,17 @@ __global__ void __launch_bounds__(128) head_backward_kernel(int n, int NH, int h
         const int st = col >= hidden, j = st ? col - hidden : col;
         float gb = 0.f;
         if (!st) {
-            float w[MAX_ACTIONS], gw[MAX_ACTIONS];
+            float w[AMAX], gw[AMAX];
 #pragma unroll
-            for (int a = 0; a < MAX_ACTIONS; ++a) { w[a] = a < A ? hw0[j * A + a] : 0.f; gw[a] = 0.f; }
+            for (int a = 0; a < AMAX; ++a) { w[a] = a < A ? hw0[j * A + a] : 0.f; gw[a] = 0.f; }
+#pragma unroll 4
             for (int i = 0; i < n; ++i) {
                 const float hv = hid[(size_t)i * NH + col];
                 const float d = s_dq[i];
                 const int ai = s_act[i];
                 float g = 0.f;
 #pragma unroll
-                for (int a = 0; a < MAX_ACTIONS; ++a) {
+                for (int a = 0; a < AMAX; ++a) {
                     if (a < A) {
                         // dQ = one_hot(a_i) * dq ; dueling: dA = dQ - mean_a(dQ)
                         const float da = dueling ? d * ((a == ai ? 1.f : 0.f) - invA) : (a == ai ? d : 0.f);
@@ -125,11 +127,12 @@ __global__ void __launch_bounds__(128) head_backward_kernel(int n, int NH, int h
                 gb += dh;
             }
 #pragma unroll
-            for (int a = 0; a < MAX_ACTIONS; ++a) if (a < A) g_hw0[j * A + a] = gw[a];
+            for (int a = 0; a < AMAX; ++a) if (a < A) g_hw0[j * A + a] = gw[a];
             g_fb0[j] = gb;
         } else {
             const float w = hw1[j];
             float gw = 0.f;
+#pragma unroll 4
             for (int i = 0; i < n; ++i) {
                 const float hv = hid[(size_t)i * NH + col];
                 const float d = s_dq[i];  // dV = sum_a dQ = dq
@@ -163,10 +166,17 @@ void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions) {
     const float* P = h->online;
     float* G = h->grads;
     const size_t smem = (size_t)n * 4 + ((n + 3) / 4) * 4;
-    head_backward_kernel<<<ceil_div(net.NH, 128), 128, smem, h->stream>>>(
-        n, net.NH, net.hidden, net.A, net.dueling, h->acts_on.hid, h->b_dq, actions, P + net.off_hd_w[0],
-        P + net.off_hd_w[1], h->d_hid, G + net.off_hd_w[0], G + net.off_hd_b[0], G + net.off_hd_w[1], G + net.off_hd_b[1],
-        G + net.off_fc_b[0], G + net.off_fc_b[1]);
+    const int threads = 32;  // many small CTAs: the per-thread work is a serial walk over the batch
+#define HEAD_BWD(AMAX)                                                                                                  \
+    head_backward_kernel<AMAX><<<ceil_div(net.NH, threads), threads, smem, h->stream>>>(                                \
+        n, net.NH, net.hidden, net.A, net.dueling, h->acts_on.hid, h->b_dq, actions, P + net.off_hd_w[0],              \
+        P + net.off_hd_w[1], h->d_hid, G + net.off_hd_w[0], G + net.off_hd_b[0], G + net.off_hd_w[1],                  \
+        G + net.off_hd_b[1], G + net.off_fc_b[0], G + net.off_fc_b[1])
+    if (net.A <= 4) HEAD_BWD(4);
+    else if (net.A <= 8) HEAD_BWD(8);
+    else if (net.A <= 16) HEAD_BWD(16);
+    else HEAD_BWD(31);
+#undef HEAD_BWD
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
 }

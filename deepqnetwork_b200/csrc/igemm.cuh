@@ -89,14 +89,14 @@ struct OpConvFwdA {
     }
     __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
         const int tap = k >> g.cin_log2, ci = k & (g.cin - 1);
-        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int kh = fdiv(tap, g.m_k, g.k), kw = tap - kh * g.k;
         const int iy = r.iy0 + kh, ix = r.ix0 + kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
         return load_px4(in, is_u8, r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci);
     }
     __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {  // f32 input only
         const int tap = k >> g.cin_log2, ci = k & (g.cin - 1);
-        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int kh = fdiv(tap, g.m_k, g.k), kw = tap - kh * g.k;
         const int iy = r.iy0 + kh, ix = r.ix0 + kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
         return static_cast<const float*>(in) + r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci;
@@ -115,16 +115,16 @@ struct OpConvWgradA {
     }
     __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
         const int hw = g.oh * g.ow;
-        const int n = k / hw, rem = k - n * hw;
-        const int oy = rem / g.ow, ox = rem - oy * g.ow;
+        const int n = fdiv(k, g.m_hw, hw), rem = k - n * hw;
+        const int oy = fdiv(rem, g.m_ow, g.ow), ox = rem - oy * g.ow;
         const int iy = oy * g.s - g.pt + r.kh, ix = ox * g.s - g.pl + r.kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return make_float4(0.f, 0.f, 0.f, 0.f);
         return load_px4(in, is_u8, (((size_t)n * g.ih + iy) * g.iw + ix) * g.cin + r.ci);
     }
     __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {  // f32 input only
         const int hw = g.oh * g.ow;
-        const int n = k / hw, rem = k - n * hw;
-        const int oy = rem / g.ow, ox = rem - oy * g.ow;
+        const int n = fdiv(k, g.m_hw, hw), rem = k - n * hw;
+        const int oy = fdiv(rem, g.m_ow, g.ow), ox = rem - oy * g.ow;
         const int iy = oy * g.s - g.pt + r.kh, ix = ox * g.s - g.pl + r.kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
         return static_cast<const float*>(in) + (((size_t)n * g.ih + iy) * g.iw + ix) * g.cin + r.ci;
@@ -162,18 +162,18 @@ struct OpConvDgradA {
         return r;
     }
     __device__ __forceinline__ float4 load4(const Row& r, int, int k, int) const {
-        const int kt = c.g.k / c.g.s;  // taps per axis in one class
+        const int kt = c.g.kt;  // taps per axis in one class
         const int tap = k >> cout_log2, co = k & (c.g.cout - 1);
-        const int jh = tap / kt, jw = tap - jh * kt;
+        const int jh = fdiv(tap, c.g.m_kt, kt), jw = tap - jh * kt;
         const int oy = r.oy0 - jh, ox = r.ox0 - jw;
         if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow)
             return make_float4(0.f, 0.f, 0.f, 0.f);
         return *reinterpret_cast<const float4*>(dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co);
     }
     __device__ __forceinline__ const float* addr4(const Row& r, int, int k, int) const {
-        const int kt = c.g.k / c.g.s;
+        const int kt = c.g.kt;
         const int tap = k >> cout_log2, co = k & (c.g.cout - 1);
-        const int jh = tap / kt, jw = tap - jh * kt;
+        const int jh = fdiv(tap, c.g.m_kt, kt), jw = tap - jh * kt;
         const int oy = r.oy0 - jh, ox = r.ox0 - jw;
         if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow) return nullptr;
         return dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co;
@@ -186,18 +186,18 @@ struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
     typedef int Row;
     __device__ __forceinline__ Row row(int n, int) const { return n; }
     __device__ __forceinline__ float4 load4(Row ci, int, int k, int z) const {
-        const int ry = z / g.s, rx = z - ry * g.s;
-        const int kt = g.k / g.s;
+        const int ry = fdiv(z, g.m_s, g.s), rx = z - ry * g.s;
+        const int kt = g.kt;
         const int tap = k >> cout_log2, co = k & (g.cout - 1);
-        const int jh = tap / kt, jw = tap - jh * kt;
+        const int jh = fdiv(tap, g.m_kt, kt), jw = tap - jh * kt;
         const int kh = ry + g.s * jh, kw = rx + g.s * jw;
         return *reinterpret_cast<const float4*>(w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co);
     }
     __device__ __forceinline__ const float* addr4(Row ci, int, int k, int z) const {
-        const int ry = z / g.s, rx = z - ry * g.s;
-        const int kt = g.k / g.s;
+        const int ry = fdiv(z, g.m_s, g.s), rx = z - ry * g.s;
+        const int kt = g.kt;
         const int tap = k >> cout_log2, co = k & (g.cout - 1);
-        const int jh = tap / kt, jw = tap - jh * kt;
+        const int jh = fdiv(tap, g.m_kt, kt), jw = tap - jh * kt;
         const int kh = ry + g.s * jh, kw = rx + g.s * jw;
         return w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co;
     }

@@ -9,7 +9,12 @@
 struct ConvGeom {
     int ih, iw, cin, oh, ow, cout, k, s, pt, pl;
     int cin_log2;
+    // ceil(2^32/d) magics: x/d == __umulhi(x, magic) for x*d < 2^32 (all index ranges here)
+    unsigned m_k, m_ow, m_hw, m_kt, m_s;
+    int kt;  // k / s: taps per axis that reach one stride-parity class
 };
+__host__ __device__ inline unsigned fastdiv_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ int fdiv(int x, unsigned magic, int d) { return d <= 1 ? x : (int)__umulhi((unsigned)x, magic); }
 
 struct TensorInfo {
     std::string name;
@@ -42,6 +47,13 @@ struct dqn_learner {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // second stream + events: independent kernels of one step (target tower vs online tower, wgrads vs the dgrad
+    // chain) are forked onto it so that the small batch-32 grids overlap; inside a captured graph these become
+    // parallel branches
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev[12] = {};
+    int fork_used = 0;
+    bool overlap = true;
     std::string err;
     int64_t launches = 0;
 
@@ -134,7 +146,13 @@ struct dqn_learner {
 };
 
 // ---- kernels / launchers (defined across the .cu files) ----
-void prof_mark(dqn_learner* h, const char* name);  // api.cu: CUDA-event boundary, active only in profile mode
+void prof_mark(dqn_learner* h, const char* name);
+// stream fork/join helpers (api.cu). side_begin: side stream waits for everything issued on the main stream so far
+// and becomes the launch stream; side_end: back to the main stream; main_wait_side / side_wait_main: cross edges.
+bool overlap_enabled(const dqn_learner* h);
+void side_begin(dqn_learner* h, cudaStream_t& saved);
+void side_end(dqn_learner* h, cudaStream_t saved);
+void main_wait_side(dqn_learner* h);  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);
 
 // replay.cu

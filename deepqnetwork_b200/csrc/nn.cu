@@ -31,6 +31,8 @@ void net_describe(NetDesc& net, const dqn_config& cfg) {
             g.oh = (ih - g.k) / g.s + 1; g.ow = (iw - g.k) / g.s + 1; g.pt = g.pl = 0;
         }
         g.cin_log2 = ilog2(cin);
+        g.m_k = fastdiv_magic(g.k); g.m_ow = fastdiv_magic(g.ow); g.m_hw = fastdiv_magic(g.oh * g.ow);
+        g.kt = g.k / g.s; g.m_kt = fastdiv_magic(g.kt); g.m_s = fastdiv_magic(g.s);
         DQN_REQUIRE((1 << g.cin_log2) == cin && cin % 4 == 0, "channel counts must be powers of two >= 4");
         DQN_REQUIRE(g.k % g.s == 0, "kernel size must be a multiple of the stride");
         ih = g.oh; iw = g.ow; cin = g.cout;
@@ -116,62 +118,85 @@ void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n) 
 }
 
 // ---- dense hidden layer: reduce split-K partials, bias, ReLU, then the head dot products and dueling combine
-#define MAX_ACTIONS 32
-__global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __restrict__ part, int splits, int rows, int NH,
-                                                              int hidden, int A, int dueling,
-                                                              const float* __restrict__ b0, const float* __restrict__ b1,
-                                                              const float* __restrict__ hw0, const float* __restrict__ hb0,
-                                                              const float* __restrict__ hw1, const float* __restrict__ hb1,
-                                                              float* __restrict__ hid, float* __restrict__ q) {
+// One CTA per batch row, one thread per hidden column: sum the split-K partials (independent loads), bias, ReLU,
+// then A (+1) dot products reduced across the CTA.  AMAX = compile-time bound on the action count.
+template <int AMAX>
+__global__ void __launch_bounds__(1024) fc_reduce_heads_kernel(const float* __restrict__ part, int splits, int rows, int NH,
+                                                               int hidden, int A, int dueling,
+                                                               const float* __restrict__ b0, const float* __restrict__ b1,
+                                                               const float* __restrict__ hw0, const float* __restrict__ hb0,
+                                                               const float* __restrict__ hw1, const float* __restrict__ hb1,
+                                                               float* __restrict__ hid, float* __restrict__ q) {
     const int row = blockIdx.x;
-    float acc[MAX_ACTIONS + 1];
+    float acc[AMAX + 1];
 #pragma unroll
-    for (int a = 0; a <= MAX_ACTIONS; ++a) acc[a] = 0.f;
+    for (int a = 0; a <= AMAX; ++a) acc[a] = 0.f;
     for (int col = threadIdx.x; col < NH; col += blockDim.x) {
+        const float* p = part + (size_t)row * NH + col;
+        const size_t zs = (size_t)rows * NH;
         float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += part[((size_t)z * rows + row) * NH + col];
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {  // four partial loads in flight; summation order stays z ascending
+            const float v0 = p[(size_t)z * zs], v1 = p[(size_t)(z + 1) * zs], v2 = p[(size_t)(z + 2) * zs], v3 = p[(size_t)(z + 3) * zs];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; z < splits; ++z) s += p[(size_t)z * zs];
         const int st = col >= hidden, j = st ? col - hidden : col;
         s += st ? b1[j] : b0[j];
         const float hv = fmaxf(s, 0.f);  // tf.nn.relu (deep_q_model.py:316,325,339)
         hid[(size_t)row * NH + col] = hv;
         if (!st) {
 #pragma unroll
-            for (int a = 0; a < MAX_ACTIONS; ++a)
+            for (int a = 0; a < AMAX; ++a)
                 if (a < A) acc[a] = fmaf(hv, hw0[j * A + a], acc[a]);
         } else {
-            acc[MAX_ACTIONS] = fmaf(hv, hw1[j], acc[MAX_ACTIONS]);
+            acc[AMAX] = fmaf(hv, hw1[j], acc[AMAX]);
         }
     }
-    __shared__ float red[8][MAX_ACTIONS + 1];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ float red[32][AMAX + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-    for (int a = 0; a <= MAX_ACTIONS; ++a) {
-        if (a < A || a == MAX_ACTIONS) {
-            float v = acc[a];
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[w][a] = v;
-        }
+    for (int a = 0; a <= AMAX; ++a) {
+        float v = acc[a];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][a] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float adv[MAX_ACTIONS];
-        float mean = 0.f;
-        for (int a = 0; a < A; ++a) {
-            float v = 0.f;
-            for (int ww = 0; ww < 8; ++ww) v += red[ww][a];
-            adv[a] = v + hb0[a];
-            mean += adv[a];
+    if (w == 0) {
+        // lane a finishes output a (a < A: advantage / Q head, a == A: value head)
+        const int a = lane;
+        float v = 0.f;
+        if (a <= A) {
+            const int src = a < A ? a : AMAX;
+            for (int ww = 0; ww < nw; ++ww) v += red[ww][src];
+            v += a < A ? hb0[a] : (dueling ? hb1[0] : 0.f);
         }
         if (dueling) {
-            float val = 0.f;
-            for (int ww = 0; ww < 8; ++ww) val += red[ww][MAX_ACTIONS];
-            val += hb1[0];
-            mean /= (float)A;  // tf.reduce_mean(advantage, axis=1) (deep_q_model.py:332-334)
-            for (int a = 0; a < A; ++a) q[(size_t)row * A + a] = val + (adv[a] - mean);
-        } else {
-            for (int a = 0; a < A; ++a) q[(size_t)row * A + a] = adv[a];
+            float sum = a < A ? v : 0.f;
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / (float)A;  // tf.reduce_mean(advantage, axis=1) (deep_q_model.py:332-334)
+            const float val = __shfl_sync(0xffffffffu, v, A);
+            if (a < A) q[(size_t)row * A + a] = val + (v - mean);
+        } else if (a < A) {
+            q[(size_t)row * A + a] = v;
         }
     }
+}
+
+static void launch_fc_reduce_heads(dqn_learner* h, const float* P, int splits, int rows, TowerActs& acts) {
+    const NetDesc& net = h->net;
+    const int threads = std::min(1024, ((net.NH + 31) / 32) * 32);
+#define FC_HEADS(AMAX)                                                                                                  \
+    fc_reduce_heads_kernel<AMAX><<<rows, threads, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, \
+        net.dueling, P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0], P + net.off_hd_b[0],               \
+        P + net.off_hd_w[1], P + net.off_hd_b[1], acts.hid, acts.q)
+    if (net.A <= 4) FC_HEADS(4);
+    else if (net.A <= 8) FC_HEADS(8);
+    else if (net.A <= 16) FC_HEADS(16);
+    else FC_HEADS(31);
+#undef FC_HEADS
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
 }
 
 static int fc_kchunk() { return 256; }
@@ -214,12 +239,7 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
         igemm_auto<true>(h, a, b, e, rows, net.NH, net.flat, splits, kchunk);
     }
     prof_mark(h, tg ? "tg_fc_reduce_heads" : "on_fc_reduce_heads");
-    fc_reduce_heads_kernel<<<rows, 256, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, net.dueling,
-                                                        P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0],
-                                                        P + net.off_hd_b[0], P + net.off_hd_w[1], P + net.off_hd_b[1],
-                                                        acts.hid, acts.q);
-    DQN_CUDA_OK(cudaGetLastError());
-    h->launches++;
+    launch_fc_reduce_heads(h, P, splits, rows, acts);
 }
 
 // ---- backward ------------------------------------------------------------------------------------------
@@ -262,13 +282,18 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     const float* P = h->online;
     float* G = h->grads;
     TowerActs& acts = h->acts_on;
+    // Weight gradients do not feed anything before the optimizer, so each one is forked onto the side stream as soon
+    // as its dY exists, while the main stream continues down the dgrad chain.
+    cudaStream_t saved;
     // dense hidden: dW = X^T dH (K = batch), written straight into the gradient slab
     {
+        side_begin(h, saved);
         prof_mark(h, "fc_wgrad");
         OpColContig a{acts.act[2], net.flat};
         OpColContig b{h->d_hid, net.NH};
         EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
         gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+        side_end(h, saved);
     }
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
@@ -291,6 +316,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
         // wgrad (+bias) split over the pixel dimension
         {
+            side_begin(h, saved);  // needs d_act[l], which the main stream has just produced
             const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
             int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
@@ -310,6 +336,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
                                                                                           G + net.off_cw[l], G + net.off_cb[l]);
             DQN_CUDA_OK(cudaGetLastError());
             h->launches++;
+            side_end(h, saved);
         }
         if (l == 0) break;  // no gradient flows into the input image
         // dgrad into the previous activation, gated by its ReLU
@@ -326,8 +353,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             gemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
         }
     }
+    main_wait_side(h);  // all weight gradients are in the slab before the optimizer runs
 }
-
 
 // ---- GEMM self-test: plain matrices through either engine (dqn_selftest_gemm) ----------------------------------------
 // A is [M][K] (a_kcontig) or [K][M]; B is [N][K] (b_kcontig) or [K][N]; C is [M][N].

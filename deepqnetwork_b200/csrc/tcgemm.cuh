@@ -107,9 +107,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major no-swizzle tile [R rows x 32 k]: element (r,k) at (r/8)*SBO + (k/4)*LBO + (r%8)*16 + (k%4)*4,
-// LBO = 144 (128-byte core matrix + 16 bytes of padding), SBO = 8*LBO.
-constexpr uint32_t LBO = 144, SBO = 8 * LBO;
+// K-major no-swizzle tile [R rows x 32 k]: element (r,k) at (r/8)*SBO + (k/4)*LBO + (r%8)*16 + (k%4)*4.
+// LBO = 144 (128-byte core matrix + 16 bytes) and SBO = 8*LBO + 16 are padded so that both producer patterns are
+// bank-conflict free while their GLOBAL side stays coalesced:
+//   K-contiguous operand : 8 lanes x 16 B = one 128-byte row piece -> chunk stride LBO: banks 4*c (mod 32), distinct
+//   MN-contiguous operand: 8 lanes x 16 B along M/N at 4 consecutive k -> 4-byte stores at word
+//                          292*(r/8) + 4*(r%8) + k%4 == 4*(r/8) + 16*((r/4)%2) + 4*j + k%4 (mod 32), distinct
+constexpr uint32_t LBO = 144, SBO = 8 * LBO + 16;
 template <int R>
 struct Tile {
     static constexpr int BYTES = (R / 8) * SBO;
@@ -120,20 +124,24 @@ struct Tile {
     __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int ks) { return make_desc(tile_addr + ks * 2 * LBO, LBO, SBO); }
 };
 // chunk f of a tile -> (first row, first k) of the 16 global bytes it covers
-//   K-contiguous operand : 4 consecutive k of one row; consecutive lanes take consecutive rows
-//   MN-contiguous operand: 4 consecutive rows at one k; consecutive lanes take consecutive k
+//   K-contiguous operand : 4 consecutive k of one row; 8 consecutive lanes walk the 128 bytes of one row
+//   MN-contiguous operand: 4 consecutive rows at one k; 8 consecutive lanes walk 128 bytes along M/N, 4 k per warp
 template <bool KCONTIG, int R>
 __device__ __forceinline__ void chunk_rk(int f, int& r, int& k) {
-    if (KCONTIG) { r = f % R; k = (f / R) * 4; }
-    else { k = f & 31; r = (f >> 5) * 4; }
+    if (KCONTIG) { k = (f & 7) * 4; r = f >> 3; }
+    else {
+        const int rest = f >> 5;
+        r = ((rest % (R / 32)) * 8 + (f & 7)) * 4;
+        k = (rest / (R / 32)) * 4 + ((f >> 3) & 3);
+    }
 }
 
 template <int BN, int NTERMS>
 struct SmemPlan {
     static constexpr int A_BYTES = Tile<BM>::BYTES, B_BYTES = Tile<BN>::BYTES;
     static constexpr int STAGE = (A_BYTES + B_BYTES) * (NTERMS == 3 ? 2 : 1);
-    static constexpr int MAX_STAGES = (200 * 1024) / STAGE;
-    static constexpr int STAGES = MAX_STAGES > 4 ? 4 : (MAX_STAGES < 2 ? 2 : MAX_STAGES);
+    static constexpr int MAX_STAGES = (212 * 1024) / STAGE;
+    static constexpr int STAGES = MAX_STAGES > 5 ? 5 : (MAX_STAGES < 3 ? 3 : MAX_STAGES);
     static constexpr int BYTES = STAGES * STAGE + 256;
 };
 
@@ -148,7 +156,6 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
     using TB = Tile<BN>;
     constexpr int LA = TA::CHUNKS / PRODUCERS;
     constexpr int LB = (TB::CHUNKS + PRODUCERS - 1) / PRODUCERS;
-    constexpr int PF = 2;  // register prefetch distance (k-blocks) for MN-contiguous operands
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t bars = sbase + S * Plan::STAGE;  // full[S], empty[S], accum, tmem slot
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
     const int nkb = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), PRODUCERS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), PRODUCERS / 32); mbar_init(empty_bar(s), 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -230,17 +237,18 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
                 }
             }
         };
-        // MN-contiguous operands: 16-byte loads into registers, PF k-blocks ahead
-        float4 a_pf[AOp::KCONTIG ? 1 : PF][AOp::KCONTIG ? 1 : LA];
-        float4 b_pf[BOp::KCONTIG ? 1 : PF][BOp::KCONTIG ? 1 : LB];
-        auto load_regs = [&](int kb, int slot) {
+        // MN-contiguous operands: 16-byte loads into registers, two k-blocks ahead (two named register sets so the
+        // compiler keeps them in registers)
+        constexpr int NA = AOp::KCONTIG ? 1 : LA, NB = BOp::KCONTIG ? 1 : LB;
+        float4 a_pf0[NA], a_pf1[NA], b_pf0[NB], b_pf1[NB];
+        auto load_regs = [&](int kb, float4 (&ap)[NA], float4 (&bp)[NB]) {
             const int k0 = kbeg + kb * BK;
             if (!AOp::KCONTIG) {
 #pragma unroll
                 for (int i = 0; i < LA; ++i) {
                     const int r = m0 + a_r[i], k = k0 + a_k[i];
                     const float* src = (kb < nkb && r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                    a_pf[slot][i] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ap[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (!BOp::KCONTIG) {
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
                 for (int i = 0; i < LB; ++i) {
                     const int r = n0 + b_r[i], k = k0 + b_k[i];
                     const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                    b_pf[slot][i] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bp[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         };
@@ -257,11 +265,11 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16], %2;\n\tst.shared.f32 [%0+32], %3;\n\tst.shared.f32 [%0+48], %4;"
                          ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         };
-        auto store_regs = [&](int s, int slot) {
+        auto store_regs = [&](int s, const float4 (&ap)[NA], const float4 (&bp)[NB]) {
             if (!AOp::KCONTIG) {
 #pragma unroll
                 for (int i = 0; i < LA; ++i) {
-                    const float4 v = a_pf[slot][i];
+                    const float4 v = ap[i];
                     sts_t(stage_a(s) + a_off[i], v);
                     if (NTERMS == 3) sts_t(stage_alo(s) + a_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
                 }
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
 #pragma unroll
                 for (int i = 0; i < LB; ++i) {
                     if (b_r[i] >= 0) {
-                        const float4 v = b_pf[slot][i];
+                        const float4 v = bp[i];
                         sts_t(stage_b(s) + b_off[i], v);
                         if (NTERMS == 3) sts_t(stage_blo(s) + b_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
                     }
@@ -284,19 +292,13 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
                          "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
         };
-        for (int kb = 0; kb < S - 1; ++kb) {
-            if (kb < nkb) issue_async(kb);
-            cp_async_commit();
-        }
-#pragma unroll
-        for (int p = 0; p < PF; ++p) load_regs(p, p);
-        for (int kb = 0; kb < nkb; ++kb) {
+        // one k-block: registers -> stage, wait for the cp.async part, low parts, hand the stage to the MMA warp, refill
+        auto block = [&](int kb, float4 (&ap)[NA], float4 (&bp)[NB]) {
             const int s = kb % S;
-            // stage s is free: block kb-S (its previous user) was waited for before block kb-1's refill below
-#pragma unroll
-            for (int p = 0; p < PF; ++p)
-                if ((kb % PF) == p) { store_regs(s, p); load_regs(kb + PF, p); }
-            cp_async_wait<S - 2>();  // this thread's cp.async chunks of block kb have landed
+            // stage s is free: its previous user (block kb-S) was waited for at iteration kb-S+2
+            store_regs(s, ap, bp);
+            load_regs(kb + 2, ap, bp);
+            cp_async_wait<S - 3>();  // this thread's cp.async chunks of block kb have landed
             if (NTERMS == 3) {
                 if (AOp::KCONTIG) {
 #pragma unroll
@@ -309,13 +311,26 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
                 }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
-            mbar_arrive(full_bar(s));
-            const int nxt = kb + S - 1;  // goes into the stage block kb-1 used
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));  // one arrival per producer warp
+            // refill the stage block kb-2 used: its MMAs were committed a whole iteration ago, so this wait does not
+            // put the producers in lock-step with the tensor core (one stage of slack)
+            const int nxt = kb + S - 2;
             if (nxt < nkb) {
-                if (kb >= 1) mbar_wait(empty_bar((kb - 1) % S), ((kb - 1) / S) & 1);
+                if (kb >= 2) mbar_wait(empty_bar((kb - 2) % S), ((kb - 2) / S) & 1);
                 issue_async(nxt);
             }
             cp_async_commit();
+        };
+        for (int kb = 0; kb < S - 2; ++kb) {
+            if (kb < nkb) issue_async(kb);
+            cp_async_commit();
+        }
+        load_regs(0, a_pf0, b_pf0);
+        load_regs(1, a_pf1, b_pf1);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            block(kb, a_pf0, b_pf0);
+            if (kb + 1 < nkb) block(kb + 1, a_pf1, b_pf1);
         }
         // ---------------- epilogue ----------------
         if (nkb > 0) {
