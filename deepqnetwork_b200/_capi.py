@@ -70,6 +70,7 @@ _SIGS = {
     'dqn_get_profile': [_P, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int32,
                         C.POINTER(C.c_int64)],
     'dqn_selftest_gemm': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P],
+    'dqn_bench_gemm': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
     'dqn_save': [_P, C.c_char_p],
     'dqn_restore': [_P, C.c_char_p],
 }

@@ -987,3 +987,31 @@ extern "C" int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_
     cudaFree(dA); cudaFree(dB); cudaFree(dC);
     API_END(h)
 }
+
+
+// GEMM engine micro-benchmark: device-resident random-free operands, `iters` launches timed with CUDA events.
+extern "C" int dqn_bench_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,
+                              int32_t b_kcontig, int32_t iters, float* ms_per_launch) {
+    API_BEGIN(h)
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    dmalloc(dA, (size_t)M * K); dmalloc(dB, (size_t)N * K); dmalloc(dC, (size_t)M * N);
+    cudaEvent_t e0, e1;
+    DQN_CUDA_OK(cudaEventCreate(&e0)); DQN_CUDA_OK(cudaEventCreate(&e1));
+    try {
+        DQN_CUDA_OK(cudaMemsetAsync(dA, 0x3c, (size_t)M * K * 4, h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(dB, 0x3c, (size_t)N * K * 4, h->stream));
+        for (int i = 0; i < 3; ++i) selftest_gemm(h, mode, M, N, K, a_kcontig, b_kcontig, dA, dB, dC);
+        DQN_CUDA_OK(cudaEventRecord(e0, h->stream));
+        for (int i = 0; i < iters; ++i) selftest_gemm(h, mode, M, N, K, a_kcontig, b_kcontig, dA, dB, dC);
+        DQN_CUDA_OK(cudaEventRecord(e1, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        DQN_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_per_launch = ms / iters;
+    } catch (...) {
+        cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        throw;
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    API_END(h)
+}

@@ -3,8 +3,8 @@
 // fp32-grade products.  It takes the same operand / epilogue functors as the FFMA kernel in igemm.cuh, so every
 // layer (conv im2col forward, dgrad, wgrad, dense layers, transposed operands) runs on it unchanged.
 //
-// Structure of one CTA (one 128 x BN output tile, 288 threads):
-//   warps 0-7  producers, then epilogue.  Both operands are staged K-major in the canonical no-swizzle UMMA layout
+// Structure of one CTA (one 128 x BN output tile, 544 threads):
+//   warps 0-15 producers, then epilogue.  Both operands are staged K-major in the canonical no-swizzle UMMA layout
 //              (8-row x 16-byte core matrices; LBO padded to 144 bytes so every store pattern below is bank-conflict
 //              free).  Operands that are contiguous along K in global memory are gathered with 16-byte cp.async
 //              (zero-fill for padding / ragged edges), S stages deep: one global chunk is exactly one core-matrix
@@ -13,10 +13,10 @@
 //              (kind::tf32 has no 16-byte-granular MN-major layout).  For NTERMS=3 the low parts (x - tf32(x)) go
 //              into the *_lo tiles: from registers for the transposed operands, by re-reading its own chunks for
 //              the cp.async ones.
-//   warp 8     allocates TMEM, and one elected lane issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per k-step,
+//   warp 16    allocates TMEM, and one elected lane issues tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per k-step,
 //              releasing smem stages with tcgen05.commit -> mbarrier.
-//   epilogue   tcgen05.ld 32x32b.x16: thread (warp%4, lane) owns accumulator row 32*(warp%4)+lane, warps 4-7 take the
-//              upper half of the columns; values go through the epilogue functor (bias/ReLU/gating/partials/...).
+//   epilogue   tcgen05.ld 32x32b: thread (warp%4, lane) owns accumulator row 32*(warp%4)+lane, warp/4 selects a quarter
+//              of the columns; values go through the epilogue functor (bias/ReLU/gating/partials/...).
 #pragma once
 #include "igemm.cuh"
 
@@ -24,7 +24,8 @@ namespace tc {
 
 constexpr int BM = 128;       // UMMA M
 constexpr int BK = 32;        // floats per k-block (4 MMAs of K=8)
-constexpr int PRODUCERS = 256;
+constexpr int PRODUCERS = 512;  // 16 producer warps: the per-k-block address/convert work is split thin enough that
+                                 // a single warp's serial instruction stream no longer bounds the k-loop
 constexpr int THREADS = PRODUCERS + 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +108,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major no-swizzle tile [R rows x 32 k]: element (r,k) at (r/8)*SBO + (k/4)*LBO + (r%8)*16 + (k%4)*4.
 // LBO = 144 (128-byte core matrix + 16 bytes) and SBO = 8*LBO + 16 are padded so that both producer patterns are
 // bank-conflict free while their GLOBAL side stays coalesced:
@@ -123,18 +134,29 @@ struct Tile {
     }
     __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int ks) { return make_desc(tile_addr + ks * 2 * LBO, LBO, SBO); }
 };
-// chunk f of a tile -> (first row, first k) of the 16 global bytes it covers
-//   K-contiguous operand : 4 consecutive k of one row; 8 consecutive lanes walk the 128 bytes of one row
-//   MN-contiguous operand: 4 consecutive rows at one k; 8 consecutive lanes walk 128 bytes along M/N, 4 k per warp
+// Producer work assignment (PRODUCERS threads, tile of R rows x 32 k = R*8 chunks of 16 bytes):
+//   K-contiguous operand : thread owns ONE row and RUN consecutive chunks of it (one row state, contiguous global
+//                          bytes); 8/RUN neighbouring lanes cover the 128 bytes of a row
+//   MN-contiguous operand: 8 lanes walk 128 bytes along M/N, 4 consecutive k per warp; all chunks of a thread share k
 template <bool KCONTIG, int R>
-__device__ __forceinline__ void chunk_rk(int f, int& r, int& k) {
-    if (KCONTIG) { k = (f & 7) * 4; r = f >> 3; }
-    else {
-        const int rest = f >> 5;
-        r = ((rest % (R / 32)) * 8 + (f & 7)) * 4;
-        k = (rest / (R / 32)) * 4 + ((f >> 3) & 3);
+struct Assign {
+    static constexpr int RUN = KCONTIG ? (R * 8 >= PRODUCERS ? R * 8 / PRODUCERS : 1) : 1;   // chunks per row run
+    static constexpr int N = KCONTIG ? RUN : (R >= 64 ? R / 64 : 1);                           // chunks per thread
+    // chunk i of thread tid -> (row, k offset inside the k-block) or row < 0 if the thread has no i-th chunk
+    __device__ static __forceinline__ void rk(int tid, int i, int& r, int& k) {
+        if (KCONTIG) {
+            constexpr int TPR = 8 / RUN;  // threads per row
+            r = tid / TPR;
+            k = ((tid % TPR) * RUN + i) * 4;
+            if (r >= R) r = -1;
+        } else {
+            const int w = tid >> 5;
+            const int g = (w >> 3) + 2 * i;            // group of 8 row-quads
+            r = g < R / 32 ? (g * 8 + (tid & 7)) * 4 : -1;
+            k = (w & 7) * 4 + ((tid >> 3) & 3);
+        }
     }
-}
+};
 
 template <int BN, int NTERMS>
 struct SmemPlan {
@@ -149,13 +171,14 @@ __device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(_
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
-                                                            int kchunk, const float* __restrict__ zeros16) {
+                                                            int kchunk, const float* __restrict__ /*zeros16*/) {
     using Plan = SmemPlan<BN, NTERMS>;
     constexpr int S = Plan::STAGES;
     using TA = Tile<BM>;
     using TB = Tile<BN>;
-    constexpr int LA = TA::CHUNKS / PRODUCERS;
-    constexpr int LB = (TB::CHUNKS + PRODUCERS - 1) / PRODUCERS;
+    using AA = Assign<AOp::KCONTIG, BM>;
+    using AB = Assign<BOp::KCONTIG, BN>;
+    constexpr int LA = AA::N, LB = AB::N;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t bars = sbase + S * Plan::STAGE;  // full[S], empty[S], accum, tmem slot
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         fence_barrier_init();
     }
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    if (warp == 8) {
+    if (warp == PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
     auto stage_b = [&](int s) { return stage_a(s) + Plan::A_BYTES * (NTERMS == 3 ? 2 : 1); };
     auto stage_blo = [&](int s) { return stage_b(s) + Plan::B_BYTES; };
 
-    if (warp < 8) {
+    if (warp < PRODUCERS / 32) {
         // ---------------- producers ----------------
         int a_r[LA], a_k[LA], b_r[LB], b_k[LB];
         uint32_t a_off[LA], b_off[LB];
@@ -200,178 +223,146 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         typename BOp::Row b_row[LB];
 #pragma unroll
         for (int i = 0; i < LA; ++i) {
-            chunk_rk<AOp::KCONTIG, BM>(tid + i * PRODUCERS, a_r[i], a_k[i]);
-            a_off[i] = TA::off(a_r[i], a_k[i]);
-            a_row[i] = a.row(min(m0 + a_r[i], M - 1), z);
+            AA::rk(tid, i, a_r[i], a_k[i]);
+            a_off[i] = a_r[i] >= 0 ? TA::off(a_r[i], a_k[i]) : 0;
+            a_row[i] = a.row(min(m0 + max(a_r[i], 0), M - 1), z);
         }
 #pragma unroll
         for (int i = 0; i < LB; ++i) {
-            const int f = tid + i * PRODUCERS;
-            if (f < TB::CHUNKS) {
-                chunk_rk<BOp::KCONTIG, BN>(f, b_r[i], b_k[i]);
-                b_off[i] = TB::off(b_r[i], b_k[i]);
-            } else { b_r[i] = -1; b_k[i] = 0; b_off[i] = 0; }
+            AB::rk(tid, i, b_r[i], b_k[i]);
+            b_off[i] = b_r[i] >= 0 ? TB::off(b_r[i], b_k[i]) : 0;
             b_row[i] = b.row(min(n0 + max(b_r[i], 0), N - 1), z);
         }
-        // K-contiguous operands: asynchronous 16-byte copies straight into the stage
-        auto issue_async = [&](int kb) {
-            const int s = kb % S, k0 = kbeg + kb * BK;
-            if (AOp::KCONTIG) {
-                const uint32_t ta = stage_a(s);
-#pragma unroll
-                for (int i = 0; i < LA; ++i) {
-                    const int r = m0 + a_r[i], k = k0 + a_k[i];
-                    const float* src = (r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                    cp_async16(ta + a_off[i], src ? src : zeros16, src != nullptr);
-                }
-            }
-            if (BOp::KCONTIG) {
-                const uint32_t tb = stage_b(s);
-#pragma unroll
-                for (int i = 0; i < LB; ++i) {
-                    if (b_r[i] >= 0) {
-                        const int r = n0 + b_r[i], k = k0 + b_k[i];
-                        const float* src = (r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                        cp_async16(tb + b_off[i], src ? src : zeros16, src != nullptr);
-                    }
-                }
-            }
-        };
-        // MN-contiguous operands: 16-byte loads into registers, two k-blocks ahead (two named register sets so the
-        // compiler keeps them in registers)
-        constexpr int NA = AOp::KCONTIG ? 1 : LA, NB = BOp::KCONTIG ? 1 : LB;
-        float4 a_pf0[NA], a_pf1[NA], b_pf0[NB], b_pf1[NB];
-        auto load_regs = [&](int kb, float4 (&ap)[NA], float4 (&bp)[NB]) {
+        // Operand tiles go global -> registers -> shared, PF k-blocks ahead.  (An earlier revision used cp.async for the
+        // K-contiguous operands; the fence.proxy.async that the thread-written tiles need compiles to MEMBAR.ALL.CTA,
+        // which drains every async copy still in flight and serialised the k-loop on memory latency.  With plain
+        // loads the fence is issued BEFORE the next loads, so nothing is outstanding when it executes.)
+        constexpr int PF = 2;  // k-blocks of loads in flight per thread
+        float4 a_pf[PF][LA], b_pf[PF][LB];
+        auto load_regs = [&](int kb, float4 (&ap)[LA], float4 (&bp)[LB]) {
             const int k0 = kbeg + kb * BK;
-            if (!AOp::KCONTIG) {
 #pragma unroll
-                for (int i = 0; i < LA; ++i) {
-                    const int r = m0 + a_r[i], k = k0 + a_k[i];
-                    const float* src = (kb < nkb && r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                    ap[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int i = 0; i < LA; ++i) {
+                const int r = m0 + a_r[i], k = k0 + a_k[i];
+                const float* src = (kb < nkb && a_r[i] >= 0 && r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
+                ap[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (!BOp::KCONTIG) {
 #pragma unroll
-                for (int i = 0; i < LB; ++i) {
-                    const int r = n0 + b_r[i], k = k0 + b_k[i];
-                    const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                    bp[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int i = 0; i < LB; ++i) {
+                const int r = n0 + b_r[i], k = k0 + b_k[i];
+                const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
+                bp[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        // transpose store: rows r..r+3 of column k (row stride inside a core matrix is 16 bytes; r%8 is 0 or 4)
+        // K-contiguous chunk: 4 consecutive k of one row = one 16-byte core-matrix row
+        auto sts_v = [&](uint32_t addr, const float4& v) {
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        };
+        // MN-contiguous chunk: rows r..r+3 of column k (row stride inside a core matrix is 16 bytes; r%8 is 0 or 4)
         auto sts_t = [&](uint32_t addr, const float4& v) {
             asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16], %2;\n\tst.shared.f32 [%0+32], %3;\n\tst.shared.f32 [%0+48], %4;"
                          ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         };
-        auto store_regs = [&](int s, const float4 (&ap)[NA], const float4 (&bp)[NB]) {
-            if (!AOp::KCONTIG) {
+        auto store_regs = [&](int s, const float4 (&ap)[LA], const float4 (&bp)[LB]) {
 #pragma unroll
-                for (int i = 0; i < LA; ++i) {
+            for (int i = 0; i < LA; ++i) {
+                if (a_r[i] >= 0) {
                     const float4 v = ap[i];
-                    sts_t(stage_a(s) + a_off[i], v);
-                    if (NTERMS == 3) sts_t(stage_alo(s) + a_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
+                    // the tensor core reads the upper 19 bits of each word (tf32); what it drops goes into the lo tile
+                    const float4 l = make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
+                    if (AOp::KCONTIG) { sts_v(stage_a(s) + a_off[i], v); if (NTERMS == 3) sts_v(stage_alo(s) + a_off[i], l); }
+                    else { sts_t(stage_a(s) + a_off[i], v); if (NTERMS == 3) sts_t(stage_alo(s) + a_off[i], l); }
                 }
             }
-            if (!BOp::KCONTIG) {
 #pragma unroll
-                for (int i = 0; i < LB; ++i) {
-                    if (b_r[i] >= 0) {
-                        const float4 v = bp[i];
-                        sts_t(stage_b(s) + b_off[i], v);
-                        if (NTERMS == 3) sts_t(stage_blo(s) + b_off[i], make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)));
-                    }
+            for (int i = 0; i < LB; ++i) {
+                if (b_r[i] >= 0) {
+                    const float4 v = bp[i];
+                    const float4 l = make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
+                    if (BOp::KCONTIG) { sts_v(stage_b(s) + b_off[i], v); if (NTERMS == 3) sts_v(stage_blo(s) + b_off[i], l); }
+                    else { sts_t(stage_b(s) + b_off[i], v); if (NTERMS == 3) sts_t(stage_blo(s) + b_off[i], l); }
                 }
             }
         };
-        auto split_lo = [&](uint32_t hi_addr, uint32_t lo_addr) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi_addr));
-            // the tensor core reads the upper 19 bits of each operand (tf32); what it drops goes into the lo tile
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
-                         "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
-        };
-        // one k-block: registers -> stage, wait for the cp.async part, low parts, hand the stage to the MMA warp, refill
-        auto block = [&](int kb, float4 (&ap)[NA], float4 (&bp)[NB]) {
+        auto block = [&](int kb, float4 (&ap)[LA], float4 (&bp)[LB]) {
             const int s = kb % S;
-            // stage s is free: its previous user (block kb-S) was waited for at iteration kb-S+2
+            if (kb >= S) mbar_wait(empty_bar(s), ((kb / S) - 1) & 1);  // the MMAs of block kb-S are done with this stage
             store_regs(s, ap, bp);
-            load_regs(kb + 2, ap, bp);
-            cp_async_wait<S - 3>();  // this thread's cp.async chunks of block kb have landed
-            if (NTERMS == 3) {
-                if (AOp::KCONTIG) {
-#pragma unroll
-                    for (int i = 0; i < LA; ++i) split_lo(stage_a(s) + a_off[i], stage_alo(s) + a_off[i]);
-                }
-                if (BOp::KCONTIG) {
-#pragma unroll
-                    for (int i = 0; i < LB; ++i)
-                        if (b_r[i] >= 0) split_lo(stage_b(s) + b_off[i], stage_blo(s) + b_off[i]);
-                }
-            }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(s));  // one arrival per producer warp
-            // refill the stage block kb-2 used: its MMAs were committed a whole iteration ago, so this wait does not
-            // put the producers in lock-step with the tensor core (one stage of slack)
-            const int nxt = kb + S - 2;
-            if (nxt < nkb) {
-                if (kb >= 2) mbar_wait(empty_bar((kb - 2) % S), ((kb - 2) / S) & 1);
-                issue_async(nxt);
-            }
-            cp_async_commit();
+            load_regs(kb + PF, ap, bp);               // issued after the fence: the fence never waits on these
         };
-        for (int kb = 0; kb < S - 2; ++kb) {
-            if (kb < nkb) issue_async(kb);
-            cp_async_commit();
-        }
-        load_regs(0, a_pf0, b_pf0);
-        load_regs(1, a_pf1, b_pf1);
-        for (int kb = 0; kb < nkb; kb += 2) {
-            block(kb, a_pf0, b_pf0);
-            if (kb + 1 < nkb) block(kb + 1, a_pf1, b_pf1);
+#pragma unroll
+        for (int p = 0; p < PF; ++p) load_regs(p, a_pf[p], b_pf[p]);
+        for (int kb = 0; kb < nkb; kb += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p)
+                if (kb + p < nkb) block(kb + p, a_pf[p], b_pf[p]);
         }
         // ---------------- epilogue ----------------
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        const int sub = warp & 3, half = warp >> 2;
+        const int sub = warp & 3, quarter = warp >> 2;
         const int m = m0 + sub * 32 + lane;
-        constexpr int HALF_COLS = BN / 2;
-#pragma unroll
-        for (int c = 0; c < HALF_COLS; c += 16) {
-            const int col = half * HALF_COLS + c;
-            float v[16];
-            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)col, v);
+        constexpr int QCOLS = BN / 4;  // columns per warp: 8, 16 or 32
+        const uint32_t trow = tmem_base + ((uint32_t)(sub * 32) << 16);
+        if (QCOLS == 8) {
+            const int col = quarter * 8;
+            float v[8];
+            if (nkb > 0) tmem_ld8(trow + (uint32_t)col, v);
             else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
             }
-            if (m < M && n0 + col < N) epi.template store<16>(m, n0 + col, v, z);
+            if (m < M && n0 + col < N) epi.template store<8>(m, n0 + col, v, z);
+        } else {
+#pragma unroll
+            for (int c = 0; c < QCOLS; c += 16) {
+                const int col = quarter * QCOLS + c;
+                float v[16];
+                if (nkb > 0) tmem_ld16(trow + (uint32_t)col, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                if (m < M && n0 + col < N) epi.template store<16>(m, n0 + col, v, z);
+            }
         }
         tc_fence_before();
     } else {
         // ---------------- MMA issuer ----------------
+        // Every lane computes the (warp-uniform) descriptors so they live in uniform registers; one elected lane
+        // issues.  A divergent `if (lane == 0)` around the whole loop makes the compiler wrap each tcgen05.mma in a
+        // waterfall loop and the issue loop, not the tensor core, becomes the bottleneck.
         const uint32_t idesc = make_idesc(BN, false, false);  // both operands are staged K-major
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        const uint64_t da0 = TA::desc(stage_a(0), 0), db0 = TB::desc(stage_b(0), 0);
+        const uint64_t dal0 = TA::desc(stage_alo(0), 0), dbl0 = TB::desc(stage_blo(0), 0);
+        constexpr uint64_t STAGE16 = Plan::STAGE >> 4, KS16 = (2 * LBO) >> 4;  // descriptor address units (16 bytes)
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             mbar_wait(full_bar(s), (kb / S) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            const uint64_t so = (uint64_t)s * STAGE16;
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t da = TA::desc(stage_a(s), ks), db = TB::desc(stage_b(s), ks);
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t o = so + ks * KS16;
+                const uint32_t acc = (kb | ks) != 0;
+                if (leader) {
                     if (NTERMS == 3) {
-                        const uint64_t dal = TA::desc(stage_alo(s), ks), dbl = TB::desc(stage_blo(s), ks);
-                        mma_tf32(tmem_base, da, dbl, idesc, (kb | ks) != 0);
-                        mma_tf32(tmem_base, dal, db, idesc, 1);
-                        mma_tf32(tmem_base, da, db, idesc, 1);
+                        mma_tf32(tmem_base, da0 + o, dbl0 + o, idesc, acc);
+                        mma_tf32(tmem_base, dal0 + o, db0 + o, idesc, 1);
+                        mma_tf32(tmem_base, da0 + o, db0 + o, idesc, 1);
                     } else {
-                        mma_tf32(tmem_base, da, db, idesc, (kb | ks) != 0);
+                        mma_tf32(tmem_base, da0 + o, db0 + o, idesc, acc);
                     }
                 }
+            }
+            if (leader) {
                 mma_commit(empty_bar(s));                    // frees the stage when these MMAs retire
                 if (kb == nkb - 1) mma_commit(accum_bar);    // accumulator complete
             }
@@ -380,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == PRODUCERS / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }

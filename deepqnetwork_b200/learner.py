@@ -303,6 +303,12 @@ class Learner:
         self._c(self._lib.dqn_selftest_gemm(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(a), ptr(b), ptr(c)))
         return c
 
+    def bench_gemm(self, mode, M, N, K, a_kcontig=True, b_kcontig=True, iters=20):
+        ms = C.c_float()
+        m = {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
+        self._c(self._lib.dqn_bench_gemm(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), iters, C.byref(ms)))
+        return ms.value
+
     # -- persistence ---------------------------------------------------------------------------
     def save(self, prefix):
         self._c(self._lib.dqn_save(self._h, str(prefix).encode()))

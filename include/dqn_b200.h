@@ -167,6 +167,10 @@ int dqn_get_profile(dqn_learner* h, int32_t* n, const char** names, float* ms, i
 int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,
                       int32_t b_kcontig, const float* h_A, const float* h_B, float* h_C);
 
+/* GEMM engine micro-benchmark on device-resident operands: average ms per launch over `iters` launches */
+int dqn_bench_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_t b_kcontig,
+                   int32_t iters, float* ms_per_launch);
+
 /* ---- persistence (own container format; TF-bundle compatibility is SURVEY.md 8f-3) -- */
 int dqn_save(dqn_learner* h, const char* prefix);     /* Model.save, rl/model/model.py:60-68 */
 int dqn_restore(dqn_learner* h, const char* prefix);  /* Model.restore :71-83; returns 1 if absent */
