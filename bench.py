@@ -236,6 +236,8 @@ def main():
     ap.add_argument('--capacity', type=int, default=1000000, help='replay transitions resident in HBM')
     ap.add_argument('--math', default='tc3x', choices=['fp32', 'tc3x', 'tc1x'],
                     help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
+    ap.add_argument('--no-fuse', action='store_true', help='ablation: optimizer as a separate pass over the gradient slab')
+    ap.add_argument('--no-overlap', action='store_true', help='ablation: single stream, no forked branches in the step graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
@@ -295,6 +297,10 @@ def main():
     torch.cuda.set_stream(stream)
     L.set_stream(stream.cuda_stream)  # so that torch.cuda.Event brackets exactly the learner's work
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
+    if args.no_fuse:
+        L.set_option('fuse_fc_adam', 0)
+    if args.no_overlap:
+        L.set_option('overlap', 0)
     L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)
     L.set_tower(init_tower_params(shapes, 43 + 2 * rank), 1)
     L.replay_fill_synthetic(args.capacity, seed=1234 + rank)

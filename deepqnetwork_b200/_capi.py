@@ -65,12 +65,14 @@ _SIGS = {
     'dqn_train_step': [_P, _P, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_float)],
     'dqn_train_steps': [_P, C.c_int64],
     'dqn_train_step_phase': [_P, C.c_int32, C.c_double],
+    'dqn_set_option': [_P, C.c_char_p, C.c_int32],
     'dqn_launch_count': [_P, C.POINTER(C.c_int64)],
     'dqn_set_profile': [_P, C.c_int32],
     'dqn_get_profile': [_P, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int32,
                         C.POINTER(C.c_int64)],
     'dqn_selftest_gemm': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P],
     'dqn_bench_gemm': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)],
+    'dqn_debug_timeline': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P],
     'dqn_save': [_P, C.c_char_p],
     'dqn_restore': [_P, C.c_char_p],
 }

@@ -576,7 +576,7 @@ void prof_mark(dqn_learner* h, const char* name) {
 
 // forward both towers, TD epilogue and (train) backward on a [2n,S] batch laid out as rows [0,n)=s, [n,2n)=s'
 static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8_t* actions, const uint8_t* rewards,
-                      const uint8_t* cont, const float* isw, int train, double grad_scale) {
+                      const uint8_t* cont, const float* isw, int train, double grad_scale, int per_update = 0) {
     const size_t S = h->state_bytes;
     const int A = h->net.A;
     const float* xf = nullptr;
@@ -599,6 +599,15 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
                        grad_scale);
+    if (train && per_update) {
+        // replay_sampler.update_sum_tree(tree_idxes, _make_priority(losses)) (deep_q_agent.py:341-347): it only needs
+        // the TD errors, so it runs on the side stream underneath the whole backward pass
+        cudaStream_t sv;
+        side_begin(h, sv);
+        prof_mark(h, "tree_update");
+        launch_tree_update(h, n, h->b_tree_idx, h->b_newprio, 1);
+        side_end(h, sv);
+    }
     if (train) {
         prof_mark(h, "head_backward");
         launch_head_backward(h, n, actions);
@@ -608,7 +617,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
 
 static void finish_step(dqn_learner* h, int per_update) {
     prof_mark(h, "optimizer");
-    launch_optimizer(h);
+    launch_optimizer(h, h->fuse_fc_adam);
     prof_mark(h, "post_step");
     launch_post_step(h, per_update);
     prof_mark(h, "end");
@@ -667,11 +676,16 @@ static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* ro
 }
 
 static void fused_step_launches(dqn_learner* h, const double* u, const int64_t* rows, double grad_scale, int phases) {
+    // whole step in one call: the dense wgrad carries the optimizer (no gradient round trip through HBM);
+    // the split (data-parallel) form keeps the gradient slab for the external all-reduce
+    h->fuse_fc_adam = (phases == 3) && h->fuse_enabled;
     if (phases & 1) {
         sample_into_batch(h, u, rows);
-        step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1, grad_scale);
+        step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1, grad_scale,
+                  h->cfg.use_per);
     }
-    if (phases & 2) finish_step(h, h->cfg.use_per);
+    if (phases & 2) finish_step(h, 0);
+    h->fuse_fc_adam = false;
 }
 
 static void after_step_host(dqn_learner* h) {
@@ -873,6 +887,17 @@ extern "C" int dqn_debug_read(dqn_learner* h, const char* what, float* out, int6
     API_END(h)
 }
 
+extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
+    API_BEGIN(h)
+    const std::string n = name;
+    if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
+    else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
+    else throw std::string("unknown option: ") + n;
+    h->graph_valid = false;
+    if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
+    API_END(h)
+}
+
 extern "C" int dqn_launch_count(const dqn_learner* h, int64_t* n) {
     if (!h) return 2;
     if (n) *n = h->launches;
@@ -1013,5 +1038,28 @@ extern "C" int dqn_bench_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N
         throw;
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    API_END(h)
+}
+
+
+// In-kernel timeline of the first CTA of one tcgen05 GEMM launch: out[kb*8 + {0..3}] = producer thread 0 clocks
+// (loop top, after empty wait, after stores, after arrive+next loads), {4..7} = MMA thread (before full wait, after,
+// after fences, after issue+commit).  Debug aid for the k-loop pipeline.
+extern "C" int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,
+                                  int32_t b_kcontig, unsigned long long* out512) {
+    API_BEGIN(h)
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    unsigned long long* dT = nullptr;
+    dmalloc(dA, (size_t)M * K); dmalloc(dB, (size_t)N * K); dmalloc(dC, (size_t)M * N); dmalloc(dT, 512);
+    DQN_CUDA_OK(cudaMemsetAsync(dA, 0x3c, (size_t)M * K * 4, h->stream));
+    DQN_CUDA_OK(cudaMemsetAsync(dB, 0x3c, (size_t)N * K * 4, h->stream));
+    DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 512 * 8, h->stream));
+    selftest_gemm(h, mode, M, N, K, a_kcontig, b_kcontig, dA, dB, dC);  // warm
+    h->tc_dbg = dT;
+    try { selftest_gemm(h, mode, M, N, K, a_kcontig, b_kcontig, dA, dB, dC); } catch (...) { h->tc_dbg = nullptr; throw; }
+    h->tc_dbg = nullptr;
+    DQN_CUDA_OK(cudaMemcpyAsync(out512, dT, 512 * 8, cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT);
     API_END(h)
 }

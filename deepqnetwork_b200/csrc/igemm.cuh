@@ -265,12 +265,64 @@ struct EpiDgradGate {  // conv dgrad: row m of class z -> pixel (n,iy,ix); out =
 };
 
 struct EpiFcWgrad {  // dW of the two hidden streams: column n -> stream n/hid, grads laid out like the params
+    static constexpr bool COALESCE = true;
     float* g0; float* g1; int hid;
+    struct State {};
+    __device__ __forceinline__ void load(int, int, State&) const {}
+    __device__ __forceinline__ void apply(int m, int n, const float4& g, State&, float) const {
+        *reinterpret_cast<float4*>((n < hid ? g0 + n : g1 + (n - hid)) + (size_t)m * hid) = g;
+    }
+    __device__ __forceinline__ float step_size() const { return 0.f; }
     template <int TN>
     __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
         float* o = (n < hid ? g0 + n : g1 + (n - hid)) + (size_t)m * hid;
 #pragma unroll
         for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
+// dense wgrad with the optimizer in the epilogue: dW never reaches HBM.  Adam (TF ApplyAdam) or Nesterov momentum
+// (TF ApplyMomentum) on the element this thread just reduced; layout of w/m/v = the parameter slab.
+struct EpiFcWgradAdam {
+    static constexpr bool COALESCE = true;  // tensor-core epilogue: go through smem so lanes run along n
+    float* w0; float* w1; float* m0; float* m1; float* v0; float* v1; int hid;
+    const dqn_learner::Scalars* sc; float lr; float mom; int use_momentum;
+    struct State { float4 w, m, v; };
+    __device__ __forceinline__ size_t index(int m, int n) const { return (size_t)m * hid + (n < hid ? n : n - hid); }
+    // two-phase form (used by the coalesced tensor-core epilogue to keep several rows of loads in flight)
+    __device__ __forceinline__ void load(int m, int n, State& st) const {
+        const size_t o = index(m, n);
+        st.w = *reinterpret_cast<const float4*>((n < hid ? w0 : w1) + o);
+        st.m = *reinterpret_cast<const float4*>((n < hid ? m0 : m1) + o);
+        if (!use_momentum) st.v = *reinterpret_cast<const float4*>((n < hid ? v0 : v1) + o);
+    }
+    __device__ __forceinline__ void apply(int m, int n, const float4& g, State& st, float lr_t) const {
+        const size_t o = index(m, n);
+        if (use_momentum) {
+#define MOM1(c) st.m.c = st.m.c * mom + g.c; st.w.c = st.w.c - (g.c * lr + st.m.c * mom * lr);
+            MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+        } else {
+            const float omb1 = 1.0f - 0.9f, omb2 = 1.0f - 0.999f, eps = 1e-8f;
+#define ADAM1(c) st.m.c = st.m.c + (g.c - st.m.c) * omb1; st.v.c = st.v.c + (g.c * g.c - st.v.c) * omb2; \
+                 st.w.c = st.w.c - (st.m.c * lr_t) / (sqrtf(st.v.c) + eps);
+            ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+            *reinterpret_cast<float4*>((n < hid ? v0 : v1) + o) = st.v;
+        }
+        *reinterpret_cast<float4*>((n < hid ? m0 : m1) + o) = st.m;
+        *reinterpret_cast<float4*>((n < hid ? w0 : w1) + o) = st.w;
+    }
+    __device__ __forceinline__ float step_size() const { return use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p); }
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&g)[TN], int) const {
+        const float lr_t = step_size();
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            State st;
+            load(m, n + j, st);
+            apply(m, n + j, make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]), st, lr_t);
+        }
     }
 };
 

@@ -54,6 +54,8 @@ struct dqn_learner {
     cudaEvent_t fork_ev[12] = {};
     int fork_used = 0;
     bool overlap = true;
+    bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
+    bool fuse_fc_adam = false;  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
     std::string err;
     int64_t launches = 0;
 
@@ -120,6 +122,7 @@ struct dqn_learner {
     int fc_splits = 1;
 
     // tcgen05 path helpers
+    unsigned long long* tc_dbg = nullptr;  // optional in-kernel timeline capture (dqn_debug_timeline)
     float* zeros16 = nullptr;   // 16 zero bytes (cp.async dummy source)
     float* ones_row = nullptr;  // {1,0,0,0}: the bias row appended to conv wgrad A^T
     float* x_f32 = nullptr;     // u8 batch converted to f32 (x/255) for cp.async loaders: [2*max_rows][S]
@@ -179,6 +182,6 @@ void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q
 void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions);
 
 // optim.cu
-void launch_optimizer(dqn_learner* h);
+void launch_optimizer(dqn_learner* h, bool skip_fc);
 void launch_post_step(dqn_learner* h, int per_update);
 void launch_copy_network(dqn_learner* h);

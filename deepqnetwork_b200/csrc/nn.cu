@@ -265,9 +265,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int Z, int m
     const int total4 = (mreal + 1) * N / 4;
     const size_t zstride = (size_t)(mreal + 4) * N;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const float* p = part + (size_t)i * 4;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < Z; ++z) {
-            const float4 v = *reinterpret_cast<const float4*>(part + z * zstride + (size_t)i * 4);
+        int z = 0;
+        for (; z + 8 <= Z; z += 8) {  // eight partial loads in flight, summed in z order (deterministic)
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(p + (size_t)(z + j) * zstride);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+        }
+        for (; z < Z; ++z) {
+            const float4 v = *reinterpret_cast<const float4*>(p + (size_t)z * zstride);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
         const int e = i * 4;
@@ -285,16 +294,26 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     // Weight gradients do not feed anything before the optimizer, so each one is forked onto the side stream as soon
     // as its dY exists, while the main stream continues down the dgrad chain.
     cudaStream_t saved;
-    // dense hidden: dW = X^T dH (K = batch), written straight into the gradient slab
-    {
+    auto fc_wgrad = [&]() {
+        // dense hidden: dW = X^T dH (K = batch).  Fused mode applies Adam/momentum in the epilogue (dW never lands
+        // in HBM); otherwise dW goes to the gradient slab (data-parallel all-reduce, gradient read-back).
         side_begin(h, saved);
         prof_mark(h, "fc_wgrad");
         OpColContig a{acts.act[2], net.flat};
         OpColContig b{h->d_hid, net.NH};
-        EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
-        gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+        if (h->fuse_fc_adam) {
+            float* W = h->online;
+            EpiFcWgradAdam e{W + net.off_fc_w[0], W + net.off_fc_w[1], h->slot_m + net.off_fc_w[0], h->slot_m + net.off_fc_w[1],
+                             h->slot_v + net.off_fc_w[0], h->slot_v + net.off_fc_w[1], net.hidden, h->d_sc,
+                             (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum};
+            gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+        } else {
+            EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
+            gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
+        }
         side_end(h, saved);
-    }
+    };
+    if (!h->fuse_fc_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
@@ -310,6 +329,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             igemm_auto<false>(h, a, b, e, rows, net.flat, net.NH, 1, 0);
         }
     }
+    if (h->fuse_fc_adam) fc_wgrad();  // fused: it overwrites W, so it starts only after the dgrad has read W
     float* part = h->wg_part;
     for (int l = 2; l >= 0; --l) {
         const ConvGeom& g = net.conv[l];
@@ -332,7 +352,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             gemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
             static const char* kR[3] = {"conv1_wgrad_reduce", "conv2_wgrad_reduce", "conv3_wgrad_reduce"};
             prof_mark(h, kR[l]);
-            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 256), 256, 0, h->stream>>>(part, Z, mreal, N,
+            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 64), 64, 0, h->stream>>>(part, Z, mreal, N,
                                                                                           G + net.off_cw[l], G + net.off_cb[l]);
             DQN_CUDA_OK(cudaGetLastError());
             h->launches++;

@@ -8,6 +8,7 @@
 // var -= m*lr_t/(sqrt(v)+eps).  ApplyMomentum(nesterov): acc = acc*mom + g; var -= g*lr + acc*mom*lr.
 // All parameters live in one slab, so "multi-tensor apply" is a single elementwise pass.
 #include "learner.h"
+#include <algorithm>
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, size_t n4, float lr,
@@ -42,17 +43,33 @@ __global__ void __launch_bounds__(256) momentum_kernel(float4* __restrict__ p, f
     }
 }
 
-void launch_optimizer(dqn_learner* h) {
-    const size_t n4 = (size_t)h->net.slab / 4;
-    const int blocks = h->sm_count * 8;
+static void optimizer_range(dqn_learner* h, int64_t beg, int64_t end) {
+    if (end <= beg) return;
+    const size_t n4 = (size_t)(end - beg) / 4, o4 = (size_t)beg / 4;
+    const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
     if (h->cfg.use_momentum)
-        momentum_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online, (float4*)h->slot_m, (const float4*)h->grads, n4,
-                                                       (float)h->cfg.learning_rate, (float)h->cfg.momentum);
+        momentum_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online + o4, (float4*)h->slot_m + o4,
+                                                       (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate,
+                                                       (float)h->cfg.momentum);
     else
-        adam_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online, (float4*)h->slot_m, (float4*)h->slot_v,
-                                                   (const float4*)h->grads, n4, (float)h->cfg.learning_rate, h->d_sc);
+        adam_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online + o4, (float4*)h->slot_m + o4, (float4*)h->slot_v + o4,
+                                                   (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, h->d_sc);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
+}
+
+// skip_fc: the two dense hidden kernels were already updated in the wgrad epilogue (EpiFcWgradAdam)
+void launch_optimizer(dqn_learner* h, bool skip_fc) {
+    const NetDesc& net = h->net;
+    if (!skip_fc) return optimizer_range(h, 0, net.slab);
+    const int64_t fcw = (int64_t)net.flat * net.hidden;
+    optimizer_range(h, 0, net.off_fc_w[0]);
+    if (net.dueling) {
+        optimizer_range(h, net.off_fc_w[0] + fcw, net.off_fc_w[1]);
+        optimizer_range(h, net.off_fc_w[1] + fcw, net.slab);
+    } else {
+        optimizer_range(h, net.off_fc_w[0] + fcw, net.slab);
+    }
 }
 
 // after the optimizer: global_step += 1, beta powers advance (AdamOptimizer._finish), RNG counter advances

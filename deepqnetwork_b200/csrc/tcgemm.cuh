@@ -167,11 +167,16 @@ struct SmemPlan {
     static constexpr int BYTES = STAGES * STAGE + 256;
 };
 
+// epilogue functors may ask for a shared-memory transpose so that global accesses run along n (row-major outputs whose
+// row pitch is much larger than the tile: dense wgrad)
+template <class E, class = void> struct wants_coalesce { static constexpr bool value = false; };
+template <class E> struct wants_coalesce<E, decltype((void)E::COALESCE)> { static constexpr bool value = E::COALESCE; };
+
 __device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
-                                                            int kchunk, const float* __restrict__ /*zeros16*/) {
+                                                            int kchunk, unsigned long long* __restrict__ dbg) {
     using Plan = SmemPlan<BN, NTERMS>;
     constexpr int S = Plan::STAGES;
     using TA = Tile<BM>;
@@ -189,7 +194,9 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.z;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // n-tile is the fastest-varying block index: CTAs that run together share the same A rows (L2) and, for the dense
+    // wgrad, touch whole contiguous parameter rows (DRAM page locality of the fused optimizer epilogue)
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = SPLIT ? z * kchunk : 0;
     const int kend = SPLIT ? min(K, kbeg + kchunk) : K;
     const int nkb = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
@@ -233,11 +240,10 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             b_off[i] = b_r[i] >= 0 ? TB::off(b_r[i], b_k[i]) : 0;
             b_row[i] = b.row(min(n0 + max(b_r[i], 0), N - 1), z);
         }
-        // Operand tiles go global -> registers -> shared, PF k-blocks ahead.  (An earlier revision used cp.async for the
-        // K-contiguous operands; the fence.proxy.async that the thread-written tiles need compiles to MEMBAR.ALL.CTA,
-        // which drains every async copy still in flight and serialised the k-loop on memory latency.  With plain
-        // loads the fence is issued BEFORE the next loads, so nothing is outstanding when it executes.)
-        constexpr int PF = 2;  // k-blocks of loads in flight per thread
+        // Operand tiles go global -> registers -> shared, PF k-blocks ahead.  (A producer-side fence.proxy.async compiles
+        // to MEMBAR.ALL.CTA, which waits for every load/async copy the thread still has in flight and serialised the
+        // k-loop on memory latency; the fence therefore lives on the consumer side, after the barrier acquire.)
+        constexpr int PF = 4;  // k-blocks of loads in flight per thread
         float4 a_pf[PF][LA], b_pf[PF][LB];
         auto load_regs = [&](int kb, float4 (&ap)[LA], float4 (&bp)[LB]) {
             const int k0 = kbeg + kb * BK;
@@ -286,12 +292,18 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         };
         auto block = [&](int kb, float4 (&ap)[LA], float4 (&bp)[LB]) {
             const int s = kb % S;
+            if (dbg && tid == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 0] = clock64();
             if (kb >= S) mbar_wait(empty_bar(s), ((kb / S) - 1) & 1);  // the MMAs of block kb-S are done with this stage
+            if (dbg && tid == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 1] = clock64();
             store_regs(s, ap, bp);
-            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+            if (dbg && tid == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 2] = clock64();
+            // Publish the tile: release-arrive on the stage barrier (one arrival per producer warp).  The generic->async
+            // proxy fence is executed by the MMA thread after it acquires the barrier (see the issuer loop): a fence
+            // here would compile to MEMBAR.ALL.CTA and drain this thread's prefetch loads every k-block.
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));  // one arrival per producer warp
-            load_regs(kb + PF, ap, bp);               // issued after the fence: the fence never waits on these
+            if (lane == 0) mbar_arrive(full_bar(s));
+            load_regs(kb + PF, ap, bp);
+            if (dbg && tid == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 3] = clock64();
         };
 #pragma unroll
         for (int p = 0; p < PF; ++p) load_regs(p, a_pf[p], b_pf[p]);
@@ -309,7 +321,56 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         const int m = m0 + sub * 32 + lane;
         constexpr int QCOLS = BN / 4;  // columns per warp: 8, 16 or 32
         const uint32_t trow = tmem_base + ((uint32_t)(sub * 32) << 16);
-        if (QCOLS == 8) {
+        if constexpr (wants_coalesce<Epi>::value) {
+            // accumulators -> smem tile [128][BN+4] (stage buffers are idle now) -> rows handed to whole warps
+            constexpr int PITCH = BN + 4;
+            float* tile = reinterpret_cast<float*>(smem + (sbase - smem_u32(smem)));
+            const int row = sub * 32 + lane;
+            if (QCOLS == 8) {
+                float v[8];
+                if (nkb > 0) tmem_ld8(trow + (uint32_t)(quarter * 8), v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i += 4)
+                    *reinterpret_cast<float4*>(tile + row * PITCH + quarter * 8 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < QCOLS; c += 16) {
+                    float v[16];
+                    if (nkb > 0) tmem_ld16(trow + (uint32_t)(quarter * QCOLS + c), v);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(tile + row * PITCH + quarter * QCOLS + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+            constexpr int LANES_PER_ROW = BN / 4;            // float4 per row
+            constexpr int ROWS_PER_PASS = PRODUCERS / LANES_PER_ROW;
+            const int c4 = (tid % LANES_PER_ROW) * 4;
+            const float step = epi.step_size();
+            constexpr int RB = 4;  // rows per batch: all their read-modify-write loads are issued before any store
+            for (int r0 = tid / LANES_PER_ROW; r0 < BM; r0 += ROWS_PER_PASS * RB) {
+                typename Epi::State st[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int r = r0 + j * ROWS_PER_PASS;
+                    if (r < BM && m0 + r < M && n0 + c4 < N) epi.load(m0 + r, n0 + c4, st[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int r = r0 + j * ROWS_PER_PASS;
+                    if (r < BM && m0 + r < M && n0 + c4 < N)
+                        epi.apply(m0 + r, n0 + c4, *reinterpret_cast<const float4*>(tile + r * PITCH + c4), st[j], step);
+                }
+            }
+        } else if (QCOLS == 8) {
             const int col = quarter * 8;
             float v[8];
             if (nkb > 0) tmem_ld8(trow + (uint32_t)col, v);
@@ -345,8 +406,12 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
         constexpr uint64_t STAGE16 = Plan::STAGE >> 4, KS16 = (2 * LBO) >> 4;  // descriptor address units (16 bytes)
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
-            mbar_wait(full_bar(s), (kb / S) & 1);
+            if (dbg && lane == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 4] = clock64();
+            mbar_wait(full_bar(s), (kb / S) & 1);   // acquire: the producers' shared-memory stores are visible here
+            if (dbg && lane == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 5] = clock64();
+            fence_proxy_async();                      // ... and from here on to the tensor core's async proxy
             tc_fence_after();
+            if (dbg && lane == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 6] = clock64();
             const uint64_t so = (uint64_t)s * STAGE16;
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
@@ -366,6 +431,7 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
                 mma_commit(empty_bar(s));                    // frees the stage when these MMAs retire
                 if (kb == nkb - 1) mma_commit(accum_bar);    // accumulator complete
             }
+            if (dbg && lane == 0 && blockIdx.x + blockIdx.y + blockIdx.z == 0 && kb < 64) dbg[kb * 8 + 7] = clock64();
             __syncwarp();
         }
         tc_fence_before();
@@ -386,8 +452,8 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::BYTES + 1024));
         configured = true;
     }
-    dim3 grid(ceil_div(M, BM), ceil_div(N, BN), Z);
-    kern<<<grid, THREADS, Plan::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16);
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
+    kern<<<grid, THREADS, Plan::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->tc_dbg);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
 }

@@ -279,6 +279,9 @@ class Learner:
     def train_step_phase(self, phase, grad_scale=1.0):
         self._c(self._lib.dqn_train_step_phase(self._h, int(phase), float(grad_scale)))
 
+    def set_option(self, name, value):
+        self._c(self._lib.dqn_set_option(self._h, name.encode(), int(value)))
+
     def launch_count(self):
         n = C.c_int64()
         self._c(self._lib.dqn_launch_count(self._h, C.byref(n)))
@@ -308,6 +311,12 @@ class Learner:
         m = {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
         self._c(self._lib.dqn_bench_gemm(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), iters, C.byref(ms)))
         return ms.value
+
+    def debug_timeline(self, mode, M, N, K, a_kcontig=True, b_kcontig=True):
+        out = np.zeros(512, np.uint64)
+        m = {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
+        self._c(self._lib.dqn_debug_timeline(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(out)))
+        return out.reshape(64, 8)
 
     # -- persistence ---------------------------------------------------------------------------
     def save(self, prefix):

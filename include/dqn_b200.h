@@ -154,6 +154,10 @@ int dqn_train_steps(dqn_learner* h, int64_t n);
  * in the "grads" slab for an external all-reduce), phase 1 = optimizer + priority write-back.
  * grad_scale multiplies dL/dq (1/world_size for a global mean). */
 int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale);
+/* execution options (ablation / tests): "overlap" (fork independent kernels of a step onto a second stream, default 1),
+ * "fuse_fc_adam" (apply the optimizer in the dense wgrad epilogue inside dqn_train_step(s); default 0: measured no
+ * faster than the separate slab pass on B200 because the tile-wise read-modify-write loses DRAM page locality) */
+int dqn_set_option(dqn_learner* h, const char* name, int32_t value);
 /* per-kernel launch counter since creation (bench.py reports gpu_launches from this) */
 int dqn_launch_count(const dqn_learner* h, int64_t* n);
 /* CUDA-event time per step segment (sample, gather, forward_online, forward_target, td_epilogue, backward,
@@ -170,6 +174,10 @@ int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_
 /* GEMM engine micro-benchmark on device-resident operands: average ms per launch over `iters` launches */
 int dqn_bench_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_t b_kcontig,
                    int32_t iters, float* ms_per_launch);
+
+/* debug: in-kernel clock64 timeline of the k-loop of one tcgen05 GEMM launch (first CTA, first 64 k-blocks x 8 marks) */
+int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig, int32_t b_kcontig,
+                       unsigned long long* h_out512);
 
 /* ---- persistence (own container format; TF-bundle compatibility is SURVEY.md 8f-3) -- */
 int dqn_save(dqn_learner* h, const char* prefix);     /* Model.save, rl/model/model.py:60-68 */

@@ -306,3 +306,23 @@ def test_tc1x_single_pass_tf32_is_close_but_not_fp32_grade():
     ref = nn_ref.forward(nn_ref.to_torch(on, torch.float64), x, spec, torch.float64).numpy()
     assert 1e-6 < rel_err(q, ref) < 5e-3
     L.close()
+
+
+@pytest.mark.parametrize('math_mode', MODES)
+def test_fused_optimizer_and_overlap_do_not_change_results(math_mode):
+    """The dense-wgrad+Adam epilogue and the two-stream overlap are pure scheduling: weights, slots and the sum tree
+    after 5 steps are bit-identical with both switched off."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    res = []
+    for fuse, overlap in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        L, spec, shapes, on, tg = make(cfg, capacity=4096, math_mode=math_mode)
+        L.set_option('fuse_fc_adam', fuse); L.set_option('overlap', overlap)
+        L.replay_fill_synthetic(4096, seed=5)
+        L.train_steps(5); L.sync()
+        res.append((L.get_tower(0), L.get_tower(0, slot=1), L.get_tower(0, slot=2), L.tree_read()[0]))
+        L.close()
+    for r in res[1:]:
+        for a, b in zip(res[0][:3], r[:3]):
+            for k in a:
+                assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(res[0][3], r[3])
