@@ -76,6 +76,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side2_stream, cudaStreamNonBlocking));
         for (auto& e : h->fork_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         net_describe(h->net, h->cfg);
         const NetDesc& net = h->net;
@@ -170,6 +171,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -538,25 +540,26 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 bool overlap_enabled(const dqn_learner* h) { return h->overlap && !h->profile; }
 
 static cudaEvent_t next_fork_event(dqn_learner* h) {
-    DQN_REQUIRE(h->fork_used < 12, "fork event pool exhausted");
+    DQN_REQUIRE(h->fork_used < 16, "fork event pool exhausted");
     return h->fork_ev[h->fork_used++];
 }
 
-void side_begin(dqn_learner* h, cudaStream_t& saved) {
+void side_begin(dqn_learner* h, cudaStream_t& saved, int which) {
     saved = h->stream;
     if (!overlap_enabled(h)) return;
+    cudaStream_t side = which ? h->side2_stream : h->side_stream;
     cudaEvent_t e = next_fork_event(h);
     DQN_CUDA_OK(cudaEventRecord(e, saved));
-    DQN_CUDA_OK(cudaStreamWaitEvent(h->side_stream, e, 0));
-    h->stream = h->side_stream;
+    DQN_CUDA_OK(cudaStreamWaitEvent(side, e, 0));
+    h->stream = side;
 }
 
 void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; }
 
-void main_wait_side(dqn_learner* h) {
+void main_wait_side(dqn_learner* h, int which) {
     if (!overlap_enabled(h)) return;
     cudaEvent_t e = next_fork_event(h);
-    DQN_CUDA_OK(cudaEventRecord(e, h->side_stream));
+    DQN_CUDA_OK(cudaEventRecord(e, which ? h->side2_stream : h->side_stream));
     DQN_CUDA_OK(cudaStreamWaitEvent(h->stream, e, 0));
 }
 
@@ -617,7 +620,8 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
 
 static void finish_step(dqn_learner* h, int per_update) {
     prof_mark(h, "optimizer");
-    launch_optimizer(h, h->fuse_fc_adam);
+    launch_optimizer(h, h->fuse_fc_adam || h->fc_adam_done);
+    h->fc_adam_done = false;
     prof_mark(h, "post_step");
     launch_post_step(h, per_update);
     prof_mark(h, "end");
@@ -679,13 +683,14 @@ static void fused_step_launches(dqn_learner* h, const double* u, const int64_t* 
     // whole step in one call: the dense wgrad carries the optimizer (no gradient round trip through HBM);
     // the split (data-parallel) form keeps the gradient slab for the external all-reduce
     h->fuse_fc_adam = (phases == 3) && h->fuse_enabled;
+    h->early_fc_adam = (phases == 3) && !h->fuse_fc_adam;
     if (phases & 1) {
         sample_into_batch(h, u, rows);
         step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1, grad_scale,
                   h->cfg.use_per);
     }
     if (phases & 2) finish_step(h, 0);
-    h->fuse_fc_adam = false;
+    h->fuse_fc_adam = false; h->early_fc_adam = false;
 }
 
 static void after_step_host(dqn_learner* h) {
@@ -814,7 +819,11 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     DQN_REQUIRE(!h->cfg.use_per || isw, "use_per: is_weights are required");
     h->prof_used = 0; h->prof_marks.clear();
     upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
-    step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
+    h->early_fc_adam = true;
+    try {
+        step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
+    } catch (...) { h->early_fc_adam = false; throw; }
+    h->early_fc_adam = false;
     finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
     d2h(h, losses, h->b_losses_out, n);
     read_scalars(h);

@@ -50,12 +50,14 @@ struct dqn_learner {
     // second stream + events: independent kernels of one step (target tower vs online tower, wgrads vs the dgrad
     // chain) are forked onto it so that the small batch-32 grids overlap; inside a captured graph these become
     // parallel branches
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t fork_ev[12] = {};
+    cudaStream_t side_stream = nullptr, side2_stream = nullptr;
+    cudaEvent_t fork_ev[16] = {};
     int fork_used = 0;
     bool overlap = true;
     bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
-    bool fuse_fc_adam = false;  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
+    bool fuse_fc_adam = false;
+    bool early_fc_adam = false;  // set per launch sequence: optimizer for the dense kernels runs inside backward (side stream)
+    bool fc_adam_done = false;  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
     std::string err;
     int64_t launches = 0;
 
@@ -153,9 +155,10 @@ void prof_mark(dqn_learner* h, const char* name);
 // stream fork/join helpers (api.cu). side_begin: side stream waits for everything issued on the main stream so far
 // and becomes the launch stream; side_end: back to the main stream; main_wait_side / side_wait_main: cross edges.
 bool overlap_enabled(const dqn_learner* h);
-void side_begin(dqn_learner* h, cudaStream_t& saved);
+void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0);
 void side_end(dqn_learner* h, cudaStream_t saved);
-void main_wait_side(dqn_learner* h);  // api.cu: CUDA-event boundary, active only in profile mode
+void main_wait_side(dqn_learner* h, int which = 0);
+void launch_optimizer_fc(dqn_learner* h);  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);
 
 // replay.cu

@@ -330,13 +330,22 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         }
     }
     if (h->fuse_fc_adam) fc_wgrad();  // fused: it overwrites W, so it starts only after the dgrad has read W
+    if (h->early_fc_adam && !h->fuse_fc_adam) {
+        // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
+        // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
+        side_begin(h, saved, 0);
+        prof_mark(h, "optimizer_fc");
+        launch_optimizer_fc(h);
+        side_end(h, saved);
+        h->fc_adam_done = true;
+    }
     float* part = h->wg_part;
     for (int l = 2; l >= 0; --l) {
         const ConvGeom& g = net.conv[l];
         const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
         // wgrad (+bias) split over the pixel dimension
         {
-            side_begin(h, saved);  // needs d_act[l], which the main stream has just produced
+            side_begin(h, saved, 1);  // needs d_act[l], which the main stream has just produced
             const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
             int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
@@ -373,7 +382,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             gemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
         }
     }
-    main_wait_side(h);  // all weight gradients are in the slab before the optimizer runs
+    main_wait_side(h, 0);  // all weight gradients are in the slab (and the dense kernels updated) before the
+    main_wait_side(h, 1);  // optimizer pass over the remaining tensors runs
 }
 
 // ---- GEMM self-test: plain matrices through either engine (dqn_selftest_gemm) ----------------------------------------

@@ -58,6 +58,15 @@ static void optimizer_range(dqn_learner* h, int64_t beg, int64_t end) {
     h->launches++;
 }
 
+// optimizer for the dense hidden kernels only (98.6% of the parameters): issued from inside the backward pass as soon
+// as their gradient exists and nothing reads the old weights any more
+void launch_optimizer_fc(dqn_learner* h) {
+    const NetDesc& net = h->net;
+    const int64_t fcw = (int64_t)net.flat * net.hidden;
+    optimizer_range(h, net.off_fc_w[0], net.off_fc_w[0] + fcw);
+    if (net.dueling) optimizer_range(h, net.off_fc_w[1], net.off_fc_w[1] + fcw);
+}
+
 // skip_fc: the two dense hidden kernels were already updated in the wgrad epilogue (EpiFcWgradAdam)
 void launch_optimizer(dqn_learner* h, bool skip_fc) {
     const NetDesc& net = h->net;
