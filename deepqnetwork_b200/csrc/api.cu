@@ -901,6 +901,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     const std::string n = name;
     if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
     else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
+    else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }

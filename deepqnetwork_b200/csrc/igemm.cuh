@@ -36,6 +36,7 @@ struct OpColContig {  // Op(r,k) = p[k*ld + r]
         return *reinterpret_cast<const float4*>(rw + (size_t)k * ld);
     }
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * ld; }
+    __device__ __forceinline__ const float* addr1(Row rw, int, int k, int) const { return rw + (size_t)k * ld; }
 };
 
 // hidden-layer weights of the (up to) two streams seen as one [flat, NH] matrix: B(k,n) = W[n/hid][k][n%hid]
@@ -48,6 +49,7 @@ struct OpFcWeightFwd {
         return *reinterpret_cast<const float4*>(rw + (size_t)k * hid);
     }
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * hid; }
+    __device__ __forceinline__ const float* addr1(Row rw, int, int k, int) const { return rw + (size_t)k * hid; }
 };
 
 // transposed view for dgrad: B(k,n) = W[k/hid][n][k%hid]

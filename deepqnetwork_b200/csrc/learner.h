@@ -54,6 +54,7 @@ struct dqn_learner {
     cudaEvent_t fork_ev[16] = {};
     int fork_used = 0;
     bool overlap = true;
+    bool ts_gemm = true;        // tcgen05 GEMMs take A from tensor memory where the operand functor allows it
     bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
     bool fuse_fc_adam = false;
     bool early_fc_adam = false;  // set per launch sequence: optimizer for the dense kernels runs inside backward (side stream)

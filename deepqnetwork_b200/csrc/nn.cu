@@ -4,7 +4,7 @@
 // dense 512 ReLU, optional dueling streams) and its autodiff backward (rl/deep_q_model.py:391 optimizer.minimize).
 // Layout: activations NHWC f32, conv kernels HWIO (== row-major [KH*KW*Cin, Cout]), dense kernels [in,out] --
 // the TF layouts, so tensors copy 1:1 to/from checkpoints.
-#include "tcgemm.cuh"
+#include "tsgemm.cuh"
 #include <algorithm>
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -87,6 +87,13 @@ static void igemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e,
 // ---- math-mode dispatch: tcgen05 tensor cores (TF32 x1 / x3) or the FFMA kernel ------------------------------------
 template <int BN, bool SPLIT, class AOp, class BOp, class Epi>
 static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+    if constexpr (ts::capable<AOp>::value) {
+        if (h->ts_gemm) {  // A through tensor memory
+            if (h->cfg.math_mode == DQN_MATH_TC3X) ts::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+            else ts::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+            return;
+        }
+    }
     if (h->cfg.math_mode == DQN_MATH_TC3X) tc::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
     else tc::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
 }

@@ -176,7 +176,8 @@ __device__ __forceinline__ float lo_part(float x) { return x - __uint_as_float(_
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
-                                                            int kchunk, unsigned long long* __restrict__ dbg) {
+                                                            int kchunk, const float* __restrict__ zeros,
+                                                            unsigned long long* __restrict__ dbg) {
     using Plan = SmemPlan<BN, NTERMS>;
     constexpr int S = Plan::STAGES;
     using TA = Tile<BM>;
@@ -251,13 +252,16 @@ __global__ void __launch_bounds__(THREADS, 1) tcgemm_kernel(const AOp a, const B
             for (int i = 0; i < LA; ++i) {
                 const int r = m0 + a_r[i], k = k0 + a_k[i];
                 const float* src = (kb < nkb && a_r[i] >= 0 && r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                ap[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // padding / ragged edges read a 16-byte block of zeros: the select is on the ADDRESS, so nothing depends
+                // on the loaded value until the shared-memory store PF k-blocks later (a select on the value would
+                // stall this thread for a full memory round trip every k-block)
+                ap[i] = __ldg(reinterpret_cast<const float4*>(src ? src : zeros));
             }
 #pragma unroll
             for (int i = 0; i < LB; ++i) {
                 const int r = n0 + b_r[i], k = k0 + b_k[i];
                 const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                bp[i] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bp[i] = __ldg(reinterpret_cast<const float4*>(src ? src : zeros));
             }
         };
         // K-contiguous chunk: 4 consecutive k of one row = one 16-byte core-matrix row
@@ -453,7 +457,7 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    kern<<<grid, THREADS, Plan::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->tc_dbg);
+    kern<<<grid, THREADS, Plan::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16, h->tc_dbg);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
 }
