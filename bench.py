@@ -239,6 +239,7 @@ def main():
     ap.add_argument('--math', default='tc3x', choices=['fp32', 'tc3x', 'tc1x'],
                     help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
     ap.add_argument('--no-fuse', action='store_true', help='ablation: optimizer as a separate pass over the gradient slab')
+    ap.add_argument('--fuse', action='store_true', help='ablation: Adam for the dense kernels in the dense wgrad epilogue')
     ap.add_argument('--no-overlap', action='store_true', help='ablation: single stream, no forked branches in the step graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -301,6 +302,8 @@ def main():
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
     if args.no_fuse:
         L.set_option('fuse_fc_adam', 0)
+    if args.fuse:
+        L.set_option('fuse_fc_adam', 1)
     if args.no_overlap:
         L.set_option('overlap', 0)
     L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)

@@ -25,6 +25,11 @@ struct OpRowMajorK {  // Op(r,k) = p[r*ld + k]
     __device__ __forceinline__ Row row(int r, int) const { return p + (size_t)r * ld; }
     __device__ __forceinline__ float4 load4(Row rw, int, int k, int) const { return *reinterpret_cast<const float4*>(rw + k); }
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + k; }
+    // cursor form (tsgemm.cuh): k position shared by all rows of a thread, advanced by 32 per k-block
+    typedef int Cur;
+    __device__ __forceinline__ Cur cur(int k, int) const { return k; }
+    __device__ __forceinline__ void next(Cur& c) const { c += 32; }
+    __device__ __forceinline__ const float* ptr(Row rw, int, const Cur& c) const { return rw + c; }
 };
 
 struct OpColContig {  // Op(r,k) = p[k*ld + r]
@@ -37,6 +42,11 @@ struct OpColContig {  // Op(r,k) = p[k*ld + r]
     }
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * ld; }
     __device__ __forceinline__ const float* addr1(Row rw, int, int k, int) const { return rw + (size_t)k * ld; }
+    typedef size_t Cur;  // element offset k*ld
+    __device__ __forceinline__ Cur cur(int k, int) const { return (size_t)k * ld; }
+    __device__ __forceinline__ void next(Cur& c) const { c += (size_t)32 * ld; }
+    __device__ __forceinline__ const float* ptr(Row rw, int, const Cur& c) const { return rw + c; }
+    __device__ __forceinline__ int kstride() const { return ld; }
 };
 
 // hidden-layer weights of the (up to) two streams seen as one [flat, NH] matrix: B(k,n) = W[n/hid][k][n%hid]
@@ -50,6 +60,11 @@ struct OpFcWeightFwd {
     }
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const { return rw + (size_t)k * hid; }
     __device__ __forceinline__ const float* addr1(Row rw, int, int k, int) const { return rw + (size_t)k * hid; }
+    typedef size_t Cur;
+    __device__ __forceinline__ Cur cur(int k, int) const { return (size_t)k * hid; }
+    __device__ __forceinline__ void next(Cur& c) const { c += (size_t)32 * hid; }
+    __device__ __forceinline__ const float* ptr(Row rw, int, const Cur& c) const { return rw + c; }
+    __device__ __forceinline__ int kstride() const { return hid; }
 };
 
 // transposed view for dgrad: B(k,n) = W[k/hid][n][k%hid]
@@ -66,6 +81,12 @@ struct OpFcWeightBwd {
     __device__ __forceinline__ const float* addr4(Row rw, int, int k, int) const {
         return (k < hid ? w0 : w1) + rw + (k < hid ? k : k - hid);
     }
+    typedef int Cur;  // k (a 32-wide k-block never straddles the two streams: hid % 32 == 0)
+    __device__ __forceinline__ Cur cur(int k, int) const { return k; }
+    __device__ __forceinline__ void next(Cur& c) const { c += 32; }
+    __device__ __forceinline__ const float* ptr(Row rw, int, const Cur& c) const {
+        return (c < hid ? w0 + c : w1 + (c - hid)) + rw;
+    }
 };
 
 __device__ __forceinline__ float4 load_px4(const void* in, int is_u8, size_t idx) {
@@ -80,6 +101,7 @@ __device__ __forceinline__ float4 load_px4(const void* in, int is_u8, size_t idx
 // conv forward A: rows m=(n,oy,ox), k=(kh,kw,ci) -- the im2col view of an NHWC tensor (u8 or f32)
 struct OpConvFwdA {
     static constexpr bool KCONTIG = true;
+    static constexpr bool HEAVY = true;  // im2col address arithmetic per chunk (tsgemm.cuh: 8 loader warps)
     const void* in; ConvGeom g; int is_u8;
     struct Row { size_t base; int iy0, ix0; };
     __device__ __forceinline__ Row row(int m, int) const {
@@ -102,6 +124,23 @@ struct OpConvFwdA {
         const int iy = r.iy0 + kh, ix = r.ix0 + kw;
         if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
         return static_cast<const float*>(in) + r.base + ((size_t)(iy * g.iw + ix) << g.cin_log2) + ci;
+    }
+    struct Cur { int kh, kw, ci; };
+    __device__ __forceinline__ Cur cur(int k, int) const {
+        const int tap = k >> g.cin_log2;
+        Cur c; c.ci = k & (g.cin - 1); c.kh = fdiv(tap, g.m_k, g.k); c.kw = tap - c.kh * g.k;
+        return c;
+    }
+    __device__ __forceinline__ void next(Cur& c) const {
+        c.ci += 32;
+        c.kw += c.ci >> g.cin_log2;
+        c.ci &= g.cin - 1;
+        while (c.kw >= g.k) { c.kw -= g.k; ++c.kh; }
+    }
+    __device__ __forceinline__ const float* ptr(const Row& r, int, const Cur& c) const {
+        const int iy = r.iy0 + c.kh, ix = r.ix0 + c.kw;
+        if ((unsigned)iy >= (unsigned)g.ih || (unsigned)ix >= (unsigned)g.iw) return nullptr;
+        return static_cast<const float*>(in) + r.base + ((iy * g.iw + ix) << g.cin_log2) + c.ci;
     }
 };
 
@@ -148,6 +187,7 @@ struct DgradClass {
 
 struct OpConvDgradA {
     static constexpr bool KCONTIG = true;
+    static constexpr bool HEAVY = true;
     const float* dy; DgradClass c; int cout_log2; int nimg;
     struct Row { size_t base; int oy0, ox0; int ok; };
     __device__ __forceinline__ Row row(int m, int z) const {
@@ -180,6 +220,23 @@ struct OpConvDgradA {
         if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow) return nullptr;
         return dy + ((r.base + (size_t)oy * c.g.ow + ox) << cout_log2) + co;
     }
+    struct Cur { int jh, jw, co; };
+    __device__ __forceinline__ Cur cur(int k, int) const {
+        const int tap = k >> cout_log2;
+        Cur q; q.co = k & (c.g.cout - 1); q.jh = fdiv(tap, c.g.m_kt, c.g.kt); q.jw = tap - q.jh * c.g.kt;
+        return q;
+    }
+    __device__ __forceinline__ void next(Cur& q) const {
+        q.co += 32;
+        q.jw += q.co >> cout_log2;
+        q.co &= c.g.cout - 1;
+        while (q.jw >= c.g.kt) { q.jw -= c.g.kt; ++q.jh; }
+    }
+    __device__ __forceinline__ const float* ptr(const Row& r, int, const Cur& q) const {
+        const int oy = r.oy0 - q.jh, ox = r.ox0 - q.jw;
+        if (!r.ok || (unsigned)oy >= (unsigned)c.g.oh || (unsigned)ox >= (unsigned)c.g.ow) return nullptr;
+        return dy + ((r.base + (size_t)(oy * c.g.ow + ox)) << cout_log2) + q.co;
+    }
 };
 
 struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
@@ -202,6 +259,23 @@ struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
         const int jh = fdiv(tap, g.m_kt, kt), jw = tap - jh * kt;
         const int kh = ry + g.s * jh, kw = rx + g.s * jw;
         return w + ((((size_t)kh * g.k + kw) * g.cin + ci) << cout_log2) + co;
+    }
+    struct Cur { int kh, kw0, kw, co; };  // kernel tap reached by (jh, jw) of this parity class, and the channel
+    __device__ __forceinline__ Cur cur(int k, int z) const {
+        const int ry = fdiv(z, g.m_s, g.s), rx = z - ry * g.s;
+        const int tap = k >> cout_log2;
+        const int jh = fdiv(tap, g.m_kt, g.kt), jw = tap - jh * g.kt;
+        Cur q; q.co = k & (g.cout - 1); q.kh = ry + g.s * jh; q.kw0 = rx; q.kw = rx + g.s * jw;
+        return q;
+    }
+    __device__ __forceinline__ void next(Cur& q) const {
+        q.co += 32;
+        q.kw += (q.co >> cout_log2) * g.s;
+        q.co &= g.cout - 1;
+        while (q.kw >= q.kw0 + g.kt * g.s) { q.kw -= g.kt * g.s; q.kh += g.s; }
+    }
+    __device__ __forceinline__ const float* ptr(Row ci, int, const Cur& q) const {
+        return w + (((q.kh * g.k + q.kw) * g.cin + ci) << cout_log2) + q.co;
     }
 };
 

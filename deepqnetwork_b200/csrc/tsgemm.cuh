@@ -15,8 +15,17 @@
 // Per k-block and CTA the shared-memory traffic drops from 2*(A+B) written + 3*(A+B) read to A written once and read
 // once (K-contiguous A) or nothing (M-contiguous A), plus 2*B written + 3*B read.
 //
-// Thread roles (544 threads): warps 0-15 producers/converters, then the epilogue (warp w owns TMEM lanes
-// 32*(w%4).., column group w/4); warp 16 allocates TMEM and one elected lane issues the MMAs.
+// Thread roles (544 threads).  The k-loop of the first version was bound by the INSTRUCTIONS its 16 producer warps
+// issued per k-block (every thread paid the barrier / stage / predicate bookkeeping for two 16-byte chunks), so the
+// roles are split and each thread amortises that bookkeeping over a whole row or 4-8 chunks:
+//   warps 0-3   A loaders (K-contiguous A): 8 cp.async chunks per thread and k-block, one shared k cursor;
+//               they run ahead of the converters by the depth of the ring
+//   warps 4-7   B producers: global -> registers (2-3 k-blocks ahead) -> hi/lo shared-memory tiles
+//   warps 8-15  A converters, two groups taking alternate k-blocks: thread == row, 128 bytes of the staging row (or 32
+//               coalesced scalar loads when A is M-contiguous; warps 0-3 then form a third group) -> hi/lo -> two
+//               tcgen05.st.x32
+//   warp 16     allocates TMEM; one elected lane issues the MMAs
+// and all 16 then run the epilogue (warp w owns TMEM lanes 32*(w%4).., column group w/4).
 #pragma once
 #include "tcgemm.cuh"
 
@@ -38,6 +47,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // the mbarrier receives one (pre-counted) arrival once all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -50,13 +74,17 @@ template <class Op>
 struct has_addr1<Op, decltype((void)static_cast<const float*>(std::declval<const Op&>().addr1(std::declval<const typename Op::Row&>(), 0, 0, 0)))> {
     static constexpr bool value = true;
 };
-template <class AOp> struct capable { static constexpr bool value = AOp::KCONTIG || has_addr1<AOp>::value; };
+template <class AOp> struct capable { static constexpr bool value = AOp::KCONTIG || has_addr1<AOp>::value; };  // M-contiguous: needs kstride()
+
+// operand functors whose per-chunk address needs im2col arithmetic ask for 8 loader warps instead of 4
+template <class Op, class = void> struct is_heavy { static constexpr bool value = false; };
+template <class Op> struct is_heavy<Op, decltype((void)Op::HEAVY)> { static constexpr bool value = Op::HEAVY; };
 
 constexpr int A_PITCH = 144;  // staging row pitch: 128 data bytes + 16, so that 8 consecutive rows hit 8 distinct 16-byte bank groups
 
-template <int BN, int NTERMS, bool A_DIRECT>
+template <int BN, int NTERMS>
 struct Plan {
-    static constexpr int A_STAGE = A_DIRECT ? 0 : BM * A_PITCH;
+    static constexpr int A_STAGE = BM * A_PITCH;  // K-contiguous: [128 rows][144]; M-contiguous: [32 k][512] fits too
     static constexpr int B_BYTES = Tile<BN>::BYTES;
     static constexpr int STAGE = A_STAGE + B_BYTES * (NTERMS == 3 ? 2 : 1);
     static constexpr int DCOLS = BN < 32 ? 32 : BN;
@@ -66,7 +94,7 @@ struct Plan {
     static constexpr int S0 = S_TMEM < S_SMEM ? S_TMEM : S_SMEM;
     static constexpr int STAGES = S0 > 6 ? 6 : S0;
     static_assert(STAGES >= 3, "pipeline too shallow");
-    static constexpr int DA = STAGES - 2 > 4 ? 4 : STAGES - 2;  // cp.async issue distance (k-blocks ahead of the convert)
+    static constexpr int NG = 2;                                // converter groups (take k-blocks round-robin)
     static constexpr int EPI_BYTES = BM * (BN + 4) * 4;         // coalesced-epilogue transpose tile
     static constexpr int PIPE_BYTES = STAGES * STAGE;
     static constexpr int BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + 256;
@@ -75,15 +103,15 @@ struct Plan {
 };
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
-__global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
-                                                            int kchunk, const float* __restrict__ zeros) {
-    constexpr bool A_DIRECT = !AOp::KCONTIG;
-    using P = Plan<BN, NTERMS, A_DIRECT>;
-    constexpr int S = P::STAGES;
+__global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
+                                                            int kchunk, const float* __restrict__ zeros,
+                                                            unsigned long long* __restrict__ dbg) {
+    constexpr bool A_MC = !AOp::KCONTIG;  // A contiguous along M: staged as [k][m], converters read a column
+    using P = Plan<BN, NTERMS>;
+    constexpr int S = P::STAGES, NG = P::NG;
+    constexpr int NLA = is_heavy<AOp>::value ? 8 : 4;  // loader warps; then 4 B-producer warps, 8 converter warps, 1 MMA warp
+    constexpr int MMA_WARP = NLA + 12;
     using TB = Tile<BN>;
-    using AA = Assign<true, BM>;  // cp.async assignment of the K-contiguous A path
-    using AB = Assign<BOp::KCONTIG, BN>;
-    constexpr int LA = A_DIRECT ? 1 : AA::N, LB = AB::N;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t bars = sbase + P::BYTES - 256;  // full[S], empty[S], afull[S], accum, tmem slot
@@ -99,17 +127,20 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
     const int kbeg = SPLIT ? z * kchunk : 0;
     const int kend = SPLIT ? min(K, kbeg + kchunk) : K;
     const int nkb = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+    const int ktot = kend - kbeg;
+    const bool cta0 = dbg && (blockIdx.x + blockIdx.y + blockIdx.z == 0);  // in-kernel timeline (dqn_debug_timeline)
+#define TS_STAMP(cond, kb, col) do { if (cta0 && (cond) && (kb) < 64) dbg[(kb) * 8 + (col)] = clock64(); } while (0)
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), PRODUCERS / 32);
+            mbar_init(full_bar(s), 8);      // 4 converter warps (the group that owns the block) + 4 B-producer warps
             mbar_init(empty_bar(s), 1);
-            mbar_init(afull_bar(s), PRODUCERS);
+            mbar_init(afull_bar(s), 32 * NLA);  // one pre-counted cp.async arrival per A-loader thread
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == PRODUCERS / 32) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(P::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -123,140 +154,192 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
     auto stage_b = [&](int s) { return sbase + s * P::STAGE + P::A_STAGE; };
     auto stage_blo = [&](int s) { return stage_b(s) + P::B_BYTES; };
     auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(P::DCOLS + s * P::ACOLS); };
+    // number of k-blocks in which k offset `koff` (inside a block) is still below kend
+    auto nvalid = [&](int koff) { return ktot > koff ? (ktot - koff + BK - 1) / BK : 0; };
 
-    if (warp < PRODUCERS / 32) {
-        // ---------------- producers / converters ----------------
-        const int grp = warp & 3, cgrp = warp >> 2;  // TMEM lane group (rows 32*grp..), column group (k 8*cgrp..)
-        const int my_row = grp * 32 + lane;          // the A row this thread converts
-        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
-        // K-contiguous A: cp.async assignment (coalesced along K)
-        int a_r[LA], a_k[LA];
-        typename AOp::Row a_row[LA];
-        // M-contiguous A: the thread's own row
-        const bool my_row_ok = m0 + my_row < M;
-        if constexpr (A_DIRECT) {
-            a_r[0] = my_row; a_k[0] = cgrp * 8;
-            a_row[0] = a.row(min(m0 + my_row, M - 1), z);
-        } else {
-#pragma unroll
-            for (int i = 0; i < LA; ++i) {
-                AA::rk(tid, i, a_r[i], a_k[i]);
-                a_row[i] = a.row(min(m0 + max(a_r[i], 0), M - 1), z);
-            }
-        }
-        int b_r[LB], b_k[LB];
-        uint32_t b_off[LB];
-        typename BOp::Row b_row[LB];
-#pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            AB::rk(tid, i, b_r[i], b_k[i]);
-            b_off[i] = b_r[i] >= 0 ? TB::off(b_r[i], b_k[i]) : 0;
-            b_row[i] = b.row(min(n0 + max(b_r[i], 0), N - 1), z);
-        }
-        constexpr int PF = 4;  // k-blocks of register-staged loads in flight per thread
-        float4 b_pf[PF][LB];
-        float a_pf[PF][A_DIRECT ? 8 : 1];
-
-        auto load_regs = [&](int kb, float4 (&bp)[LB], float (&ap)[A_DIRECT ? 8 : 1]) {
-            const int k0 = kbeg + kb * BK;
-            if constexpr (A_DIRECT) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = k0 + a_k[0] + j;
-                    // ragged edges read zeros: the select is on the address, nothing waits on the value here
-                    const float* src = (kb < nkb && my_row_ok && k < kend) ? a.addr1(a_row[0], m0 + my_row, k, z) : zeros;
-                    ap[j] = __ldg(src);
-                }
-            }
+    if (warp < MMA_WARP) {
+        const bool is_b = warp >= NLA && warp < NLA + 4;
+        const bool is_loader = warp < NLA;
+        if (is_b) {
+            // ================= B producers (warps 4-7) =================
+            const int t = tid - 32 * NLA, w4 = warp - NLA;
+            // K-contiguous: 16-byte chunk (t & 7) of rows (t >> 3) + 16 i.  N-contiguous: the transposing assignment of
+            // tcgemm.cuh folded onto 4 warps: k = 4*(w4 + 4 u) + (lane >> 3) % 4, rows 32 h + 4 (lane & 7) .. +3
+            constexpr int NH = BN / 32;
+            constexpr int LB = BOp::KCONTIG ? BN / 16 : 2 * NH;
+            const int koff0 = BOp::KCONTIG ? (t & 7) * 4 : w4 * 4 + ((lane >> 3) & 3);
+            int b_r[LB];
+            uint32_t b_off[LB];
+            bool b_ok[LB];
+            typename BOp::Row b_row[LB];
 #pragma unroll
             for (int i = 0; i < LB; ++i) {
-                const int r = n0 + b_r[i], k = k0 + b_k[i];
-                const float* src = (kb < nkb && b_r[i] >= 0 && r < N && k < kend) ? b.addr4(b_row[i], r, k, z) : nullptr;
-                bp[i] = __ldg(reinterpret_cast<const float4*>(src ? src : zeros));
+                const int koff = BOp::KCONTIG ? koff0 : koff0 + 16 * (i / NH);
+                b_r[i] = BOp::KCONTIG ? (t >> 3) + 16 * i : 32 * (i % NH) + 4 * (lane & 7);
+                b_off[i] = TB::off(b_r[i], koff);
+                b_ok[i] = n0 + b_r[i] < N;
+                b_row[i] = b.row(min(n0 + b_r[i], N - 1), z);
             }
-        };
-        auto issue_a = [&](int kb) {  // K-contiguous A: cp.async block kb into its staging tile
-            const int s = kb % S;
-            const int k0 = kbeg + kb * BK;
+            const int nv0 = nvalid(koff0), nv1 = nvalid(koff0 + 16);
+            typename BOp::Cur b_cur = b.cur(kbeg + koff0, z);
+            constexpr int PF = LB <= 4 ? 3 : 2;  // k-blocks of loads in flight per thread
+            float4 pf[PF][LB];
+            int kload = 0;
+            auto load_regs = [&](float4 (&bp)[LB]) {
 #pragma unroll
-            for (int i = 0; i < LA; ++i) {
-                if (a_r[i] >= 0) {
-                    const int r = m0 + a_r[i], k = k0 + a_k[i];
-                    const float* src = (r < M && k < kend) ? a.addr4(a_row[i], r, k, z) : nullptr;
-                    cp_async16(stage_a(s) + a_r[i] * A_PITCH + a_k[i] * 4, src ? src : zeros, src != nullptr);
+                for (int i = 0; i < LB; ++i) {
+                    const float* src = nullptr;
+                    if constexpr (BOp::KCONTIG) {
+                        if (b_ok[i] && kload < nv0) src = b.ptr(b_row[i], n0 + b_r[i], b_cur);
+                    } else {
+                        const bool second = i >= NH;
+                        if (b_ok[i] && kload < (second ? nv1 : nv0)) {
+                            src = b.ptr(b_row[i], n0 + b_r[i], b_cur);
+                            if (second) src += (size_t)16 * b.kstride();
+                        }
+                    }
+                    // ragged edges read 16 zero bytes: the select is on the ADDRESS, nothing waits on the value here
+                    bp[i] = __ldg(reinterpret_cast<const float4*>(src ? src : zeros));
                 }
-            }
-            cp_async_arrive_noinc(afull_bar(s));
-        };
-        auto sts_v = [&](uint32_t addr, const float4& v) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        };
-        auto sts_t = [&](uint32_t addr, const float4& v) {
-            asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16], %2;\n\tst.shared.f32 [%0+32], %3;\n\tst.shared.f32 [%0+48], %4;"
-                         ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        };
-        auto block = [&](int kb, float4 (&bp)[LB], float (&ap)[A_DIRECT ? 8 : 1]) {
-            const int s = kb % S;
-            if constexpr (!A_DIRECT) {
-                // keep DA blocks of A copies in flight; stage of block kb+DA was last used by block kb+DA-S
-                const int j = kb + P::DA;
-                if (j < nkb) {
-                    if (j >= S) mbar_wait(empty_bar(j % S), ((j / S) - 1) & 1);
-                    issue_a(j);
-                }
-            } else {
-                if (kb >= S) mbar_wait(empty_bar(s), ((kb / S) - 1) & 1);  // MMAs of block kb-S are done with stage s
-            }
-            // ---- A(kb) -> TMEM (hi = the raw fp32 word: the tensor core reads its top 19 bits; lo = the rest)
-            float hi[8];
-            if constexpr (A_DIRECT) {
+                b.next(b_cur);
+                ++kload;
+            };
+            auto sts_v = [&](uint32_t addr, const float4& v) {
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            };
+            auto sts_t = [&](uint32_t addr, const float4& v) {
+                asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+16], %2;\n\tst.shared.f32 [%0+32], %3;\n\tst.shared.f32 [%0+48], %4;"
+                             ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            };
+            int s = 0, ph = 0;
+            auto block = [&](int kb, float4 (&bp)[LB]) {
+                if (kb >= S) mbar_wait(empty_bar(s), ph ^ 1);  // MMAs of block kb-S are done with stage s
+                TS_STAMP(t == 0, kb, 4);
+                const uint32_t hi_t = stage_b(s), lo_t = stage_blo(s);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hi[j] = ap[j];
-            } else {
-                mbar_wait(afull_bar(s), (kb / S) & 1);  // every producer's copies for this block have landed
-                const uint32_t src = stage_a(s) + my_row * A_PITCH + cgrp * 32;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(hi[0]), "=f"(hi[1]), "=f"(hi[2]), "=f"(hi[3]) : "r"(src));
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(hi[4]), "=f"(hi[5]), "=f"(hi[6]), "=f"(hi[7]) : "r"(src));
-            }
-            const uint32_t ta = tmem_a(s) + lane_base + (uint32_t)(cgrp * 8);
-            tmem_st8(ta, hi);
-            if (NTERMS == 3) {
-                float lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) lo[j] = lo_part(hi[j]);
-                tmem_st8(ta + BK, lo);
-            }
-            // ---- B(kb) -> shared memory tiles (hi / lo), K-major no-swizzle UMMA layout
-#pragma unroll
-            for (int i = 0; i < LB; ++i) {
-                if (b_r[i] >= 0) {
+                for (int i = 0; i < LB; ++i) {
                     const float4 v = bp[i];
                     const float4 l = make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
-                    if (BOp::KCONTIG) { sts_v(stage_b(s) + b_off[i], v); if (NTERMS == 3) sts_v(stage_blo(s) + b_off[i], l); }
-                    else { sts_t(stage_b(s) + b_off[i], v); if (NTERMS == 3) sts_t(stage_blo(s) + b_off[i], l); }
+                    if (BOp::KCONTIG) { sts_v(hi_t + b_off[i], v); if (NTERMS == 3) sts_v(lo_t + b_off[i], l); }
+                    else { sts_t(hi_t + b_off[i], v); if (NTERMS == 3) sts_t(lo_t + b_off[i], l); }
+                }
+                // release-arrive, one per warp; the generic->async proxy fence runs on the MMA thread after its acquire
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+                TS_STAMP(t == 0, kb, 5);
+                if (++s == S) { s = 0; ph ^= 1; }
+                load_regs(bp);
+            };
+#pragma unroll
+            for (int p = 0; p < PF; ++p) load_regs(pf[p]);
+            for (int kb = 0; kb < nkb; kb += PF) {
+#pragma unroll
+                for (int p = 0; p < PF; ++p)
+                    if (kb + p < nkb) block(kb + p, pf[p]);
+            }
+        } else if (is_loader) {
+            // ================= A loaders (warps 0-3): cp.async ring, S-1 k-blocks (16 KB each) in flight =================
+            int sj = 0, phj = 0;
+            if constexpr (!A_MC) {
+                // K-contiguous A: chunk c of rows r0 + RS i (8 lanes cover 128 contiguous bytes); staging [row][144]
+                constexpr int RS = 4 * NLA, NCH = 32 / NLA;  // row step, chunks per thread
+                const int c = tid & 7, r0 = tid >> 3;
+                typename AOp::Row a_row[NCH];
+                unsigned ok = 0;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int r = m0 + r0 + RS * i;
+                    if (r < M) ok |= 1u << i;
+                    a_row[i] = a.row(min(r, M - 1), z);
+                }
+                const int nv = nvalid(c * 4);
+                typename AOp::Cur cur = a.cur(kbeg + c * 4, z);
+                const uint32_t dst0 = (uint32_t)(r0 * A_PITCH + c * 16);
+                for (int j = 0; j < nkb; ++j) {
+                    if (j >= S) mbar_wait(empty_bar(sj), phj ^ 1);  // stage sj was last used by block j-S
+                    TS_STAMP(tid == 0, j, 0);
+                    const uint32_t dst = stage_a(sj) + dst0;
+                    const unsigned okj = j < nv ? ok : 0u;
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        const float* src = ((okj >> i) & 1u) ? a.ptr(a_row[i], m0 + r0 + RS * i, cur) : nullptr;
+                        cp_async16(dst + i * RS * A_PITCH, src ? src : zeros, src != nullptr);
+                    }
+                    cp_async_arrive_noinc(afull_bar(sj));
+                    TS_STAMP(tid == 0, j, 1);
+                    a.next(cur);
+                    if (++sj == S) { sj = 0; phj ^= 1; }
+                }
+            } else {
+                // M-contiguous A: 16-byte chunk mq along M (a warp covers 512 contiguous bytes of one k), k rows
+                // (tid >> 5) + 4 i; staging [k][512 bytes]
+                static_assert(NLA == 4, "M-contiguous loader is written for 4 warps");
+                const int mq = tid & 31, k0 = tid >> 5;
+                const bool m_ok = m0 + 4 * mq < M;
+                typename AOp::Row a_row = a.row(min(m0 + 4 * mq, M - 1), z);
+                typename AOp::Cur cur = a.cur(kbeg + k0, z);
+                const size_t kstep = (size_t)4 * a.kstride();
+                const uint32_t dst0 = (uint32_t)(k0 * 512 + mq * 16);
+                int left = ktot - k0;  // k rows of this thread still inside [kbeg, kend): i valid iff 4 i < left
+                for (int j = 0; j < nkb; ++j) {
+                    if (j >= S) mbar_wait(empty_bar(sj), phj ^ 1);
+                    TS_STAMP(tid == 0, j, 0);
+                    const uint32_t dst = stage_a(sj) + dst0;
+                    const float* p = a.ptr(a_row, m0 + 4 * mq, cur);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool v = m_ok && 4 * i < left;
+                        cp_async16(dst + i * 4 * 512, v ? p + i * kstep : zeros, v);
+                    }
+                    cp_async_arrive_noinc(afull_bar(sj));
+                    TS_STAMP(tid == 0, j, 1);
+                    a.next(cur);
+                    left -= BK;
+                    if (++sj == S) { sj = 0; phj ^= 1; }
                 }
             }
-            // ---- publish: TMEM stores complete, then release-arrive (one per warp); the generic->async proxy fence
-            // for the B tile is executed by the MMA thread after its acquire
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
-            load_regs(kb + PF, bp, ap);
-        };
-        if constexpr (!A_DIRECT) {
+        } else {
+            // ================= A converters: thread == row, the two groups take alternate k-blocks =================
+            const int grp = warp & 3;
+            const int g = (warp - NLA - 4) >> 2;  // converter group
+            const int my_row = grp * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+            int s = g % S, ph = 0;
+            for (int kb = g; kb < nkb; kb += NG) {
+                if (kb >= S) mbar_wait(empty_bar(s), ph ^ 1);  // TMEM stage s is free again
+                mbar_wait(afull_bar(s), ph);                   // every loader's copies for this block have landed
+                TS_STAMP(grp == 0 && lane == 0, kb, 2);
+                float hi[32];
+                if constexpr (!A_MC) {
+                    const uint32_t src = stage_a(s) + my_row * A_PITCH;  // 8 consecutive rows -> 8 distinct bank groups
 #pragma unroll
-            for (int j = 0; j < P::DA; ++j)
-                if (j < nkb) issue_a(j);
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + c * 16));
+                } else {
+                    const uint32_t src = stage_a(s) + my_row * 4;        // lanes read consecutive words of one k row
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[j]) : "r"(src + j * 512));
+                }
+                // hi = the raw fp32 word (the tensor core reads its top 19 bits); lo = what that drops
+                const uint32_t ta = tmem_a(s) + lane_base;
+                tmem_st32(ta, hi);
+                if (NTERMS == 3) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+                    tmem_st32(ta + BK, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                TS_STAMP(grp == 0 && lane == 0, kb, 3);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+                s += NG; if (s >= S) { s -= S; ph ^= 1; }
+            }
         }
-#pragma unroll
-        for (int p = 0; p < PF; ++p) load_regs(p, b_pf[p], a_pf[p]);
-        for (int kb = 0; kb < nkb; kb += PF) {
-#pragma unroll
-            for (int p = 0; p < PF; ++p)
-                if (kb + p < nkb) block(kb + p, b_pf[p], a_pf[p]);
-        }
-        // ---------------- epilogue ----------------
+        // ---------------- epilogue (warps 0-15) ----------------
+        if (warp < PRODUCERS / 32) {
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
@@ -336,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
                 if (m < M && n0 + col < N) epi.template store<16>(m, n0 + col, v, z);
             }
         }
+        }
         tc_fence_before();
     } else {
         // ---------------- MMA issuer ----------------
@@ -344,9 +428,10 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         const uint64_t db0 = TB::desc(stage_b(0), 0), dbl0 = TB::desc(stage_blo(0), 0);
         constexpr uint64_t STAGE16 = P::STAGE >> 4, KS16 = (2 * LBO) >> 4;  // descriptor address units (16 bytes)
+        int s = 0, ph = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % S;
-            mbar_wait(full_bar(s), (kb / S) & 1);   // acquire: B tile stores and A TMEM stores of this block
+            mbar_wait(full_bar(s), ph);             // acquire: B tile stores and A TMEM stores of this block
+            TS_STAMP(lane == 0, kb, 6);
             fence_proxy_async();                      // B tile: generic -> async proxy
             tc_fence_after();
             const uint64_t so = (uint64_t)s * STAGE16;
@@ -369,12 +454,14 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
                 mma_commit(empty_bar(s));                    // frees the stage (smem B, staging A, TMEM A) when these retire
                 if (kb == nkb - 1) mma_commit(accum_bar);    // accumulator complete
             }
+            TS_STAMP(lane == 0, kb, 7);
             __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1; }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == PRODUCERS / 32) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P::TMEM_COLS));
     }
@@ -382,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) tsgemm_kernel(const AOp a, const B
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
-    using P = Plan<BN, NTERMS, !AOp::KCONTIG>;
+    using P = Plan<BN, NTERMS>;
     auto kern = tsgemm_kernel<BN, NTERMS, SPLIT, AOp, BOp, Epi>;
     static bool configured = false;  // one per template instantiation
     if (!configured) {
@@ -390,9 +477,10 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    kern<<<grid, THREADS, P::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16);
+    kern<<<grid, (is_heavy<AOp>::value ? 21 : 17) * 32, P::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16, h->tc_dbg);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
 }
 
+#undef TS_STAMP
 }  // namespace ts
