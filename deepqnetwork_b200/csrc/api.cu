@@ -129,8 +129,9 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             h->wg_part_floats = std::max<int64_t>(h->wg_part_floats, (int64_t)64 * (g.k * g.k * g.cin + 4) * g.cout);
         }
         dmalloc(h->wg_part, (size_t)h->wg_part_floats);
-        dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4);
+        dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4); dmalloc(h->opt_ticket, 1);
         DQN_CUDA_OK(cudaMemsetAsync(h->zeros16, 0, 16, h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(h->opt_ticket, 0, 4, h->stream));
         {
             const float one[4] = {1.f, 0.f, 0.f, 0.f};
             DQN_CUDA_OK(cudaMemcpyAsync(h->ones_row, one, 16, cudaMemcpyHostToDevice, h->stream));
@@ -161,7 +162,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions, h->in_rewards, h->in_cont, h->in_isw,
                     h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
@@ -584,8 +585,11 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     const int A = h->net.A;
     const float* xf = nullptr;
     if (h->cfg.math_mode != DQN_MATH_FP32) {
-        prof_mark(h, "u8_to_f32");
-        launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S);
+        if (!(h->xf_from_gather && states2 == h->b_states)) {  // host-fed batch: convert here; sampled batch: gather did
+            prof_mark(h, "u8_to_f32");
+            launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S);
+        }
+        h->xf_from_gather = false;
         xf = h->x_f32;
     }
     h->fork_used = 0;

@@ -82,69 +82,80 @@ void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q
     h->launches++;
 }
 
-// dH (gated by the hidden ReLU), head weight/bias grads and hidden bias grads: thread per hidden column
-// (coalesced across the CTA), a serial walk over the batch with fixed summation order (deterministic).
+// dH (gated by the hidden ReLU), head weight/bias grads and hidden bias grads.  CTA = 32 hidden columns x 32 samples:
+// every (sample, column) is one thread (coalesced along the column), the sums over the batch are then formed from
+// shared memory by one thread per (column, output) in ascending sample order with the same fmaf chain a serial walk
+// would use (deterministic).
 template <int AMAX>
-__global__ void __launch_bounds__(128) head_backward_kernel(int n, int NH, int hidden, int A, int dueling,
-                                                            const float* __restrict__ hid, const float* __restrict__ dq,
-                                                            const uint8_t* __restrict__ actions,
-                                                            const float* __restrict__ hw0, const float* __restrict__ hw1,
-                                                            float* __restrict__ d_hid, float* __restrict__ g_hw0,
-                                                            float* __restrict__ g_hb0, float* __restrict__ g_hw1,
-                                                            float* __restrict__ g_hb1, float* __restrict__ g_fb0,
-                                                            float* __restrict__ g_fb1) {
+__global__ void __launch_bounds__(1024) head_backward_kernel(int n, int NH, int hidden, int A, int dueling,
+                                                             const float* __restrict__ hid, const float* __restrict__ dq,
+                                                             const uint8_t* __restrict__ actions,
+                                                             const float* __restrict__ hw0, const float* __restrict__ hw1,
+                                                             float* __restrict__ d_hid, float* __restrict__ g_hw0,
+                                                             float* __restrict__ g_hb0, float* __restrict__ g_hw1,
+                                                             float* __restrict__ g_hb1, float* __restrict__ g_fb0,
+                                                             float* __restrict__ g_fb1) {
     extern __shared__ float sm[];
-    float* s_dq = sm;                                     // [n]
-    uint8_t* s_act = reinterpret_cast<uint8_t*>(sm + n);  // [n]
+    float* s_dh = sm;                 // [32][33]
+    float* s_hv = sm + 32 * 33;       // [32][33]
+    float* s_dq = sm + 2 * 32 * 33;   // [n]
+    uint8_t* s_act = reinterpret_cast<uint8_t*>(s_dq + n);  // [n]
     for (int i = threadIdx.x; i < n; i += blockDim.x) { s_dq[i] = dq[i]; s_act[i] = actions[i]; }
     __syncthreads();
     const float invA = 1.0f / (float)A;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < NH) {
-        const int st = col >= hidden, j = st ? col - hidden : col;
-        float gb = 0.f;
-        if (!st) {
-            float w[AMAX], gw[AMAX];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + c;           // NH is a multiple of 32
+    const int st = col >= hidden, j = st ? col - hidden : col;
+    float w[AMAX];
 #pragma unroll
-            for (int a = 0; a < AMAX; ++a) { w[a] = a < A ? hw0[j * A + a] : 0.f; gw[a] = 0.f; }
-#pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-                const float hv = hid[(size_t)i * NH + col];
-                const float d = s_dq[i];
+    for (int a = 0; a < AMAX; ++a) w[a] = (!st && a < A) ? hw0[j * A + a] : 0.f;
+    const float w1 = st ? hw1[j] : 0.f;
+    float acc = 0.f;  // r == 0: hidden bias grad; r == a+1: head weight grad for output a (value stream: r == 1)
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + r;
+        float hv = 0.f, dh = 0.f;
+        if (i < n) {
+            hv = hid[(size_t)i * NH + col];
+            const float d = s_dq[i];
+            float g;
+            if (!st) {
                 const int ai = s_act[i];
-                float g = 0.f;
+                g = 0.f;
 #pragma unroll
-                for (int a = 0; a < AMAX; ++a) {
+                for (int a = 0; a < AMAX; ++a)
                     if (a < A) {
                         // dQ = one_hot(a_i) * dq ; dueling: dA = dQ - mean_a(dQ)
                         const float da = dueling ? d * ((a == ai ? 1.f : 0.f) - invA) : (a == ai ? d : 0.f);
                         g = fmaf(da, w[a], g);
-                        gw[a] = fmaf(hv, da, gw[a]);
                     }
-                }
-                const float dh = hv > 0.f ? g : 0.f;
-                d_hid[(size_t)i * NH + col] = dh;
-                gb += dh;
+            } else {
+                g = d * w1;  // dV = sum_a dQ = dq
             }
-#pragma unroll
-            for (int a = 0; a < AMAX; ++a) if (a < A) g_hw0[j * A + a] = gw[a];
-            g_fb0[j] = gb;
-        } else {
-            const float w = hw1[j];
-            float gw = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-                const float hv = hid[(size_t)i * NH + col];
-                const float d = s_dq[i];  // dV = sum_a dQ = dq
-                const float dh = hv > 0.f ? d * w : 0.f;
-                d_hid[(size_t)i * NH + col] = dh;
-                gw = fmaf(hv, d, gw);
-                gb += dh;
-            }
-            g_hw1[j] = gw;
-            g_fb1[j] = gb;
+            dh = hv > 0.f ? g : 0.f;
+            d_hid[(size_t)i * NH + col] = dh;
         }
+        s_dh[r * 33 + c] = dh;
+        s_hv[r * 33 + c] = hv;
+        __syncthreads();
+        const int cnt = min(32, n - i0);
+        if (r == 0) {
+            for (int q = 0; q < cnt; ++q) acc += s_dh[q * 33 + c];
+        } else if (!st && r <= A) {
+            const int a = r - 1;
+            for (int q = 0; q < cnt; ++q) {
+                const float d = s_dq[i0 + q];
+                const int ai = s_act[i0 + q];
+                const float da = dueling ? d * ((a == ai ? 1.f : 0.f) - invA) : (a == ai ? d : 0.f);
+                acc = fmaf(s_hv[q * 33 + c], da, acc);
+            }
+        } else if (st && r == 1) {
+            for (int q = 0; q < cnt; ++q) acc = fmaf(s_hv[q * 33 + c], s_dq[i0 + q], acc);
+        }
+        __syncthreads();
     }
+    if (r == 0) { if (st) g_fb1[j] = acc; else g_fb0[j] = acc; }
+    else if (!st && r <= A) g_hw0[j * A + (r - 1)] = acc;
+    else if (st && r == 1) g_hw1[j] = acc;
     if (blockIdx.x == 0 && threadIdx.x <= A) {  // head biases
         const int a = threadIdx.x;
         float s = 0.f;
@@ -165,10 +176,10 @@ void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions) {
     const NetDesc& net = h->net;
     const float* P = h->online;
     float* G = h->grads;
-    const size_t smem = (size_t)n * 4 + ((n + 3) / 4) * 4;
-    const int threads = 32;  // many small CTAs: the per-thread work is a serial walk over the batch
+    const size_t smem = (size_t)2 * 32 * 33 * 4 + (size_t)n * 4 + ((n + 3) / 4) * 4;
+    DQN_REQUIRE(net.NH % 32 == 0 && net.A <= 31, "head backward tiling");
 #define HEAD_BWD(AMAX)                                                                                                  \
-    head_backward_kernel<AMAX><<<ceil_div(net.NH, threads), threads, smem, h->stream>>>(                                \
+    head_backward_kernel<AMAX><<<net.NH / 32, 1024, smem, h->stream>>>(                                                 \
         n, net.NH, net.hidden, net.A, net.dueling, h->acts_on.hid, h->b_dq, actions, P + net.off_hd_w[0],              \
         P + net.off_hd_w[1], h->d_hid, G + net.off_hd_w[0], G + net.off_hd_b[0], G + net.off_hd_w[1],                  \
         G + net.off_hd_b[1], G + net.off_fc_b[0], G + net.off_fc_b[1])

@@ -77,6 +77,7 @@ struct dqn_learner {
         int has_max_weight;
         unsigned long long rng_counter;
     };
+    unsigned int* opt_ticket = nullptr;  // last-CTA-done counter of optimizer_tail_kernel
     Scalars* d_sc = nullptr;
     Scalars* h_sc = nullptr;  // pinned mirror for reads
     // host-owned sizes mirrored on the device so that captured graphs see current values
@@ -129,6 +130,7 @@ struct dqn_learner {
     float* zeros16 = nullptr;   // 16 zero bytes (cp.async dummy source)
     float* ones_row = nullptr;  // {1,0,0,0}: the bias row appended to conv wgrad A^T
     float* x_f32 = nullptr;     // u8 batch converted to f32 (x/255) for cp.async loaders: [2*max_rows][S]
+    bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
     // staging
     uint8_t* dev_stage = nullptr;
     size_t dev_stage_bytes = 0;

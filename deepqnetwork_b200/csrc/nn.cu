@@ -267,28 +267,40 @@ struct OpConvWgradABias {
 };
 
 // grads[w_off + i] = sum_z part[z][i] for i < mreal*N ; grads[b_off + n] = sum_z part[z][mreal][n]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int Z, int mreal, int N, float* __restrict__ gw,
-                                    float* __restrict__ gb) {
+// CTA = 64 float4 outputs x 4 z-groups: each group adds its contiguous quarter of the partials in z order (8 loads in
+// flight), the four group sums are then added in group order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int Z, int mreal, int N,
+                                                           float* __restrict__ gw, float* __restrict__ gb) {
+    __shared__ float4 s_sum[4][64];
     const int total4 = (mreal + 1) * N / 4;
     const size_t zstride = (size_t)(mreal + 4) * N;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
+    const int zq = (Z + 3) / 4, zb = grp * zq, ze = min(Z, zb + zq);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total4) {
         const float* p = part + (size_t)i * 4;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        int z = 0;
-        for (; z + 8 <= Z; z += 8) {  // eight partial loads in flight, summed in z order (deterministic)
+        int z = zb;
+        for (; z + 8 <= ze; z += 8) {
             float4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(p + (size_t)(z + j) * zstride);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
         }
-        for (; z < Z; ++z) {
+        for (; z < ze; ++z) {
             const float4 v = *reinterpret_cast<const float4*>(p + (size_t)z * zstride);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
-        const int e = i * 4;
-        if (e < mreal * N) *reinterpret_cast<float4*>(gw + e) = s;
-        else *reinterpret_cast<float4*>(gb + (e - mreal * N)) = s;
+    }
+    s_sum[grp][e] = s;
+    __syncthreads();
+    if (grp == 0 && i < total4) {
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { const float4 v = s_sum[q][e]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        const int el = i * 4;
+        if (el < mreal * N) *reinterpret_cast<float4*>(gw + el) = s;
+        else *reinterpret_cast<float4*>(gb + (el - mreal * N)) = s;
     }
 }
 
@@ -368,7 +380,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             gemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
             static const char* kR[3] = {"conv1_wgrad_reduce", "conv2_wgrad_reduce", "conv3_wgrad_reduce"};
             prof_mark(h, kR[l]);
-            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 64), 64, 0, h->stream>>>(part, Z, mreal, N,
+            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 64), 256, 0, h->stream>>>(part, Z, mreal, N,
                                                                                           G + net.off_cw[l], G + net.off_cb[l]);
             DQN_CUDA_OK(cudaGetLastError());
             h->launches++;

@@ -67,33 +67,79 @@ void launch_optimizer_fc(dqn_learner* h) {
     if (net.dueling) optimizer_range(h, net.off_fc_w[1], net.off_fc_w[1] + fcw);
 }
 
-// skip_fc: the two dense hidden kernels were already updated in the wgrad epilogue (EpiFcWgradAdam)
-void launch_optimizer(dqn_learner* h, bool skip_fc) {
-    const NetDesc& net = h->net;
-    if (!skip_fc) return optimizer_range(h, 0, net.slab);
-    const int64_t fcw = (int64_t)net.flat * net.hidden;
-    optimizer_range(h, 0, net.off_fc_w[0]);
-    if (net.dueling) {
-        optimizer_range(h, net.off_fc_w[0] + fcw, net.off_fc_w[1]);
-        optimizer_range(h, net.off_fc_w[1] + fcw, net.slab);
-    } else {
-        optimizer_range(h, net.off_fc_w[0] + fcw, net.slab);
+// Up to three slab ranges in ONE launch, followed by the step bookkeeping (global_step += 1, beta powers,
+// RNG counter: AdamOptimizer._finish / rl/deep_q_model.py:391) done by whichever CTA finishes last -- the betas are
+// read by every CTA before its ticket is taken, so the update cannot race with them.
+struct OptRanges { long long beg4[3], n4[3]; int count; };
+
+__global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                                             const float4* __restrict__ g, OptRanges rg, float lr, float mom,
+                                                             int use_momentum, dqn_learner::Scalars* sc,
+                                                             unsigned int* __restrict__ ticket) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    for (int q = 0; q < rg.count; ++q) {
+        const size_t o = (size_t)rg.beg4[q], n4 = (size_t)rg.n4[q];
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 gg = g[o + i];
+            float4 mm = m[o + i], pp = p[o + i];
+            if (use_momentum) {
+#define MOM1(c) mm.c = mm.c * mom + gg.c; pp.c = pp.c - (gg.c * lr + mm.c * mom * lr);
+                MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+            } else {
+                float4 vv = v[o + i];
+#define ADAM1(c) mm.c = mm.c + (gg.c - mm.c) * omb1; vv.c = vv.c + (gg.c * gg.c - vv.c) * omb2; \
+                 pp.c = pp.c - (mm.c * lr_t) / (sqrtf(vv.c) + eps);
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                v[o + i] = vv;
+            }
+            m[o + i] = mm; p[o + i] = pp;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0;
+            sc->step += 1;
+            if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
+            sc->rng_counter += 1;
+        }
     }
 }
 
-// after the optimizer: global_step += 1, beta powers advance (AdamOptimizer._finish), RNG counter advances
-__global__ void advance_step_kernel(dqn_learner::Scalars* sc, int adam) {
-    sc->step += 1;
-    if (adam) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
-    sc->rng_counter += 1;
+// skip_fc: the two dense hidden kernels were already updated (inside backward, or in the wgrad epilogue)
+void launch_optimizer(dqn_learner* h, bool skip_fc) {
+    const NetDesc& net = h->net;
+    OptRanges rg; rg.count = 0;
+    auto add = [&](int64_t beg, int64_t end) {
+        if (end <= beg) return;
+        rg.beg4[rg.count] = beg / 4; rg.n4[rg.count] = (end - beg) / 4; rg.count++;
+    };
+    const int64_t fcw = (int64_t)net.flat * net.hidden;
+    if (!skip_fc) add(0, net.slab);
+    else {
+        add(0, net.off_fc_w[0]);
+        if (net.dueling) { add(net.off_fc_w[0] + fcw, net.off_fc_w[1]); add(net.off_fc_w[1] + fcw, net.slab); }
+        else add(net.off_fc_w[0] + fcw, net.slab);
+    }
+    long long most = 1;
+    for (int q = 0; q < rg.count; ++q) most = std::max(most, rg.n4[q]);
+    const int blocks = (int)std::min<long long>((most + 255) / 256, (long long)h->sm_count * 8);
+    optimizer_tail_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online, (float4*)h->slot_m, (float4*)h->slot_v,
+                                                        (const float4*)h->grads, rg, (float)h->cfg.learning_rate,
+                                                        (float)h->cfg.momentum, h->cfg.use_momentum, h->d_sc, h->opt_ticket);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
 }
 
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
 
+// the step bookkeeping now rides on the optimizer launch; what is left is the optional priority write-back
 void launch_post_step(dqn_learner* h, int per_update) {
-    advance_step_kernel<<<1, 1, 0, h->stream>>>(h->d_sc, h->cfg.use_momentum ? 0 : 1);
-    DQN_CUDA_OK(cudaGetLastError());
-    h->launches++;
     // replay_sampler.update_sum_tree(tree_idxes, _make_priority(losses))  (deep_q_agent.py:341-347)
     if (per_update) launch_tree_update(h, h->B, h->b_tree_idx, h->b_newprio, 1);
 }

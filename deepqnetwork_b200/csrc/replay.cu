@@ -14,7 +14,7 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ states, const uin
                                    const long long* __restrict__ rows, int n, size_t state_bytes,
                                    uint8_t* __restrict__ b_states, uint8_t* __restrict__ b_actions,
                                    uint8_t* __restrict__ b_rewards, uint8_t* __restrict__ b_cont,
-                                   __half* __restrict__ b_losses) {
+                                   __half* __restrict__ b_losses, float4* __restrict__ x_f32) {
     const int slot = blockIdx.y;
     const int j = slot < n ? slot : slot - n;
     const long long row = rows[j];
@@ -35,6 +35,22 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ states, const uin
         int v = v0 + k * blockDim.x;
         if (v < nvec) dst[v] = r[k];
     }
+    if (x_f32) {
+        // tensor-core path: the same bytes as f32 / 255 (tf.cast + tf.divide, rl/deep_q_model.py:226-227), written here so
+        // that the step needs no separate conversion pass over the batch
+        float4* xd = x_f32 + ((size_t)slot * state_bytes >> 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int v = v0 + k * blockDim.x;
+            if (v < nvec) {
+                const uint32_t w[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xd[(size_t)v * 4 + q] = make_float4(u8_to_unit(w[q] & 255u), u8_to_unit((w[q] >> 8) & 255u),
+                                                        u8_to_unit((w[q] >> 16) & 255u), u8_to_unit(w[q] >> 24));
+            }
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0 && slot < n) {
         b_actions[j] = actions[row];
         b_rewards[j] = rewards[row];
@@ -50,9 +66,11 @@ void launch_gather(dqn_learner* h, const long long* d_rows, int n) {
     // the batch buffer keeps s in rows [0,n) and s' in rows [n,2n): one contiguous [2n,S] input for the online tower
     gather_rows_kernel<<<grid, threads, 0, h->stream>>>(h->r_states, h->r_next, h->r_actions, h->r_rewards, h->r_cont,
                                                         h->r_losses, d_rows, n, h->state_bytes, h->b_states,
-                                                        h->b_actions, h->b_rewards, h->b_cont, h->b_losses);
+                                                        h->b_actions, h->b_rewards, h->b_cont, h->b_losses,
+                                                        h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : nullptr);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
+    h->xf_from_gather = h->cfg.math_mode != DQN_MATH_FP32;
 }
 
 // ---- synthetic fill: states/next_states ~ U{0..255}; actions ~ U{0..A-1};
