@@ -240,6 +240,7 @@ def main():
                     help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
     ap.add_argument('--no-fuse', action='store_true', help='ablation: optimizer as a separate pass over the gradient slab')
     ap.add_argument('--fuse', action='store_true', help='ablation: Adam for the dense kernels in the dense wgrad epilogue')
+    ap.add_argument('--no-pdl', action='store_true', help='ablation: no programmatic dependent launch between consecutive kernels')
     ap.add_argument('--no-overlap', action='store_true', help='ablation: single stream, no forked branches in the step graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -306,6 +307,8 @@ def main():
         L.set_option('fuse_fc_adam', 1)
     if args.no_overlap:
         L.set_option('overlap', 0)
+    if args.no_pdl:
+        L.set_option('pdl', 0)
     L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)
     L.set_tower(init_tower_params(shapes, 43 + 2 * rank), 1)
     L.replay_fill_synthetic(args.capacity, seed=1234 + rank)

@@ -112,7 +112,16 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         const size_t R = (size_t)h->max_rows;
         dmalloc(h->b_states, 2 * R * h->state_bytes); dmalloc(h->in_states, 2 * R * h->state_bytes);
         dmalloc(h->b_actions, R); dmalloc(h->b_rewards, R); dmalloc(h->b_cont, R); dmalloc(h->b_losses, R);
-        dmalloc(h->in_actions, R); dmalloc(h->in_rewards, R); dmalloc(h->in_cont, R); dmalloc(h->in_isw, R);
+        {   // the small per-sample inputs of a host-fed batch share one device block and one pinned staging block, so
+            // that a batch upload is the two state copies plus ONE small copy
+            const size_t Rp = (R + 15) / 16 * 16;
+            h->in_small_bytes = 3 * Rp + 4 * R;
+            uint8_t* blk = nullptr;
+            dmalloc(blk, h->in_small_bytes);
+            h->in_actions = blk; h->in_rewards = blk + Rp; h->in_cont = blk + 2 * Rp; h->in_isw = reinterpret_cast<float*>(blk + 3 * Rp);
+            DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_in_small, std::max<size_t>(h->in_small_bytes, 16 * R), cudaHostAllocDefault));
+            DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+        }
         dmalloc(h->b_tree_idx, R); dmalloc(h->b_data_idx, R); dmalloc(h->b_mem_idx, R);
         dmalloc(h->b_prio, R); dmalloc(h->b_isw64, R); dmalloc(h->b_isw, R); dmalloc(h->b_u, R);
         dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_losses_out, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
@@ -159,7 +168,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->prof_graph) cudaGraphExecDestroy(h->prof_graph);
     void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
-                    h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions, h->in_rewards, h->in_cont, h->in_isw,
+                    h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
                     h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket};
@@ -169,10 +178,13 @@ extern "C" int dqn_destroy(dqn_learner* h) {
         cudaFree(t->fc_part); cudaFree(t->hid); cudaFree(t->q);
     }
     if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_in_small) cudaFreeHost(h->h_in_small);
+    if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
+    if (h->batch_graph) cudaGraphExecDestroy(h->batch_graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -190,7 +202,7 @@ extern "C" int dqn_set_stream(dqn_learner* h, void* s) {
     API_BEGIN(h)
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     h->stream = s ? (cudaStream_t)s : h->own_stream;
-    h->graph_valid = false;
+    h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }
@@ -446,12 +458,26 @@ extern "C" int dqn_tree_add(dqn_learner* h, int64_t n, const float* scores, cons
 
 extern "C" int dqn_tree_update(dqn_learner* h, int64_t n, const int64_t* idx, const float* scores, int32_t store_losses) {
     API_BEGIN(h)
+    for (int64_t j = 0; j < n; ++j) DQN_REQUIRE(idx[j] >= h->cap - 1 && idx[j] < 2 * h->cap - 1, "tree_idx is not a leaf");
+    if (n <= h->max_rows) {
+        // the per-step write-back (B rows): indices and scores ride one pinned staging copy, no host sync -- the
+        // update is ordered on the handle's stream like every later call
+        DQN_CUDA_OK(cudaEventSynchronize(h->stage_ev));
+        uint8_t* hs = h->h_in_small;
+        memcpy(hs, idx, (size_t)n * 8);
+        memcpy(hs + (size_t)n * 8, scores, (size_t)n * 4);
+        long long* d_i = (long long*)h->dev_stage;
+        float* d_s = (float*)(h->dev_stage + (size_t)n * 8);
+        DQN_CUDA_OK(cudaMemcpyAsync(d_i, hs, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+        DQN_CUDA_OK(cudaEventRecord(h->stage_ev, h->stream));
+        launch_tree_update(h, (int)n, d_i, d_s, store_losses);
+        return 0;
+    }
     const int64_t max_chunk = (int64_t)(h->dev_stage_bytes / 16);
     for (int64_t done = 0; done < n;) {
         const int64_t m = std::min(n - done, max_chunk);
         long long* d_i = (long long*)h->dev_stage;
         float* d_s = (float*)(h->dev_stage + h->dev_stage_bytes / 2);
-        for (int64_t j = 0; j < m; ++j) DQN_REQUIRE(idx[done + j] >= h->cap - 1 && idx[done + j] < 2 * h->cap - 1, "tree_idx is not a leaf");
         DQN_CUDA_OK(cudaMemcpyAsync(d_i, idx + done, m * 8, cudaMemcpyHostToDevice, h->stream));
         DQN_CUDA_OK(cudaMemcpyAsync(d_s, scores + done, m * 4, cudaMemcpyHostToDevice, h->stream));
         launch_tree_update(h, (int)m, d_i, d_s, store_losses);
@@ -670,7 +696,7 @@ static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* ro
         if (u) DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, h->B * 8, cudaMemcpyHostToDevice, h->stream));
         launch_tree_sample(h, h->B, u ? 0 : 1, -1.0);
         prof_mark(h, "gather");
-        launch_gather(h, h->b_mem_idx, h->B);
+        launch_gather(h, h->b_mem_idx, h->B, true);
     } else {
         if (rows) DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows, h->B * 8, cudaMemcpyHostToDevice, h->stream));
         else {
@@ -679,7 +705,7 @@ static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* ro
             h->launches++;
         }
         prof_mark(h, "gather");
-        launch_gather(h, h->b_rows, h->B);
+        launch_gather(h, h->b_rows, h->B, true);
     }
 }
 
@@ -810,10 +836,15 @@ static void upload_batch(dqn_learner* h, int n, const uint8_t* st, const uint8_t
     const size_t S = h->state_bytes;
     DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st, n * S, cudaMemcpyHostToDevice, h->stream));
     DQN_CUDA_OK(cudaMemcpyAsync(h->in_states + n * S, ns, n * S, cudaMemcpyHostToDevice, h->stream));
-    DQN_CUDA_OK(cudaMemcpyAsync(h->in_actions, ac, n, cudaMemcpyHostToDevice, h->stream));
-    DQN_CUDA_OK(cudaMemcpyAsync(h->in_rewards, rw, n, cudaMemcpyHostToDevice, h->stream));
-    DQN_CUDA_OK(cudaMemcpyAsync(h->in_cont, ct, n, cudaMemcpyHostToDevice, h->stream));
-    if (isw) DQN_CUDA_OK(cudaMemcpyAsync(h->in_isw, isw, n * 4, cudaMemcpyHostToDevice, h->stream));
+    // actions / rewards / continues / is_weights: packed through the pinned staging block (mirrors the device block)
+    DQN_CUDA_OK(cudaEventSynchronize(h->stage_ev));  // the previous upload has left the staging block
+    uint8_t* hs = h->h_in_small;
+    memcpy(hs + (h->in_actions - h->in_actions), ac, n);
+    memcpy(hs + (h->in_rewards - h->in_actions), rw, n);
+    memcpy(hs + (h->in_cont - h->in_actions), ct, n);
+    if (isw) memcpy(hs + (reinterpret_cast<uint8_t*>(h->in_isw) - h->in_actions), isw, (size_t)n * 4);
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_actions, hs, h->in_small_bytes, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaEventRecord(h->stage_ev, h->stream));
 }
 
 extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw,
@@ -823,12 +854,40 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     DQN_REQUIRE(!h->cfg.use_per || isw, "use_per: is_weights are required");
     h->prof_used = 0; h->prof_marks.clear();
     upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
-    h->early_fc_adam = true;
-    try {
-        step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
-    } catch (...) { h->early_fc_adam = false; throw; }
-    h->early_fc_adam = false;
-    finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
+    auto launches = [&]() {
+        h->early_fc_adam = true;
+        try {
+            step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
+        } catch (...) { h->early_fc_adam = false; throw; }
+        h->early_fc_adam = false;
+        finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
+    };
+    if (h->profile || !h->batch_graph_enabled) {
+        launches();
+    } else {
+        // the ~28 launches of one host-fed step replayed as one graph (inputs/outputs sit in fixed device buffers);
+        // re-captured when the batch size or an option changes
+        if (!h->batch_graph || h->batch_graph_n != n || !h->graph_valid_batch) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = h->launches, s0 = h->host_step;
+            DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            try { launches(); } catch (...) {
+                cudaStreamEndCapture(h->stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+            h->batch_graph_launches = h->launches - l0;
+            h->launches = l0; h->host_step = s0;
+            if (h->batch_graph) { cudaGraphExecDestroy(h->batch_graph); h->batch_graph = nullptr; }
+            DQN_CUDA_OK(cudaGraphInstantiate(&h->batch_graph, g, 0));
+            DQN_CUDA_OK(cudaGraphDestroy(g));
+            h->batch_graph_n = n; h->graph_valid_batch = true;
+        }
+        DQN_CUDA_OK(cudaGraphLaunch(h->batch_graph, h->stream));
+        h->launches += h->batch_graph_launches;
+        h->host_step++;
+    }
     d2h(h, losses, h->b_losses_out, n);
     read_scalars(h);
     if (step) *step = h->h_sc->step;
@@ -905,9 +964,11 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     const std::string n = name;
     if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
     else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
+    else if (n == "batch_graph") h->batch_graph_enabled = value != 0;  // dqn_train_batch replays a captured graph
+    else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else throw std::string("unknown option: ") + n;
-    h->graph_valid = false;
+    h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }

@@ -26,6 +26,23 @@
         }                                                                                     \
     } while (0)
 
+// Programmatic dependent launch: a kernel launched with the attribute may start (prologue: barrier init, TMEM
+// allocation) while its stream predecessor is still running; it must execute pdl_wait() before touching anything the
+// predecessor writes.  Kernels call pdl_launch_dependents() as early as possible.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline void launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    DQN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

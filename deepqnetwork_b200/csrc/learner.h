@@ -54,6 +54,7 @@ struct dqn_learner {
     cudaEvent_t fork_ev[16] = {};
     int fork_used = 0;
     bool overlap = true;
+    bool pdl = true;            // programmatic dependent launch for the kernels that call pdl_wait()
     bool ts_gemm = true;        // tcgen05 GEMMs take A from tensor memory where the operand functor allows it
     bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
     bool fuse_fc_adam = false;
@@ -107,6 +108,9 @@ struct dqn_learner {
     uint8_t* in_states = nullptr;
     uint8_t *in_actions = nullptr, *in_rewards = nullptr, *in_cont = nullptr;
     float* in_isw = nullptr;
+    size_t in_small_bytes = 0;         // in_actions/in_rewards/in_cont/in_isw are carved from one device block
+    uint8_t* h_in_small = nullptr;     // pinned mirror of that block (also stages the per-step tree write-back)
+    cudaEvent_t stage_ev = nullptr;    // last copy out of h_in_small
     long long* b_rows = nullptr;       // uniform-sampler rows
     __half* b_losses = nullptr;
     long long* b_tree_idx = nullptr;   // [B]
@@ -139,6 +143,11 @@ struct dqn_learner {
     // graph for the fused step
     cudaGraphExec_t step_graph = nullptr;
     bool graph_valid = false;
+    // graph of one host-fed step (dqn_train_batch), keyed by the batch size
+    cudaGraphExec_t batch_graph = nullptr;
+    int batch_graph_n = 0;
+    bool graph_valid_batch = false, batch_graph_enabled = true;
+    int64_t batch_graph_launches = 0;
     int64_t graph_launches = 0;
 
     // per-segment CUDA-event timing (dqn_set_profile)
@@ -165,7 +174,8 @@ void launch_optimizer_fc(dqn_learner* h);  // api.cu: CUDA-event boundary, activ
 void net_describe(NetDesc& net, const dqn_config& cfg);
 
 // replay.cu
-void launch_gather(dqn_learner* h, const long long* d_rows, int n);
+// with_f32: also write the batch as f32/255 (the fused step feeds the tensor-core loaders from it)
+void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32 = false);
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
 
 // sumtree.cu

@@ -59,7 +59,7 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ states, const uin
     }
 }
 
-void launch_gather(dqn_learner* h, const long long* d_rows, int n) {
+void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32) {
     const int threads = 256;
     const int nvec = (int)(h->state_bytes >> 4);
     dim3 grid(ceil_div(nvec, threads * 4), 2 * n);
@@ -67,10 +67,10 @@ void launch_gather(dqn_learner* h, const long long* d_rows, int n) {
     gather_rows_kernel<<<grid, threads, 0, h->stream>>>(h->r_states, h->r_next, h->r_actions, h->r_rewards, h->r_cont,
                                                         h->r_losses, d_rows, n, h->state_bytes, h->b_states,
                                                         h->b_actions, h->b_rewards, h->b_cont, h->b_losses,
-                                                        h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : nullptr);
+                                                        with_f32 && h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : nullptr);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
-    h->xf_from_gather = h->cfg.math_mode != DQN_MATH_FP32;
+    h->xf_from_gather = with_f32 && h->cfg.math_mode != DQN_MATH_FP32;
 }
 
 // ---- synthetic fill: states/next_states ~ U{0..255}; actions ~ U{0..A-1};

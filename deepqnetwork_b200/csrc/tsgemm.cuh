@@ -149,6 +149,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();  // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
     auto stage_a = [&](int s) { return sbase + s * P::STAGE; };  // raw staging tile (K-contiguous A only)
     auto stage_b = [&](int s) { return sbase + s * P::STAGE + P::A_STAGE; };
@@ -338,6 +339,9 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
                 s += NG; if (s >= S) { s -= S; ph ^= 1; }
             }
         }
+        // the k-loop work of this warp is issued: let the stream successor start its prologue (it occupies a whole SM,
+        // so triggering any earlier would take idle SMs away from the kernels of the other streams)
+        pdl_launch_dependents();
         // ---------------- epilogue (warps 0-15) ----------------
         if (warp < PRODUCERS / 32) {
         if (nkb > 0) {
@@ -477,8 +481,8 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    kern<<<grid, (is_heavy<AOp>::value ? 21 : 17) * 32, P::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16, h->tc_dbg);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(h->pdl, kern, grid, dim3((is_heavy<AOp>::value ? 21 : 17) * 32), (size_t)P::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk,
+                  (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
 
