@@ -82,6 +82,8 @@ def kernel_bytes(name, cfg, nn):
         return in_b + wts[l] * 4 + rows * acts[l] * 4
     if base == 'fc_fwd':
         return rows * flat * 4 + flat * 512 * st * 4 + rows * 512 * st * 4
+    if base == 'fc_dgrad_reduce':
+        return 2 * B * flat * 4 * 2 + B * flat * 4
     if base == 'fc_reduce_heads':
         return rows * 512 * st * 4 * 2
     if base == 'fc_wgrad':

@@ -98,9 +98,15 @@ static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int 
     else tc::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
 }
 
+// bn_hint: force the N tile (0 = choose).  A wide tile reads the 128-row operand once -- what an HBM-streamed A wants --
+// while the automatic choice trades re-reads of an L2-resident A for more CTAs.
 template <bool SPLIT, class AOp, class BOp, class Epi>
-static void gemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+static void gemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk,
+                      int bn_hint = 0) {
     if (h->cfg.math_mode == DQN_MATH_FP32 || (N % 32) != 0) return igemm_auto<SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (bn_hint == 128 && N % 128 == 0) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (bn_hint == 64 && N % 64 == 0) return tc_go<64, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (bn_hint == 32) return tc_go<32, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
     const int64_t mt = (int64_t)ceil_div(M, tc::BM) * Z;
     // widest N tile that still gives about one CTA per SM; narrower tiles re-read A from L2 but fill the chip
     if (N % 128 == 0 && mt * (N / 128) >= h->sm_count) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
@@ -237,7 +243,8 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
         OpFcWeightFwd a{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
         OpRowMajorK b{acts.act[2], net.flat};
         EpiPartialT e{acts.fc_part, rows, net.NH};
-        gemm_auto<true>(h, a, b, e, net.NH, rows, net.flat, splits, kchunk);
+        // the weights are the HBM-streamed operand: one N tile over the whole batch, so every byte of W is read once
+        gemm_auto<true>(h, a, b, e, net.NH, rows, net.flat, splits, kchunk, rows % 64 == 0 ? 64 : 32);
     } else {
         DQN_REQUIRE(splits <= h->fc_splits, "fc split workspace too small");
         OpRowMajorK a{acts.act[2], net.flat};
@@ -304,6 +311,21 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
+// out = (sum_z part[z]) * (gate > 0): split-K consumer of the dense dgrad (ReLU backward of conv3 fused in)
+__global__ void __launch_bounds__(256) sum_gate_kernel(const float* __restrict__ part, int Z, int total4,
+                                                       const float* __restrict__ gate, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    float4 s = *reinterpret_cast<const float4*>(part + (size_t)i * 4);
+    for (int z = 1; z < Z; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)z * total4 + i) * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float4 g = *reinterpret_cast<const float4*>(gate + (size_t)i * 4);
+    *reinterpret_cast<float4*>(out + (size_t)i * 4) =
+        make_float4(g.x > 0.f ? s.x : 0.f, g.y > 0.f ? s.y : 0.f, g.z > 0.f ? s.z : 0.f, g.w > 0.f ? s.w : 0.f);
+}
+
 void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows) {
     const NetDesc& net = h->net;
     const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
@@ -336,11 +358,21 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
-        if (tcm && rows % 32 == 0) {  // swap-AB: weights are the 128-row operand, K-major as stored
+        if (tcm && rows % 32 == 0) {
+            // swap-AB (weights = the 128-row operand, K-major as stored, streamed through the cp.async ring) and
+            // split-K over the hidden units so that 2 x flat/128 = 120 CTAs pull W from HBM; the partial sums are
+            // added and gated by a small consumer kernel
+            const int Z = 2, kchunk = net.NH / Z;
+            DQN_REQUIRE((int64_t)Z * net.flat <= (int64_t)h->fc_splits * net.NH && kchunk % 32 == 0, "dense dgrad split workspace");
             OpFcWeightBwd a{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
             OpRowMajorK b{h->d_hid, net.NH};
-            EpiGateStoreT e{h->d_act[2], acts.act[2], rows, net.flat};
-            gemm_auto<false>(h, a, b, e, net.flat, rows, net.NH, 1, 0);
+            EpiPartialT e{acts.fc_part, rows, net.flat};  // the forward split-K workspace is idle during backward
+            gemm_auto<true>(h, a, b, e, net.flat, rows, net.NH, Z, kchunk, 32);
+            prof_mark(h, "fc_dgrad_reduce");
+            const int total4 = rows * net.flat / 4;
+            sum_gate_kernel<<<ceil_div(total4, 256), 256, 0, h->stream>>>(acts.fc_part, Z, total4, acts.act[2], h->d_act[2]);
+            DQN_CUDA_OK(cudaGetLastError());
+            h->launches++;
         } else {
             OpRowMajorK a{h->d_hid, net.NH};
             OpFcWeightBwd b{P + net.off_fc_w[0], P + net.off_fc_w[1], net.hidden};
