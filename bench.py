@@ -82,6 +82,9 @@ def kernel_bytes(name, cfg, nn):
         return in_b + wts[l] * 4 + rows * acts[l] * 4
     if base == 'fc_fwd':
         return rows * flat * 4 + flat * 512 * st * 4 + rows * 512 * st * 4
+    if base.endswith('_dgrad_reduce') and base.startswith('conv'):
+        l = int(base[4]) - 1
+        return 4 * B * acts[l - 1] * 4
     if base == 'fc_dgrad_reduce':
         return 2 * B * flat * 4 * 2 + B * flat * 4
     if base == 'fc_reduce_heads':
@@ -100,6 +103,8 @@ def kernel_bytes(name, cfg, nn):
     if base.endswith('_dgrad'):
         l = int(base[4]) - 1
         return B * acts[l] * 4 + wts[l] * 4 + 2 * B * acts[l - 1] * 4
+    if base == 'fc_wgrad_adam':    # read w,m,v + write w,m,v of the dense kernels; activations / dH tiles come from L2
+        return 6 * 4 * flat * 512 * st + B * flat * 4 + B * 512 * st * 4
     if base == 'optimizer_fc':     # dense hidden kernels only (98.6% of P), issued from inside the backward pass
         return 7 * 4 * flat * 512 * st
     if base == 'optimizer':        # read g,p,m,v ; write p,m,v over whatever optimizer_fc has not already updated
@@ -242,6 +247,7 @@ def main():
                     help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
     ap.add_argument('--no-fuse', action='store_true', help='ablation: optimizer as a separate pass over the gradient slab')
     ap.add_argument('--fuse', action='store_true', help='ablation: Adam for the dense kernels in the dense wgrad epilogue')
+    ap.add_argument('--ffma-adam', action='store_true', help='ablation: dense wgrad + optimizer as one fp32 FFMA pass')
     ap.add_argument('--no-pdl', action='store_true', help='ablation: no programmatic dependent launch between consecutive kernels')
     ap.add_argument('--no-overlap', action='store_true', help='ablation: single stream, no forked branches in the step graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -311,6 +317,8 @@ def main():
         L.set_option('overlap', 0)
     if args.no_pdl:
         L.set_option('pdl', 0)
+    if args.ffma_adam:
+        L.set_option('fc_ffma_adam', 1)
     L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)
     L.set_tower(init_tower_params(shapes, 43 + 2 * rank), 1)
     L.replay_fill_synthetic(args.capacity, seed=1234 + rank)
@@ -356,7 +364,7 @@ def main():
         prof, n = L.get_profile()
         L.set_profile(False)
         per_kernel = {k: v / n * 1000.0 for k, v in prof.items()}  # us per step
-        nn['early_fc'] = 'optimizer_fc' in per_kernel
+        nn['early_fc'] = 'optimizer_fc' in per_kernel or 'fc_wgrad_adam' in per_kernel
         total_us = sum(per_kernel.values())
         dom = max(per_kernel, key=per_kernel.get)
         kb = kernel_bytes(dom, cfg, nn)

@@ -855,11 +855,11 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     h->prof_used = 0; h->prof_marks.clear();
     upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
     auto launches = [&]() {
-        h->early_fc_adam = true;
+        h->early_fc_adam = true; h->fc_grads_needed = true;  // the seam-2 path keeps the full gradient slab readable
         try {
             step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
-        } catch (...) { h->early_fc_adam = false; throw; }
-        h->early_fc_adam = false;
+        } catch (...) { h->early_fc_adam = false; h->fc_grads_needed = false; throw; }
+        h->early_fc_adam = false; h->fc_grads_needed = false;
         finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
     };
     if (h->profile || !h->batch_graph_enabled) {
@@ -965,6 +965,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
     else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
     else if (n == "batch_graph") h->batch_graph_enabled = value != 0;  // dqn_train_batch replays a captured graph
+    else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else throw std::string("unknown option: ") + n;

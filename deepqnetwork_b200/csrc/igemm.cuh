@@ -340,6 +340,24 @@ struct EpiDgradGate {  // conv dgrad: row m of class z -> pixel (n,iy,ix); out =
     }
 };
 
+struct EpiDgradPartial {  // conv dgrad, class + split-K launch: part[split][pixel][ci] = acc (no gate; summed by the consumer)
+    float* part; DgradClass c; int nimg; int nclass; size_t slab;
+    template <int TN>
+    __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int zz) const {
+        const int z = zz % nclass, split = zz / nclass;
+        int ry, rx, y0, x0, cy, cx; c.cls(z, ry, rx, y0, x0, cy, cx);
+        const int per = cy * cx;
+        if (per == 0) return;
+        const int img = m / per, rem = m - img * per;
+        if (img >= nimg) return;
+        const int a = rem / cx, b = rem - a * cx;
+        const int iy = y0 + c.g.s * a, ix = x0 + c.g.s * b;
+        float* o = part + split * slab + (((size_t)img * c.g.ih + iy) * c.g.iw + ix) * c.g.cin + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
 struct EpiFcWgrad {  // dW of the two hidden streams: column n -> stream n/hid, grads laid out like the params
     static constexpr bool COALESCE = true;
     float* g0; float* g1; int hid;

@@ -59,7 +59,10 @@ struct dqn_learner {
     bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
     bool fuse_fc_adam = false;
     bool early_fc_adam = false;  // set per launch sequence: optimizer for the dense kernels runs inside backward (side stream)
-    bool fc_adam_done = false;  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
+    bool fc_adam_done = false;
+    bool fc_ffma_adam = false;    // option: dense wgrad + optimizer as one fp32 FFMA pass (no gradient round trip); measured
+                                  // slower than tensor-core wgrad + streaming Adam (instruction-bound: 61 us vs 17 + 45 us)
+    bool fc_grads_needed = false; // set per launch sequence: that pass also stores dW (seam-2 / parity path)  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
     std::string err;
     int64_t launches = 0;
 
@@ -170,7 +173,9 @@ bool overlap_enabled(const dqn_learner* h);
 void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0);
 void side_end(dqn_learner* h, cudaStream_t saved);
 void main_wait_side(dqn_learner* h, int which = 0);
-void launch_optimizer_fc(dqn_learner* h);  // api.cu: CUDA-event boundary, active only in profile mode
+void launch_optimizer_fc(dqn_learner* h);
+bool fc_wgrad_adam_supported(const dqn_learner* h);
+void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g);  // optim.cu: dense wgrad + optimizer in one FFMA pass  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);
 
 // replay.cu

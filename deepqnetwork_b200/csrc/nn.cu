@@ -86,14 +86,15 @@ static void igemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e,
 
 // ---- math-mode dispatch: tcgen05 tensor cores (TF32 x1 / x3) or the FFMA kernel ------------------------------------
 template <int BN, bool SPLIT, class AOp, class BOp, class Epi>
-static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk, int nclass = 0) {
     if constexpr (ts::capable<AOp>::value) {
-        if (h->ts_gemm) {  // A through tensor memory
-            if (h->cfg.math_mode == DQN_MATH_TC3X) ts::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
-            else ts::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+        if (h->ts_gemm || nclass > 0) {  // A through tensor memory
+            if (h->cfg.math_mode == DQN_MATH_TC3X) ts::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk, nclass);
+            else ts::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk, nclass);
             return;
         }
     }
+    DQN_REQUIRE(nclass == 0, "class + split launches need the tensor-memory kernel");
     if (h->cfg.math_mode == DQN_MATH_TC3X) tc::launch<BN, 3, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
     else tc::launch<BN, 1, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
 }
@@ -102,11 +103,11 @@ static void tc_go(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int 
 // while the automatic choice trades re-reads of an L2-resident A for more CTAs.
 template <bool SPLIT, class AOp, class BOp, class Epi>
 static void gemm_auto(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk,
-                      int bn_hint = 0) {
+                      int bn_hint = 0, int nclass = 0) {
     if (h->cfg.math_mode == DQN_MATH_FP32 || (N % 32) != 0) return igemm_auto<SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
-    if (bn_hint == 128 && N % 128 == 0) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
-    if (bn_hint == 64 && N % 64 == 0) return tc_go<64, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
-    if (bn_hint == 32) return tc_go<32, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
+    if (bn_hint == 128 && N % 128 == 0) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk, nclass);
+    if (bn_hint == 64 && N % 64 == 0) return tc_go<64, SPLIT>(h, a, b, e, M, N, K, Z, kchunk, nclass);
+    if (bn_hint == 32) return tc_go<32, SPLIT>(h, a, b, e, M, N, K, Z, kchunk, nclass);
     const int64_t mt = (int64_t)ceil_div(M, tc::BM) * Z;
     // widest N tile that still gives about one CTA per SM; narrower tiles re-read A from L2 but fill the chip
     if (N % 128 == 0 && mt * (N / 128) >= h->sm_count) return tc_go<128, SPLIT>(h, a, b, e, M, N, K, Z, kchunk);
@@ -354,7 +355,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         }
         side_end(h, saved);
     };
-    if (!h->fuse_fc_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
+    const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && fc_wgrad_adam_supported(h);
+    if (!h->fuse_fc_adam && !ffma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
@@ -385,8 +387,13 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
         // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
         side_begin(h, saved, 0);
-        prof_mark(h, "optimizer_fc");
-        launch_optimizer_fc(h);
+        if (ffma_adam) {
+            prof_mark(h, "fc_wgrad_adam");
+            launch_fc_wgrad_adam(h, rows, h->fc_grads_needed);
+        } else {
+            prof_mark(h, "optimizer_fc");
+            launch_optimizer_fc(h);
+        }
         side_end(h, saved);
         h->fc_adam_done = true;
     }
@@ -429,8 +436,23 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             const int Mc = rows * cy * cx;  // upper bound over classes
             OpConvDgradA a{h->d_act[l], c, cl2, rows};
             OpConvDgradB b{P + net.off_cw[l], g, cl2};
-            EpiDgradGate e{h->d_act[l - 1], acts.act[l - 1], c, rows};
-            gemm_auto<false>(h, a, b, e, Mc, g.cin, (g.k / g.s) * (g.k / g.s) * g.cout, Zc, 0);
+            const int Kd = (g.k / g.s) * (g.k / g.s) * g.cout;
+            const int ctas = ceil_div(Mc, tc::BM) * ceil_div(g.cin, 32) * Zc;
+            if (tcm && h->ts_gemm && 2 * ctas <= h->sm_count && Kd % 64 == 0 && g.cin % 32 == 0 &&
+                (int64_t)2 * rows * g.ih * g.iw * g.cin <= (int64_t)h->fc_splits * rows * net.NH) {
+                // too few tiles to fill the chip (conv3: 60): split K in two as well; the halves are added and gated by
+                // the consumer kernel.  Workspace: the forward split-K buffer (idle here).
+                EpiDgradPartial e{acts.fc_part, c, rows, Zc, (size_t)rows * g.ih * g.iw * g.cin};
+                gemm_auto<true>(h, a, b, e, Mc, g.cin, Kd, 2 * Zc, Kd / 2, 32, Zc);
+                prof_mark(h, l == 2 ? "conv3_dgrad_reduce" : "conv2_dgrad_reduce");
+                const int total4 = rows * g.ih * g.iw * g.cin / 4;
+                sum_gate_kernel<<<ceil_div(total4, 256), 256, 0, h->stream>>>(acts.fc_part, 2, total4, acts.act[l - 1], h->d_act[l - 1]);
+                DQN_CUDA_OK(cudaGetLastError());
+                h->launches++;
+            } else {
+                EpiDgradGate e{h->d_act[l - 1], acts.act[l - 1], c, rows};
+                gemm_auto<false>(h, a, b, e, Mc, g.cin, Kd, Zc, 0);
+            }
         }
     }
     main_wait_side(h, 0);  // all weight gradients are in the slab (and the dense kernels updated) before the

@@ -67,6 +67,110 @@ void launch_optimizer_fc(dqn_learner* h) {
     if (net.dueling) optimizer_range(h, net.off_fc_w[1], net.off_fc_w[1] + fcw);
 }
 
+// Dense hidden layers: weight gradient AND optimizer in one pass (the default for a whole step on one GPU).
+//   dW[k][n] = sum_b act3[b][k] * dH[b][n]   (K = batch = 32 MACs per element: plain fp32 FFMA, exact like the reference)
+// is formed in registers from shared-memory tiles and consumed on the spot by Adam / Nesterov momentum, so the 31.5 MB
+// gradient of the dense kernels never makes its HBM round trip and the kernel is bound by the unavoidable
+// read(w, m, v) + write(w, m, v) = 6 x 4 bytes per parameter.
+// CTA = 256 threads = 16 k rows x 256 n columns; thread = 4 k x 4 n.  WRITE_G also stores dW (parity / debugging path).
+template <bool WRITE_G>
+__global__ void __launch_bounds__(256, 4) fc_wgrad_adam_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
+                                                            int Bn, int flat, int NH, int hid,
+                                                            float* __restrict__ w0, float* __restrict__ w1,
+                                                            float* __restrict__ m0, float* __restrict__ m1,
+                                                            float* __restrict__ v0, float* __restrict__ v1,
+                                                            float* __restrict__ g0, float* __restrict__ g1,
+                                                            float lr, float mom, int use_momentum,
+                                                            const dqn_learner::Scalars* __restrict__ sc) {
+    __shared__ __align__(16) float sa[32][16];    // act3 tile  [b][k]
+    __shared__ __align__(16) float sd[32][256];   // dH tile    [b][n]
+    const int tid = threadIdx.x;
+    const int kt = blockIdx.x * 16, nt = blockIdx.y * 256;
+    const int tn = (tid & 63) * 4, tk = (tid >> 6) * 4;
+    const int st = nt >= hid;                     // a 256-wide n tile never straddles the two streams (hid % 256 == 0)
+    const int ncol = nt + tn - (st ? hid : 0);
+    float* W = st ? w1 : w0; float* Mo = st ? m1 : m0; float* V = st ? v1 : v0; float* G = st ? g1 : g0;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int b0 = 0; b0 < Bn; b0 += 32) {
+        const int nb = min(32, Bn - b0);
+        if (tid < 128) {  // 32 b x 4 float4 of act3
+            const int b = tid >> 2, q = tid & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < nb) v = *reinterpret_cast<const float4*>(act3 + (size_t)(b0 + b) * flat + kt + q * 4);
+            *reinterpret_cast<float4*>(&sa[b][q * 4]) = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // 32 b x 64 float4 of dH
+            const int f = tid + i * 256, b = f >> 6, q = f & 63;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < nb) v = *reinterpret_cast<const float4*>(dhid + (size_t)(b0 + b) * NH + nt + q * 4);
+            *reinterpret_cast<float4*>(&sd[b][q * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {  // ascending sample order, one fmaf chain per element (deterministic)
+            const float4 a = *reinterpret_cast<const float4*>(&sa[b][tk]);
+            const float4 d = *reinterpret_cast<const float4*>(&sd[b][tn]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], dv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const size_t o = (size_t)(kt + tk + i) * hid + ncol;
+        const float4 gg = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        // 64 registers per thread -> 4 CTAs per SM: the memory latency of these loads is hidden by occupancy
+        float4 mm = *reinterpret_cast<const float4*>(Mo + o), pp = *reinterpret_cast<const float4*>(W + o);
+        if (use_momentum) {
+#define MOM1(c) mm.c = mm.c * mom + gg.c; pp.c = pp.c - (gg.c * lr + mm.c * mom * lr);
+            MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+        } else {
+            float4 vv = *reinterpret_cast<const float4*>(V + o);
+#define ADAM1(c) mm.c = mm.c + (gg.c - mm.c) * omb1; vv.c = vv.c + (gg.c * gg.c - vv.c) * omb2; \
+                 pp.c = pp.c - (mm.c * lr_t) / (sqrtf(vv.c) + eps);
+            ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+            *reinterpret_cast<float4*>(V + o) = vv;
+        }
+        *reinterpret_cast<float4*>(Mo + o) = mm;
+        *reinterpret_cast<float4*>(W + o) = pp;
+        if (WRITE_G) *reinterpret_cast<float4*>(G + o) = gg;
+    }
+}
+
+bool fc_wgrad_adam_supported(const dqn_learner* h) {
+    const NetDesc& net = h->net;
+    return net.flat % 16 == 0 && net.hidden % 256 == 0;
+}
+
+void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g) {
+    const NetDesc& net = h->net;
+    const int o0 = (int)0; (void)o0;
+    float *W = h->online, *M = h->slot_m, *V = h->slot_v, *G = h->grads;
+    dim3 grid(net.flat / 16, net.NH / 256);
+    auto args = [&](auto kern) {
+        kern<<<grid, 256, 0, h->stream>>>(h->acts_on.act[2], h->d_hid, rows, net.flat, net.NH, net.hidden,
+                                          W + net.off_fc_w[0], W + net.off_fc_w[1], M + net.off_fc_w[0], M + net.off_fc_w[1],
+                                          V + net.off_fc_w[0], V + net.off_fc_w[1], G + net.off_fc_w[0], G + net.off_fc_w[1],
+                                          (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum, h->d_sc);
+    };
+    if (write_g) args(fc_wgrad_adam_kernel<true>); else args(fc_wgrad_adam_kernel<false>);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
+}
+
 // Up to three slab ranges in ONE launch, followed by the step bookkeeping (global_step += 1, beta powers,
 // RNG counter: AdamOptimizer._finish / rl/deep_q_model.py:391) done by whichever CTA finishes last -- the betas are
 // read by every CTA before its ticket is taken, so the update cannot race with them.

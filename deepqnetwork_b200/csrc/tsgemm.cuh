@@ -104,7 +104,7 @@ struct Plan {
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
-                                                            int kchunk, const float* __restrict__ zeros,
+                                                            int kchunk, int nclass, const float* __restrict__ zeros,
                                                             unsigned long long* __restrict__ dbg) {
     constexpr bool A_MC = !AOp::KCONTIG;  // A contiguous along M: staged as [k][m], converters read a column
     using P = Plan<BN, NTERMS>;
@@ -122,9 +122,12 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
     const uint32_t tmem_slot = bars + 8u * (3 * S + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int z = blockIdx.z;
+    // blockIdx.z: split-K index, or a group id handed to the functors (dgrad parity class), or -- nclass > 0 -- both:
+    // class = blockIdx.z % nclass for the operand functors, split = blockIdx.z / nclass; the epilogue sees blockIdx.z
+    const int z = nclass > 0 ? blockIdx.z % nclass : blockIdx.z;
+    const int zsplit = nclass > 0 ? blockIdx.z / nclass : blockIdx.z;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = SPLIT ? z * kchunk : 0;
+    const int kbeg = SPLIT ? zsplit * kchunk : 0;
     const int kend = SPLIT ? min(K, kbeg + kchunk) : K;
     const int nkb = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
     const int ktot = kend - kbeg;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = 0.f;
             }
-            if (m < M && n0 + col < N) epi.template store<8>(m, n0 + col, v, z);
+            if (m < M && n0 + col < N) epi.template store<8>(m, n0 + col, v, (int)blockIdx.z);
         } else {
 #pragma unroll
             for (int c = 0; c < QCOLS; c += 16) {
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 }
-                if (m < M && n0 + col < N) epi.template store<16>(m, n0 + col, v, z);
+                if (m < M && n0 + col < N) epi.template store<16>(m, n0 + col, v, (int)blockIdx.z);
             }
         }
         }
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
 }
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
-static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
+static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk, int nclass = 0) {
     using P = Plan<BN, NTERMS>;
     auto kern = tsgemm_kernel<BN, NTERMS, SPLIT, AOp, BOp, Epi>;
     static bool configured = false;  // one per template instantiation
@@ -481,7 +484,7 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    launch_kernel(h->pdl, kern, grid, dim3((is_heavy<AOp>::value ? 21 : 17) * 32), (size_t)P::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk,
+    launch_kernel(h->pdl, kern, grid, dim3((is_heavy<AOp>::value ? 21 : 17) * 32), (size_t)P::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk, nclass,
                   (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }

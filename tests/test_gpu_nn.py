@@ -326,3 +326,21 @@ def test_fused_optimizer_and_overlap_do_not_change_results(math_mode):
             for k in a:
                 assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(res[0][3], r[3])
+
+
+def test_ffma_dense_wgrad_adam_option_is_fp32_grade():
+    """Option fc_ffma_adam: dense wgrad + optimizer as one fp32 FFMA pass.  Not bit-identical to the tensor-core
+    wgrad (different summation), so it is held to the end-to-end weight bound: 1e-4 * |w|_inf + 2.5 * lr."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    res = []
+    for opt in (0, 1):
+        L, spec, shapes, on, tg = make(cfg, capacity=4096, math_mode='tc3x')
+        L.set_option('fc_ffma_adam', opt)
+        L.replay_fill_synthetic(4096, seed=5)
+        L.train_steps(3); L.sync()
+        res.append((L.get_tower(0), L.tree_read()[0]))
+        L.close()
+    lr = 0.00025 if not hasattr(spec, 'learning_rate') else spec.learning_rate
+    for k in res[0][0]:
+        a, b = res[0][0][k].astype(np.float64), res[1][0][k].astype(np.float64)
+        assert np.max(np.abs(a - b)) <= TOL * max(np.max(np.abs(a)), 1e-30) + 2.5 * lr, k
