@@ -8,6 +8,7 @@ static std::string g_create_error;
 
 // launchers living in other translation units
 void launch_tree_stats(dqn_learner* h, double per_b_override);
+void debug_conv_layer(dqn_learner* h, int layer, int rows);
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
 
 long long* tree_size_ptr(dqn_learner* h) { return &h->d_dev->tree_size; }
@@ -147,6 +148,8 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
         }
         dmalloc(h->x_f32, 2 * R * h->state_bytes);
+        alloc_packed_conv(h);
+        launch_pack_conv(h, 0); launch_pack_conv(h, 1);
         h->dev_stage_bytes = 8u << 20;
         dmalloc(h->dev_stage, h->dev_stage_bytes);
         dmalloc(h->stats_scratch, 8192);
@@ -171,7 +174,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
@@ -253,6 +256,7 @@ extern "C" int dqn_set_param(dqn_learner* h, int32_t tower, int32_t slot, const 
     const TensorInfo& t = find_tensor(h, name);
     DQN_REQUIRE(count == t.count, "parameter element count mismatch");
     DQN_CUDA_OK(cudaMemcpyAsync(slab_of(h, tower, slot) + t.offset, in, count * 4, cudaMemcpyHostToDevice, h->stream));
+    if (slot == 0 && t.name.find("conv") != std::string::npos) launch_pack_conv(h, tower);
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     API_END(h)
 }
@@ -968,6 +972,8 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
+    else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
+    else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
@@ -1057,6 +1063,7 @@ extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
         set_ll(h, &h->d_sc->game_count, hd.game_count);
         set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, hd.b1p, &h->d_sc->b2p, hd.b2p);
         h->host_step = hd.step;
+        launch_pack_conv(h, 0); launch_pack_conv(h, 1);
         DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     } catch (const std::string& e) {
         if (f) fclose(f);
@@ -1126,6 +1133,19 @@ extern "C" int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32
     API_BEGIN(h)
     float *dA = nullptr, *dB = nullptr, *dC = nullptr;
     unsigned long long* dT = nullptr;
+    if (mode >= 16) {  // conv layer (mode - 16) of the online tower over M images, in place on the tower's buffers
+        DQN_REQUIRE(mode - 16 < 3 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
+        dmalloc(dT, 512);
+        DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 512 * 8, h->stream));
+        debug_conv_layer(h, mode - 16, M);
+        h->tc_dbg = dT;
+        try { debug_conv_layer(h, mode - 16, M); } catch (...) { h->tc_dbg = nullptr; throw; }
+        h->tc_dbg = nullptr;
+        DQN_CUDA_OK(cudaMemcpyAsync(out512, dT, 512 * 8, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        cudaFree(dT);
+        return 0;
+    }
     dmalloc(dA, (size_t)M * K); dmalloc(dB, (size_t)N * K); dmalloc(dC, (size_t)M * N); dmalloc(dT, 512);
     DQN_CUDA_OK(cudaMemsetAsync(dA, 0x3c, (size_t)M * K * 4, h->stream));
     DQN_CUDA_OK(cudaMemsetAsync(dB, 0x3c, (size_t)N * K * 4, h->stream));

@@ -1,0 +1,339 @@
+// Image-resident convolution on tcgen05: one CTA = one image of the batch.
+//
+// Why (profiles/README.md, r01b): the generic implicit-GEMM kernel (tsgemm.cuh) gathers every 128 x 32 im2col tile
+// from L2 with 16-byte cp.async, and ALL CTAs re-stage the same weight tile through registers.  At batch 32-64 the
+// k-loop is then bound by the ~2300 warp instructions per k-block that the im2col loaders, the B producers and the
+// hi/lo converters issue -- the tensor pipe is 16 % busy and DRAM idle.  A conv layer of this network has a much
+// smaller footprint than its im2col view (conv3: 30 KB per image vs 480 KB of im2col rows), so here
+//   * the zero-padded input image is copied ONCE into shared memory (16-byte cp.async, zero-fill for the SAME
+//     padding), columns de-interleaved by stride phase and pixels padded to cin*4+16 bytes so that the row-per-thread
+//     reads below are bank-conflict free;
+//   * the weights arrive pre-split (hi = fp32 word, lo = x - tf32(x)) and pre-tiled in the canonical K-major UMMA
+//     layout (pack_conv_kernel, run once per optimizer step), so one elected thread streams them with
+//     cp.async.bulk (TMA) straight into the B ring: no B-producer warps;
+//   * per k-block the only thread work left is the A converter: thread == output pixel reads its 128 contiguous
+//     bytes (one tap x 32 channels, or one kernel row of a 4-channel input) from the resident image at
+//     base(pixel) + offset(k-block), splits hi/lo and stores both to TENSOR MEMORY (tcgen05.st); the MMA takes A
+//     from TMEM and B through a shared-memory descriptor, exactly as in tsgemm.cuh.
+// Layers whose output has more than 128 pixels per image (conv1: 23 x 20) are processed as bands of whole output rows
+// with one accumulator (BN TMEM columns) per band; the image and the TMEM allocation are shared by the bands.
+//
+// Thread roles (320 threads): warps 0-7 image loaders, then A converters (two groups of 4 warps take alternate
+// k-blocks), then the epilogue; warp 8 allocates TMEM and one elected lane issues the MMAs; warp 9: one elected lane
+// issues the weight TMA copies.
+#pragma once
+#include "tsgemm.cuh"
+
+namespace cv {
+using namespace tc;
+
+struct ImgGeom {
+    int ih, iw, cin, oh, ow, cout, k, s, pt, pl;
+    int hp;       // padded rows resident in shared memory: (oh-1)*s + k
+    int wps;      // columns per stride phase: ceil(((ow-1)*s + k) / s)
+    int wcols;    // s * wps
+    int pitch;    // bytes per pixel in shared memory (cin*4, +16 when that is a multiple of 128)
+    int cpp;      // 16-byte chunks per pixel
+    int nkb;      // k*k*cin / 32
+    int th;       // output rows per band (th * ow <= 128)
+    int nbands;   // ceil(oh / th)
+    int img_bytes;
+    unsigned m_wcols, m_wps;  // fastdiv magics (learner.h)
+};
+
+static inline bool img_geom(const ConvGeom& g, ImgGeom& q) {
+    q.ih = g.ih; q.iw = g.iw; q.cin = g.cin; q.oh = g.oh; q.ow = g.ow; q.cout = g.cout; q.k = g.k; q.s = g.s; q.pt = g.pt; q.pl = g.pl;
+    if (!((g.cin % 32 == 0) || (g.cin == 4 && g.k == 8))) return false;  // a k-block = 128 contiguous source bytes
+    if (g.ow > 128 || (g.cout != 32 && g.cout != 64)) return false;
+    q.hp = (g.oh - 1) * g.s + g.k;
+    q.wps = ((g.ow - 1) * g.s + g.k + g.s - 1) / g.s;
+    q.wcols = g.s * q.wps;
+    q.cpp = g.cin / 4;
+    q.pitch = g.cin * 4 + ((g.cin * 4) % 128 == 0 ? 16 : 0);
+    q.nkb = g.k * g.k * g.cin / 32;
+    q.th = 128 / g.ow; if (q.th > g.oh) q.th = g.oh;
+    q.nbands = (g.oh + q.th - 1) / q.th;
+    q.img_bytes = ((q.hp * q.wcols * q.pitch + 127) / 128) * 128;
+    if (q.nkb > 64 || q.nkb < 1) return false;
+    q.m_wcols = fastdiv_magic((unsigned)q.wcols); q.m_wps = fastdiv_magic((unsigned)q.wps);
+    return true;
+}
+
+// packed weights of one layer: [k-block][hi, lo][tile], tile = cout rows x 32 k in the dense canonical K-major layout
+// (8-row x 16-byte core matrices, LBO 128, SBO 1024): element (n, k) at (n/8)*1024 + (k/4)*128 + (n%8)*16 + (k%4)*4
+constexpr uint32_t PK_LBO = 128, PK_SBO = 1024;
+static inline size_t packed_floats(const ConvGeom& g) { return (size_t)g.k * g.k * g.cin * g.cout * 2; }
+
+// W is HWIO: W[kk][n], kk = (kh*k + kw)*cin + c.  flip: the dgrad operand Wd[(kh',kw',co)][ci] = W[k-1-kh'][k-1-kw'][ci][co]
+__global__ void pack_conv_kernel(const float* __restrict__ W, float* __restrict__ packed, int K, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const int kk = i / N, n = i - kk * N;
+    const float v = W[i];
+    const int kb = kk >> 5, kin = kk & 31;
+    const size_t tile = (size_t)N * 32;  // floats per tile
+    const size_t off = (size_t)kb * 2 * tile + ((n >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (n & 7) * 16 + (kin & 3) * 4) / 4;
+    packed[off] = v;
+    packed[off + tile] = lo_part(v);
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int BN, int NTERMS>
+struct CvPlan {
+    static constexpr int S = 6;                                   // ring depth: B tiles in smem, A tiles in TMEM
+    static constexpr int B_TILE = BN * 128;                       // bytes of one hi (or lo) tile
+    static constexpr int B_STAGE = B_TILE * 2;                    // hi + lo travel together
+    static constexpr int ACOLS = BK * (NTERMS == 3 ? 2 : 1);
+    static constexpr int MAXB = 4;                                // bands (accumulators) per image
+    static constexpr int BAR_BYTES = 1024;                        // barriers + tmem slot + k-block offset table
+};
+
+constexpr int CV_THREADS = 320;
+
+template <int BN, int NTERMS, class Epi>
+__global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in, const float* __restrict__ packed,
+                                                               const Epi epi, const ImgGeom g, const float* __restrict__ zeros,
+                                                               unsigned long long* __restrict__ dbg) {
+    using P = CvPlan<BN, NTERMS>;
+    const bool cta0 = dbg && blockIdx.x == 0;  // in-kernel timeline (dqn_debug_timeline, mode >= 16)
+#define CV_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 64) dbg[(row) * 8 + (col)] = clock64(); } while (0)
+    CV_STAMP(threadIdx.x == 0, 63, 0);
+    constexpr int S = P::S;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t ring = sbase;                                  // S x B_STAGE (1024-aligned tiles)
+    const uint32_t bars = ring + S * P::B_STAGE;                  // afull[S], bfull[S], empty[S], accum[MAXB], tmem slot
+    const uint32_t kbtab = bars + 256;                            // int kboff[64]
+    const uint32_t bias_s = bars + 512;                           // float bias[BN]
+    const uint32_t img = bars + P::BAR_BYTES;
+    auto afull_bar = [&](int s) { return bars + 8u * s; };
+    auto bfull_bar = [&](int s) { return bars + 8u * (S + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * S + s); };
+    auto accum_bar = [&](int b) { return bars + 8u * (3 * S + b); };
+    const uint32_t tmem_slot = bars + 8u * (3 * S + P::MAXB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int image = blockIdx.x;
+    const int nsteps = g.nbands * g.nkb;
+    constexpr int DCOLS_MIN = 32;
+    const int dcols = g.nbands * BN < DCOLS_MIN ? DCOLS_MIN : g.nbands * BN;  // accumulators: band b at column b*BN
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(afull_bar(s), 4);   // the 4 converter warps of the group that owns the block
+            mbar_init(bfull_bar(s), 1);   // the TMA thread's expect_tx arrival (+ the bytes)
+            mbar_init(empty_bar(s), 1);   // tcgen05.commit
+        }
+        for (int b = 0; b < P::MAXB; ++b) mbar_init(accum_bar(b), 1);
+        fence_barrier_init();
+    }
+    if (tid < g.nkb) {
+        // k-block kb covers K elements [32 kb, 32 kb + 32) of (kh, kw, c): its 128 source bytes start at this offset
+        // from the pixel a thread owns (cin >= 32: one tap, channel chunk; cin == 4: one kernel row, all kw)
+        const int kk = tid * 32;
+        const int tap = kk / g.cin, c = kk - tap * g.cin;
+        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int off = (kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + c * 4;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(kbtab + 4u * tid), "r"(off) : "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    CV_STAMP(threadIdx.x == 0, 63, 1);
+    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(dcols + s * P::ACOLS); };
+    auto stage_b = [&](int s) { return ring + s * P::B_STAGE; };
+
+    if (warp < 8) {
+        pdl_wait();  // the input image is the stream predecessor's output
+        CV_STAMP(tid == 0, 63, 2);
+        // ---------------- image -> shared memory (once) ----------------
+        {
+            const float* src_img = in + (size_t)image * g.ih * g.iw * g.cin;
+            // thread -> fixed 16-byte chunk c of pixels p0, p0 + 256/cpp, ... (cpp divides 256)
+            const int c = tid % g.cpp, pstep = 256 / g.cpp, npix = g.hp * g.wcols;
+            if (tid < BN) {
+                const float bv = epi.bias[tid];
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
+            }
+            for (int p = tid / g.cpp; p < npix; p += pstep) {
+                const int iyp = fdiv(p, g.m_wcols, g.wcols), col = p - iyp * g.wcols;
+                const int phase = fdiv(col, g.m_wps, g.wps), j = col - phase * g.wps;
+                const int iy = iyp - g.pt, ix = j * g.s + phase - g.pl;
+                const bool ok = (unsigned)iy < (unsigned)g.ih && (unsigned)ix < (unsigned)g.iw;
+                const float* src = ok ? src_img + ((size_t)(iy * g.iw + ix) * g.cin + c * 4) : zeros;
+                cp_async16(img + (uint32_t)(p * g.pitch + c * 16), src, ok);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        CV_STAMP(tid == 0, 63, 3);
+        // ---------------- A converters ----------------
+        const int grp = warp & 3, cg = warp >> 2;  // TMEM lane quarter, converter group
+        const int m = grp * 32 + lane;             // row of the band tile
+        const int oyl = m / g.ow, ox = m - oyl * g.ow;
+        const bool row_ok = oyl < g.th;
+        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        // the 8 chunks of a k-block: consecutive channels of one pixel, or (cin == 4) consecutive kw of one kernel row
+        uint32_t choff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) choff[j] = g.cin >= 32 ? 16u * j : (uint32_t)(((j % g.s) * g.wps + j / g.s) * g.pitch);
+        int step = cg;
+        for (int band = 0; band < g.nbands; ++band) {
+            const int oy = band * g.th + oyl;
+            const uint32_t base = img + ((row_ok && oy < g.oh) ? (uint32_t)((oy * g.s * g.wcols + ox) * g.pitch) : 0u);
+            const int step_end = (band + 1) * g.nkb;
+            for (; step < step_end; step += 2) {
+                const int kb = step - band * g.nkb;
+                const int s = step % S, ph = (step / S) & 1;
+                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);  // TMEM stage s is free again
+                CV_STAMP(grp == 0 && lane == 0, step, 0);
+                uint32_t koff;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(koff) : "r"(kbtab + 4u * kb));
+                const uint32_t src = base + koff;
+                float hi[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + choff[c]));
+                const uint32_t ta = tmem_a(s) + lane_base;
+                ts::tmem_st32(ta, hi);
+                if (NTERMS == 3) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+                    ts::tmem_st32(ta + BK, lo);
+                }
+                ts::tmem_st_wait();
+                tc_fence_before();
+                CV_STAMP(grp == 0 && lane == 0, step, 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull_bar(s));
+            }
+        }
+        CV_STAMP(tid == 0, 63, 4);
+        pdl_launch_dependents();
+        // ---------------- epilogue: warp (grp, cg) owns TMEM lanes 32 grp.., columns [cg BN/2, +BN/2) of every band ----------------
+        constexpr int HC = BN / 2;
+        for (int band = 0; band < g.nbands; ++band) {
+            mbar_wait(accum_bar(band), 0);
+            tc_fence_after();
+            CV_STAMP(tid == 0 && band == 0, 63, 5);
+            const int oy = band * g.th + oyl;
+            const bool ok = row_ok && oy < g.oh;
+            const int mg = image * g.oh * g.ow + oy * g.ow + ox;
+            const uint32_t trow = tmem_base + lane_base + (uint32_t)(band * BN + cg * HC);
+#pragma unroll
+            for (int c = 0; c < HC; c += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c, v);
+                if (ok) epi.template store_b<16>(mg, cg * HC + c, v, bias_s + 4u * (cg * HC + c));
+            }
+        }
+        tc_fence_before();
+        CV_STAMP(tid == 0, 63, 6);
+    } else if (warp == 8) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = make_idesc(BN, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        int s = 0, ph = 0, step = 0;
+        bool ready = false;  // barriers of the current step already seen complete (tested during the previous step)
+        for (int band = 0; band < g.nbands; ++band) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(band * BN);
+            for (int kb = 0; kb < g.nkb; ++kb, ++step) {
+                if (!ready) {
+                    mbar_wait(afull_bar(s), ph);   // A tile of this step is in tensor memory
+                    mbar_wait(bfull_bar(s), ph);   // B tile has landed (TMA, async proxy: no proxy fence needed)
+                }
+                CV_STAMP(lane == 0, step, 3);
+                tc_fence_after();
+                // the tensor pipe queues only a few MMAs: look at the NEXT step's barriers before issuing this step's,
+                // so that the mbarrier round trip overlaps their execution instead of draining the queue
+                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
+                ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1) && mbar_test(bfull_bar(s1), ph1);
+                const uint64_t db = make_desc(stage_b(s), PK_LBO, PK_SBO);
+                const uint64_t dbl = make_desc(stage_b(s) + P::B_TILE, PK_LBO, PK_SBO);
+                const uint32_t ta = tmem_a(s);
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2 * PK_LBO) >> 4;
+                    const uint32_t acc = (kb | ks) != 0;
+                    if (leader) {
+                        if (NTERMS == 3) {
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, dbl + o, idesc, acc);      // A_hi * B_lo
+                            ts::mma_tf32_ts(tmem_d, ta + BK + ks * 8, db + o, idesc, 1);   // A_lo * B_hi
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, 1);        // A_hi * B_hi
+                        } else {
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, acc);
+                        }
+                    }
+                }
+                if (leader) {
+                    mma_commit(empty_bar(s));
+                    if (kb == g.nkb - 1) mma_commit(accum_bar(band));
+                }
+                CV_STAMP(lane == 0, step, 4);
+                __syncwarp();
+                s = s1; ph = ph1;
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- weight TMA producer (warp 9, one lane) ----------------
+        if (lane == 0) {
+            pdl_wait();
+            int s = 0, ph = 0, kb = 0;
+            for (int step = 0; step < nsteps; ++step) {
+                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
+                CV_STAMP(true, step, 5);
+                mbar_expect_tx(bfull_bar(s), P::B_STAGE);
+                tma_bulk_g2s(stage_b(s), packed + (size_t)kb * (P::B_STAGE / 4), P::B_STAGE, bfull_bar(s));
+                if (++kb == g.nkb) kb = 0;
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+template <int BN, int NTERMS, class Epi>
+static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, int images) {
+    using P = CvPlan<BN, NTERMS>;
+    auto kern = cvconv_kernel<BN, NTERMS, Epi>;
+    const size_t bytes = (size_t)P::S * P::B_STAGE + P::BAR_BYTES + g.img_bytes + 1024;
+    DQN_REQUIRE(bytes <= 227 * 1024, "image-resident conv: shared memory budget");
+    DQN_REQUIRE(g.nbands <= P::MAXB && g.nbands * BN + P::S * P::ACOLS <= 512, "image-resident conv: tensor memory budget");
+    static size_t configured = 0;  // one per template instantiation
+    if (bytes > configured) {
+        DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    launch_kernel(h->pdl, kern, dim3(images), dim3(CV_THREADS), bytes, h->stream, in, packed, e, g, (const float*)h->zeros16, h->tc_dbg);
+    h->launches++;
+}
+
+#undef CV_STAMP
+}  // namespace cv

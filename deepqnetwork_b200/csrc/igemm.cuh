@@ -282,6 +282,18 @@ struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
 // ---------------- epilogues ----------------
 struct EpiBiasRelu {  // out[m][n] = relu(acc + bias[n])
     float* out; const float* bias; int ldo;
+    // bias staged in shared memory by the caller (cvgemm.cuh): sbias = shared address of bias[n]
+    template <int TN>
+    __device__ __forceinline__ void store_b(int m, int n, const float (&v)[TN], uint32_t sbias) const {
+        float* o = out + (size_t)m * ldo + n;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sbias + 4u * j));
+            *reinterpret_cast<float4*>(o + j) = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f),
+                                                            fmaxf(v[j + 2] + b.z, 0.f), fmaxf(v[j + 3] + b.w, 0.f));
+        }
+    }
     template <int TN>
     __device__ __forceinline__ void store(int m, int n, const float (&v)[TN], int) const {
         float* o = out + (size_t)m * ldo + n;

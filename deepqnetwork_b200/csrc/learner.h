@@ -137,6 +137,12 @@ struct dqn_learner {
     float* zeros16 = nullptr;   // 16 zero bytes (cp.async dummy source)
     float* ones_row = nullptr;  // {1,0,0,0}: the bias row appended to conv wgrad A^T
     float* x_f32 = nullptr;     // u8 batch converted to f32 (x/255) for cp.async loaders: [2*max_rows][S]
+    // image-resident conv kernels (cvgemm.cuh): pre-split, pre-tiled conv weights per tower ([0]=online, [1]=target),
+    // kept in sync with the parameter slabs by launch_pack_conv (after every optimizer step / copy / set_param)
+    float* packed[2] = {nullptr, nullptr};
+    int64_t pk_off[3] = {0, 0, 0};
+    int64_t pk_floats = 0;
+    bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
     // staging
     uint8_t* dev_stage = nullptr;
@@ -193,6 +199,8 @@ void launch_tree_stats(dqn_learner* h, double per_b_override);
 // x_f32: the same rows as d_states already converted to f32 (used by the tcgen05 path; may be null in FP32 mode)
 void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts);
 void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows);
+void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of the packed conv weights
+void launch_pack_conv(dqn_learner* h, int tower);  // re-pack one tower's conv weights from its parameter slab
 void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n);
 int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, int b_kcontig, const float* dA, const float* dB, float* dC);
 

@@ -5,6 +5,7 @@
 // Layout: activations NHWC f32, conv kernels HWIO (== row-major [KH*KW*Cin, Cout]), dense kernels [in,out] --
 // the TF layouts, so tensors copy 1:1 to/from checkpoints.
 #include "tsgemm.cuh"
+#include "cvgemm.cuh"
 #include <algorithm>
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -215,6 +216,37 @@ static void launch_fc_reduce_heads(dqn_learner* h, const float* P, int splits, i
 
 static int fc_kchunk() { return 256; }
 
+// ---- image-resident conv path (cvgemm.cuh) -------------------------------------------------------------------------
+void alloc_packed_conv(dqn_learner* h) {
+    int64_t off = 0;
+    for (int l = 0; l < 3; ++l) { h->pk_off[l] = off; off += (int64_t)cv::packed_floats(h->net.conv[l]); }
+    h->pk_floats = off;
+    for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->packed[t], (size_t)off * sizeof(float)));
+}
+
+void launch_pack_conv(dqn_learner* h, int tower) {
+    if (h->cfg.math_mode == DQN_MATH_FP32 || !h->packed[tower]) return;
+    const float* P = tower ? h->target : h->online;
+    for (int l = 0; l < 3; ++l) {
+        const ConvGeom& g = h->net.conv[l];
+        const int K = g.k * g.k * g.cin, N = g.cout;
+        if (K % 32 != 0) continue;
+        cv::pack_conv_kernel<<<ceil_div(K * N, 256), 256, 0, h->stream>>>(P + h->net.off_cw[l], h->packed[tower] + h->pk_off[l], K, N);
+        DQN_CUDA_OK(cudaGetLastError());
+        h->launches++;
+    }
+}
+
+template <class Epi>
+static bool conv_image_resident(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ConvGeom& g, int images) {
+    cv::ImgGeom q;
+    if (!h->img_conv || !cv::img_geom(g, q)) return false;
+    const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
+    if (g.cout == 64) { if (x3) cv::launch_conv<64, 3>(h, in, packed, e, q, images); else cv::launch_conv<64, 1>(h, in, packed, e, q, images); }
+    else              { if (x3) cv::launch_conv<32, 3>(h, in, packed, e, q, images); else cv::launch_conv<32, 1>(h, in, packed, e, q, images); }
+    return true;
+}
+
 void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts) {
     const NetDesc& net = h->net;
     const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
@@ -228,7 +260,10 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
         OpConvFwdA a{in, g, (l == 0 && !tcm) ? 1 : 0};
         OpColContig b{P + net.off_cw[l], g.cout};
         EpiBiasRelu e{acts.act[l], P + net.off_cb[l], g.cout};
-        gemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
+        const int tw = P == h->online ? 0 : 1;
+        if (!(tcm && (P == h->online || P == h->target) &&
+              conv_image_resident(h, (const float*)in, h->packed[tw] + h->pk_off[l], e, g, rows)))
+            gemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
         in = acts.act[l];
     }
     int kchunk = fc_kchunk();
@@ -255,6 +290,19 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
     }
     prof_mark(h, tg ? "tg_fc_reduce_heads" : "on_fc_reduce_heads");
     launch_fc_reduce_heads(h, P, splits, rows, acts);
+}
+
+// debug: conv layer `layer` of the online tower alone on `rows` images (dqn_debug_timeline, mode 16 + layer)
+void debug_conv_layer(dqn_learner* h, int layer, int rows) {
+    const NetDesc& net = h->net;
+    const ConvGeom& g = net.conv[layer];
+    const float* P = h->online;
+    const void* in = layer == 0 ? (const void*)h->x_f32 : (const void*)h->acts_on.act[layer - 1];
+    OpConvFwdA a{in, g, 0};
+    OpColContig b{P + net.off_cw[layer], g.cout};
+    EpiBiasRelu e{h->acts_on.act[layer], P + net.off_cb[layer], g.cout};
+    if (!conv_image_resident(h, (const float*)in, h->packed[0] + h->pk_off[layer], e, g, rows))
+        gemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
 }
 
 // ---- backward ------------------------------------------------------------------------------------------

@@ -238,6 +238,7 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
                                                         (float)h->cfg.momentum, h->cfg.use_momentum, h->d_sc, h->opt_ticket);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
+    launch_pack_conv(h, 0);  // the image-resident conv kernels read the online conv weights pre-split and pre-tiled
 }
 
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
@@ -250,4 +251,6 @@ void launch_post_step(dqn_learner* h, int per_update) {
 
 void launch_copy_network(dqn_learner* h) {
     DQN_CUDA_OK(cudaMemcpyAsync(h->target, h->online, (size_t)h->net.slab * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->packed[0] && h->cfg.math_mode != DQN_MATH_FP32)
+        DQN_CUDA_OK(cudaMemcpyAsync(h->packed[1], h->packed[0], (size_t)h->pk_floats * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
 }

@@ -314,7 +314,7 @@ class Learner:
 
     def debug_timeline(self, mode, M, N, K, a_kcontig=True, b_kcontig=True):
         out = np.zeros(512, np.uint64)
-        m = {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
+        m = mode if isinstance(mode, int) else {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
         self._c(self._lib.dqn_debug_timeline(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(out)))
         return out.reshape(64, 8)
 
