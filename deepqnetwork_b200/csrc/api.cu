@@ -12,11 +12,17 @@ void debug_conv_layer(dqn_learner* h, int layer, int rows);
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
 
 long long* tree_size_ptr(dqn_learner* h) { return &h->d_dev->tree_size; }
+void select_set(dqn_learner* h, int k);  // point the b_* batch aliases at buffer set k
 
-#define API_BEGIN(h)                        \
+// every entry point except dqn_train_steps drops the batch that was sampled ahead (it may change the tree, the ring,
+// the counters or the batch buffers); the next fused step then samples eagerly -- same draws, same result
+#define API_BEGIN_KEEP(h)                   \
     if (!(h)) return 2;                     \
     try {                                   \
         DQN_CUDA_OK(cudaSetDevice((h)->device));
+#define API_BEGIN(h)                        \
+    API_BEGIN_KEEP(h)                       \
+        (h)->pf_valid = false;
 #define API_END(h)                          \
     } catch (const std::string& e) {        \
         (h)->err = e;                       \
@@ -78,6 +84,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         h->stream = h->own_stream;
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side2_stream, cudaStreamNonBlocking));
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side3_stream, cudaStreamNonBlocking));
         for (auto& e : h->fork_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         net_describe(h->net, h->cfg);
         const NetDesc& net = h->net;
@@ -148,6 +155,16 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
         }
         dmalloc(h->x_f32, 2 * R * h->state_bytes);
+        {
+            dqn_learner::BatchSet& a = h->sets[0];
+            a.states = h->b_states; a.actions = h->b_actions; a.rewards = h->b_rewards; a.cont = h->b_cont; a.losses = h->b_losses;
+            a.tree_idx = h->b_tree_idx; a.data_idx = h->b_data_idx; a.mem_idx = h->b_mem_idx; a.rows = h->b_rows;
+            a.prio = h->b_prio; a.isw64 = h->b_isw64; a.u = h->b_u; a.isw = h->b_isw; a.x_f32 = h->x_f32;
+            dqn_learner::BatchSet& b = h->sets[1];
+            dmalloc(b.states, 2 * R * h->state_bytes); dmalloc(b.actions, R); dmalloc(b.rewards, R); dmalloc(b.cont, R);
+            dmalloc(b.losses, R); dmalloc(b.tree_idx, R); dmalloc(b.data_idx, R); dmalloc(b.mem_idx, R); dmalloc(b.rows, R);
+            dmalloc(b.prio, R); dmalloc(b.isw64, R); dmalloc(b.u, R); dmalloc(b.isw, R); dmalloc(b.x_f32, 2 * R * h->state_bytes);
+        }
         alloc_packed_conv(h);
         launch_pack_conv(h, 0); launch_pack_conv(h, 1);
         h->dev_stage_bytes = 8u << 20;
@@ -167,6 +184,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->sets[0].states) select_set(h, 0);  // the b_* aliases freed below must be set 0 (set 1 is freed separately)
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
     if (h->prof_graph) cudaGraphExecDestroy(h->prof_graph);
     void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
@@ -187,6 +205,14 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
+    if (h->side3_stream) cudaStreamDestroy(h->side3_stream);
+    for (int k = 0; k < 2; ++k) if (h->pipe_graph[k]) cudaGraphExecDestroy(h->pipe_graph[k]);
+    {
+        dqn_learner::BatchSet& b = h->sets[1];
+        void* p2[] = {b.states, b.actions, b.rewards, b.cont, b.losses, b.tree_idx, b.data_idx, b.mem_idx, b.rows, b.prio,
+                      b.isw64, b.u, b.isw, b.x_f32};
+        for (void* p : p2) if (p) cudaFree(p);
+    }
     if (h->batch_graph) cudaGraphExecDestroy(h->batch_graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -571,14 +597,14 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 bool overlap_enabled(const dqn_learner* h) { return h->overlap && !h->profile; }
 
 static cudaEvent_t next_fork_event(dqn_learner* h) {
-    DQN_REQUIRE(h->fork_used < 16, "fork event pool exhausted");
+    DQN_REQUIRE(h->fork_used < 24, "fork event pool exhausted");
     return h->fork_ev[h->fork_used++];
 }
 
 void side_begin(dqn_learner* h, cudaStream_t& saved, int which) {
     saved = h->stream;
     if (!overlap_enabled(h)) return;
-    cudaStream_t side = which ? h->side2_stream : h->side_stream;
+    cudaStream_t side = which == 2 ? h->side3_stream : which ? h->side2_stream : h->side_stream;
     cudaEvent_t e = next_fork_event(h);
     DQN_CUDA_OK(cudaEventRecord(e, saved));
     DQN_CUDA_OK(cudaStreamWaitEvent(side, e, 0));
@@ -590,7 +616,7 @@ void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; }
 void main_wait_side(dqn_learner* h, int which) {
     if (!overlap_enabled(h)) return;
     cudaEvent_t e = next_fork_event(h);
-    DQN_CUDA_OK(cudaEventRecord(e, which ? h->side2_stream : h->side_stream));
+    DQN_CUDA_OK(cudaEventRecord(e, which == 2 ? h->side3_stream : which ? h->side2_stream : h->side_stream));
     DQN_CUDA_OK(cudaStreamWaitEvent(h->stream, e, 0));
 }
 
@@ -607,6 +633,15 @@ void prof_mark(dqn_learner* h, const char* name) {
     h->prof_marks.push_back(name);
     h->prof_used++;
 }
+
+void select_set(dqn_learner* h, int k) {
+    const dqn_learner::BatchSet& a = h->sets[k];
+    h->b_states = a.states; h->b_actions = a.actions; h->b_rewards = a.rewards; h->b_cont = a.cont; h->b_losses = a.losses;
+    h->b_tree_idx = a.tree_idx; h->b_data_idx = a.data_idx; h->b_mem_idx = a.mem_idx; h->b_rows = a.rows;
+    h->b_prio = a.prio; h->b_isw64 = a.isw64; h->b_u = a.u; h->b_isw = a.isw; h->x_f32 = a.x_f32;
+    h->cur_set = k;
+}
+static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* rows);
 
 // forward both towers, TD epilogue and (train) backward on a [2n,S] batch laid out as rows [0,n)=s, [n,2n)=s'
 static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8_t* actions, const uint8_t* rewards,
@@ -636,19 +671,33 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
                        grad_scale);
-    if (train && per_update) {
+    if (train && (per_update || h->pf_capture)) {
         // replay_sampler.update_sum_tree(tree_idxes, _make_priority(losses)) (deep_q_agent.py:341-347): it only needs
-        // the TD errors, so it runs on the side stream underneath the whole backward pass
+        // the TD errors, so it runs on a side stream underneath the whole backward pass ...
         cudaStream_t sv;
-        side_begin(h, sv);
-        prof_mark(h, "tree_update");
-        launch_tree_update(h, n, h->b_tree_idx, h->b_newprio, 1);
+        const int which = h->pf_capture ? 2 : 0;
+        side_begin(h, sv, which);
+        if (per_update) {
+            prof_mark(h, "tree_update");
+            launch_tree_update(h, n, h->b_tree_idx, h->b_newprio, 1);
+        }
+        if (h->pf_capture) {
+            // ... and the NEXT step's batch is sampled from the updated tree and gathered into the other buffer set
+            // right behind it (counters read with +1: the optimizer kernel bumps them at the end of this step)
+            const int cur = h->cur_set;
+            select_set(h, cur ^ 1);
+            h->sample_ahead = 1;
+            try { sample_into_batch(h, nullptr, nullptr); } catch (...) { h->sample_ahead = 0; select_set(h, cur); throw; }
+            h->sample_ahead = 0;
+            select_set(h, cur);
+        }
         side_end(h, sv);
     }
     if (train) {
         prof_mark(h, "head_backward");
         launch_head_backward(h, n, actions);
         tower_backward(h, states2, xf, n);
+        if (h->pf_capture) main_wait_side(h, 2);  // the look-ahead batch is complete before the counters are bumped
     }
 }
 
@@ -662,29 +711,31 @@ static void finish_step(dqn_learner* h, int per_update) {
     h->host_step++;
 }
 
-static void maybe_refresh_stats(dqn_learner* h);
+static bool maybe_refresh_stats(dqn_learner* h);
 static void maybe_refresh_stats_noprof(dqn_learner* h) {
     const int p = h->profile; h->profile = 0;
     maybe_refresh_stats(h);
     h->profile = p;
 }
-static void maybe_refresh_stats(dqn_learner* h) {
+static bool maybe_refresh_stats(dqn_learner* h) {
     // deep_q_agent.py:505: step % per_calculate_steps == 0 or last_max_weight is None
     if (h->cfg.use_per && (!h->has_max_weight || h->host_step % h->cfg.per_calculate_steps == 0)) {
         launch_tree_stats(h, -1.0);
         h->has_max_weight = true;
+        return true;
     }
+    return false;
 }
 
 __global__ void uniform_rows_kernel(int batch, const long long* p_len, uint64_t seed, dqn_learner::Scalars* sc,
-                                    long long* rows) {
+                                    long long* rows, int ahead) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     // replay_sampler.py:27-30: size = len/B ; randint(int(i*size), int((i+1)*size - 1)) inclusive
     const double size = (double)(*p_len) / (double)batch;
     const long long lo = (long long)((double)i * size), hi = (long long)((double)(i + 1) * size - 1.0);
     uint32_t r[4];
-    const unsigned long long ctr = sc->rng_counter;
+    const unsigned long long ctr = sc->rng_counter + (unsigned long long)ahead;
     philox4x32((uint32_t)i, 1u, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
     long long span = hi - lo + 1;
     if (span < 1) span = 1;
@@ -704,7 +755,7 @@ static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* ro
     } else {
         if (rows) DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows, h->B * 8, cudaMemcpyHostToDevice, h->stream));
         else {
-            uniform_rows_kernel<<<ceil_div(h->B, 128), 128, 0, h->stream>>>(h->B, &h->d_dev->ring_len, h->cfg.seed, h->d_sc, h->b_rows);
+            uniform_rows_kernel<<<ceil_div(h->B, 128), 128, 0, h->stream>>>(h->B, &h->d_dev->ring_len, h->cfg.seed, h->d_sc, h->b_rows, h->sample_ahead);
             DQN_CUDA_OK(cudaGetLastError());
             h->launches++;
         }
@@ -749,8 +800,9 @@ extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* ro
 }
 
 extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
-    API_BEGIN(h)
+    API_BEGIN_KEEP(h)
     DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+    if (h->profile || !h->prefetch) h->pf_valid = false;
     if (h->profile) {
         if (!h->prof_graph) {
             cudaGraph_t g = nullptr;
@@ -788,6 +840,57 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
                 if (!found) h->prof_acc.push_back({h->prof_marks[s], ms});
             }
             h->prof_steps++;
+        }
+        return 0;
+    }
+    if (h->prefetch) {
+        // Pipelined replay: graph k consumes the batch in sets[k] and, behind its priority write-back, samples and
+        // gathers the next batch into sets[1-k].  Same draws, same tree states, same results as the serial order.
+        if (!h->graph_valid) {
+            for (int k = 0; k < 2; ++k) {
+                cudaGraph_t g = nullptr;
+                const int64_t l0 = h->launches, s0 = h->host_step;
+                select_set(h, k);
+                DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                h->pf_capture = true;
+                try {
+                    h->fuse_fc_adam = h->fuse_enabled; h->early_fc_adam = !h->fuse_fc_adam;
+                    h->xf_from_gather = true;  // the look-ahead gather of the previous step wrote x_f32 of this set
+                    step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1,
+                              1.0, h->cfg.use_per);
+                    finish_step(h, 0);
+                } catch (...) {
+                    h->pf_capture = false; h->fuse_fc_adam = false; h->early_fc_adam = false;
+                    cudaStreamEndCapture(h->stream, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                h->pf_capture = false; h->fuse_fc_adam = false; h->early_fc_adam = false;
+                DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+                h->graph_launches = h->launches - l0;
+                h->launches = l0; h->host_step = s0;
+                if (h->pipe_graph[k]) { cudaGraphExecDestroy(h->pipe_graph[k]); h->pipe_graph[k] = nullptr; }
+                DQN_CUDA_OK(cudaGraphInstantiate(&h->pipe_graph[k], g, 0));
+                DQN_CUDA_OK(cudaGraphDestroy(g));
+            }
+            h->graph_valid = true;
+            h->pf_valid = false;
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            const bool refreshed = maybe_refresh_stats(h);
+            if (!h->pf_valid || refreshed) {
+                // first step after anything else touched the handle, or new PER normalisers (deep_q_agent.py:505-510):
+                // sample eagerly with the counters as they are (the look-ahead sample used the same draws)
+                select_set(h, h->pf_set);
+                sample_into_batch(h, nullptr, nullptr);
+                h->pf_valid = true;
+            }
+            select_set(h, h->pf_set);  // the batch this step trains on (what dqn_batch_read shows afterwards)
+            DQN_CUDA_OK(cudaGraphLaunch(h->pipe_graph[h->pf_set], h->stream));
+            h->pf_set ^= 1;
+            h->launches += h->graph_launches;
+            h->host_step++;
+            after_step_host(h);
         }
         return 0;
     }
@@ -973,7 +1076,8 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
-    else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
+    else if (n == "img_conv") h->img_conv = value != 0;
+    else if (n == "prefetch") h->prefetch = value != 0;   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }

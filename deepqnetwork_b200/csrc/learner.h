@@ -50,8 +50,8 @@ struct dqn_learner {
     // second stream + events: independent kernels of one step (target tower vs online tower, wgrads vs the dgrad
     // chain) are forked onto it so that the small batch-32 grids overlap; inside a captured graph these become
     // parallel branches
-    cudaStream_t side_stream = nullptr, side2_stream = nullptr;
-    cudaEvent_t fork_ev[16] = {};
+    cudaStream_t side_stream = nullptr, side2_stream = nullptr, side3_stream = nullptr;
+    cudaEvent_t fork_ev[24] = {};
     int fork_used = 0;
     bool overlap = true;
     bool pdl = true;            // programmatic dependent launch for the kernels that call pdl_wait()
@@ -125,6 +125,23 @@ struct dqn_learner {
     double* b_u = nullptr;             // uniforms
     float *b_y = nullptr, *b_maxq = nullptr, *b_losses_out = nullptr, *b_dq = nullptr, *b_newprio = nullptr;
 
+    // The sampled batch is double-buffered: inside the graph of step i the batch of step i+1 is sampled and gathered
+    // (side branch, right after the priority write-back of step i) into the other set, so sampling leaves the critical
+    // path.  The b_* pointers above always alias sets[cur]; select_set() switches them.
+    struct BatchSet {
+        uint8_t *states, *actions, *rewards, *cont;
+        __half* losses;
+        long long *tree_idx, *data_idx, *mem_idx, *rows;
+        double *prio, *isw64, *u;
+        float *isw, *x_f32;
+    } sets[2] = {};
+    int cur_set = 0;
+    bool pf_valid = false;    // sets[pf_set] holds the batch the next fused step consumes (sampled ahead)
+    int pf_set = 0;
+    bool pf_capture = false;  // set while capturing a pipelined step graph: step_core appends the look-ahead sample
+    int sample_ahead = 0;     // the sampler reads step / rng counter + sample_ahead (1 for the look-ahead sample)
+    bool prefetch = true;     // option
+
     // activations / workspaces
     TowerActs acts_on, acts_tg;
     float *d_hid = nullptr, *d_act[3] = {nullptr, nullptr, nullptr};
@@ -151,6 +168,7 @@ struct dqn_learner {
 
     // graph for the fused step
     cudaGraphExec_t step_graph = nullptr;
+    cudaGraphExec_t pipe_graph[2] = {nullptr, nullptr};  // pipelined step consuming sets[k], sampling into sets[1-k]
     bool graph_valid = false;
     // graph of one host-fed step (dqn_train_batch), keyed by the batch size
     cudaGraphExec_t batch_graph = nullptr;

@@ -66,7 +66,8 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
                                    dqn_learner::Scalars* sc, PerParams pp, int use_per_weights,
                                    long long* __restrict__ o_tree_idx, long long* __restrict__ o_data_idx,
                                    long long* __restrict__ o_mem_idx, double* __restrict__ o_prio,
-                                   double* __restrict__ o_isw64, float* __restrict__ o_isw, double* __restrict__ o_u) {
+                                   double* __restrict__ o_isw64, float* __restrict__ o_isw, double* __restrict__ o_u,
+                                   int ahead) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= batch) return;
@@ -75,7 +76,7 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
     double u;
     if (device_rng) {
         uint32_t r[4];
-        unsigned long long ctr = sc->rng_counter;
+        unsigned long long ctr = sc->rng_counter + (unsigned long long)ahead;  // look-ahead sample: counters not bumped yet
         philox4x32((uint32_t)i, 0u, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
         u = u53(r[0], r[1]);
     } else {
@@ -98,7 +99,7 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
         if (o_u) o_u[i] = u;
         if (use_per_weights) {
             // deep_q_agent.py:518-519 (float64 array maths on f32 tree values)
-            const double per_b = current_per_b(pp, sc->step);
+            const double per_b = current_per_b(pp, sc->step + ahead);
             const double prob = (double)p / (double)total;
             const double w = pow((double)batch * prob, -per_b) / (double)sc->last_max_weight;
             if (o_isw64) o_isw64[i] = w;
@@ -246,7 +247,7 @@ void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b)
     tree_sample_kernel<<<ceil_div(batch, wpb), wpb * 32, 0, h->stream>>>(
         h->tree, h->tree_data, h->cap, tree_size_ptr(h), batch, h->b_u, device_rng, h->cfg.seed, h->d_sc,
         make_pp(h, per_b), h->cfg.use_per, h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64,
-        h->b_isw, device_rng ? h->b_u : nullptr);
+        h->b_isw, device_rng ? h->b_u : nullptr, h->sample_ahead);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches++;
 }

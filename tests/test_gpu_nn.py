@@ -274,7 +274,8 @@ def test_graph_replay_equals_eager_steps(math_mode):
     for k in res[0][0]:
         assert np.array_equal(res[0][0][k], res[1][0][k]), k
     assert np.array_equal(res[0][1], res[1][1])
-    assert res[0][2] == res[1][2] > 6 * 20
+    # the pipelined replay samples one batch ahead: one extra sample + gather launch pair over the whole run
+    assert res[0][2] > 6 * 20 and res[1][2] - res[0][2] in (0, 2)
 
 
 def test_save_restore_roundtrip(tmp_path):
