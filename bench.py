@@ -311,7 +311,9 @@ def main():
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
                 use_per=cfg['per'], batch_size=BATCH, replay_capacity=args.capacity, conv_variant=cfg['variant'],
                 math_mode=args.math, seed=7 + rank, device=local_rank)
-    stream = torch.cuda.Stream()      # a real (non-default) stream: stream capture is illegal on the legacy stream
+    # a real (non-default) stream: stream capture is illegal on the legacy stream; high priority, because the learner's
+    # own side streams (weight gradients, optimizer, look-ahead sampling) only carry work with slack
+    stream = torch.cuda.Stream(priority=-1)
     torch.cuda.set_stream(stream)
     L.set_stream(stream.cuda_stream)  # so that torch.cuda.Event brackets exactly the learner's work
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])

@@ -80,7 +80,13 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         cudaDeviceProp prop;
         DQN_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
         h->sm_count = prop.multiProcessorCount;
-        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        {   // the main stream carries the critical path of a step (forward, dgrad chain); the side streams only hold
+            // work that has slack (weight gradients, optimizer, look-ahead sampling): give the main stream priority
+            int lo = 0, hi = 0;
+            DQN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            h->prio_lo = lo; h->prio_hi = hi;
+            DQN_CUDA_OK(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi));
+        }
         h->stream = h->own_stream;
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side2_stream, cudaStreamNonBlocking));
@@ -601,9 +607,17 @@ static cudaEvent_t next_fork_event(dqn_learner* h) {
     return h->fork_ev[h->fork_used++];
 }
 
-void side_begin(dqn_learner* h, cudaStream_t& saved, int which) {
+static int prio_of(const dqn_learner* h, int prio_class) {
+    if (!h->use_prio) return h->prio_lo;
+    const int p = prio_class >= 2 ? h->prio_hi : prio_class == 1 ? h->prio_hi + 1 : h->prio_lo;
+    return p > h->prio_lo ? h->prio_lo : p;
+}
+
+void side_begin(dqn_learner* h, cudaStream_t& saved, int which, int prio_class) {
     saved = h->stream;
+    h->saved_prio = g_launch_priority;
     if (!overlap_enabled(h)) return;
+    g_launch_priority = prio_of(h, prio_class);
     cudaStream_t side = which == 2 ? h->side3_stream : which ? h->side2_stream : h->side_stream;
     cudaEvent_t e = next_fork_event(h);
     DQN_CUDA_OK(cudaEventRecord(e, saved));
@@ -611,7 +625,7 @@ void side_begin(dqn_learner* h, cudaStream_t& saved, int which) {
     h->stream = side;
 }
 
-void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; }
+void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; g_launch_priority = h->saved_prio; }
 
 void main_wait_side(dqn_learner* h, int which) {
     if (!overlap_enabled(h)) return;
@@ -649,6 +663,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     const size_t S = h->state_bytes;
     const int A = h->net.A;
     const float* xf = nullptr;
+    g_launch_priority = prio_of(h, 2);  // everything issued on the main stream of a step is the critical chain
     if (h->cfg.math_mode != DQN_MATH_FP32) {
         if (!(h->xf_from_gather && states2 == h->b_states)) {  // host-fed batch: convert here; sampled batch: gather did
             prof_mark(h, "u8_to_f32");
@@ -660,7 +675,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     h->fork_used = 0;
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
-    side_begin(h, saved);
+    side_begin(h, saved, 0, 2);
     h->prof_tag = "tg_";
     tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
     side_end(h, saved);
@@ -676,7 +691,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         // the TD errors, so it runs on a side stream underneath the whole backward pass ...
         cudaStream_t sv;
         const int which = h->pf_capture ? 2 : 0;
-        side_begin(h, sv, which);
+        side_begin(h, sv, which, 1);
         if (per_update) {
             prof_mark(h, "tree_update");
             launch_tree_update(h, n, h->b_tree_idx, h->b_newprio, 1);
@@ -755,8 +770,7 @@ static void sample_into_batch(dqn_learner* h, const double* u, const int64_t* ro
     } else {
         if (rows) DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows, h->B * 8, cudaMemcpyHostToDevice, h->stream));
         else {
-            uniform_rows_kernel<<<ceil_div(h->B, 128), 128, 0, h->stream>>>(h->B, &h->d_dev->ring_len, h->cfg.seed, h->d_sc, h->b_rows, h->sample_ahead);
-            DQN_CUDA_OK(cudaGetLastError());
+            launch_kernel(false, uniform_rows_kernel, dim3(ceil_div(h->B, 128)), dim3(128), 0, h->stream, h->B, (const long long*)&h->d_dev->ring_len, (uint64_t)h->cfg.seed, h->d_sc, h->b_rows, h->sample_ahead);
             h->launches++;
         }
         prof_mark(h, "gather");
@@ -870,7 +884,7 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
                 h->graph_launches = h->launches - l0;
                 h->launches = l0; h->host_step = s0;
                 if (h->pipe_graph[k]) { cudaGraphExecDestroy(h->pipe_graph[k]); h->pipe_graph[k] = nullptr; }
-                DQN_CUDA_OK(cudaGraphInstantiate(&h->pipe_graph[k], g, 0));
+                DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->pipe_graph[k], g, cudaGraphInstantiateFlagUseNodePriority));
                 DQN_CUDA_OK(cudaGraphDestroy(g));
             }
             h->graph_valid = true;
@@ -910,7 +924,7 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
         h->graph_launches = h->launches - l0;
         h->launches = l0; h->host_step = s0;
         if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
-        DQN_CUDA_OK(cudaGraphInstantiate(&h->step_graph, g, 0));
+        DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->step_graph, g, cudaGraphInstantiateFlagUseNodePriority));
         DQN_CUDA_OK(cudaGraphDestroy(g));
         h->graph_valid = true;
     }
@@ -987,7 +1001,7 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
             h->batch_graph_launches = h->launches - l0;
             h->launches = l0; h->host_step = s0;
             if (h->batch_graph) { cudaGraphExecDestroy(h->batch_graph); h->batch_graph = nullptr; }
-            DQN_CUDA_OK(cudaGraphInstantiate(&h->batch_graph, g, 0));
+            DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->batch_graph, g, cudaGraphInstantiateFlagUseNodePriority));
             DQN_CUDA_OK(cudaGraphDestroy(g));
             h->batch_graph_n = n; h->graph_valid_batch = true;
         }
@@ -1077,7 +1091,8 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;
-    else if (n == "prefetch") h->prefetch = value != 0;   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
+    else if (n == "prefetch") h->prefetch = value != 0;
+    else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }

@@ -32,14 +32,22 @@
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Launch priority of the kernels being issued (CUDA stream-priority scale: lower value = dispatched first).  The
+// compute work distributor hands out CTAs grid by grid within one priority level, so a multi-wave side kernel (dense
+// wgrad: 480 CTAs, Adam: 1184 CTAs) would hold back every later kernel of the critical chain until its last wave is
+// dispatched (measured with tools/cupti_trace: 10-16 us stalls in front of 4 us kernels).  The step orchestration sets
+// this around the side branches; inside a captured graph the attribute is recorded on the kernel node.
+inline int g_launch_priority = 0;
+
 template <class... KArgs, class... Args>
 static inline void launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    at[n].id = cudaLaunchAttributePriority; at[n].val.priority = g_launch_priority; ++n;
+    if (pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.attrs = at; cfg.numAttrs = n;
     DQN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
 }
 

@@ -101,6 +101,21 @@ struct CvPlan {
     static constexpr int BAR_BYTES = 1024;                        // barriers + tmem slot + k-block offset table
 };
 
+// zero-padded, stride-phase-split copy of one NHWC image into shared memory (layout in the header comment); nthreads
+// threads cooperate (cpp divides nthreads); the caller waits for the copies and synchronises
+__device__ __forceinline__ void load_image_async(uint32_t img, const float* __restrict__ src_img, const ImgGeom& g, int tid,
+                                                 int nthreads, const float* __restrict__ zeros) {
+    const int c = tid % g.cpp, pstep = nthreads / g.cpp, npix = g.hp * g.wcols;
+    for (int p = tid / g.cpp; p < npix; p += pstep) {
+        const int iyp = fdiv(p, g.m_wcols, g.wcols), col = p - iyp * g.wcols;
+        const int phase = fdiv(col, g.m_wps, g.wps), j = col - phase * g.wps;
+        const int iy = iyp - g.pt, ix = j * g.s + phase - g.pl;
+        const bool ok = (unsigned)iy < (unsigned)g.ih && (unsigned)ix < (unsigned)g.iw;
+        const float* src = ok ? src_img + ((size_t)(iy * g.iw + ix) * g.cin + c * 4) : zeros;
+        cp_async16(img + (uint32_t)(p * g.pitch + c * 16), src, ok);
+    }
+}
+
 constexpr int CV_THREADS = 320;
 
 template <int BN, int NTERMS, class Epi>
@@ -168,20 +183,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         // ---------------- image -> shared memory (once) ----------------
         {
             const float* src_img = in + (size_t)image * g.ih * g.iw * g.cin;
-            // thread -> fixed 16-byte chunk c of pixels p0, p0 + 256/cpp, ... (cpp divides 256)
-            const int c = tid % g.cpp, pstep = 256 / g.cpp, npix = g.hp * g.wcols;
             if (tid < BN) {
                 const float bv = epi.bias[tid];
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
             }
-            for (int p = tid / g.cpp; p < npix; p += pstep) {
-                const int iyp = fdiv(p, g.m_wcols, g.wcols), col = p - iyp * g.wcols;
-                const int phase = fdiv(col, g.m_wps, g.wps), j = col - phase * g.wps;
-                const int iy = iyp - g.pt, ix = j * g.s + phase - g.pl;
-                const bool ok = (unsigned)iy < (unsigned)g.ih && (unsigned)ix < (unsigned)g.iw;
-                const float* src = ok ? src_img + ((size_t)(iy * g.iw + ix) * g.cin + c * 4) : zeros;
-                cp_async16(img + (uint32_t)(p * g.pitch + c * 16), src, ok);
-            }
+            load_image_async(img, src_img, g, tid, 256, zeros);
             asm volatile("cp.async.wait_all;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -336,4 +342,240 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
 }
 
 #undef CV_STAMP
+
+// ---- weight gradient, image-resident ---------------------------------------------------------------------------------
+// dW[(kh,kw,ci)][co] = sum over pixels of X[pixel + tap][ci] * dY[pixel][co], one CTA per (image, slice of the M tiles):
+// the CTA writes the image's partial sum part[image][(kh,kw,ci)][co] (+ the bias row sum_pixels dY), and
+// wgrad_reduce_kernel adds the images in order.  Operands:
+//   A (TMEM, rows m = (tap, ci), k = pixel): thread == row; for pixel p it reads X at pixoff[p] + tapoff(m) from the
+//     resident padded image -- consecutive lanes are consecutive ci, so the 32 scalar reads of a k-block are
+//     conflict-free -- splits hi/lo and stores both to tensor memory;
+//   B (smem, rows n = co, k = pixel): dY of the image, transposed once into the dense K-major hi/lo tiles, resident.
+// Accumulators are double-buffered (2 x 64 TMEM columns): a dedicated epilogue warpgroup drains M tile i while the
+// converters and the MMA thread work on tile i+1.
+constexpr int WG_THREADS = 512;  // warps 0-7 converters, 8 MMA, 9 bias row, 10-11 idle, 12-15 epilogue
+
+template <int BN, int NTERMS>
+__global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                float* __restrict__ part, const ImgGeom g, int mreal,
+                                                                int mtiles_per_cta, const float* __restrict__ zeros) {
+    constexpr int S = 6, ACOLS = BK * (NTERMS == 3 ? 2 : 1), B_TILE = BN * 128, B_KB = B_TILE * 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    const int npix = g.oh * g.ow, nkb = (npix + 31) / 32;
+    const uint32_t btiles = sbase;                         // nkb x {hi, lo} tiles
+    const uint32_t bars = btiles + nkb * B_KB;             // afull[S], empty[S], acc_full[2], acc_empty[2], tmem slot
+    const uint32_t pixtab = bars + 256;                    // int pixoff[nkb * 32]
+    const uint32_t img = pixtab + 4u * nkb * 32;
+    auto afull_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+    auto accf_bar = [&](int b) { return bars + 8u * (2 * S + b); };
+    auto acce_bar = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int image = blockIdx.x;
+    const int mtiles = (mreal + BM - 1) / BM;
+    const int mt0 = blockIdx.y * mtiles_per_cta, mt1 = min(mtiles, mt0 + mtiles_per_cta);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(afull_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int p = tid; p < nkb * 32; p += WG_THREADS) {
+        const int oy = p / g.ow, ox = p - oy * g.ow;
+        const int off = p < npix ? (oy * g.s * g.wcols + ox) * g.pitch : 0;  // padding pixels: any finite data (B is 0 there)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(pixtab + 4u * p), "r"(off) : "memory");
+    }
+    pdl_wait();
+    // ---- stage the image and dY (all threads) ----
+    load_image_async(img, x + (size_t)image * g.ih * g.iw * g.cin, g, tid, WG_THREADS, zeros);
+    {
+        // dY[p][co] -> B(co, p): a warp covers 4 pixels x 8 channels per pass, lane = (p % 4) + 4 * (co % 8), so the
+        // 32 scalar stores of a pass fall into 32 consecutive words of one core matrix (conflict-free)
+        const float* dimg = dy + (size_t)image * npix * BN;
+        const int pq = lane & 3, cq = lane >> 2;
+        const int groups = (nkb * 8) * (BN / 8);  // (pixel quad, channel octet) pairs
+        for (int gi = warp; gi < groups; gi += WG_THREADS / 32) {
+            const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
+            const int p = p4 * 4 + pq, co = c8 * 8 + cq;
+            const float v = p < npix ? __ldg(dimg + (size_t)p * BN + co) : 0.f;
+            const int kb = p >> 5, kin = p & 31;
+            const uint32_t a = btiles + (uint32_t)(kb * B_KB + (co >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (co & 7) * 16 + (kin & 3) * 4);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+            if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v)) : "memory");
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    fence_proxy_async();  // the B tiles were written through the generic proxy and are read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(2 * BN + s * ACOLS); };
+    const int nsteps = (mt1 - mt0) * nkb;
+
+    if (warp < 8) {
+        // ---------------- A converters: thread == row m = (tap, ci) of the current M tile ----------------
+        const int grp = warp & 3, cg = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        int step = cg;
+        for (int mt = mt0; mt < mt1; ++mt) {
+            const int m = mt * BM + grp * 32 + lane;
+            uint32_t base = img;  // rows past mreal: finite garbage, their outputs are never stored
+            if (m < mreal) {
+                const int tap = m / g.cin, ci = m - tap * g.cin;
+                const int kh = tap / g.k, kw = tap - kh * g.k;
+                base = img + (uint32_t)((kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + ci * 4);
+            }
+            const int step_end = (mt - mt0 + 1) * nkb;
+            for (; step < step_end; step += 2) {
+                const int kb = step - (mt - mt0) * nkb;
+                const int s = step % S, ph = (step / S) & 1;
+                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
+                float hi[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t o0, o1, o2, o3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3)
+                                 : "r"(pixtab + 4u * (kb * 32 + q * 4)));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q]) : "r"(base + o0));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 1]) : "r"(base + o1));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 2]) : "r"(base + o2));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 3]) : "r"(base + o3));
+                }
+                const uint32_t ta = tmem_a(s) + lane_base;
+                ts::tmem_st32(ta, hi);
+                if (NTERMS == 3) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+                    ts::tmem_st32(ta + BK, lo);
+                }
+                ts::tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull_bar(s));
+            }
+        }
+        pdl_launch_dependents();
+    } else if (warp == 8) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = make_idesc(BN, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        int s = 0, ph = 0, step = 0;
+        bool ready = false;
+        for (int mt = mt0; mt < mt1; ++mt) {
+            const int ab = (mt - mt0) & 1, use = (mt - mt0) >> 1;
+            if (use >= 1) { mbar_wait(acce_bar(ab), (use - 1) & 1); tc_fence_after(); }  // epilogue has drained this accumulator
+            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
+            for (int kb = 0; kb < nkb; ++kb, ++step) {
+                if (!ready) mbar_wait(afull_bar(s), ph);
+                tc_fence_after();
+                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
+                ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1);
+                const uint64_t db = make_desc(btiles + kb * B_KB, PK_LBO, PK_SBO);
+                const uint64_t dbl = make_desc(btiles + kb * B_KB + B_TILE, PK_LBO, PK_SBO);
+                const uint32_t ta = tmem_a(s);
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2 * PK_LBO) >> 4;
+                    const uint32_t acc = (kb | ks) != 0;
+                    if (leader) {
+                        if (NTERMS == 3) {
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, dbl + o, idesc, acc);
+                            ts::mma_tf32_ts(tmem_d, ta + BK + ks * 8, db + o, idesc, 1);
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, 1);
+                        } else {
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, acc);
+                        }
+                    }
+                }
+                if (leader) {
+                    mma_commit(empty_bar(s));
+                    if (kb == nkb - 1) mma_commit(accf_bar(ab));
+                }
+                __syncwarp();
+                s = s1; ph = ph1;
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 9) {
+        // ---------------- bias row: db[co] = sum over pixels of dY (ascending pixel order) ----------------
+        if (blockIdx.y == 0) {
+            float* prow = part + ((size_t)image * (mreal + 4) + mreal) * BN;
+            for (int co = lane; co < BN; co += 32) {
+                float sacc = 0.f;
+                for (int p = 0; p < npix; ++p) {
+                    float v;
+                    const uint32_t a = btiles + (uint32_t)((p >> 5) * B_KB + (co >> 3) * PK_SBO + ((p & 31) >> 2) * PK_LBO + (co & 7) * 16 + (p & 3) * 4);
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+                    sacc += v;
+                }
+                prow[co] = sacc;
+            }
+        }
+    } else if (warp >= 12) {
+        // ---------------- epilogue warpgroup: accumulator of M tile i -> part[image][m][co] ----------------
+        const int grp = warp & 3;
+        const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        for (int mt = mt0; mt < mt1; ++mt) {
+            const int ab = (mt - mt0) & 1, use = (mt - mt0) >> 1;
+            mbar_wait(accf_bar(ab), use & 1);
+            tc_fence_after();
+            const int m = mt * BM + grp * 32 + lane;
+            float* o = part + ((size_t)image * (mreal + 4) + m) * BN;
+#pragma unroll
+            for (int c = 0; c < BN; c += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * BN + c), v);
+                if (c + 16 >= BN) {  // all columns of this accumulator are in registers: hand it back to the MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce_bar(ab));
+                }
+                if (m < mreal) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// true if launched: part[image][mreal + 4][N] holds the per-image partial sums (bias row at m = mreal)
+template <int BN, int NTERMS>
+static bool launch_wgrad(dqn_learner* h, const float* x, const float* dy, float* part, const ImgGeom& g, int images) {
+    const int mreal = g.k * g.k * g.cin;
+    const int npix = g.oh * g.ow, nkb = (npix + 31) / 32;
+    if (g.cin % 32 != 0 || npix > 128 || g.cout != BN) return false;
+    const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + g.img_bytes + 1024 + 128;
+    if (bytes > 227 * 1024) return false;
+    const int mtiles = (mreal + BM - 1) / BM;
+    const int per_cta = mtiles >= 8 ? mtiles / 2 : mtiles;  // two CTAs per image once an image carries >= 8 M tiles
+    auto kern = cvwgrad_kernel<BN, NTERMS>;
+    static size_t configured = 0;
+    if (bytes > configured) {
+        DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    launch_kernel(h->pdl, kern, dim3(images, (mtiles + per_cta - 1) / per_cta), dim3(WG_THREADS), bytes, h->stream, x, dy, part, g, mreal,
+                  per_cta, (const float*)h->zeros16);
+    h->launches++;
+    return true;
+}
+
 }  // namespace cv

@@ -74,11 +74,9 @@ void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q
                         int train, double grad_scale) {
     int threads = ((n + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
-    td_epilogue_kernel<<<1, threads, 0, h->stream>>>(n, h->net.A, h->cfg.use_double, h->cfg.use_per, h->cfg.discount_rate,
-                                                     (float)h->cfg.per_a, grad_scale, train, q_on, q_on_next, q_tg_next,
-                                                     actions, rewards, cont, isw, h->b_y, h->b_maxq, h->b_losses_out,
-                                                     h->b_dq, h->b_newprio, h->d_sc);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, td_epilogue_kernel, dim3(1), dim3(threads), 0, h->stream, n, h->net.A, h->cfg.use_double, h->cfg.use_per,
+                  h->cfg.discount_rate, (float)h->cfg.per_a, grad_scale, train, q_on, q_on_next, q_tg_next, actions, rewards, cont,
+                  isw, h->b_y, h->b_maxq, h->b_losses_out, h->b_dq, h->b_newprio, h->d_sc);
     h->launches++;
 }
 
@@ -179,7 +177,7 @@ void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions) {
     const size_t smem = (size_t)2 * 32 * 33 * 4 + (size_t)n * 4 + ((n + 3) / 4) * 4;
     DQN_REQUIRE(net.NH % 32 == 0 && net.A <= 31, "head backward tiling");
 #define HEAD_BWD(AMAX)                                                                                                  \
-    head_backward_kernel<AMAX><<<net.NH / 32, 1024, smem, h->stream>>>(                                                 \
+    launch_kernel(false, head_backward_kernel<AMAX>, dim3(net.NH / 32), dim3(1024), smem, h->stream,                    \
         n, net.NH, net.hidden, net.A, net.dueling, h->acts_on.hid, h->b_dq, actions, P + net.off_hd_w[0],              \
         P + net.off_hd_w[1], h->d_hid, G + net.off_hd_w[0], G + net.off_hd_b[0], G + net.off_hd_w[1],                  \
         G + net.off_hd_b[1], G + net.off_fc_b[0], G + net.off_fc_b[1])

@@ -581,7 +581,6 @@ __global__ void __launch_bounds__(Cfg::THREADS) igemm_kernel(const AOp a, const 
 template <class Cfg, bool SPLIT, class AOp, class BOp, class Epi>
 static void launch_igemm(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, int Z, int kchunk) {
     dim3 grid(ceil_div(M, Cfg::BM), ceil_div(N, Cfg::BN), Z);
-    igemm_kernel<Cfg, SPLIT, AOp, BOp, Epi><<<grid, Cfg::THREADS, 0, h->stream>>>(a, b, e, M, N, K, kchunk);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, igemm_kernel<Cfg, SPLIT, AOp, BOp, Epi>, grid, dim3(Cfg::THREADS), 0, h->stream, a, b, e, M, N, K, kchunk);
     h->launches++;
 }

@@ -54,6 +54,9 @@ struct dqn_learner {
     cudaEvent_t fork_ev[24] = {};
     int fork_used = 0;
     bool overlap = true;
+    int prio_hi = 0, prio_lo = 0;  // device stream-priority range (hi is numerically lower)
+    int saved_prio = 0;
+    bool use_prio = true;       // option: launch priorities by branch
     bool pdl = true;            // programmatic dependent launch for the kernels that call pdl_wait()
     bool ts_gemm = true;        // tcgen05 GEMMs take A from tensor memory where the operand functor allows it
     bool fuse_enabled = false;  // allow the fused dense-wgrad+optimizer epilogue in dqn_train_step(s)
@@ -194,7 +197,9 @@ void prof_mark(dqn_learner* h, const char* name);
 // stream fork/join helpers (api.cu). side_begin: side stream waits for everything issued on the main stream so far
 // and becomes the launch stream; side_end: back to the main stream; main_wait_side / side_wait_main: cross edges.
 bool overlap_enabled(const dqn_learner* h);
-void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0);
+// prio_class: launch priority of the branch (common.cuh g_launch_priority): 0 = work with slack (dense wgrad, optimizer),
+// 1 = needed soon (conv wgrads, look-ahead sampling), 2 = critical path (same as the main stream)
+void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0, int prio_class = 0);
 void side_end(dqn_learner* h, cudaStream_t saved);
 void main_wait_side(dqn_learner* h, int which = 0);
 void launch_optimizer_fc(dqn_learner* h);

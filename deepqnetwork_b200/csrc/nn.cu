@@ -127,8 +127,8 @@ __global__ void u8_to_f32_kernel(const uint32_t* __restrict__ src, float4* __res
 void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n) {
     const size_t n4 = n / 4;
     int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
-    u8_to_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<float4*>(dst), n4);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, u8_to_f32_kernel, dim3(blocks), dim3(256), 0, h->stream, reinterpret_cast<const uint32_t*>(src),
+                  reinterpret_cast<float4*>(dst), n4);
     h->launches++;
 }
 
@@ -202,7 +202,7 @@ static void launch_fc_reduce_heads(dqn_learner* h, const float* P, int splits, i
     const NetDesc& net = h->net;
     const int threads = std::min(1024, ((net.NH + 31) / 32) * 32);
 #define FC_HEADS(AMAX)                                                                                                  \
-    fc_reduce_heads_kernel<AMAX><<<rows, threads, 0, h->stream>>>(acts.fc_part, splits, rows, net.NH, net.hidden, net.A, \
+    launch_kernel(false, fc_reduce_heads_kernel<AMAX>, dim3(rows), dim3(threads), 0, h->stream, acts.fc_part, splits, rows, net.NH, net.hidden, net.A, \
         net.dueling, P + net.off_fc_b[0], P + net.off_fc_b[1], P + net.off_hd_w[0], P + net.off_hd_b[0],               \
         P + net.off_hd_w[1], P + net.off_hd_b[1], acts.hid, acts.q)
     if (net.A <= 4) FC_HEADS(4);
@@ -231,8 +231,8 @@ void launch_pack_conv(dqn_learner* h, int tower) {
         const ConvGeom& g = h->net.conv[l];
         const int K = g.k * g.k * g.cin, N = g.cout;
         if (K % 32 != 0) continue;
-        cv::pack_conv_kernel<<<ceil_div(K * N, 256), 256, 0, h->stream>>>(P + h->net.off_cw[l], h->packed[tower] + h->pk_off[l], K, N);
-        DQN_CUDA_OK(cudaGetLastError());
+        launch_kernel(false, cv::pack_conv_kernel, dim3(ceil_div(K * N, 256)), dim3(256), 0, h->stream, P + h->net.off_cw[l],
+                      h->packed[tower] + h->pk_off[l], K, N);
         h->launches++;
     }
 }
@@ -403,7 +403,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         }
         side_end(h, saved);
     };
-    const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && fc_wgrad_adam_supported(h);
+    const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && rows <= 32 && fc_wgrad_adam_supported(h);
     if (!h->fuse_fc_adam && !ffma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
@@ -420,8 +420,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             gemm_auto<true>(h, a, b, e, net.flat, rows, net.NH, Z, kchunk, 32);
             prof_mark(h, "fc_dgrad_reduce");
             const int total4 = rows * net.flat / 4;
-            sum_gate_kernel<<<ceil_div(total4, 256), 256, 0, h->stream>>>(acts.fc_part, Z, total4, acts.act[2], h->d_act[2]);
-            DQN_CUDA_OK(cudaGetLastError());
+            launch_kernel(false, sum_gate_kernel, dim3(ceil_div(total4, 256)), dim3(256), 0, h->stream, acts.fc_part, Z, total4,
+                          acts.act[2], h->d_act[2]);
             h->launches++;
         } else {
             OpRowMajorK a{h->d_hid, net.NH};
@@ -451,7 +451,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
         // wgrad (+bias) split over the pixel dimension
         {
-            side_begin(h, saved, 1);  // needs d_act[l], which the main stream has just produced
+            side_begin(h, saved, 1, 1);  // needs d_act[l], which the main stream has just produced
             const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
             int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
@@ -461,15 +461,26 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             static const char* kW[3] = {"conv1_wgrad", "conv2_wgrad", "conv3_wgrad"};
             prof_mark(h, kW[l]);
             const void* in0 = tcm ? (const void*)x_f32 : (const void*)d_states;
-            OpConvWgradABias a{OpConvWgradA{l == 0 ? in0 : (const void*)acts.act[l - 1], g, (l == 0 && !tcm) ? 1 : 0}, mreal, h->ones_row};
-            OpColContig b{h->d_act[l], N};
-            EpiPartial e{part, mreal + 4, N};
-            gemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
+            bool done = false;
+            cv::ImgGeom q;
+            if (tcm && h->img_conv && l > 0 && rows <= 64 && cv::img_geom(g, q)) {
+                // image-resident kernel: one partial per image (Z = rows), summed in image order by the reduce below
+                const float* xin = acts.act[l - 1];
+                const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
+                if (N == 64) done = x3 ? cv::launch_wgrad<64, 3>(h, xin, h->d_act[l], part, q, rows) : cv::launch_wgrad<64, 1>(h, xin, h->d_act[l], part, q, rows);
+                else if (N == 32) done = x3 ? cv::launch_wgrad<32, 3>(h, xin, h->d_act[l], part, q, rows) : cv::launch_wgrad<32, 1>(h, xin, h->d_act[l], part, q, rows);
+                if (done) Z = rows;
+            }
+            if (!done) {
+                OpConvWgradABias a{OpConvWgradA{l == 0 ? in0 : (const void*)acts.act[l - 1], g, (l == 0 && !tcm) ? 1 : 0}, mreal, h->ones_row};
+                OpColContig b{h->d_act[l], N};
+                EpiPartial e{part, mreal + 4, N};
+                gemm_auto<true>(h, a, b, e, mreal + 4, N, K, Z, kchunk);
+            }
             static const char* kR[3] = {"conv1_wgrad_reduce", "conv2_wgrad_reduce", "conv3_wgrad_reduce"};
             prof_mark(h, kR[l]);
-            wgrad_reduce_kernel<<<ceil_div((mreal + 1) * N / 4, 64), 256, 0, h->stream>>>(part, Z, mreal, N,
-                                                                                          G + net.off_cw[l], G + net.off_cb[l]);
-            DQN_CUDA_OK(cudaGetLastError());
+            launch_kernel(false, wgrad_reduce_kernel, dim3(ceil_div((mreal + 1) * N / 4, 64)), dim3(256), 0, h->stream, part, Z, mreal,
+                          N, G + net.off_cw[l], G + net.off_cb[l]);
             h->launches++;
             side_end(h, saved);
         }
@@ -494,8 +505,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
                 gemm_auto<true>(h, a, b, e, Mc, g.cin, Kd, 2 * Zc, Kd / 2, 32, Zc);
                 prof_mark(h, l == 2 ? "conv3_dgrad_reduce" : "conv2_dgrad_reduce");
                 const int total4 = rows * g.ih * g.iw * g.cin / 4;
-                sum_gate_kernel<<<ceil_div(total4, 256), 256, 0, h->stream>>>(acts.fc_part, 2, total4, acts.act[l - 1], h->d_act[l - 1]);
-                DQN_CUDA_OK(cudaGetLastError());
+                launch_kernel(false, sum_gate_kernel, dim3(ceil_div(total4, 256)), dim3(256), 0, h->stream, acts.fc_part, 2, total4,
+                              acts.act[l - 1], h->d_act[l - 1]);
                 h->launches++;
             } else {
                 EpiDgradGate e{h->d_act[l - 1], acts.act[l - 1], c, rows};

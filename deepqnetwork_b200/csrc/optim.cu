@@ -48,13 +48,11 @@ static void optimizer_range(dqn_learner* h, int64_t beg, int64_t end) {
     const size_t n4 = (size_t)(end - beg) / 4, o4 = (size_t)beg / 4;
     const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
     if (h->cfg.use_momentum)
-        momentum_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online + o4, (float4*)h->slot_m + o4,
-                                                       (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate,
-                                                       (float)h->cfg.momentum);
+        launch_kernel(false, momentum_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online + o4, (float4*)h->slot_m + o4,
+                      (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, (float)h->cfg.momentum);
     else
-        adam_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online + o4, (float4*)h->slot_m + o4, (float4*)h->slot_v + o4,
-                                                   (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, h->d_sc);
-    DQN_CUDA_OK(cudaGetLastError());
+        launch_kernel(false, adam_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online + o4, (float4*)h->slot_m + o4,
+                      (float4*)h->slot_v + o4, (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, h->d_sc);
     h->launches++;
 }
 
@@ -72,9 +70,13 @@ void launch_optimizer_fc(dqn_learner* h) {
 // is formed in registers from shared-memory tiles and consumed on the spot by Adam / Nesterov momentum, so the 31.5 MB
 // gradient of the dense kernels never makes its HBM round trip and the kernel is bound by the unavoidable
 // read(w, m, v) + write(w, m, v) = 6 x 4 bytes per parameter.
-// CTA = 256 threads = 16 k rows x 256 n columns; thread = 4 k x 4 n.  WRITE_G also stores dW (parity / debugging path).
+// Persistent CTAs (2 per SM): a CTA owns one 256-column n tile, keeps the dH tile [32 b][256 n] resident in shared
+// memory and walks 16-row k sub-tiles with a grid stride.  Per sub-tile the optimizer state of the thread's 4 x 4
+// outputs (w, m, v: 12 float4) is requested FIRST, the 32-deep fmaf chains run while those loads are in flight (and
+// while the act3 tile of the next sub-tile is fetched into a register), then Adam / Nesterov consumes both.  Two CTAs
+// x 256 threads x 192 bytes keep ~98 KB of HBM requests in flight per SM.  WRITE_G also stores dW (parity path).
 template <bool WRITE_G>
-__global__ void __launch_bounds__(256, 4) fc_wgrad_adam_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
+__global__ void __launch_bounds__(256, 2) fc_wgrad_adam_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
                                                             int Bn, int flat, int NH, int hid,
                                                             float* __restrict__ w0, float* __restrict__ w1,
                                                             float* __restrict__ m0, float* __restrict__ m1,
@@ -82,38 +84,55 @@ __global__ void __launch_bounds__(256, 4) fc_wgrad_adam_kernel(const float* __re
                                                             float* __restrict__ g0, float* __restrict__ g1,
                                                             float lr, float mom, int use_momentum,
                                                             const dqn_learner::Scalars* __restrict__ sc) {
-    __shared__ __align__(16) float sa[32][16];    // act3 tile  [b][k]
-    __shared__ __align__(16) float sd[32][256];   // dH tile    [b][n]
+    __shared__ __align__(16) float sa[2][32][16];  // act3 tiles [b][k], double-buffered
+    __shared__ __align__(16) float sd[32][256];    // dH tile    [b][n], resident
     const int tid = threadIdx.x;
-    const int kt = blockIdx.x * 16, nt = blockIdx.y * 256;
+    const int nt = blockIdx.y * 256;
     const int tn = (tid & 63) * 4, tk = (tid >> 6) * 4;
     const int st = nt >= hid;                     // a 256-wide n tile never straddles the two streams (hid % 256 == 0)
     const int ncol = nt + tn - (st ? hid : 0);
     float* W = st ? w1 : w0; float* Mo = st ? m1 : m0; float* V = st ? v1 : v0; float* G = st ? g1 : g0;
-    float acc[4][4];
+    const int nsub = flat / 16;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i) {  // 32 b x 64 float4 of dH
+        const int f = tid + i * 256, b = f >> 6, q = f & 63;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < Bn) v = *reinterpret_cast<const float4*>(dhid + (size_t)b * NH + nt + q * 4);
+        *reinterpret_cast<float4*>(&sd[b][q * 4]) = v;
+    }
+    const int ab = tid >> 2, aq = tid & 3;  // threads 0..127 fetch the act3 tile: 32 b x 4 float4
+    auto load_a = [&](int sub) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 128 && ab < Bn && sub < nsub) v = *reinterpret_cast<const float4*>(act3 + (size_t)ab * flat + sub * 16 + aq * 4);
+        return v;
+    };
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    float4 anext = load_a(blockIdx.x);
+    int buf = 0;
+    for (int sub = blockIdx.x; sub < nsub; sub += gridDim.x, buf ^= 1) {
+        // optimizer state first: these loads fly under the fmaf chains
+        float4 mm[4], pp[4], vv[4];
+        size_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int b0 = 0; b0 < Bn; b0 += 32) {
-        const int nb = min(32, Bn - b0);
-        if (tid < 128) {  // 32 b x 4 float4 of act3
-            const int b = tid >> 2, q = tid & 3;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b < nb) v = *reinterpret_cast<const float4*>(act3 + (size_t)(b0 + b) * flat + kt + q * 4);
-            *reinterpret_cast<float4*>(&sa[b][q * 4]) = v;
+        for (int i = 0; i < 4; ++i) {
+            o[i] = (size_t)(sub * 16 + tk + i) * hid + ncol;
+            mm[i] = __ldcs(reinterpret_cast<const float4*>(Mo + o[i]));
+            pp[i] = __ldcs(reinterpret_cast<const float4*>(W + o[i]));
+            if (!use_momentum) vv[i] = __ldcs(reinterpret_cast<const float4*>(V + o[i]));
         }
+        if (tid < 128) *reinterpret_cast<float4*>(&sa[buf][ab][aq * 4]) = anext;
+        __syncthreads();  // sa[buf] (and, first time, sd) visible; everyone is done with sa[buf] of two iterations ago
+        anext = load_a(sub + gridDim.x);
+        float acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {  // 32 b x 64 float4 of dH
-            const int f = tid + i * 256, b = f >> 6, q = f & 63;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b < nb) v = *reinterpret_cast<const float4*>(dhid + (size_t)(b0 + b) * NH + nt + q * 4);
-            *reinterpret_cast<float4*>(&sd[b][q * 4]) = v;
-        }
-        __syncthreads();
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 8
         for (int b = 0; b < 32; ++b) {  // ascending sample order, one fmaf chain per element (deterministic)
-            const float4 a = *reinterpret_cast<const float4*>(&sa[b][tk]);
+            const float4 a = *reinterpret_cast<const float4*>(&sa[buf][b][tk]);
             const float4 d = *reinterpret_cast<const float4*>(&sd[b][tn]);
             const float av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -121,32 +140,24 @@ __global__ void __launch_bounds__(256, 4) fc_wgrad_adam_kernel(const float* __re
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], dv[j], acc[i][j]);
         }
-        __syncthreads();
-    }
-    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-    const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
-    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const size_t o = (size_t)(kt + tk + i) * hid + ncol;
-        const float4 gg = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        // 64 registers per thread -> 4 CTAs per SM: the memory latency of these loads is hidden by occupancy
-        float4 mm = *reinterpret_cast<const float4*>(Mo + o), pp = *reinterpret_cast<const float4*>(W + o);
-        if (use_momentum) {
-#define MOM1(c) mm.c = mm.c * mom + gg.c; pp.c = pp.c - (gg.c * lr + mm.c * mom * lr);
-            MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+        for (int i = 0; i < 4; ++i) {
+            const float4 gg = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (use_momentum) {
+#define MOM1(c) mm[i].c = mm[i].c * mom + gg.c; pp[i].c = pp[i].c - (gg.c * lr + mm[i].c * mom * lr);
+                MOM1(x) MOM1(y) MOM1(z) MOM1(w)
 #undef MOM1
-        } else {
-            float4 vv = *reinterpret_cast<const float4*>(V + o);
-#define ADAM1(c) mm.c = mm.c + (gg.c - mm.c) * omb1; vv.c = vv.c + (gg.c * gg.c - vv.c) * omb2; \
-                 pp.c = pp.c - (mm.c * lr_t) / (sqrtf(vv.c) + eps);
-            ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+            } else {
+#define ADAM1(c) mm[i].c = mm[i].c + (gg.c - mm[i].c) * omb1; vv[i].c = vv[i].c + (gg.c * gg.c - vv[i].c) * omb2; \
+                 pp[i].c = pp[i].c - (mm[i].c * lr_t) / (sqrtf(vv[i].c) + eps);
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
 #undef ADAM1
-            *reinterpret_cast<float4*>(V + o) = vv;
+                __stcs(reinterpret_cast<float4*>(V + o[i]), vv[i]);
+            }
+            __stcs(reinterpret_cast<float4*>(Mo + o[i]), mm[i]);
+            *reinterpret_cast<float4*>(W + o[i]) = pp[i];
+            if (WRITE_G) *reinterpret_cast<float4*>(G + o[i]) = gg;
         }
-        *reinterpret_cast<float4*>(Mo + o) = mm;
-        *reinterpret_cast<float4*>(W + o) = pp;
-        if (WRITE_G) *reinterpret_cast<float4*>(G + o) = gg;
     }
 }
 
@@ -157,17 +168,20 @@ bool fc_wgrad_adam_supported(const dqn_learner* h) {
 
 void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g) {
     const NetDesc& net = h->net;
-    const int o0 = (int)0; (void)o0;
+    DQN_REQUIRE(rows <= 32, "fused dense wgrad + optimizer pass: at most 32 samples");
     float *W = h->online, *M = h->slot_m, *V = h->slot_v, *G = h->grads;
-    dim3 grid(net.flat / 16, net.NH / 256);
-    auto args = [&](auto kern) {
-        kern<<<grid, 256, 0, h->stream>>>(h->acts_on.act[2], h->d_hid, rows, net.flat, net.NH, net.hidden,
-                                          W + net.off_fc_w[0], W + net.off_fc_w[1], M + net.off_fc_w[0], M + net.off_fc_w[1],
-                                          V + net.off_fc_w[0], V + net.off_fc_w[1], G + net.off_fc_w[0], G + net.off_fc_w[1],
-                                          (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum, h->d_sc);
+    const int ntiles = net.NH / 256;
+    int per_tile = (2 * h->sm_count) / ntiles;  // two resident CTAs per SM, split evenly over the n tiles
+    if (per_tile < 1) per_tile = 1;
+    if (per_tile > net.flat / 16) per_tile = net.flat / 16;
+    dim3 grid(per_tile, ntiles);
+    auto go = [&](auto kern) {
+        launch_kernel(false, kern, grid, dim3(256), 0, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid, rows,
+                      net.flat, net.NH, net.hidden, W + net.off_fc_w[0], W + net.off_fc_w[1], M + net.off_fc_w[0],
+                      M + net.off_fc_w[1], V + net.off_fc_w[0], V + net.off_fc_w[1], G + net.off_fc_w[0], G + net.off_fc_w[1],
+                      (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum, (const dqn_learner::Scalars*)h->d_sc);
     };
-    if (write_g) args(fc_wgrad_adam_kernel<true>); else args(fc_wgrad_adam_kernel<false>);
-    DQN_CUDA_OK(cudaGetLastError());
+    if (write_g) go(fc_wgrad_adam_kernel<true>); else go(fc_wgrad_adam_kernel<false>);
     h->launches++;
 }
 
@@ -233,10 +247,9 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
     long long most = 1;
     for (int q = 0; q < rg.count; ++q) most = std::max(most, rg.n4[q]);
     const int blocks = (int)std::min<long long>((most + 255) / 256, (long long)h->sm_count * 8);
-    optimizer_tail_kernel<<<blocks, 256, 0, h->stream>>>((float4*)h->online, (float4*)h->slot_m, (float4*)h->slot_v,
-                                                        (const float4*)h->grads, rg, (float)h->cfg.learning_rate,
-                                                        (float)h->cfg.momentum, h->cfg.use_momentum, h->d_sc, h->opt_ticket);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, optimizer_tail_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online, (float4*)h->slot_m,
+                  (float4*)h->slot_v, (const float4*)h->grads, rg, (float)h->cfg.learning_rate, (float)h->cfg.momentum,
+                  h->cfg.use_momentum, h->d_sc, h->opt_ticket);
     h->launches++;
     launch_pack_conv(h, 0);  // the image-resident conv kernels read the online conv weights pre-split and pre-tiled
 }

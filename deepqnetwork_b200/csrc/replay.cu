@@ -64,11 +64,9 @@ void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32
     const int nvec = (int)(h->state_bytes >> 4);
     dim3 grid(ceil_div(nvec, threads * 4), 2 * n);
     // the batch buffer keeps s in rows [0,n) and s' in rows [n,2n): one contiguous [2n,S] input for the online tower
-    gather_rows_kernel<<<grid, threads, 0, h->stream>>>(h->r_states, h->r_next, h->r_actions, h->r_rewards, h->r_cont,
-                                                        h->r_losses, d_rows, n, h->state_bytes, h->b_states,
-                                                        h->b_actions, h->b_rewards, h->b_cont, h->b_losses,
-                                                        with_f32 && h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : nullptr);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, gather_rows_kernel, grid, dim3(threads), 0, h->stream, h->r_states, h->r_next, h->r_actions, h->r_rewards,
+                  h->r_cont, h->r_losses, d_rows, n, h->state_bytes, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->b_losses,
+                  with_f32 && h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : (float4*)nullptr);
     h->launches++;
     h->xf_from_gather = with_f32 && h->cfg.math_mode != DQN_MATH_FP32;
 }

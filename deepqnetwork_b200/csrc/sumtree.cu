@@ -244,18 +244,16 @@ long long* tree_size_ptr(dqn_learner* h);  // api.cu: device mirror of tree_size
 
 void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b) {
     const int wpb = 8;
-    tree_sample_kernel<<<ceil_div(batch, wpb), wpb * 32, 0, h->stream>>>(
+    launch_kernel(false, tree_sample_kernel, dim3(ceil_div(batch, wpb)), dim3(wpb * 32), 0, h->stream,
         h->tree, h->tree_data, h->cap, tree_size_ptr(h), batch, h->b_u, device_rng, h->cfg.seed, h->d_sc,
         make_pp(h, per_b), h->cfg.use_per, h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64,
-        h->b_isw, device_rng ? h->b_u : nullptr, h->sample_ahead);
-    DQN_CUDA_OK(cudaGetLastError());
+        h->b_isw, device_rng ? h->b_u : (double*)nullptr, h->sample_ahead);
     h->launches++;
 }
 
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses) {
-    tree_update_kernel<<<1, 1024, 0, h->stream>>>(h->tree, h->tree_data, h->r_losses, h->cap, d_tree_idx, d_scores, n,
-                                                   store_losses, -1);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, tree_update_kernel, dim3(1), dim3(1024), 0, h->stream, h->tree, h->tree_data, h->r_losses, h->cap,
+                  d_tree_idx, d_scores, n, store_losses, -1);
     h->launches++;
 }
 

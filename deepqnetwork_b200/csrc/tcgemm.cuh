@@ -457,8 +457,7 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    kern<<<grid, THREADS, Plan::BYTES + 1024, h->stream>>>(a, b, e, M, N, K, kchunk, h->zeros16, h->tc_dbg);
-    DQN_CUDA_OK(cudaGetLastError());
+    launch_kernel(false, kern, grid, dim3(THREADS), (size_t)Plan::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk, (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
 
