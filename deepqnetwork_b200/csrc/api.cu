@@ -198,12 +198,13 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1]};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
         cudaFree(t->fc_part); cudaFree(t->hid); cudaFree(t->q);
     }
+    if (h->fa_maps) free(h->fa_maps);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_in_small) cudaFreeHost(h->h_in_small);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
@@ -1086,11 +1087,13 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
     else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
     else if (n == "batch_graph") h->batch_graph_enabled = value != 0;  // dqn_train_batch replays a captured graph
+    else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;
+    else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "prefetch") h->prefetch = value != 0;
     else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
     else throw std::string("unknown option: ") + n;

@@ -41,6 +41,17 @@ struct ImgGeom {
     unsigned m_wcols, m_wps;  // fastdiv magics (learner.h)
 };
 
+// What the (up to 4) accumulators of one CTA cover.  A band is a set of <= 128 output pixels (a, b), a0 <= a < a0 + na,
+// b0 <= b < b0 + nb: thread row m = (a - a0) * nb + (b - b0) reads the resident image at pixel (a * rs, b) (+ the tap
+// of the k-block) and its result goes to output pixel (a * ym + ya, b * xm + xa) of an out_h x out_w map.
+//   forward : bands = groups of whole output rows, rs = stride, identity output map, one set of packed weights
+//   dgrad   : bands = stride-parity classes (ry, rx) of the input pixels, image = dY, rs = 1, ym = xm = stride,
+//             ya = ry - pad, each class with its own packed (flipped, transposed) weights starting at k-block pk_kb0
+struct Bands {
+    int n, rs, ym, xm, out_w, out_hw;
+    struct B { int a0, na, b0, nb, ya, xa, pk_kb0; } c[4];
+};
+
 static inline bool img_geom(const ConvGeom& g, ImgGeom& q) {
     q.ih = g.ih; q.iw = g.iw; q.cin = g.cin; q.oh = g.oh; q.ow = g.ow; q.cout = g.cout; q.k = g.k; q.s = g.s; q.pt = g.pt; q.pl = g.pl;
     if (!((g.cin % 32 == 0) || (g.cin == 4 && g.k == 8))) return false;  // a k-block = 128 contiguous source bytes
@@ -59,6 +70,45 @@ static inline bool img_geom(const ConvGeom& g, ImgGeom& q) {
     return true;
 }
 
+static inline void forward_bands(const ImgGeom& q, Bands& bd) {
+    bd.n = q.nbands; bd.rs = q.s; bd.ym = 1; bd.xm = 1; bd.out_w = q.ow; bd.out_hw = q.oh * q.ow;
+    for (int b = 0; b < q.nbands && b < 4; ++b) {
+        const int a0 = b * q.th;
+        bd.c[b] = {a0, q.oh - a0 < q.th ? q.oh - a0 : q.th, 0, q.ow, 0, 0, 0};
+    }
+}
+
+// data gradient of conv g as an image-resident convolution over dY: q describes the resident (padded) dY image and
+// the k-blocks (taps (th, tw) of the k/s x k/s sub-kernel x cout), bd the stride-parity classes.
+//   dX[s a + ry - pt][s b + rx - pl][ci] = sum_{th, tw, co} dYpad[a + th][b + tw][co] * W[ry + s (kt-1-th)][rx + s (kt-1-tw)][ci][co]
+// with kt - 1 zero rows / columns in front of dY.
+static inline bool dgrad_geom(const ConvGeom& g, ImgGeom& q, Bands& bd) {
+    if (g.k % g.s != 0 || g.cout % 32 != 0 || (g.cin != 32 && g.cin != 64) || g.s * g.s > 4) return false;
+    const int kt = g.k / g.s;
+    int amax = 0, bmax = 0;
+    bd.n = g.s * g.s; bd.rs = 1; bd.ym = g.s; bd.xm = g.s; bd.out_w = g.iw; bd.out_hw = g.ih * g.iw;
+    const int nkb_class = kt * kt * g.cout / 32;
+    for (int ry = 0; ry < g.s; ++ry)
+        for (int rx = 0; rx < g.s; ++rx) {
+            const int a0 = g.pt > ry ? (g.pt - ry + g.s - 1) / g.s : 0, b0 = g.pl > rx ? (g.pl - rx + g.s - 1) / g.s : 0;
+            const int na = (g.ih - 1 - ry + g.pt) / g.s - a0 + 1, nb = (g.iw - 1 - rx + g.pl) / g.s - b0 + 1;
+            if (na < 1 || nb < 1 || na * nb > 128) return false;
+            bd.c[ry * g.s + rx] = {a0, na, b0, nb, ry - g.pt, rx - g.pl, (ry * g.s + rx) * nkb_class};
+            if (a0 + na > amax) amax = a0 + na;
+            if (b0 + nb > bmax) bmax = b0 + nb;
+        }
+    q.ih = g.oh; q.iw = g.ow; q.cin = g.cout; q.oh = g.ih; q.ow = g.iw; q.cout = g.cin; q.k = kt; q.s = 1;
+    q.pt = kt - 1; q.pl = kt - 1;
+    q.hp = amax + kt - 1; q.wps = bmax + kt - 1; q.wcols = q.wps;
+    q.cpp = q.cin / 4;
+    q.pitch = q.cin * 4 + ((q.cin * 4) % 128 == 0 ? 16 : 0);
+    q.nkb = nkb_class;
+    q.th = 0; q.nbands = bd.n;
+    q.img_bytes = ((q.hp * q.wcols * q.pitch + 127) / 128) * 128;
+    q.m_wcols = fastdiv_magic((unsigned)q.wcols); q.m_wps = fastdiv_magic((unsigned)q.wps);
+    return q.nkb >= 1 && q.nkb <= 64;
+}
+
 // packed weights of one layer: [k-block][hi, lo][tile], tile = cout rows x 32 k in the dense canonical K-major layout
 // (8-row x 16-byte core matrices, LBO 128, SBO 1024): element (n, k) at (n/8)*1024 + (k/4)*128 + (n%8)*16 + (k%4)*4
 constexpr uint32_t PK_LBO = 128, PK_SBO = 1024;
@@ -73,6 +123,27 @@ __global__ void pack_conv_kernel(const float* __restrict__ W, float* __restrict_
     const int kb = kk >> 5, kin = kk & 31;
     const size_t tile = (size_t)N * 32;  // floats per tile
     const size_t off = (size_t)kb * 2 * tile + ((n >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (n & 7) * 16 + (kin & 3) * 4) / 4;
+    packed[off] = v;
+    packed[off + tile] = lo_part(v);
+}
+
+// dgrad operand of conv g, per stride class (ry, rx): Wd[(th, tw, co)][ci] = W[ry + s (kt-1-th)][rx + s (kt-1-tw)][ci][co],
+// packed like the forward weights (N = cin rows); class c starts at k-block c * kt*kt*cout/32
+__global__ void pack_dgrad_kernel(const float* __restrict__ W, float* __restrict__ packed, int k, int s, int cin, int cout) {
+    const int kt = k / s, Kc = kt * kt * cout;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s * s * Kc * cin) return;
+    const int ci = i % cin;
+    int r = i / cin;
+    const int kk = r % Kc, cls = r / Kc;
+    const int co = kk % cout, tap = kk / cout;
+    const int th = tap / kt, tw = tap - th * kt;
+    const int ry = cls / s, rx = cls - ry * s;
+    const int kh = ry + s * (kt - 1 - th), kw = rx + s * (kt - 1 - tw);
+    const float v = W[((size_t)(kh * k + kw) * cin + ci) * cout + co];
+    const int kb = cls * (Kc / 32) + (kk >> 5), kin = kk & 31;
+    const size_t tile = (size_t)cin * 32;
+    const size_t off = (size_t)kb * 2 * tile + ((ci >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (ci & 7) * 16 + (kin & 3) * 4) / 4;
     packed[off] = v;
     packed[off + tile] = lo_part(v);
 }
@@ -98,7 +169,7 @@ struct CvPlan {
     static constexpr int B_STAGE = B_TILE * 2;                    // hi + lo travel together
     static constexpr int ACOLS = BK * (NTERMS == 3 ? 2 : 1);
     static constexpr int MAXB = 4;                                // bands (accumulators) per image
-    static constexpr int BAR_BYTES = 1024;                        // barriers + tmem slot + k-block offset table
+    static constexpr int BAR_BYTES = 1024 + 4 * 128 * 8;          // barriers, tmem slot, k-block offsets, bias; row tables of 4 bands
 };
 
 // zero-padded, stride-phase-split copy of one NHWC image into shared memory (layout in the header comment); nthreads
@@ -120,8 +191,8 @@ constexpr int CV_THREADS = 320;
 
 template <int BN, int NTERMS, class Epi>
 __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in, const float* __restrict__ packed,
-                                                               const Epi epi, const ImgGeom g, const float* __restrict__ zeros,
-                                                               unsigned long long* __restrict__ dbg) {
+                                                               const Epi epi, const ImgGeom g, const Bands bd,
+                                                               const float* __restrict__ zeros, unsigned long long* __restrict__ dbg) {
     using P = CvPlan<BN, NTERMS>;
     const bool cta0 = dbg && blockIdx.x == 0;  // in-kernel timeline (dqn_debug_timeline, mode >= 16)
 #define CV_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 64) dbg[(row) * 8 + (col)] = clock64(); } while (0)
@@ -132,7 +203,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
     const uint32_t ring = sbase;                                  // S x B_STAGE (1024-aligned tiles)
     const uint32_t bars = ring + S * P::B_STAGE;                  // afull[S], bfull[S], empty[S], accum[MAXB], tmem slot
     const uint32_t kbtab = bars + 256;                            // int kboff[64]
-    const uint32_t bias_s = bars + 512;                           // float bias[BN]
+    const uint32_t bias_s = bars + 512;                           // float bias[BN] (epilogue staging area)
+    const uint32_t rowtab = bars + 1024;                          // per band and tile row: {image byte offset, output pixel or -1}
     const uint32_t img = bars + P::BAR_BYTES;
     auto afull_bar = [&](int s) { return bars + 8u * s; };
     auto bfull_bar = [&](int s) { return bars + 8u * (S + s); };
@@ -142,9 +214,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int image = blockIdx.x;
-    const int nsteps = g.nbands * g.nkb;
+    const int nsteps = bd.n * g.nkb;
     constexpr int DCOLS_MIN = 32;
-    const int dcols = g.nbands * BN < DCOLS_MIN ? DCOLS_MIN : g.nbands * BN;  // accumulators: band b at column b*BN
+    const int dcols = bd.n * BN < DCOLS_MIN ? DCOLS_MIN : bd.n * BN;  // accumulators: band b at column b*BN
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -163,6 +235,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         const int kh = tap / g.k, kw = tap - kh * g.k;
         const int off = (kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + c * 4;
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kbtab + 4u * tid), "r"(off) : "memory");
+    }
+    for (int e = tid; e < bd.n * 128; e += CV_THREADS) {
+        const int band = e >> 7, m = e & 127;
+        const Bands::B& c = bd.c[band];
+        const int ai = m / c.nb, bi = m - ai * c.nb;
+        int off = 0, opix = -1;  // rows past the band: any finite data, never stored
+        if (ai < c.na) {
+            const int a = c.a0 + ai, b = c.b0 + bi;
+            off = (a * bd.rs * g.wcols + b) * g.pitch;
+            opix = image * bd.out_hw + (a * bd.ym + c.ya) * bd.out_w + (b * bd.xm + c.xa);
+        }
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowtab + 8u * e), "r"(off), "r"(opix) : "memory");
     }
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
@@ -183,10 +267,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         // ---------------- image -> shared memory (once) ----------------
         {
             const float* src_img = in + (size_t)image * g.ih * g.iw * g.cin;
-            if (tid < BN) {
-                const float bv = epi.bias[tid];
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
-            }
+            epi.stage(tid, BN, bias_s);
             load_image_async(img, src_img, g, tid, 256, zeros);
             asm volatile("cp.async.wait_all;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -195,17 +276,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         // ---------------- A converters ----------------
         const int grp = warp & 3, cg = warp >> 2;  // TMEM lane quarter, converter group
         const int m = grp * 32 + lane;             // row of the band tile
-        const int oyl = m / g.ow, ox = m - oyl * g.ow;
-        const bool row_ok = oyl < g.th;
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
         // the 8 chunks of a k-block: consecutive channels of one pixel, or (cin == 4) consecutive kw of one kernel row
         uint32_t choff[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) choff[j] = g.cin >= 32 ? 16u * j : (uint32_t)(((j % g.s) * g.wps + j / g.s) * g.pitch);
         int step = cg;
-        for (int band = 0; band < g.nbands; ++band) {
-            const int oy = band * g.th + oyl;
-            const uint32_t base = img + ((row_ok && oy < g.oh) ? (uint32_t)((oy * g.s * g.wcols + ox) * g.pitch) : 0u);
+        for (int band = 0; band < bd.n; ++band) {
+            uint32_t roff;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(roff) : "r"(rowtab + 8u * (band * 128 + m)));
+            const uint32_t base = img + roff;
             const int step_end = (band + 1) * g.nkb;
             for (; step < step_end; step += 2) {
                 const int kb = step - band * g.nkb;
@@ -239,19 +319,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         pdl_launch_dependents();
         // ---------------- epilogue: warp (grp, cg) owns TMEM lanes 32 grp.., columns [cg BN/2, +BN/2) of every band ----------------
         constexpr int HC = BN / 2;
-        for (int band = 0; band < g.nbands; ++band) {
+        for (int band = 0; band < bd.n; ++band) {
             mbar_wait(accum_bar(band), 0);
             tc_fence_after();
             CV_STAMP(tid == 0 && band == 0, 63, 5);
-            const int oy = band * g.th + oyl;
-            const bool ok = row_ok && oy < g.oh;
-            const int mg = image * g.oh * g.ow + oy * g.ow + ox;
+            int mg;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(mg) : "r"(rowtab + 8u * (band * 128 + m) + 4u));
             const uint32_t trow = tmem_base + lane_base + (uint32_t)(band * BN + cg * HC);
 #pragma unroll
             for (int c = 0; c < HC; c += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c, v);
-                if (ok) epi.template store_b<16>(mg, cg * HC + c, v, bias_s + 4u * (cg * HC + c));
+                if (mg >= 0) epi.template store_b<16>(mg, cg * HC + c, v, bias_s + 4u * (cg * HC + c));
             }
         }
         tc_fence_before();
@@ -263,7 +342,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0, step = 0;
         bool ready = false;  // barriers of the current step already seen complete (tested during the previous step)
-        for (int band = 0; band < g.nbands; ++band) {
+        for (int band = 0; band < bd.n; ++band) {
             const uint32_t tmem_d = tmem_base + (uint32_t)(band * BN);
             for (int kb = 0; kb < g.nkb; ++kb, ++step) {
                 if (!ready) {
@@ -307,14 +386,16 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         // ---------------- weight TMA producer (warp 9, one lane) ----------------
         if (lane == 0) {
             pdl_wait();
-            int s = 0, ph = 0, kb = 0;
-            for (int step = 0; step < nsteps; ++step) {
-                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
-                CV_STAMP(true, step, 5);
-                mbar_expect_tx(bfull_bar(s), P::B_STAGE);
-                tma_bulk_g2s(stage_b(s), packed + (size_t)kb * (P::B_STAGE / 4), P::B_STAGE, bfull_bar(s));
-                if (++kb == g.nkb) kb = 0;
-                if (++s == S) { s = 0; ph ^= 1; }
+            int s = 0, ph = 0, step = 0;
+            for (int band = 0; band < bd.n; ++band) {
+                const float* src = packed + (size_t)bd.c[band].pk_kb0 * (P::B_STAGE / 4);
+                for (int kb = 0; kb < g.nkb; ++kb, ++step) {
+                    if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
+                    CV_STAMP(true, step, 5);
+                    mbar_expect_tx(bfull_bar(s), P::B_STAGE);
+                    tma_bulk_g2s(stage_b(s), src + (size_t)kb * (P::B_STAGE / 4), P::B_STAGE, bfull_bar(s));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
             }
         }
     }
@@ -326,18 +407,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
 }
 
 template <int BN, int NTERMS, class Epi>
-static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, int images) {
+static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, const Bands& bd, int images) {
     using P = CvPlan<BN, NTERMS>;
     auto kern = cvconv_kernel<BN, NTERMS, Epi>;
     const size_t bytes = (size_t)P::S * P::B_STAGE + P::BAR_BYTES + g.img_bytes + 1024;
     DQN_REQUIRE(bytes <= 227 * 1024, "image-resident conv: shared memory budget");
-    DQN_REQUIRE(g.nbands <= P::MAXB && g.nbands * BN + P::S * P::ACOLS <= 512, "image-resident conv: tensor memory budget");
+    DQN_REQUIRE(bd.n <= P::MAXB && bd.n * BN + P::S * P::ACOLS <= 512, "image-resident conv: tensor memory budget");
     static size_t configured = 0;  // one per template instantiation
     if (bytes > configured) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    launch_kernel(h->pdl, kern, dim3(images), dim3(CV_THREADS), bytes, h->stream, in, packed, e, g, (const float*)h->zeros16, h->tc_dbg);
+    launch_kernel(h->pdl, kern, dim3(images), dim3(CV_THREADS), bytes, h->stream, in, packed, e, g, bd, (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
 

@@ -1,0 +1,243 @@
+// Dense hidden layers: weight gradient on tcgen05 AND the optimizer in one pass, with the optimizer state staged by TMA.
+//
+//   dW[k][n] = sum_b act3[b][k] * dH[b][n]   (K = batch <= 32: ONE k-block per output tile)
+// The dense kernels hold 98.6 % of the parameters, so this pass is the HBM roofline of the step: it has to move
+// read(w, m, v) + write(w, m, v) = 24 bytes per parameter (189 MB at C2) and nothing else.  A GEMM-shaped kernel with a
+// read-modify-write epilogue keeps too few bytes in flight (measured 2.1 TB/s), a separate Adam pass moves the gradient
+// twice more (252 MB).  Here a CTA owns a 128 (k) x 32 (n) tile of W:
+//   * at CTA start one thread issues three 2-D TMA tensor copies (cp.async.bulk.tensor, 128 x 32 box, 128-byte swizzle)
+//     of the tile's w / m / v into shared memory -- 48 KB in flight per CTA, three CTAs per SM, no registers held
+//     (row-wise 128-byte bulk copies were tried first: 768 TMA operations per CTA made the pass 5x slower) -- and only then
+//   * the 128 x 32 x 32 product is formed: act3 columns -> registers -> hi/lo -> tensor memory (coalesced loads, lane ==
+//     row), dH tile transposed into a K-major hi/lo shared-memory tile, 12 tcgen05.mma (3-term TF32 split);
+//   * the epilogue reads the accumulator (tcgen05.ld) and the staged state, applies Adam / Nesterov momentum in place in
+//     shared memory (the swizzle makes the row-per-lane accesses conflict-free), and the tile goes back with three TMA
+//     tensor stores.
+// Launched after the dense dgrad has read W (it overwrites W).
+#pragma once
+#include "cvgemm.cuh"
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
+namespace fa {
+using namespace tc;
+
+constexpr int FA_BN = 32, FA_THREADS = 256;
+struct StateMaps { CUtensorMap w[2], m[2], v[2]; };  // per hidden stream: [flat][hid] f32, box 32 x 128, SWIZZLE_128B
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
+}
+
+template <int NTERMS>
+__global__ void __launch_bounds__(FA_THREADS, 3) fcwg_adam_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
+                                                                  int Bn, int flat, int NH, int hid,
+                                                                  const __grid_constant__ StateMaps maps,
+                                                                  float lr, float mom, int use_momentum,
+                                                                  const dqn_learner::Scalars* __restrict__ sc) {
+    constexpr int B_TILE = FA_BN * 128;  // bytes of the hi (or lo) tile: 32 n rows x 32 k
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    constexpr uint32_t ARR = BM * FA_BN * 4;                   // one state array of the tile: 128 rows x 128 B, swizzled
+    const uint32_t state = sbase;                              // [3 arrays] (1024-byte aligned for SWIZZLE_128B)
+    const uint32_t btile = state + 3 * ARR;                    // hi, lo
+    const uint32_t bars = btile + 2 * B_TILE;                  // state_full, afull, accum, tmem slot
+    const uint32_t st_full = bars, afull = bars + 8, accum = bars + 16, tmem_slot = bars + 24;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * FA_BN, m0r = blockIdx.y * BM;
+    const int strm = n0 >= hid;
+    const int ncol = n0 - (strm ? hid : 0);
+    const int narr = use_momentum ? 2 : 3;
+
+    if (tid == 0) {
+        mbar_init(st_full, 1); mbar_init(afull, 6); mbar_init(accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+
+    if (warp == 5) {
+        // ---- optimizer state of the tile: {w, m, v} boxes of 128 rows x 32 columns, one tensor copy each ----
+        if (lane == 0) {
+            cv::mbar_expect_tx(st_full, (uint32_t)(narr * ARR));
+            tma_load_2d(state, &maps.w[strm], ncol, m0r, st_full);
+            tma_load_2d(state + ARR, &maps.m[strm], ncol, m0r, st_full);
+            if (!use_momentum) tma_load_2d(state + 2 * ARR, &maps.v[strm], ncol, m0r, st_full);
+        }
+    } else if (warp < 4) {
+        // ---- A: act3^T, thread == row (flat index), 32 coalesced loads along the batch ----
+        const int r = warp * 32 + lane;
+        float hi[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) hi[b] = b < Bn ? __ldg(act3 + (size_t)b * flat + m0r + r) : 0.f;
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + 32u;  // columns [32,64) hi, [64,96) lo
+        ts::tmem_st32(ta, hi);
+        if (NTERMS == 3) {
+            float lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+            ts::tmem_st32(ta + 32u, lo);
+        }
+        ts::tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull);
+    } else if (warp >= 6) {
+        // ---- B: dH[b][n0 + n] -> K-major hi/lo tiles; lane = (b % 4) + 4 * (n % 8): conflict-free transposing stores ----
+        const int bq = lane & 3, nq = lane >> 2;
+        for (int gi = warp - 6; gi < 8 * (FA_BN / 8); gi += 2) {
+            const int b4 = gi / (FA_BN / 8), n8 = gi - b4 * (FA_BN / 8);
+            const int b = b4 * 4 + bq, n = n8 * 8 + nq;
+            const float v = b < Bn ? __ldg(dhid + (size_t)b * NH + n0 + n) : 0.f;
+            const uint32_t a = btile + (uint32_t)((n >> 3) * cv::PK_SBO + (b >> 2) * cv::PK_LBO + (n & 7) * 16 + (b & 3) * 4);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+            if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v)) : "memory");
+        }
+        fence_proxy_async();  // generic-proxy stores -> read by the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull);
+    } else {
+        // ---- warp 4: MMA issue ----
+        mbar_wait(afull, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(FA_BN, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        if (leader) {
+            const uint64_t db = make_desc(btile, cv::PK_LBO, cv::PK_SBO), dbl = make_desc(btile + B_TILE, cv::PK_LBO, cv::PK_SBO);
+            const uint32_t ta = tmem_base + 32u;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2 * cv::PK_LBO) >> 4;
+                if (NTERMS == 3) {
+                    ts::mma_tf32_ts(tmem_base, ta + ks * 8, dbl + o, idesc, ks != 0);
+                    ts::mma_tf32_ts(tmem_base, ta + 32u + ks * 8, db + o, idesc, 1);
+                    ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, 1);
+                } else {
+                    ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, ks != 0);
+                }
+            }
+            mma_commit(accum);
+        }
+        __syncwarp();
+    }
+    pdl_launch_dependents();
+
+    // ---- epilogue (all 8 warps): warp w -> rows 32 (w % 4) + lane, columns [16 (w / 4), +16) ----
+    {
+        const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+        const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+        const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+        const int row = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 16;
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        float g[16];
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, g);
+        mbar_wait(st_full, 0);
+        const uint32_t srow = state + row * 128;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            // SWIZZLE_128B: 16-byte chunk q of row r sits at chunk q ^ (r % 8)
+            const uint32_t sw = srow + ((uint32_t)(((c0 + j) >> 2) ^ (row & 7)) << 4), sm = sw + ARR, sv = sw + 2 * ARR;
+            float4 pp, mm, vv;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pp.x), "=f"(pp.y), "=f"(pp.z), "=f"(pp.w) : "r"(sw));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(mm.x), "=f"(mm.y), "=f"(mm.z), "=f"(mm.w) : "r"(sm));
+            const float4 gg = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+            if (use_momentum) {
+#define MOM1(c) mm.c = mm.c * mom + gg.c; pp.c = pp.c - (gg.c * lr + mm.c * mom * lr);
+                MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+            } else {
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vv.x), "=f"(vv.y), "=f"(vv.z), "=f"(vv.w) : "r"(sv));
+#define ADAM1(c) mm.c = mm.c + (gg.c - mm.c) * omb1; vv.c = vv.c + (gg.c * gg.c - vv.c) * omb2; \
+                 pp.c = pp.c - (mm.c * lr_t) / (sqrtf(vv.c) + eps);
+                ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sv), "f"(vv.x), "f"(vv.y), "f"(vv.z), "f"(vv.w) : "memory");
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sm), "f"(mm.x), "f"(mm.y), "f"(mm.z), "f"(mm.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sw), "f"(pp.x), "f"(pp.y), "f"(pp.z), "f"(pp.w) : "memory");
+        }
+        fence_proxy_async();  // the updated rows leave through the async proxy
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        if (lane == 0) {
+            tma_store_2d(&maps.w[strm], ncol, m0r, state);
+            tma_store_2d(&maps.m[strm], ncol, m0r, state + ARR);
+            if (!use_momentum) tma_store_2d(&maps.v[strm], ncol, m0r, state + 2 * ARR);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released once it has been read
+        }
+        __syncwarp();
+    } else if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    }
+}
+
+static inline bool supported(const dqn_learner* h, int rows) {
+    const NetDesc& net = h->net;
+    return rows <= 32 && net.flat % BM == 0 && net.hidden % FA_BN == 0 && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;
+}
+
+// tensor maps of the six state arrays (w, m, v of the two hidden streams), encoded once per handle
+static void encode_maps(dqn_learner* h, StateMaps& out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DQN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DQN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    const NetDesc& net = h->net;
+    float* slabs[3] = {h->online, h->slot_m, h->slot_v};
+    CUtensorMap* dst[3] = {out.w, out.m, out.v};
+    for (int a = 0; a < 3; ++a)
+        for (int st = 0; st < 2; ++st) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)net.hidden, (cuuint64_t)net.flat};
+            const cuuint64_t gstr[1] = {(cuuint64_t)net.hidden * 4};
+            const cuuint32_t box[2] = {FA_BN, BM}, estr[2] = {1, 1};
+            const CUresult r = ((EncodeFn)fn)(&dst[a][st], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, slabs[a] + net.off_fc_w[st], gdim, gstr, box,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DQN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+        }
+}
+
+static void launch(dqn_learner* h, int rows) {
+    const NetDesc& net = h->net;
+    if (!h->fa_maps) {
+        h->fa_maps = aligned_alloc(64, sizeof(StateMaps));  // released with free() in dqn_destroy
+        try { encode_maps(h, *static_cast<StateMaps*>(h->fa_maps)); } catch (...) { free(h->fa_maps); h->fa_maps = nullptr; throw; }
+    }
+    const StateMaps& maps = *static_cast<StateMaps*>(h->fa_maps);
+    const size_t bytes = 3 * BM * FA_BN * 4 + 2 * FA_BN * 128 + 64 + 1024;
+    auto go = [&](auto kern) {
+        static bool configured = false;
+        if (!configured) {
+            DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured = true;
+        }
+        launch_kernel(h->pdl, kern, dim3(net.NH / FA_BN, net.flat / BM), dim3(FA_THREADS), bytes, h->stream,
+                      (const float*)h->acts_on.act[2], (const float*)h->d_hid, rows, net.flat, net.NH, net.hidden, maps,
+                      (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum, (const dqn_learner::Scalars*)h->d_sc);
+    };
+    if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_kernel<3>); else go(fcwg_adam_kernel<1>);
+    h->launches++;
+}
+}  // namespace fa

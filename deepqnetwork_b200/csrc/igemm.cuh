@@ -282,7 +282,10 @@ struct OpConvDgradB {  // B(k=(jh,jw,co), n=ci) = W[kh][kw][ci][co]
 // ---------------- epilogues ----------------
 struct EpiBiasRelu {  // out[m][n] = relu(acc + bias[n])
     float* out; const float* bias; int ldo;
-    // bias staged in shared memory by the caller (cvgemm.cuh): sbias = shared address of bias[n]
+    // image-resident conv kernel (cvgemm.cuh): bias staged in shared memory, sbias = shared address of bias[n]
+    __device__ __forceinline__ void stage(int tid, int bn, uint32_t sarea) const {
+        if (tid < bn) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sarea + 4u * tid), "f"(bias[tid]) : "memory");
+    }
     template <int TN>
     __device__ __forceinline__ void store_b(int m, int n, const float (&v)[TN], uint32_t sbias) const {
         float* o = out + (size_t)m * ldo + n;
@@ -314,6 +317,24 @@ struct EpiPartial {  // part[z][m][n] = acc   (split-K partial sums, reduced by 
         float* o = part + ((size_t)z * M + m) * ldo + n;
 #pragma unroll
         for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+};
+
+struct EpiGatePix {  // image-resident dgrad: out[pixel][n] = acc * (gate[pixel][n] > 0)
+    float* out; const float* gate; int ldo;
+    __device__ __forceinline__ void stage(int, int, uint32_t) const {}
+    template <int TN>
+    __device__ __forceinline__ void store_b(int m, int n, const float (&v)[TN], uint32_t) const {
+        const size_t o = (size_t)m * ldo + n;
+        float4 gt[TN / 4];
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) gt[j / 4] = *reinterpret_cast<const float4*>(gate + o + j);
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const float4 g4 = gt[j / 4];
+            *reinterpret_cast<float4*>(out + o + j) = make_float4(g4.x > 0.f ? v[j] : 0.f, g4.y > 0.f ? v[j + 1] : 0.f,
+                                                                 g4.z > 0.f ? v[j + 2] : 0.f, g4.w > 0.f ? v[j + 3] : 0.f);
+        }
     }
 };
 

@@ -65,6 +65,9 @@ struct dqn_learner {
     bool fc_adam_done = false;
     bool fc_ffma_adam = false;    // option: dense wgrad + optimizer as one fp32 FFMA pass (no gradient round trip); measured
                                   // slower than tensor-core wgrad + streaming Adam (instruction-bound: 61 us vs 17 + 45 us)
+    void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
+    bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
+                                  // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)
     bool fc_grads_needed = false; // set per launch sequence: that pass also stores dW (seam-2 / parity path)  // set per launch sequence: dense wgrad applies the optimizer in its epilogue
     std::string err;
     int64_t launches = 0;
@@ -161,7 +164,10 @@ struct dqn_learner {
     // kept in sync with the parameter slabs by launch_pack_conv (after every optimizer step / copy / set_param)
     float* packed[2] = {nullptr, nullptr};
     int64_t pk_off[3] = {0, 0, 0};
+    float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
+    int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
+    bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
     // staging

@@ -6,6 +6,7 @@
 // the TF layouts, so tensors copy 1:1 to/from checkpoints.
 #include "tsgemm.cuh"
 #include "cvgemm.cuh"
+#include "fcadam.cuh"
 #include <algorithm>
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -222,6 +223,9 @@ void alloc_packed_conv(dqn_learner* h) {
     for (int l = 0; l < 3; ++l) { h->pk_off[l] = off; off += (int64_t)cv::packed_floats(h->net.conv[l]); }
     h->pk_floats = off;
     for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->packed[t], (size_t)off * sizeof(float)));
+    int64_t offd = 0;
+    for (int l = 1; l < 3; ++l) { h->pkd_off[l] = offd; offd += (int64_t)cv::packed_floats(h->net.conv[l]); }
+    DQN_CUDA_OK(cudaMalloc(&h->packed_dg, (size_t)offd * sizeof(float)));
 }
 
 void launch_pack_conv(dqn_learner* h, int tower) {
@@ -234,16 +238,23 @@ void launch_pack_conv(dqn_learner* h, int tower) {
         launch_kernel(false, cv::pack_conv_kernel, dim3(ceil_div(K * N, 256)), dim3(256), 0, h->stream, P + h->net.off_cw[l],
                       h->packed[tower] + h->pk_off[l], K, N);
         h->launches++;
+        cv::ImgGeom q; cv::Bands bd;
+        if (tower == 0 && l > 0 && cv::dgrad_geom(g, q, bd)) {
+            launch_kernel(false, cv::pack_dgrad_kernel, dim3(ceil_div(K * N, 256)), dim3(256), 0, h->stream, P + h->net.off_cw[l],
+                          h->packed_dg + h->pkd_off[l], g.k, g.s, g.cin, g.cout);
+            h->launches++;
+        }
     }
 }
 
 template <class Epi>
 static bool conv_image_resident(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ConvGeom& g, int images) {
-    cv::ImgGeom q;
-    if (!h->img_conv || !cv::img_geom(g, q)) return false;
+    cv::ImgGeom q; cv::Bands bd;
+    if (!h->img_conv || !cv::img_geom(g, q) || q.nbands > 4) return false;
+    cv::forward_bands(q, bd);
     const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
-    if (g.cout == 64) { if (x3) cv::launch_conv<64, 3>(h, in, packed, e, q, images); else cv::launch_conv<64, 1>(h, in, packed, e, q, images); }
-    else              { if (x3) cv::launch_conv<32, 3>(h, in, packed, e, q, images); else cv::launch_conv<32, 1>(h, in, packed, e, q, images); }
+    if (g.cout == 64) { if (x3) cv::launch_conv<64, 3>(h, in, packed, e, q, bd, images); else cv::launch_conv<64, 1>(h, in, packed, e, q, bd, images); }
+    else              { if (x3) cv::launch_conv<32, 3>(h, in, packed, e, q, bd, images); else cv::launch_conv<32, 1>(h, in, packed, e, q, bd, images); }
     return true;
 }
 
@@ -404,7 +415,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         side_end(h, saved);
     };
     const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && rows <= 32 && fc_wgrad_adam_supported(h);
-    if (!h->fuse_fc_adam && !ffma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
+    // default for a whole step on one GPU: tcgen05 wgrad + optimizer in one pass with TMA-staged state (fcadam.cuh)
+    const bool tma_adam = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !h->fc_grads_needed && tcm && h->fc_tma_adam &&
+                          fa::supported(h, rows);
+    if (!h->fuse_fc_adam && !ffma_adam && !tma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
@@ -435,7 +449,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
         // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
         side_begin(h, saved, 0);
-        if (ffma_adam) {
+        if (tma_adam) {
+            prof_mark(h, "fc_wgrad_adam");
+            fa::launch(h, rows);
+        } else if (ffma_adam) {
             prof_mark(h, "fc_wgrad_adam");
             launch_fc_wgrad_adam(h, rows, h->fc_grads_needed);
         } else {
@@ -497,7 +514,15 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             OpConvDgradB b{P + net.off_cw[l], g, cl2};
             const int Kd = (g.k / g.s) * (g.k / g.s) * g.cout;
             const int ctas = ceil_div(Mc, tc::BM) * ceil_div(g.cin, 32) * Zc;
-            if (tcm && h->ts_gemm && 2 * ctas <= h->sm_count && Kd % 64 == 0 && g.cin % 32 == 0 &&
+            cv::ImgGeom q; cv::Bands bd;
+            if (tcm && h->img_conv && h->img_dgrad && cv::dgrad_geom(g, q, bd)) {
+                // image-resident: one CTA per image holds dY, the stride-parity classes are its accumulators
+                EpiGatePix e{h->d_act[l - 1], acts.act[l - 1], g.cin};
+                const float* pk = h->packed_dg + h->pkd_off[l];
+                const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
+                if (g.cin == 64) { if (x3) cv::launch_conv<64, 3>(h, h->d_act[l], pk, e, q, bd, rows); else cv::launch_conv<64, 1>(h, h->d_act[l], pk, e, q, bd, rows); }
+                else             { if (x3) cv::launch_conv<32, 3>(h, h->d_act[l], pk, e, q, bd, rows); else cv::launch_conv<32, 1>(h, h->d_act[l], pk, e, q, bd, rows); }
+            } else if (tcm && h->ts_gemm && 2 * ctas <= h->sm_count && Kd % 64 == 0 && g.cin % 32 == 0 &&
                 (int64_t)2 * rows * g.ih * g.iw * g.cin <= (int64_t)h->fc_splits * rows * net.NH) {
                 // too few tiles to fill the chip (conv3: 60): split K in two as well; the halves are added and gated by
                 // the consumer kernel.  Workspace: the forward split-K buffer (idle here).
