@@ -91,6 +91,9 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side2_stream, cudaStreamNonBlocking));
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side3_stream, cudaStreamNonBlocking));
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side4_stream, cudaStreamNonBlocking));
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side5_stream, cudaStreamNonBlocking));
+        DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side6_stream, cudaStreamNonBlocking));
         for (auto& e : h->fork_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         net_describe(h->net, h->cfg);
         const NetDesc& net = h->net;
@@ -147,11 +150,15 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         dmalloc(h->d_hid, R * net.NH);
         for (int l = 0; l < 3; ++l) dmalloc(h->d_act[l], R * net.conv[l].oh * net.conv[l].ow * net.conv[l].cout);
         h->wg_part_floats = 0;
+        int64_t wg_total = 0;
         for (int l = 0; l < 3; ++l) {
             const ConvGeom& g = net.conv[l];
-            h->wg_part_floats = std::max<int64_t>(h->wg_part_floats, (int64_t)64 * (g.k * g.k * g.cin + 4) * g.cout);
+            const int64_t need = (int64_t)64 * (g.k * g.k * g.cin + 4) * g.cout;
+            h->wg_part_floats = std::max<int64_t>(h->wg_part_floats, need);
+            h->wg_off[l] = wg_total;
+            wg_total += need;
         }
-        dmalloc(h->wg_part, (size_t)h->wg_part_floats);
+        dmalloc(h->wg_part, (size_t)wg_total);
         dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4); dmalloc(h->opt_ticket, 1);
         DQN_CUDA_OK(cudaMemsetAsync(h->zeros16, 0, 16, h->stream));
         DQN_CUDA_OK(cudaMemsetAsync(h->opt_ticket, 0, 4, h->stream));
@@ -213,6 +220,9 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
     if (h->side3_stream) cudaStreamDestroy(h->side3_stream);
+    if (h->side4_stream) cudaStreamDestroy(h->side4_stream);
+    if (h->side5_stream) cudaStreamDestroy(h->side5_stream);
+    if (h->side6_stream) cudaStreamDestroy(h->side6_stream);
     for (int k = 0; k < 2; ++k) if (h->pipe_graph[k]) cudaGraphExecDestroy(h->pipe_graph[k]);
     {
         dqn_learner::BatchSet& b = h->sets[1];
@@ -608,6 +618,17 @@ static cudaEvent_t next_fork_event(dqn_learner* h) {
     return h->fork_ev[h->fork_used++];
 }
 
+static cudaStream_t side_of(const dqn_learner* h, int which) {
+    switch (which) {
+        case 0: return h->side_stream;
+        case 1: return h->side2_stream;
+        case 2: return h->side3_stream;
+        case 3: return h->side4_stream;
+        case 4: return h->side5_stream;
+        default: return h->side6_stream;
+    }
+}
+
 static int prio_of(const dqn_learner* h, int prio_class) {
     if (!h->use_prio) return h->prio_lo;
     const int p = prio_class >= 2 ? h->prio_hi : prio_class == 1 ? h->prio_hi + 1 : h->prio_lo;
@@ -619,7 +640,7 @@ void side_begin(dqn_learner* h, cudaStream_t& saved, int which, int prio_class) 
     h->saved_prio = g_launch_priority;
     if (!overlap_enabled(h)) return;
     g_launch_priority = prio_of(h, prio_class);
-    cudaStream_t side = which == 2 ? h->side3_stream : which ? h->side2_stream : h->side_stream;
+    cudaStream_t side = side_of(h, which);
     cudaEvent_t e = next_fork_event(h);
     DQN_CUDA_OK(cudaEventRecord(e, saved));
     DQN_CUDA_OK(cudaStreamWaitEvent(side, e, 0));
@@ -631,7 +652,7 @@ void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; g_launch_
 void main_wait_side(dqn_learner* h, int which) {
     if (!overlap_enabled(h)) return;
     cudaEvent_t e = next_fork_event(h);
-    DQN_CUDA_OK(cudaEventRecord(e, which == 2 ? h->side3_stream : which ? h->side2_stream : h->side_stream));
+    DQN_CUDA_OK(cudaEventRecord(e, side_of(h, which)));
     DQN_CUDA_OK(cudaStreamWaitEvent(h->stream, e, 0));
 }
 
@@ -1087,6 +1108,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     if (n == "overlap") h->overlap = value != 0;          // side-stream forks inside a step
     else if (n == "fuse_fc_adam") h->fuse_enabled = value != 0;  // optimizer in the dense wgrad epilogue
     else if (n == "batch_graph") h->batch_graph_enabled = value != 0;  // dqn_train_batch replays a captured graph
+    else if (n == "fc_split_streams") h->fc_split_streams = value != 0;
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels

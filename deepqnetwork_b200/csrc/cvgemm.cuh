@@ -148,6 +148,36 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ W, float* __restrict
     packed[off + tile] = lo_part(v);
 }
 
+// all layers of one tower in ONE launch (it runs at the tail of every step): blockIdx.y = job
+struct PackJobs {
+    int n;
+    struct J { const float* W; float* out; int K, N, k, s, cin, cout, dgrad; } j[6];
+};
+__global__ void pack_all_kernel(const PackJobs jobs) {
+    const PackJobs::J& q = jobs.j[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.K * q.N) return;
+    float v; int kb, kin, n, rows;
+    if (!q.dgrad) {
+        const int kk = i / q.N;
+        n = i - kk * q.N; v = q.W[i]; kb = kk >> 5; kin = kk & 31; rows = q.N;
+    } else {
+        const int kt = q.k / q.s, Kc = kt * kt * q.cout;
+        const int ci = i % q.cin, r = i / q.cin;
+        const int kk = r % Kc, cls = r / Kc;
+        const int co = kk % q.cout, tap = kk / q.cout;
+        const int th = tap / kt, tw = tap - th * kt;
+        const int ry = cls / q.s, rx = cls - ry * q.s;
+        const int kh = ry + q.s * (kt - 1 - th), kw = rx + q.s * (kt - 1 - tw);
+        v = q.W[((size_t)(kh * q.k + kw) * q.cin + ci) * q.cout + co];
+        kb = cls * (Kc / 32) + (kk >> 5); kin = kk & 31; n = ci; rows = q.cin;
+    }
+    const size_t tile = (size_t)rows * 32;
+    const size_t off = (size_t)kb * 2 * tile + ((n >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (n & 7) * 16 + (kin & 3) * 4) / 4;
+    q.out[off] = v;
+    q.out[off + tile] = lo_part(v);
+}
+
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"

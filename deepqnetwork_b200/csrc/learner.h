@@ -50,7 +50,7 @@ struct dqn_learner {
     // second stream + events: independent kernels of one step (target tower vs online tower, wgrads vs the dgrad
     // chain) are forked onto it so that the small batch-32 grids overlap; inside a captured graph these become
     // parallel branches
-    cudaStream_t side_stream = nullptr, side2_stream = nullptr, side3_stream = nullptr;
+    cudaStream_t side_stream = nullptr, side2_stream = nullptr, side3_stream = nullptr, side4_stream = nullptr, side5_stream = nullptr, side6_stream = nullptr;
     cudaEvent_t fork_ev[24] = {};
     int fork_used = 0;
     bool overlap = true;
@@ -65,6 +65,7 @@ struct dqn_learner {
     bool fc_adam_done = false;
     bool fc_ffma_adam = false;    // option: dense wgrad + optimizer as one fp32 FFMA pass (no gradient round trip); measured
                                   // slower than tensor-core wgrad + streaming Adam (instruction-bound: 61 us vs 17 + 45 us)
+    bool fc_split_streams = true; // dense wgrad + optimizer per hidden stream on two side streams (pipelines HBM- and tensor-bound halves)
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)
@@ -152,7 +153,8 @@ struct dqn_learner {
     TowerActs acts_on, acts_tg;
     float *d_hid = nullptr, *d_act[3] = {nullptr, nullptr, nullptr};
     float* wg_part = nullptr;  // split-K partials for conv wgrad
-    int64_t wg_part_floats = 0;
+    int64_t wg_part_floats = 0;   // per layer (64 partials of (mreal + 4) x cout)
+    int64_t wg_off[3] = {0, 0, 0};  // each layer has its own slice: the three weight gradients run on parallel streams
     int fc_splits = 1;
 
     // tcgen05 path helpers
@@ -209,6 +211,7 @@ void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0, int prio_cla
 void side_end(dqn_learner* h, cudaStream_t saved);
 void main_wait_side(dqn_learner* h, int which = 0);
 void launch_optimizer_fc(dqn_learner* h);
+void launch_optimizer_fc_stream(dqn_learner* h, int st);  // one hidden stream's dense kernel
 bool fc_wgrad_adam_supported(const dqn_learner* h);
 void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g);  // optim.cu: dense wgrad + optimizer in one FFMA pass  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);

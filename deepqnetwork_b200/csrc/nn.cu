@@ -231,20 +231,21 @@ void alloc_packed_conv(dqn_learner* h) {
 void launch_pack_conv(dqn_learner* h, int tower) {
     if (h->cfg.math_mode == DQN_MATH_FP32 || !h->packed[tower]) return;
     const float* P = tower ? h->target : h->online;
+    cv::PackJobs jobs; jobs.n = 0;
+    int most = 0;
     for (int l = 0; l < 3; ++l) {
         const ConvGeom& g = h->net.conv[l];
         const int K = g.k * g.k * g.cin, N = g.cout;
         if (K % 32 != 0) continue;
-        launch_kernel(false, cv::pack_conv_kernel, dim3(ceil_div(K * N, 256)), dim3(256), 0, h->stream, P + h->net.off_cw[l],
-                      h->packed[tower] + h->pk_off[l], K, N);
-        h->launches++;
+        jobs.j[jobs.n++] = {P + h->net.off_cw[l], h->packed[tower] + h->pk_off[l], K, N, g.k, g.s, g.cin, g.cout, 0};
+        most = std::max(most, K * N);
         cv::ImgGeom q; cv::Bands bd;
-        if (tower == 0 && l > 0 && cv::dgrad_geom(g, q, bd)) {
-            launch_kernel(false, cv::pack_dgrad_kernel, dim3(ceil_div(K * N, 256)), dim3(256), 0, h->stream, P + h->net.off_cw[l],
-                          h->packed_dg + h->pkd_off[l], g.k, g.s, g.cin, g.cout);
-            h->launches++;
-        }
+        if (tower == 0 && l > 0 && cv::dgrad_geom(g, q, bd))
+            jobs.j[jobs.n++] = {P + h->net.off_cw[l], h->packed_dg + h->pkd_off[l], K, N, g.k, g.s, g.cin, g.cout, 1};
     }
+    if (!jobs.n) return;
+    launch_kernel(false, cv::pack_all_kernel, dim3(ceil_div(most, 256), jobs.n), dim3(256), 0, h->stream, jobs);
+    h->launches++;
 }
 
 template <class Epi>
@@ -418,7 +419,20 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     // default for a whole step on one GPU: tcgen05 wgrad + optimizer in one pass with TMA-staged state (fcadam.cuh)
     const bool tma_adam = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !h->fc_grads_needed && tcm && h->fc_tma_adam &&
                           fa::supported(h, rows);
-    if (!h->fuse_fc_adam && !ffma_adam && !tma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
+    // unfused + optimizer inside backward: one wgrad launch per hidden stream, each on its own side stream, so that the
+    // optimizer pass of stream 0 (HBM-bound) overlaps the weight gradient of stream 1 (tensor-bound)
+    const bool split_fc = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !tma_adam && tcm && net.dueling && h->fc_split_streams;
+    auto fc_wgrad_stream = [&](int st) {
+        side_begin(h, saved, st == 0 ? 0 : 5, 0);
+        prof_mark(h, st == 0 ? "fc_wgrad" : "fc_wgrad1");
+        OpColContig a{acts.act[2], net.flat};
+        OpColContig b{h->d_hid + (size_t)st * net.hidden, net.NH};
+        EpiFcWgrad e{G + net.off_fc_w[st], G + net.off_fc_w[st], net.hidden};
+        gemm_auto<false>(h, a, b, e, net.flat, net.hidden, rows, 1, 0);
+        side_end(h, saved);
+    };
+    if (split_fc) { fc_wgrad_stream(0); fc_wgrad_stream(1); }
+    else if (!h->fuse_fc_adam && !ffma_adam && !tma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
@@ -445,7 +459,15 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         }
     }
     if (h->fuse_fc_adam) fc_wgrad();  // fused: it overwrites W, so it starts only after the dgrad has read W
-    if (h->early_fc_adam && !h->fuse_fc_adam) {
+    if (split_fc) {
+        for (int st = 0; st < 2; ++st) {
+            side_begin(h, saved, st == 0 ? 0 : 5, 0);  // after this stream's wgrad, and after the dgrad above has read the old W
+            prof_mark(h, st == 0 ? "optimizer_fc" : "optimizer_fc1");
+            launch_optimizer_fc_stream(h, st);
+            side_end(h, saved);
+        }
+        h->fc_adam_done = true;
+    } else if (h->early_fc_adam && !h->fuse_fc_adam) {
         // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
         // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
         side_begin(h, saved, 0);
@@ -462,13 +484,16 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         side_end(h, saved);
         h->fc_adam_done = true;
     }
-    float* part = h->wg_part;
     for (int l = 2; l >= 0; --l) {
         const ConvGeom& g = net.conv[l];
+        float* part = h->wg_part + h->wg_off[l];
         const int mreal = g.k * g.k * g.cin, N = g.cout, K = rows * g.oh * g.ow;
         // wgrad (+bias) split over the pixel dimension
         {
-            side_begin(h, saved, 1, 1);  // needs d_act[l], which the main stream has just produced
+            // needs d_act[l], which the main stream has just produced; one side stream per layer, so that a layer's
+            // weight gradient never queues behind the previous layer's
+            const int wstream = l == 2 ? 1 : l == 1 ? 3 : 4;
+            side_begin(h, saved, wstream, 1);
             const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
             int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
@@ -541,6 +566,9 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     }
     main_wait_side(h, 0);  // all weight gradients are in the slab (and the dense kernels updated) before the
     main_wait_side(h, 1);  // optimizer pass over the remaining tensors runs
+    main_wait_side(h, 3);
+    main_wait_side(h, 4);
+    if (split_fc) main_wait_side(h, 5);
 }
 
 // ---- GEMM self-test: plain matrices through either engine (dqn_selftest_gemm) ----------------------------------------

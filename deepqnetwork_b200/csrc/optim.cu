@@ -10,6 +10,10 @@
 #include "learner.h"
 #include <algorithm>
 
+// Streaming Adam over one slab range, one-wave grid-stride grid (8 CTAs per SM).  Launch shapes measured inside the
+// whole step (tools/cupti_trace): this one 5090 steps/s; one 1024-float4 chunk per short CTA (yields the SMs to the
+// higher-priority chain, but then this HBM-bound pass itself finishes last) 4690; the same plus a 48 KB shared-memory
+// reservation to cap residency 4720.
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, size_t n4, float lr,
                                                    const dqn_learner::Scalars* __restrict__ sc) {
@@ -63,6 +67,12 @@ void launch_optimizer_fc(dqn_learner* h) {
     const int64_t fcw = (int64_t)net.flat * net.hidden;
     optimizer_range(h, net.off_fc_w[0], net.off_fc_w[0] + fcw);
     if (net.dueling) optimizer_range(h, net.off_fc_w[1], net.off_fc_w[1] + fcw);
+}
+
+void launch_optimizer_fc_stream(dqn_learner* h, int st) {
+    const NetDesc& net = h->net;
+    const int64_t fcw = (int64_t)net.flat * net.hidden;
+    optimizer_range(h, net.off_fc_w[st], net.off_fc_w[st] + fcw);
 }
 
 // Dense hidden layers: weight gradient AND optimizer in one pass (the default for a whole step on one GPU).
