@@ -89,8 +89,10 @@ def kernel_bytes(name, cfg, nn):
         return 2 * B * flat * 4 * 2 + B * flat * 4
     if base == 'fc_reduce_heads':
         return rows * 512 * st * 4 * 2
-    if base == 'fc_wgrad':
-        return B * flat * 4 + B * 512 * st * 4 + flat * 512 * st * 4
+    per = nn.get('split_fc')       # dense wgrad / optimizer launched once per hidden stream ('...1' = the value stream)
+    if base in ('fc_wgrad', 'fc_wgrad1'):
+        n_st = 1 if per else st
+        return B * flat * 4 + B * 512 * n_st * 4 + flat * 512 * n_st * 4
     if base == 'fc_dgrad':
         return B * 512 * st * 4 + flat * 512 * st * 4 + 2 * B * flat * 4
     if base.endswith('_wgrad'):
@@ -105,8 +107,8 @@ def kernel_bytes(name, cfg, nn):
         return B * acts[l] * 4 + wts[l] * 4 + 2 * B * acts[l - 1] * 4
     if base == 'fc_wgrad_adam':    # read w,m,v + write w,m,v of the dense kernels; activations / dH tiles come from L2
         return 6 * 4 * flat * 512 * st + B * flat * 4 + B * 512 * st * 4
-    if base == 'optimizer_fc':     # dense hidden kernels only (98.6% of P), issued from inside the backward pass
-        return 7 * 4 * flat * 512 * st
+    if base in ('optimizer_fc', 'optimizer_fc1'):  # dense hidden kernels only (98.6% of P), issued inside the backward pass
+        return 7 * 4 * flat * 512 * (1 if per else st)
     if base == 'optimizer':        # read g,p,m,v ; write p,m,v over whatever optimizer_fc has not already updated
         return 7 * 4 * (nn['P'] - (flat * 512 * st if nn.get('early_fc') else 0))
     if base == 'gather':
@@ -161,10 +163,10 @@ def clocks_sampler_stop(handle, device_index):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per step for the kernels behind a profile name, from the ncu --set full
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind a profile name, from the ncu --set full
 # capture committed as profiles/r01b_tc3x_top_kernels_raw.csv (adam_kernel: 62.9 MB read + 1.2 MB written per launch;
 # the stores are still dirty in L2 when the kernel ends)
-NCU_TRAFFIC = {'optimizer_fc': 2 * (62.92e6 + 1.23e6)}
+NCU_TRAFFIC = {'optimizer_fc': 62.92e6 + 1.23e6, 'optimizer_fc1': 62.92e6 + 1.23e6}
 
 
 def measured_peak_hbm():
@@ -373,6 +375,7 @@ def main():
         L.set_profile(False)
         per_kernel = {k: v / n * 1000.0 for k, v in prof.items()}  # us per step
         nn['early_fc'] = 'optimizer_fc' in per_kernel or 'fc_wgrad_adam' in per_kernel
+        nn['split_fc'] = 'optimizer_fc1' in per_kernel
         total_us = sum(per_kernel.values())
         dom = max(per_kernel, key=per_kernel.get)
         kb = kernel_bytes(dom, cfg, nn)

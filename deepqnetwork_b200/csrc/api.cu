@@ -139,8 +139,17 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_in_small, std::max<size_t>(h->in_small_bytes, 16 * R), cudaHostAllocDefault));
             DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
         }
-        dmalloc(h->b_tree_idx, R); dmalloc(h->b_data_idx, R); dmalloc(h->b_mem_idx, R);
-        dmalloc(h->b_prio, R); dmalloc(h->b_isw64, R); dmalloc(h->b_isw, R); dmalloc(h->b_u, R);
+        auto carve = [&](dqn_learner::BatchSet& b) {
+            dmalloc(b.blk, 6 * R);
+            b.tree_idx = b.blk; b.prio = reinterpret_cast<double*>(b.blk + R); b.isw64 = reinterpret_cast<double*>(b.blk + 2 * R);
+            b.data_idx = b.blk + 3 * R; b.mem_idx = b.blk + 4 * R; b.u = reinterpret_cast<double*>(b.blk + 5 * R);
+        };
+        carve(h->sets[0]); carve(h->sets[1]);
+        h->b_tree_idx = h->sets[0].tree_idx; h->b_data_idx = h->sets[0].data_idx; h->b_mem_idx = h->sets[0].mem_idx;
+        h->b_prio = h->sets[0].prio; h->b_isw64 = h->sets[0].isw64; h->b_u = h->sets[0].u;
+        dmalloc(h->b_isw, R);
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2, 64 * R, cudaHostAllocDefault));
+        DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage2_ev, cudaEventDisableTiming));
         dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_losses_out, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
         dmalloc(h->b_rows, R);
 
@@ -175,8 +184,8 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             a.prio = h->b_prio; a.isw64 = h->b_isw64; a.u = h->b_u; a.isw = h->b_isw; a.x_f32 = h->x_f32;
             dqn_learner::BatchSet& b = h->sets[1];
             dmalloc(b.states, 2 * R * h->state_bytes); dmalloc(b.actions, R); dmalloc(b.rewards, R); dmalloc(b.cont, R);
-            dmalloc(b.losses, R); dmalloc(b.tree_idx, R); dmalloc(b.data_idx, R); dmalloc(b.mem_idx, R); dmalloc(b.rows, R);
-            dmalloc(b.prio, R); dmalloc(b.isw64, R); dmalloc(b.u, R); dmalloc(b.isw, R); dmalloc(b.x_f32, 2 * R * h->state_bytes);
+            dmalloc(b.losses, R); dmalloc(b.rows, R);
+            dmalloc(b.isw, R); dmalloc(b.x_f32, 2 * R * h->state_bytes);
         }
         alloc_packed_conv(h);
         launch_pack_conv(h, 0); launch_pack_conv(h, 1);
@@ -203,7 +212,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
-                    h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64, h->b_isw, h->b_u, h->b_y, h->b_maxq,
+                    h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
                     h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -214,6 +223,8 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->fa_maps) free(h->fa_maps);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_in_small) cudaFreeHost(h->h_in_small);
+    if (h->h_stage2) cudaFreeHost(h->h_stage2);
+    if (h->stage2_ev) cudaEventDestroy(h->stage2_ev);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
@@ -226,8 +237,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     for (int k = 0; k < 2; ++k) if (h->pipe_graph[k]) cudaGraphExecDestroy(h->pipe_graph[k]);
     {
         dqn_learner::BatchSet& b = h->sets[1];
-        void* p2[] = {b.states, b.actions, b.rewards, b.cont, b.losses, b.tree_idx, b.data_idx, b.mem_idx, b.rows, b.prio,
-                      b.isw64, b.u, b.isw, b.x_f32};
+        void* p2[] = {b.states, b.actions, b.rewards, b.cont, b.losses, b.rows, b.isw, b.x_f32};
         for (void* p : p2) if (p) cudaFree(p);
     }
     if (h->batch_graph) cudaGraphExecDestroy(h->batch_graph);
@@ -583,11 +593,18 @@ extern "C" int dqn_per_sample(dqn_learner* h, const double* u, int32_t refresh, 
     DQN_REQUIRE(h->cfg.use_per, "handle was created without use_per");
     DQN_REQUIRE(u != nullptr, "uniform draws are required");
     if (refresh) launch_tree_stats(h, per_b);
-    DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    // uniforms in and {tree_idx, prio, is_w} out ride one pinned staging block: one H2D, one D2H
+    const size_t R = (size_t)h->max_rows, B = (size_t)h->B;
+    uint8_t* hs = h->h_stage2;
+    memcpy(hs, u, B * 8);
+    DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, hs, B * 8, cudaMemcpyHostToDevice, h->stream));
     launch_tree_sample(h, h->B, 0, per_b);
     launch_gather(h, h->b_mem_idx, h->B);
-    d2h(h, (long long*)t_idx, h->b_tree_idx, h->B); d2h(h, prio, h->b_prio, h->B); d2h(h, isw, h->b_isw64, h->B);
+    DQN_CUDA_OK(cudaMemcpyAsync(hs + 8 * R, h->b_tree_idx, 3 * R * 8, cudaMemcpyDeviceToHost, h->stream));
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (t_idx) memcpy(t_idx, hs + 8 * R, B * 8);
+    if (prio) memcpy(prio, hs + 16 * R, B * 8);
+    if (isw) memcpy(isw, hs + 24 * R, B * 8);
     API_END(h)
 }
 
@@ -614,7 +631,7 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 bool overlap_enabled(const dqn_learner* h) { return h->overlap && !h->profile; }
 
 static cudaEvent_t next_fork_event(dqn_learner* h) {
-    DQN_REQUIRE(h->fork_used < 24, "fork event pool exhausted");
+    DQN_REQUIRE(h->fork_used < 22, "fork event pool exhausted");  // [22], [23] belong to upload_batch
     return h->fork_ev[h->fork_used++];
 }
 
@@ -977,8 +994,13 @@ extern "C" int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_s
 static void upload_batch(dqn_learner* h, int n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw, const uint8_t* ct,
                          const uint8_t* ns, const float* isw) {
     const size_t S = h->state_bytes;
+    // s on the main stream, s' on a side stream: two copy engines share the upload
+    DQN_CUDA_OK(cudaEventRecord(h->fork_ev[22], h->stream));
+    DQN_CUDA_OK(cudaStreamWaitEvent(h->side_stream, h->fork_ev[22], 0));
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_states + n * S, ns, n * S, cudaMemcpyHostToDevice, h->side_stream));
+    DQN_CUDA_OK(cudaEventRecord(h->fork_ev[23], h->side_stream));
     DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st, n * S, cudaMemcpyHostToDevice, h->stream));
-    DQN_CUDA_OK(cudaMemcpyAsync(h->in_states + n * S, ns, n * S, cudaMemcpyHostToDevice, h->stream));
+    DQN_CUDA_OK(cudaStreamWaitEvent(h->stream, h->fork_ev[23], 0));
     // actions / rewards / continues / is_weights: packed through the pinned staging block (mirrors the device block)
     DQN_CUDA_OK(cudaEventSynchronize(h->stage_ev));  // the previous upload has left the staging block
     uint8_t* hs = h->h_in_small;
@@ -1031,8 +1053,12 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
         h->launches += h->batch_graph_launches;
         h->host_step++;
     }
-    d2h(h, losses, h->b_losses_out, n);
+    // per-sample losses through the pinned staging block (a copy into pageable memory is staged by the driver and costs
+    // a second synchronisation), scalars through their pinned mirror: one stream synchronisation for both
+    float* hl = reinterpret_cast<float*>(h->h_stage2 + 32 * (size_t)h->max_rows);
+    if (losses) DQN_CUDA_OK(cudaMemcpyAsync(hl, h->b_losses_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     read_scalars(h);
+    if (losses) memcpy(losses, hl, (size_t)n * 4);
     if (step) *step = h->h_sc->step;
     if (loss) *loss = h->h_sc->loss;
     API_END(h)

@@ -141,7 +141,10 @@ struct dqn_learner {
         long long *tree_idx, *data_idx, *mem_idx, *rows;
         double *prio, *isw64, *u;
         float *isw, *x_f32;
+        long long* blk;  // tree_idx | prio | isw64 | data_idx | mem_idx | u carved from one block: one D2H for the seam outputs
     } sets[2] = {};
+    uint8_t* h_stage2 = nullptr;   // pinned: uniforms in, {tree_idx, prio, isw} out of dqn_per_sample
+    cudaEvent_t stage2_ev = nullptr;
     int cur_set = 0;
     bool pf_valid = false;    // sets[pf_set] holds the batch the next fused step consumes (sampled ahead)
     int pf_set = 0;
