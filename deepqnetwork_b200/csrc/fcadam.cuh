@@ -190,6 +190,222 @@ __global__ void __launch_bounds__(FA_THREADS, 3) fcwg_adam_kernel(const float* _
     }
 }
 
+
+// ---- persistent variant: S-stage TMA ring of optimizer state, a CTA walks a contiguous range of tiles -----------------
+// The one-tile-per-CTA kernel above keeps HBM requests in flight only during the first microseconds of a CTA's life.
+// Here a CTA owns up to 32 consecutive tiles (n fastest, so at most two different act3 slices), and one thread keeps
+// PS - 1 tiles of w / m / v loads (48 KB each) and one tile of stores in flight at all times while the other warps
+// form the gradient tile (tcgen05) and apply the optimizer in shared memory:
+//   warp 9    TMA: loads of tile i + PS - 1 are issued as soon as the stores of tile i - 1 have drained their stage
+//   warps 0-3 act3^T -> tensor memory (once per m tile); epilogue columns [0, 16)
+//   warps 4-7 dH tile i + 1 -> K-major hi/lo shared-memory tile (double-buffered); epilogue columns [16, 32)
+//   warp 8    MMA issue into double-buffered accumulators
+constexpr int PS = 4, FP_THREADS = 320;
+
+template <int NTERMS>
+__global__ void __launch_bounds__(FP_THREADS, 1) fcwg_adam_persist_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
+                                                                          int Bn, int flat, int NH, int hid,
+                                                                          const __grid_constant__ StateMaps maps,
+                                                                          float lr, float mom, int use_momentum,
+                                                                          const dqn_learner::Scalars* __restrict__ sc) {
+    constexpr int B_TILE = FA_BN * 128;
+    constexpr uint32_t ARR = BM * FA_BN * 4, STAGE = 3 * ARR;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t ring = sbase;                               // PS stages x {w, m, v}
+    const uint32_t btiles = ring + PS * STAGE;                 // 2 x {hi, lo}
+    const uint32_t bars = btiles + 2 * 2 * B_TILE;
+    auto st_full = [&](int s) { return bars + 8u * s; };
+    auto computed = [&](int s) { return bars + 8u * (PS + s); };
+    auto b_full = [&](int b) { return bars + 8u * (2 * PS + b); };
+    auto b_empty = [&](int b) { return bars + 8u * (2 * PS + 2 + b); };
+    auto acc_full = [&](int b) { return bars + 8u * (2 * PS + 4 + b); };
+    auto acc_empty = [&](int b) { return bars + 8u * (2 * PS + 6 + b); };
+    auto a_full = [&](int b) { return bars + 8u * (2 * PS + 8 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * PS + 10);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntn = NH / FA_BN, total = ntn * (flat / BM);
+    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+    const int ntiles = t1 - t0;
+    const int narr = use_momentum ? 2 : 3;
+    const int mt_first = t0 / ntn;
+
+    if (tid == 0) {
+        for (int s = 0; s < PS; ++s) { mbar_init(st_full(s), 1); mbar_init(computed(s), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(b_full(b), 4); mbar_init(b_empty(b), 1); mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 8); mbar_init(a_full(b), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    auto tmem_a = [&](int ap) { return tmem_base + 64u + (uint32_t)ap * 64u; };  // accumulators at [0,32), [32,64)
+
+    if (warp == 9) {
+        if (lane == 0 && ntiles > 0) {
+            auto issue_loads = [&](int i) {
+                const int t = t0 + i, nt = t % ntn, mt = t / ntn;
+                const int n0 = nt * FA_BN, strm = n0 >= hid, ncol = n0 - (strm ? hid : 0), m0r = mt * BM;
+                const int s = i % PS;
+                cv::mbar_expect_tx(st_full(s), (uint32_t)(narr * ARR));
+                tma_load_2d(ring + s * STAGE, &maps.w[strm], ncol, m0r, st_full(s));
+                tma_load_2d(ring + s * STAGE + ARR, &maps.m[strm], ncol, m0r, st_full(s));
+                if (!use_momentum) tma_load_2d(ring + s * STAGE + 2 * ARR, &maps.v[strm], ncol, m0r, st_full(s));
+            };
+            for (int j = 0; j < PS - 1 && j < ntiles; ++j) issue_loads(j);
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % PS;
+                mbar_wait(computed(s), (i / PS) & 1);
+                const int t = t0 + i, nt = t % ntn, mt = t / ntn;
+                const int n0 = nt * FA_BN, strm = n0 >= hid, ncol = n0 - (strm ? hid : 0), m0r = mt * BM;
+                tma_store_2d(&maps.w[strm], ncol, m0r, ring + s * STAGE);
+                tma_store_2d(&maps.m[strm], ncol, m0r, ring + s * STAGE + ARR);
+                if (!use_momentum) tma_store_2d(&maps.v[strm], ncol, m0r, ring + s * STAGE + 2 * ARR);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (i + PS - 1 < ntiles) {
+                    // stage (i - 1) % PS is the one to refill: its stores (previous group) must have read it
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    issue_loads(i + PS - 1);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (warp == 8) {
+        // ---------------- MMA issue ----------------
+        const uint32_t idesc = make_idesc(FA_BN, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        int a_seen = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int bb = i & 1, use = i >> 1;
+            const int ap = (t0 + i) / ntn - mt_first;  // 0 or 1: which act3 slice (tensor-memory A buffer)
+            if (ap >= a_seen) { mbar_wait(a_full(ap), 0); a_seen = ap + 1; }
+            mbar_wait(b_full(bb), use & 1);
+            if (use >= 1) mbar_wait(acc_empty(bb), (use - 1) & 1);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t bt = btiles + bb * 2 * B_TILE;
+                const uint64_t db = make_desc(bt, cv::PK_LBO, cv::PK_SBO), dbl = make_desc(bt + B_TILE, cv::PK_LBO, cv::PK_SBO);
+                const uint32_t ta = tmem_a(ap), td = tmem_base + (uint32_t)bb * 32u;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2 * cv::PK_LBO) >> 4;
+                    if (NTERMS == 3) {
+                        ts::mma_tf32_ts(td, ta + ks * 8, dbl + o, idesc, ks != 0);
+                        ts::mma_tf32_ts(td, ta + 32u + ks * 8, db + o, idesc, 1);
+                        ts::mma_tf32_ts(td, ta + ks * 8, db + o, idesc, 1);
+                    } else {
+                        ts::mma_tf32_ts(td, ta + ks * 8, db + o, idesc, ks != 0);
+                    }
+                }
+                mma_commit(b_empty(bb));
+                mma_commit(acc_full(bb));
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- warps 0-7: operand producers, then the optimizer epilogue of every tile ----------------
+        const int q4 = warp & 3, half = warp >> 2;
+        const int row = q4 * 32 + lane, c0 = half * 16;
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        if (warp < 4 && ntiles > 0) {
+            const int mt_last = (t1 - 1) / ntn;
+            for (int ap = 0; ap <= mt_last - mt_first && ap < 2; ++ap) {
+                const int m0r = (mt_first + ap) * BM;
+                float hi[32];
+#pragma unroll
+                for (int b = 0; b < 32; ++b) hi[b] = b < Bn ? __ldg(act3 + (size_t)b * flat + m0r + row) : 0.f;
+                const uint32_t ta = tmem_a(ap) + lane_base;
+                ts::tmem_st32(ta, hi);
+                if (NTERMS == 3) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+                    ts::tmem_st32(ta + 32u, lo);
+                }
+                ts::tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(ap));
+            }
+        }
+        auto produce_b = [&](int i) {  // warps 4-7
+            const int bb = i & 1, use = i >> 1;
+            if (use >= 1) mbar_wait(b_empty(bb), (use - 1) & 1);
+            const int n0 = ((t0 + i) % ntn) * FA_BN;
+            const uint32_t bt = btiles + bb * 2 * B_TILE;
+            const int bq = lane & 3, nq = lane >> 2;
+            for (int gi = warp - 4; gi < 8 * (FA_BN / 8); gi += 4) {
+                const int b4 = gi / (FA_BN / 8), n8 = gi - b4 * (FA_BN / 8);
+                const int b = b4 * 4 + bq, n = n8 * 8 + nq;
+                const float v = b < Bn ? __ldg(dhid + (size_t)b * NH + n0 + n) : 0.f;
+                const uint32_t a = bt + (uint32_t)((n >> 3) * cv::PK_SBO + (b >> 2) * cv::PK_LBO + (n & 7) * 16 + (b & 3) * 4);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+                if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v)) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full(bb));
+        };
+        if (warp >= 4 && ntiles > 0) produce_b(0);
+        const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+        const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+        const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+        for (int i = 0; i < ntiles; ++i) {
+            if (warp >= 4 && i + 1 < ntiles) produce_b(i + 1);
+            const int ab = i & 1, s = i % PS;
+            mbar_wait(acc_full(ab), (i >> 1) & 1);
+            tc_fence_after();
+            float g[16];
+            tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * 32 + c0), g);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(ab));
+            mbar_wait(st_full(s), (i / PS) & 1);
+            const uint32_t srow = ring + s * STAGE + row * 128;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const uint32_t sw = srow + ((uint32_t)(((c0 + j) >> 2) ^ (row & 7)) << 4), sm = sw + ARR, sv = sw + 2 * ARR;
+                float4 pp, mm, vv;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pp.x), "=f"(pp.y), "=f"(pp.z), "=f"(pp.w) : "r"(sw));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(mm.x), "=f"(mm.y), "=f"(mm.z), "=f"(mm.w) : "r"(sm));
+                const float4 gg = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+                if (use_momentum) {
+#define MOM1(c) mm.c = mm.c * mom + gg.c; pp.c = pp.c - (gg.c * lr + mm.c * mom * lr);
+                    MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+                } else {
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vv.x), "=f"(vv.y), "=f"(vv.z), "=f"(vv.w) : "r"(sv));
+#define ADAM1(c) mm.c = mm.c + (gg.c - mm.c) * omb1; vv.c = vv.c + (gg.c * gg.c - vv.c) * omb2; \
+                 pp.c = pp.c - (mm.c * lr_t) / (sqrtf(vv.c) + eps);
+                    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sv), "f"(vv.x), "f"(vv.y), "f"(vv.z), "f"(vv.w) : "memory");
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sm), "f"(mm.x), "f"(mm.y), "f"(mm.z), "f"(mm.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sw), "f"(pp.x), "f"(pp.y), "f"(pp.z), "f"(pp.w) : "memory");
+            }
+            fence_proxy_async();  // the updated tile leaves through the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(computed(s));
+        }
+        pdl_launch_dependents();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
 static inline bool supported(const dqn_learner* h, int rows) {
     const NetDesc& net = h->net;
     return rows <= 32 && net.flat % BM == 0 && net.hidden % FA_BN == 0 && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;
@@ -228,15 +444,27 @@ static void launch(dqn_learner* h, int rows) {
     const StateMaps& maps = *static_cast<StateMaps*>(h->fa_maps);
     const size_t bytes = 3 * BM * FA_BN * 4 + 2 * FA_BN * 128 + 64 + 1024;
     auto go = [&](auto kern) {
-        static bool configured = false;
-        if (!configured) {
-            DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            configured = true;
-        }
+        DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(net.NH / FA_BN, net.flat / BM), dim3(FA_THREADS), bytes, h->stream,
                       (const float*)h->acts_on.act[2], (const float*)h->d_hid, rows, net.flat, net.NH, net.hidden, maps,
                       (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum, (const dqn_learner::Scalars*)h->d_sc);
     };
+    if (h->fc_tma_ctas > 0) {
+        // persistent form: fc_tma_ctas CTAs (>= 60, so that a CTA sees at most two act3 slices), one per SM
+        const int total = (net.NH / FA_BN) * (net.flat / BM);
+        int ctas = h->fc_tma_ctas < 60 ? 60 : h->fc_tma_ctas;
+        while ((total + ctas - 1) / ctas > net.NH / FA_BN) ++ctas;
+        const size_t pbytes = (size_t)PS * 3 * BM * FA_BN * 4 + 2 * 2 * FA_BN * 128 + 256 + 1024;
+        auto gop = [&](auto kern) {
+            DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbytes));
+            launch_kernel(h->pdl, kern, dim3(ctas), dim3(FP_THREADS), pbytes, h->stream, (const float*)h->acts_on.act[2],
+                          (const float*)h->d_hid, rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate,
+                          (float)h->cfg.momentum, h->cfg.use_momentum, (const dqn_learner::Scalars*)h->d_sc);
+        };
+        if (h->cfg.math_mode == DQN_MATH_TC3X) gop(fcwg_adam_persist_kernel<3>); else gop(fcwg_adam_persist_kernel<1>);
+        h->launches++;
+        return;
+    }
     if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_kernel<3>); else go(fcwg_adam_kernel<1>);
     h->launches++;
 }

@@ -1,0 +1,242 @@
+// Dense hidden layer forward with the weights streamed by TMA.
+//
+//   hid_pre[b][n] = sum_k act3[b][k] * W[k][n]      (K = 7680, n over both hidden streams, b <= 64 batch rows)
+// At batch 32-64 this layer is a stream of the 31.5 MB weight matrix through the tensor core: HBM-bound.  The generic
+// kernel (tsgemm.cuh, swap-AB) read W with 4-byte loads -- lane == hidden unit, 32 loads per thread and k-block -- and
+// reached 2 TB/s.  Here one thread issues 2-D TMA tensor copies of 128 (n) x 32 (k) boxes of W into a 6-stage ring
+// (16 KB each, 96 KB in flight per CTA), and the converters read their column of the box from shared memory
+// (conflict-free: consecutive lanes are consecutive n), split hi/lo and feed the MMA through tensor memory:
+//   swap-AB: MMA rows (M = 128) = hidden units, MMA columns (N) = batch rows, split-K over blockIdx.y
+//   A (TMEM)  : W^T tile, thread == hidden unit
+//   B (smem)  : activation tile [rows][32 k] -> dense K-major hi/lo tiles through registers (warps 4-7)
+//   epilogue  : part[z][b][n] partial sums, reduced (+ bias, ReLU, heads) by fc_reduce_heads_kernel as before
+#pragma once
+#include "fcadam.cuh"
+
+namespace ff {
+using namespace tc;
+
+struct WMaps { CUtensorMap w[2]; };  // per hidden stream: [flat][hid] f32, box 128 (n) x 32 (k), no swizzle
+constexpr int FF_S = 6, FF_THREADS = 320;
+
+template <int BN, int NTERMS>
+__global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __restrict__ act, int rows, int flat, int NH, int hid,
+                                                              const __grid_constant__ WMaps maps, float* __restrict__ part,
+                                                              int kb_per_split) {
+    constexpr int S = FF_S, ACOLS = BK * (NTERMS == 3 ? 2 : 1);
+    constexpr uint32_t W_TILE = BM * BK * 4, B_TILE = BN * 128, STAGE = W_TILE + 2 * B_TILE;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t bars = sbase + S * STAGE;
+    auto wfull = [&](int s) { return bars + 8u * s; };
+    auto afull = [&](int s) { return bars + 8u * (S + s); };
+    auto bfull = [&](int s) { return bars + 8u * (2 * S + s); };
+    auto empty = [&](int s) { return bars + 8u * (3 * S + s); };
+    const uint32_t accum = bars + 8u * (4 * S), tmem_slot = bars + 8u * (4 * S + 1);
+    auto stage_w = [&](int s) { return sbase + s * STAGE; };
+    auto stage_b = [&](int s) { return sbase + s * STAGE + W_TILE; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * BM, z = blockIdx.y;
+    const int strm = n0 >= hid, ncol = n0 - (strm ? hid : 0);
+    const int nkb_total = flat / BK;
+    const int kb0 = z * kb_per_split, kb1 = min(nkb_total, kb0 + kb_per_split), nkb = kb1 - kb0;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(wfull(s), 1); mbar_init(afull(s), 4); mbar_init(bfull(s), 4); mbar_init(empty(s), 1); }
+        mbar_init(accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    constexpr int DCOLS = BN < 32 ? 32 : BN;
+    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(DCOLS + s * ACOLS); };
+
+    if (warp == 9) {
+        // ---------------- W boxes by TMA (weights were written by an earlier step: no dependency on the predecessor) ----------------
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int j = 0; j < nkb; ++j) {
+                if (j >= S) mbar_wait(empty(s), ph ^ 1);
+                cv::mbar_expect_tx(wfull(s), W_TILE);
+                fa::tma_load_2d(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- A converters: thread == hidden unit (column of the W box) ----------------
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t col = (uint32_t)(warp * 32 + lane) * 4u;
+        int s = 0, ph = 0;
+        for (int j = 0; j < nkb; ++j) {
+            mbar_wait(wfull(s), ph);  // (the stage's TMEM half was released together with its smem half: empty(s))
+            float hi[32];
+            const uint32_t src = stage_w(s) + col;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[k]) : "r"(src + (uint32_t)k * (BM * 4)));
+            const uint32_t ta = tmem_a(s) + lane_base;
+            ts::tmem_st32(ta, hi);
+            if (NTERMS == 3) {
+                float lo[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) lo[k] = lo_part(hi[k]);
+                ts::tmem_st32(ta + BK, lo);
+            }
+            ts::tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull(s));
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+    } else if (warp < 8) {
+        // ---------------- B producers: act[b][k0 .. k0+31] -> dense K-major hi/lo tiles ----------------
+        pdl_wait();  // the activations are the stream predecessor's output
+        const int t = tid - 128;
+        constexpr int CH = BN * 8 / 128;  // 16-byte chunks per thread
+        int s = 0, ph = 0;
+        for (int j = 0; j < nkb; ++j) {
+            if (j >= S) mbar_wait(empty(s), ph ^ 1);
+            const int k0 = (kb0 + j) * BK;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                // chunk id: row r = 8 (q / 8 ...) arranged so that 8 consecutive lanes write 8 consecutive 16-byte rows of a core matrix
+                const int q = t + i * 128;
+                const int r8 = q & 7, c = (q >> 3) & 7, rg = q >> 6;
+                const int r = rg * 8 + r8;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows) v = __ldg(reinterpret_cast<const float4*>(act + (size_t)r * flat + k0 + c * 4));
+                const uint32_t a = stage_b(s) + (uint32_t)(rg * cv::PK_SBO + c * cv::PK_LBO + r8 * 16);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                if (NTERMS == 3)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + B_TILE), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
+                                 "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bfull(s));
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+    } else {
+        // ---------------- MMA issue (warp 8) ----------------
+        const uint32_t idesc = make_idesc(BN, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        int s = 0, ph = 0;
+        for (int j = 0; j < nkb; ++j) {
+            mbar_wait(afull(s), ph);
+            mbar_wait(bfull(s), ph);
+            tc_fence_after();
+            const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO), dbl = make_desc(stage_b(s) + B_TILE, cv::PK_LBO, cv::PK_SBO);
+            const uint32_t ta = tmem_a(s);
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2 * cv::PK_LBO) >> 4;
+                const uint32_t acc = (j | ks) != 0;
+                if (leader) {
+                    if (NTERMS == 3) {
+                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, dbl + o, idesc, acc);
+                        ts::mma_tf32_ts(tmem_base, ta + BK + ks * 8, db + o, idesc, 1);
+                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, 1);
+                    } else {
+                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, acc);
+                    }
+                }
+            }
+            if (leader) {
+                mma_commit(empty(s));
+                if (j == nkb - 1) mma_commit(accum);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        tc_fence_before();
+    }
+    if (warp < 8) {
+        pdl_launch_dependents();
+        // ---------------- epilogue: part[z][b][n0 + unit], warp (q4, half): units 32 q4 + lane, batch rows [half BN/2, +BN/2) ----------------
+        const int q4 = warp & 3, half = warp >> 2;
+        if (nkb > 0) { mbar_wait(accum, 0); tc_fence_after(); }
+        constexpr int HC = BN / 2;
+        float* o = part + (size_t)z * rows * NH + n0 + q4 * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < HC; c += 16) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * HC + c), v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int b = half * HC + c + i;
+                if (b < rows) o[(size_t)b * NH] = v[i];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+static void encode_wmaps(dqn_learner* h, const float* P, WMaps& out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DQN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DQN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    const NetDesc& net = h->net;
+    for (int st = 0; st < 2; ++st) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)net.hidden, (cuuint64_t)net.flat};
+        const cuuint64_t gstr[1] = {(cuuint64_t)net.hidden * 4};
+        const cuuint32_t box[2] = {BM, BK}, estr[2] = {1, 1};
+        const CUresult r = ((EncodeFn)fn)(&out.w[st], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P) + net.off_fc_w[st], gdim, gstr,
+                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DQN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    }
+}
+
+static inline bool supported(const dqn_learner* h, int rows) {
+    const NetDesc& net = h->net;
+    return (rows == 32 || rows == 64) && net.hidden % BM == 0 && net.flat % BK == 0 && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;
+}
+
+// returns the number of split-K partials written to part[z][rows][NH]
+static int launch(dqn_learner* h, const float* P, const float* act, int rows, float* part, int max_splits) {
+    const NetDesc& net = h->net;
+    const int tw = P == h->online ? 0 : 1;
+    if (!h->ff_maps[tw]) {
+        h->ff_maps[tw] = aligned_alloc(64, sizeof(WMaps));
+        try { encode_wmaps(h, P, *static_cast<WMaps*>(h->ff_maps[tw])); } catch (...) { free(h->ff_maps[tw]); h->ff_maps[tw] = nullptr; throw; }
+    }
+    const WMaps& maps = *static_cast<WMaps*>(h->ff_maps[tw]);
+    const int mt = net.NH / BM, nkb = net.flat / BK;
+    int want = std::min(std::max(1, h->sm_count / mt), max_splits);
+    const int per = (nkb + want - 1) / want;
+    const int splits = (nkb + per - 1) / per;
+    auto go = [&](auto kern, int bn) {
+        const size_t bytes = (size_t)FF_S * (BM * BK * 4 + 2 * bn * 128) + 512 + 1024;
+        // (no static "configured" flag here: both BN instantiations share one function-pointer type, hence one lambda body)
+        DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        launch_kernel(h->pdl, kern, dim3(mt, splits), dim3(FF_THREADS), bytes, h->stream, act, rows, net.flat, net.NH, net.hidden, maps,
+                      part, per);
+    };
+    const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
+    if (rows == 64) { if (x3) go(fcfwd_kernel<64, 3>, 64); else go(fcfwd_kernel<64, 1>, 64); }
+    else            { if (x3) go(fcfwd_kernel<32, 3>, 32); else go(fcfwd_kernel<32, 1>, 32); }
+    h->launches++;
+    return splits;
+}
+}  // namespace ff

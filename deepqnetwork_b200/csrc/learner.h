@@ -66,6 +66,9 @@ struct dqn_learner {
     bool fc_ffma_adam = false;    // option: dense wgrad + optimizer as one fp32 FFMA pass (no gradient round trip); measured
                                   // slower than tensor-core wgrad + streaming Adam (instruction-bound: 61 us vs 17 + 45 us)
     bool fc_split_streams = true; // dense wgrad + optimizer per hidden stream on two side streams (pipelines HBM- and tensor-bound halves)
+    int fc_tma_ctas = 0;          // > 0: the persistent form of that pass with this many CTAs (S-stage TMA ring of optimizer state)
+    void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
+    bool fc_tma_fwd = false;      // option: dense forward with TMA-streamed weights (fcfwd.cuh); measured equal to the tsgemm path (16 us)
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)

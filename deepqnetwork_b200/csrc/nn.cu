@@ -7,6 +7,7 @@
 #include "tsgemm.cuh"
 #include "cvgemm.cuh"
 #include "fcadam.cuh"
+#include "fcfwd.cuh"
 #include <algorithm>
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -281,7 +282,9 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
     int kchunk = fc_kchunk();
     int splits = ceil_div(net.flat, kchunk);
     prof_mark(h, tg ? "tg_fc_fwd" : "on_fc_fwd");
-    if (tcm && rows % 32 == 0) {
+    if (tcm && h->fc_tma_fwd && (P == h->online || P == h->target) && ff::supported(h, rows)) {
+        splits = ff::launch(h, P, acts.act[2], rows, acts.fc_part, h->fc_splits);
+    } else if (tcm && rows % 32 == 0) {
         // swap-AB: the 128-row MMA tile spans hidden units (weights stream as the A operand), the batch is N
         const int mt = ceil_div(net.NH, tc::BM);
         int want = std::min(std::max(1, h->sm_count / mt), h->fc_splits);
