@@ -235,7 +235,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->side4_stream) cudaStreamDestroy(h->side4_stream);
     if (h->side5_stream) cudaStreamDestroy(h->side5_stream);
     if (h->side6_stream) cudaStreamDestroy(h->side6_stream);
-    for (int k = 0; k < 2; ++k) if (h->pipe_graph[k]) cudaGraphExecDestroy(h->pipe_graph[k]);
+    for (int k = 0; k < 2; ++k) for (int v = 0; v < 2; ++v) if (h->pipe_graph[k][v]) cudaGraphExecDestroy(h->pipe_graph[k][v]);
     {
         dqn_learner::BatchSet& b = h->sets[1];
         void* p2[] = {b.states, b.actions, b.rewards, b.cont, b.losses, b.rows, b.isw, b.x_f32};
@@ -713,6 +713,13 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         xf = h->x_f32;
     }
     h->fork_used = 0;
+    if (h->defer_start) {
+        // deferred from the previous step: optimizer pass over the two dense kernels (their gradients are in the slab,
+        // the beta powers of that step in b?p_prev), under this step's conv forward; joined before the dense forward
+        cudaStream_t sv;
+        side_begin(h, sv, 2, 0); launch_optimizer_fc_stream(h, 0, true); side_end(h, sv);
+        side_begin(h, sv, 5, 0); launch_optimizer_fc_stream(h, 1, true); side_end(h, sv);
+    }
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
     side_begin(h, saved, 0, 2);
@@ -832,6 +839,14 @@ static void fused_step_launches(dqn_learner* h, const double* u, const int64_t* 
     h->fuse_fc_adam = false; h->early_fc_adam = false;
 }
 
+// apply the optimizer pass over the dense kernels that the last pipelined step left pending
+static void flush_fc_adam(dqn_learner* h) {
+    if (!h->fc_adam_pending) return;
+    launch_optimizer_fc_stream(h, 0, true);
+    launch_optimizer_fc_stream(h, 1, true);
+    h->fc_adam_pending = false;
+}
+
 static void after_step_host(dqn_learner* h) {
     // deep_q_agent.py:358-360: copy online -> target every copy_network_steps (step is the post-increment value)
     if (h->cfg.copy_network_steps > 0 && h->host_step % h->cfg.copy_network_steps == 0) launch_copy_network(h);
@@ -900,13 +915,17 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
     if (h->prefetch) {
         // Pipelined replay: graph k consumes the batch in sets[k] and, behind its priority write-back, samples and
         // gathers the next batch into sets[1-k].  Same draws, same tree states, same results as the serial order.
+        const bool can_defer = h->defer_adam && h->cfg.math_mode != DQN_MATH_FP32 && h->net.dueling && h->fc_split_streams &&
+                               !h->fuse_enabled && !h->fc_ffma_adam && !h->fc_tma_adam;
         if (!h->graph_valid) {
-            for (int k = 0; k < 2; ++k) {
+            for (int kv = 0; kv < (can_defer ? 4 : 2); ++kv) {
+                const int k = kv & 1, v = kv >> 1;
                 cudaGraph_t g = nullptr;
                 const int64_t l0 = h->launches, s0 = h->host_step;
                 select_set(h, k);
                 DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 h->pf_capture = true;
+                h->defer_capture = can_defer; h->defer_start = v == 1;
                 try {
                     h->fuse_fc_adam = h->fuse_enabled; h->early_fc_adam = !h->fuse_fc_adam;
                     h->xf_from_gather = true;  // the look-ahead gather of the previous step wrote x_f32 of this set
@@ -915,16 +934,18 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
                     finish_step(h, 0);
                 } catch (...) {
                     h->pf_capture = false; h->fuse_fc_adam = false; h->early_fc_adam = false;
+                    h->defer_capture = false; h->defer_start = false;
                     cudaStreamEndCapture(h->stream, &g);
                     if (g) cudaGraphDestroy(g);
                     throw;
                 }
                 h->pf_capture = false; h->fuse_fc_adam = false; h->early_fc_adam = false;
+                h->defer_capture = false; h->defer_start = false;
                 DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
-                h->graph_launches = h->launches - l0;
+                if (v == 0) h->graph_launches = h->launches - l0;  // per step: [k][1] has two launches more, [k][0]/flush make up for them
                 h->launches = l0; h->host_step = s0;
-                if (h->pipe_graph[k]) { cudaGraphExecDestroy(h->pipe_graph[k]); h->pipe_graph[k] = nullptr; }
-                DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->pipe_graph[k], g, cudaGraphInstantiateFlagUseNodePriority));
+                if (h->pipe_graph[k][v]) { cudaGraphExecDestroy(h->pipe_graph[k][v]); h->pipe_graph[k][v] = nullptr; }
+                DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->pipe_graph[k][v], g, cudaGraphInstantiateFlagUseNodePriority));
                 DQN_CUDA_OK(cudaGraphDestroy(g));
             }
             h->graph_valid = true;
@@ -940,12 +961,17 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
                 h->pf_valid = true;
             }
             select_set(h, h->pf_set);  // the batch this step trains on (what dqn_batch_read shows afterwards)
-            DQN_CUDA_OK(cudaGraphLaunch(h->pipe_graph[h->pf_set], h->stream));
+            const int v = can_defer && h->fc_adam_pending ? 1 : 0;
+            DQN_CUDA_OK(cudaGraphLaunch(h->pipe_graph[h->pf_set][v], h->stream));
             h->pf_set ^= 1;
-            h->launches += h->graph_launches;
+            h->launches += h->graph_launches + (v ? 2 : 0);
+            if (can_defer) h->fc_adam_pending = true;
             h->host_step++;
+            // the target sync copies the online weights: they must be complete (deep_q_agent.py:358-360)
+            if (h->cfg.copy_network_steps > 0 && h->host_step % h->cfg.copy_network_steps == 0) flush_fc_adam(h);
             after_step_host(h);
         }
+        flush_fc_adam(h);  // the handle never leaves dqn_train_steps with a pending optimizer pass
         return 0;
     }
     if (!h->graph_valid) {
@@ -1146,6 +1172,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "img_conv") h->img_conv = value != 0;
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "prefetch") h->prefetch = value != 0;
+    else if (n == "defer_adam") h->defer_adam = value != 0;  // dense-kernel optimizer pass of step i under the conv forward of step i+1
     else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false; h->graph_valid_batch = false;

@@ -90,6 +90,7 @@ struct dqn_learner {
         float loss_sum;                                   // running sum for the report line
         int has_max_weight;
         unsigned long long rng_counter;
+        float b1p_prev, b2p_prev;  // beta powers of the step before the last advance (deferred dense-kernel optimizer pass)
     };
     unsigned int* opt_ticket = nullptr;  // last-CTA-done counter of optimizer_tail_kernel
     Scalars* d_sc = nullptr;
@@ -185,7 +186,14 @@ struct dqn_learner {
 
     // graph for the fused step
     cudaGraphExec_t step_graph = nullptr;
-    cudaGraphExec_t pipe_graph[2] = {nullptr, nullptr};  // pipelined step consuming sets[k], sampling into sets[1-k]
+    // pipelined step consuming sets[k], sampling into sets[1-k]; [k][1] additionally starts with the deferred optimizer
+    // pass over the dense kernels of the PREVIOUS step (it runs under this step's conv forward instead of crowding the
+    // previous step's backward), [k][0] is the first step after anything else touched the handle
+    cudaGraphExec_t pipe_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool defer_adam = false;         // option (bit-identical results); measured 3% slower: the 60 us pass does not fit under the 40 us conv forward
+    bool defer_capture = false;      // capturing a deferred-optimizer graph: backward leaves the dense kernels to the next step
+    bool defer_start = false;        // capturing variant [k][1]: step_core opens with the deferred pass
+    bool fc_adam_pending = false;    // host: dense-kernel gradients of the last step are in the slab, not yet applied
     bool graph_valid = false;
     // graph of one host-fed step (dqn_train_batch), keyed by the batch size
     cudaGraphExec_t batch_graph = nullptr;
@@ -217,7 +225,7 @@ void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0, int prio_cla
 void side_end(dqn_learner* h, cudaStream_t saved);
 void main_wait_side(dqn_learner* h, int which = 0);
 void launch_optimizer_fc(dqn_learner* h);
-void launch_optimizer_fc_stream(dqn_learner* h, int st);  // one hidden stream's dense kernel
+void launch_optimizer_fc_stream(dqn_learner* h, int st, bool prev_betas = false);  // one hidden stream's dense kernel
 bool fc_wgrad_adam_supported(const dqn_learner* h);
 void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g);  // optim.cu: dense wgrad + optimizer in one FFMA pass  // api.cu: CUDA-event boundary, active only in profile mode
 void net_describe(NetDesc& net, const dqn_config& cfg);

@@ -281,6 +281,11 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
     }
     int kchunk = fc_kchunk();
     int splits = ceil_div(net.flat, kchunk);
+    if (h->defer_start && P == h->online) {
+        // the deferred optimizer pass over the dense kernels (issued at the start of this graph) must have landed
+        main_wait_side(h, 2);
+        main_wait_side(h, 5);
+    }
     prof_mark(h, tg ? "tg_fc_fwd" : "on_fc_fwd");
     if (tcm && h->fc_tma_fwd && (P == h->online || P == h->target) && ff::supported(h, rows)) {
         splits = ff::launch(h, P, acts.act[2], rows, acts.fc_part, h->fc_splits);
@@ -462,7 +467,9 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         }
     }
     if (h->fuse_fc_adam) fc_wgrad();  // fused: it overwrites W, so it starts only after the dgrad has read W
-    if (split_fc) {
+    if (split_fc && h->defer_capture) {
+        h->fc_adam_done = true;  // applied at the start of the next step's graph (or by the flush at the end of dqn_train_steps)
+    } else if (split_fc) {
         for (int st = 0; st < 2; ++st) {
             side_begin(h, saved, st == 0 ? 0 : 5, 0);  // after this stream's wgrad, and after the dgrad above has read the old W
             prof_mark(h, st == 0 ? "optimizer_fc" : "optimizer_fc1");

@@ -16,9 +16,11 @@
 // reservation to cap residency 4720.
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, size_t n4, float lr,
-                                                   const dqn_learner::Scalars* __restrict__ sc) {
+                                                   const dqn_learner::Scalars* __restrict__ sc, int prev_betas) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-    const float lr_t = lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+    // prev_betas: the pass was deferred past the step bookkeeping (it belongs to the step before the last advance)
+    const float b1p = prev_betas ? sc->b1p_prev : sc->b1p, b2p = prev_betas ? sc->b2p_prev : sc->b2p;
+    const float lr_t = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 gg = g[i];
@@ -47,16 +49,18 @@ __global__ void __launch_bounds__(256) momentum_kernel(float4* __restrict__ p, f
     }
 }
 
-static void optimizer_range(dqn_learner* h, int64_t beg, int64_t end) {
+static void optimizer_range(dqn_learner* h, int64_t beg, int64_t end, bool prev_betas = false) {
     if (end <= beg) return;
     const size_t n4 = (size_t)(end - beg) / 4, o4 = (size_t)beg / 4;
-    const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
+    // deferred pass (prev_betas): it runs under the NEXT step's conv forward, whose CTAs must get onto the SMs at once:
+    // one float4 per thread, so every CTA is gone after a microsecond instead of holding its thread slots for the whole pass
+    const int blocks = prev_betas ? (int)((n4 + 255) / 256) : (int)std::min<size_t>((n4 + 255) / 256, (size_t)h->sm_count * 8);
     if (h->cfg.use_momentum)
         launch_kernel(false, momentum_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online + o4, (float4*)h->slot_m + o4,
                       (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, (float)h->cfg.momentum);
     else
         launch_kernel(false, adam_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online + o4, (float4*)h->slot_m + o4,
-                      (float4*)h->slot_v + o4, (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, h->d_sc);
+                      (float4*)h->slot_v + o4, (const float4*)h->grads + o4, n4, (float)h->cfg.learning_rate, h->d_sc, prev_betas ? 1 : 0);
     h->launches++;
 }
 
@@ -69,10 +73,10 @@ void launch_optimizer_fc(dqn_learner* h) {
     if (net.dueling) optimizer_range(h, net.off_fc_w[1], net.off_fc_w[1] + fcw);
 }
 
-void launch_optimizer_fc_stream(dqn_learner* h, int st) {
+void launch_optimizer_fc_stream(dqn_learner* h, int st, bool prev_betas) {
     const NetDesc& net = h->net;
     const int64_t fcw = (int64_t)net.flat * net.hidden;
-    optimizer_range(h, net.off_fc_w[st], net.off_fc_w[st] + fcw);
+    optimizer_range(h, net.off_fc_w[st], net.off_fc_w[st] + fcw, prev_betas);
 }
 
 // Dense hidden layers: weight gradient AND optimizer in one pass (the default for a whole step on one GPU).
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             *ticket = 0;
             sc->step += 1;
+            sc->b1p_prev = sc->b1p; sc->b2p_prev = sc->b2p;
             if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
             sc->rng_counter += 1;
         }
