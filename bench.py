@@ -73,6 +73,8 @@ def kernel_bytes(name, cfg, nn):
     rows_on = 2 * B if cfg['double'] else B
     base = name[3:] if name[:3] in ('on_', 'tg_') else name
     rows = rows_on if name.startswith('on_') else B
+    if base == name and base.startswith('conv') and base.endswith('_fwd'):
+        rows = rows_on + B  # both towers in one launch
     acts = [g['oh'] * g['ow'] * g['cout'] for g in geo]
     wts = [g['k'] * g['k'] * g['cin'] * g['cout'] for g in geo]
     ins = [nn['S'] // 4 * 1, acts[0], acts[1]]  # elements per sample feeding conv l (conv1 input counted as bytes below)

@@ -214,7 +214,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,
                     h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg, h->act3_pk[0], h->act3_pk[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
@@ -722,13 +722,22 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     }
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
-    side_begin(h, saved, 0, 2);
-    h->prof_tag = "tg_";
-    tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
-    side_end(h, saved);
-    h->prof_tag = "on_";
-    if (h->cfg.use_double) tower_forward(h, h->online, states2, xf, 2 * n, h->acts_on);  // s and s' share one pass
-    else tower_forward(h, h->online, states2, xf, n, h->acts_on);
+    const int rows_on = h->cfg.use_double ? 2 * n : n;  // double DQN: s and s' share one pass of the online tower
+    if (xf && towers_conv_forward_merged(h, xf, rows_on, xf + (size_t)n * S, n)) {
+        side_begin(h, saved, 0, 2);
+        h->prof_tag = "tg_";
+        tower_fc_forward(h, h->target, n, h->acts_tg);
+        side_end(h, saved);
+        h->prof_tag = "on_";
+        tower_fc_forward(h, h->online, rows_on, h->acts_on);
+    } else {
+        side_begin(h, saved, 0, 2);
+        h->prof_tag = "tg_";
+        tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
+        side_end(h, saved);
+        h->prof_tag = "on_";
+        tower_forward(h, h->online, states2, xf, rows_on, h->acts_on);
+    }
     main_wait_side(h);
     prof_mark(h, "td_epilogue");
     launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
@@ -1171,6 +1180,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
+    else if (n == "merge_towers") h->merge_towers = value != 0;
     else if (n == "prefetch") h->prefetch = value != 0;
     else if (n == "defer_adam") h->defer_adam = value != 0;  // dense-kernel optimizer pass of step i under the conv forward of step i+1
     else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
@@ -1334,7 +1344,7 @@ extern "C" int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32
     float *dA = nullptr, *dB = nullptr, *dC = nullptr;
     unsigned long long* dT = nullptr;
     if (mode >= 16) {  // conv layer (mode - 16) of the online tower over M images, in place on the tower's buffers
-        DQN_REQUIRE(mode - 16 < 3 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
+        DQN_REQUIRE(mode - 16 < 4 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
         dmalloc(dT, 512);
         DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 512 * 8, h->stream));
         debug_conv_layer(h, mode - 16, M);

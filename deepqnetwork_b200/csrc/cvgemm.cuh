@@ -220,8 +220,10 @@ __device__ __forceinline__ void load_image_async(uint32_t img, const float* __re
 constexpr int CV_THREADS = 320;
 
 template <int BN, int NTERMS, class Epi>
-__global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in, const float* __restrict__ packed,
-                                                               const Epi epi, const ImgGeom g, const Bands bd,
+__global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in_a, const float* __restrict__ packed_a,
+                                                               const Epi epi_a, int images_a, const float* __restrict__ in_b,
+                                                               const float* __restrict__ packed_b, const Epi epi_b,
+                                                               const ImgGeom g, const Bands bd,
                                                                const float* __restrict__ zeros, unsigned long long* __restrict__ dbg) {
     using P = CvPlan<BN, NTERMS>;
     const bool cta0 = dbg && blockIdx.x == 0;  // in-kernel timeline (dqn_debug_timeline, mode >= 16)
@@ -243,7 +245,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
     const uint32_t tmem_slot = bars + 8u * (3 * S + P::MAXB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int image = blockIdx.x;
+    // two problem sets in one grid (online tower on [s; s'] and target tower on s'): CTAs past images_a take set b
+    const bool set_b = (int)blockIdx.x >= images_a;
+    const int image = set_b ? blockIdx.x - images_a : blockIdx.x;
+    const float* __restrict__ in = set_b ? in_b : in_a;
+    const float* __restrict__ packed = set_b ? packed_b : packed_a;
+    const Epi& epi = set_b ? epi_b : epi_a;
     const int nsteps = bd.n * g.nkb;
     constexpr int DCOLS_MIN = 32;
     const int dcols = bd.n * BN < DCOLS_MIN ? DCOLS_MIN : bd.n * BN;  // accumulators: band b at column b*BN
@@ -437,7 +444,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
 }
 
 template <int BN, int NTERMS, class Epi>
-static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, const Bands& bd, int images) {
+static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, const Bands& bd, int images,
+                        const float* in_b = nullptr, const float* packed_b = nullptr, const Epi* e_b = nullptr, int images_b = 0) {
     using P = CvPlan<BN, NTERMS>;
     auto kern = cvconv_kernel<BN, NTERMS, Epi>;
     const size_t bytes = (size_t)P::S * P::B_STAGE + P::BAR_BYTES + g.img_bytes + 1024;
@@ -448,7 +456,8 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    launch_kernel(h->pdl, kern, dim3(images), dim3(CV_THREADS), bytes, h->stream, in, packed, e, g, bd, (const float*)h->zeros16, h->tc_dbg);
+    launch_kernel(h->pdl, kern, dim3(images + images_b), dim3(CV_THREADS), bytes, h->stream, in, packed, e, images, in_b, packed_b,
+                  e_b ? *e_b : e, g, bd, (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
 

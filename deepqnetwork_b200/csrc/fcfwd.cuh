@@ -1,11 +1,18 @@
 // Dense hidden layer forward with the weights streamed by TMA.
 //
 //   hid_pre[b][n] = sum_k act3[b][k] * W[k][n]      (K = 7680, n over both hidden streams, b <= 64 batch rows)
-// At batch 32-64 this layer is a stream of the 31.5 MB weight matrix through the tensor core: HBM-bound.  The generic
-// kernel (tsgemm.cuh, swap-AB) read W with 4-byte loads -- lane == hidden unit, 32 loads per thread and k-block -- and
-// reached 2 TB/s.  Here one thread issues 2-D TMA tensor copies of 128 (n) x 32 (k) boxes of W into a 6-stage ring
-// (16 KB each, 96 KB in flight per CTA), and the converters read their column of the box from shared memory
-// (conflict-free: consecutive lanes are consecutive n), split hi/lo and feed the MMA through tensor memory:
+// At batch 32-64 this layer is a stream of the 31.5 MB weight matrix through the tensor core.  One thread issues 2-D TMA
+// tensor copies of 128 (n) x 32 (k) boxes of W into a 6-stage ring (16 KB each, 96 KB in flight per CTA), and the
+// converters read their column of the box from shared memory (conflict-free: consecutive lanes are consecutive n),
+// split hi/lo and feed the MMA through tensor memory.  What the in-kernel timeline (scratch/fftl.py) taught:
+//   * the activation tile must not be produced by threads with row-scattered global loads: those LDGs (8 lines per
+//     instruction) share the L1tex wavefront queue with the converters' LDS and doubled the k-block time; the compiler
+//     also sank the prefetch loads to their use (volatile asm keeps them early), and a select on a just-loaded value
+//     stalls on the load.  PACKED mode removes the thread work altogether: conv3's epilogue (EpiBiasReluPack) writes the
+//     tiles, one cp.async.bulk per k-block fetches hi+lo;
+//   * with weights L2-resident (repeated predict) the kernel is no faster: it is not HBM-bound at this size but bound by
+//     the serial k-loop of 13 k-blocks per CTA + prologue/epilogue, and the two towers' 2 x 144 CTAs run as two waves.
+// Measured equal to the generic kernel within noise, so it stays an option (fc_tma_fwd).
 //   swap-AB: MMA rows (M = 128) = hidden units, MMA columns (N) = batch rows, split-K over blockIdx.y
 //   A (TMEM)  : W^T tile, thread == hidden unit
 //   B (smem)  : activation tile [rows][32 k] -> dense K-major hi/lo tiles through registers (warps 4-7)
@@ -19,11 +26,16 @@ using namespace tc;
 struct WMaps { CUtensorMap w[2]; };  // per hidden stream: [flat][hid] f32, box 128 (n) x 32 (k), no swizzle
 constexpr int FF_S = 6, FF_THREADS = 320;
 
-template <int BN, int NTERMS>
-__global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __restrict__ act, int rows, int flat, int NH, int hid,
+// PACKED: the B tiles arrive ready-made (EpiBiasReluPack wrote them), one bulk copy per k-block; warps 4-7 become a second
+// converter group instead of B producers
+template <int BN, int NTERMS, bool PACKED>
+__global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __restrict__ act, const float* __restrict__ act_pk, int rows, int flat, int NH, int hid,
                                                               const __grid_constant__ WMaps maps, float* __restrict__ part,
-                                                              int kb_per_split) {
+                                                              int kb_per_split, unsigned long long* __restrict__ dbg) {
     constexpr int S = FF_S, ACOLS = BK * (NTERMS == 3 ? 2 : 1);
+    const bool cta0 = dbg && blockIdx.x == 0 && blockIdx.y == 0;
+#define FF_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 64) dbg[(row) * 8 + (col)] = clock64(); } while (0)
+    FF_STAMP(threadIdx.x == 0, 63, 0);
     constexpr uint32_t W_TILE = BM * BK * 4, B_TILE = BN * 128, STAGE = W_TILE + 2 * B_TILE;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
@@ -56,27 +68,34 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    FF_STAMP(threadIdx.x == 0, 63, 1);
     constexpr int DCOLS = BN < 32 ? 32 : BN;
     auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(DCOLS + s * ACOLS); };
 
     if (warp == 9) {
         // ---------------- W boxes by TMA (weights were written by an earlier step: no dependency on the predecessor) ----------------
         if (lane == 0) {
+            if (PACKED) pdl_wait();  // the packed activation tiles are the stream predecessor's output
             int s = 0, ph = 0;
             for (int j = 0; j < nkb; ++j) {
                 if (j >= S) mbar_wait(empty(s), ph ^ 1);
-                cv::mbar_expect_tx(wfull(s), W_TILE);
+                FF_STAMP(true, j, 0);
+                cv::mbar_expect_tx(wfull(s), PACKED ? W_TILE + 2 * B_TILE : W_TILE);
                 fa::tma_load_2d(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s));
+                if (PACKED) cv::tma_bulk_g2s(stage_b(s), act_pk + (size_t)(kb0 + j) * (2 * BN * 32), 2 * B_TILE, wfull(s));
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp < 4) {
-        // ---------------- A converters: thread == hidden unit (column of the W box) ----------------
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        const uint32_t col = (uint32_t)(warp * 32 + lane) * 4u;
-        int s = 0, ph = 0;
-        for (int j = 0; j < nkb; ++j) {
+    } else if (warp < (PACKED ? 8 : 4)) {
+        // ---------------- A converters: thread == hidden unit (column of the W box); PACKED: two groups, alternate k-blocks ----------------
+        const int q4 = warp & 3, grp = warp >> 2;
+        constexpr int NG = PACKED ? 2 : 1;
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        const uint32_t col = (uint32_t)(q4 * 32 + lane) * 4u;
+        for (int j = grp; j < nkb; j += NG) {
+            const int s = j % S, ph = (j / S) & 1;
             mbar_wait(wfull(s), ph);  // (the stage's TMEM half was released together with its smem half: empty(s))
+            FF_STAMP(tid == 0, j, 1);
             float hi[32];
             const uint32_t src = stage_w(s) + col;
 #pragma unroll
@@ -91,37 +110,70 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
             }
             ts::tmem_st_wait();
             tc_fence_before();
+            FF_STAMP(tid == 0, j, 2);
             __syncwarp();
             if (lane == 0) mbar_arrive(afull(s));
-            if (++s == S) { s = 0; ph ^= 1; }
         }
     } else if (warp < 8) {
         // ---------------- B producers: act[b][k0 .. k0+31] -> dense K-major hi/lo tiles ----------------
         pdl_wait();  // the activations are the stream predecessor's output
+        FF_STAMP(tid == 128, 63, 2);
         const int t = tid - 128;
         constexpr int CH = BN * 8 / 128;  // 16-byte chunks per thread
+        constexpr int PF = 4;             // k-blocks of activation loads in flight per thread (L2 latency ~1 us >> a k-block)
+        // chunk q of a thread: 8 consecutive lanes write 8 consecutive 16-byte rows of a core matrix (conflict-free)
+        const float* srcp[CH];
+        uint32_t dsto[CH];
+        bool okr[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int q = t + i * 128;
+            const int r8 = q & 7, c = (q >> 3) & 7, rg = q >> 6;
+            const int r = rg * 8 + r8;
+            okr[i] = r < rows;
+            srcp[i] = act + (size_t)(okr[i] ? r : 0) * flat + (size_t)kb0 * BK + c * 4;
+            dsto[i] = (uint32_t)(rg * cv::PK_SBO + c * cv::PK_LBO + r8 * 16);
+        }
+        float4 pf[PF][CH];
+        auto load_blk = [&](int j, float4 (&v)[CH]) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+            {
+                // volatile asm: the compiler must not sink these loads to their use PF k-blocks later (it did: the timeline
+                // showed one full L2 latency per k-block); out-of-range rows / blocks read the first row (finite, unused or
+                // multiplied by nothing: rows >= `rows` are never stored, blocks >= nkb are never consumed)
+                const float* p = srcp[i] + (size_t)(j < nkb ? j : 0) * BK;
+                asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "l"(p));
+                // (no select on the loaded value: it would make the thread wait for the load right here; rows == BN is
+                // guaranteed by the launcher, so every row of the tile exists)
+            }
+        };
+#pragma unroll
+        for (int p = 0; p < PF; ++p) load_blk(p, pf[p]);
         int s = 0, ph = 0;
-        for (int j = 0; j < nkb; ++j) {
+        auto put_blk = [&](int j, float4 (&v)[CH]) {
             if (j >= S) mbar_wait(empty(s), ph ^ 1);
-            const int k0 = (kb0 + j) * BK;
+            FF_STAMP(tid == 128, j, 3);
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                // chunk id: row r = 8 (q / 8 ...) arranged so that 8 consecutive lanes write 8 consecutive 16-byte rows of a core matrix
-                const int q = t + i * 128;
-                const int r8 = q & 7, c = (q >> 3) & 7, rg = q >> 6;
-                const int r = rg * 8 + r8;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows) v = __ldg(reinterpret_cast<const float4*>(act + (size_t)r * flat + k0 + c * 4));
-                const uint32_t a = stage_b(s) + (uint32_t)(rg * cv::PK_SBO + c * cv::PK_LBO + r8 * 16);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                const uint32_t a = stage_b(s) + dsto[i];
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w) : "memory");
                 if (NTERMS == 3)
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + B_TILE), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
-                                 "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + B_TILE), "f"(lo_part(v[i].x)), "f"(lo_part(v[i].y)),
+                                 "f"(lo_part(v[i].z)), "f"(lo_part(v[i].w)) : "memory");
             }
-            fence_proxy_async();
+            // release-arrive; the generic->async proxy fence runs on the MMA thread after its acquire (a producer-side
+            // fence.proxy.async costs ~1000 cycles per k-block here: fftl timeline)
             __syncwarp();
             if (lane == 0) mbar_arrive(bfull(s));
+            FF_STAMP(tid == 128, j, 4);
             if (++s == S) { s = 0; ph ^= 1; }
+            load_blk(j + PF, v);
+        };
+        for (int j = 0; j < nkb; j += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p)
+                if (j + p < nkb) put_blk(j + p, pf[p]);
         }
     } else {
         // ---------------- MMA issue (warp 8) ----------------
@@ -131,7 +183,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         int s = 0, ph = 0;
         for (int j = 0; j < nkb; ++j) {
             mbar_wait(afull(s), ph);
-            mbar_wait(bfull(s), ph);
+            FF_STAMP(lane == 0, j, 5);
+            if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
+            else { mbar_wait(bfull(s), ph); fence_proxy_async(); }  // B tile: generic -> async proxy
+            FF_STAMP(lane == 0, j, 6);
             tc_fence_after();
             const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO), dbl = make_desc(stage_b(s) + B_TILE, cv::PK_LBO, cv::PK_SBO);
             const uint32_t ta = tmem_a(s);
@@ -153,6 +208,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
                 mma_commit(empty(s));
                 if (j == nkb - 1) mma_commit(accum);
             }
+            FF_STAMP(lane == 0, j, 7);
             __syncwarp();
             if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -163,6 +219,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         // ---------------- epilogue: part[z][b][n0 + unit], warp (q4, half): units 32 q4 + lane, batch rows [half BN/2, +BN/2) ----------------
         const int q4 = warp & 3, half = warp >> 2;
         if (nkb > 0) { mbar_wait(accum, 0); tc_fence_after(); }
+        FF_STAMP(tid == 0, 63, 3);
         constexpr int HC = BN / 2;
         float* o = part + (size_t)z * rows * NH + n0 + q4 * 32 + lane;
 #pragma unroll
@@ -180,12 +237,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
             }
         }
         tc_fence_before();
+        FF_STAMP(tid == 0, 63, 4);
     }
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+#undef FF_STAMP
 }
 
 static void encode_wmaps(dqn_learner* h, const float* P, WMaps& out) {
@@ -214,7 +273,7 @@ static inline bool supported(const dqn_learner* h, int rows) {
 }
 
 // returns the number of split-K partials written to part[z][rows][NH]
-static int launch(dqn_learner* h, const float* P, const float* act, int rows, float* part, int max_splits) {
+static int launch(dqn_learner* h, const float* P, const float* act, int rows, float* part, int max_splits, const float* act_pk = nullptr) {
     const NetDesc& net = h->net;
     const int tw = P == h->online ? 0 : 1;
     if (!h->ff_maps[tw]) {
@@ -224,18 +283,24 @@ static int launch(dqn_learner* h, const float* P, const float* act, int rows, fl
     const WMaps& maps = *static_cast<WMaps*>(h->ff_maps[tw]);
     const int mt = net.NH / BM, nkb = net.flat / BK;
     int want = std::min(std::max(1, h->sm_count / mt), max_splits);
+    if (const char* e = getenv("DQN_FC_SPLITS")) want = std::min(std::max(1, atoi(e)), max_splits);
     const int per = (nkb + want - 1) / want;
     const int splits = (nkb + per - 1) / per;
     auto go = [&](auto kern, int bn) {
         const size_t bytes = (size_t)FF_S * (BM * BK * 4 + 2 * bn * 128) + 512 + 1024;
         // (no static "configured" flag here: both BN instantiations share one function-pointer type, hence one lambda body)
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        launch_kernel(h->pdl, kern, dim3(mt, splits), dim3(FF_THREADS), bytes, h->stream, act, rows, net.flat, net.NH, net.hidden, maps,
-                      part, per);
+        launch_kernel(h->pdl, kern, dim3(mt, splits), dim3(FF_THREADS), bytes, h->stream, act, act_pk, rows, net.flat, net.NH, net.hidden, maps,
+                      part, per, h->tc_dbg);
     };
     const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
-    if (rows == 64) { if (x3) go(fcfwd_kernel<64, 3>, 64); else go(fcfwd_kernel<64, 1>, 64); }
-    else            { if (x3) go(fcfwd_kernel<32, 3>, 32); else go(fcfwd_kernel<32, 1>, 32); }
+    if (act_pk) {
+        if (rows == 64) { if (x3) go(fcfwd_kernel<64, 3, true>, 64); else go(fcfwd_kernel<64, 1, true>, 64); }
+        else            { if (x3) go(fcfwd_kernel<32, 3, true>, 32); else go(fcfwd_kernel<32, 1, true>, 32); }
+    } else {
+        if (rows == 64) { if (x3) go(fcfwd_kernel<64, 3, false>, 64); else go(fcfwd_kernel<64, 1, false>, 64); }
+        else            { if (x3) go(fcfwd_kernel<32, 3, false>, 32); else go(fcfwd_kernel<32, 1, false>, 32); }
+    }
     h->launches++;
     return splits;
 }

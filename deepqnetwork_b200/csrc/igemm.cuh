@@ -320,6 +320,39 @@ struct EpiPartial {  // part[z][m][n] = acc   (split-K partial sums, reduced by 
     }
 };
 
+// conv3 forward feeding the TMA dense forward (fcfwd.cuh): besides the NHWC activation it writes the SAME values as
+// the dense layer's B operand tiles -- [k-block of 32 flat inputs][hi, lo][pk_rows batch rows x 32 k] in the dense
+// canonical K-major UMMA layout -- so that the dense kernel fetches a k-block's tile with one bulk copy and spends no
+// thread work on it.  flat index = pixel * cout + channel (tf.layers.flatten of NHWC, deep_q_model.py:309).
+struct EpiBiasReluPack {
+    float* out; const float* bias; int ldo;
+    float* pk; int pk_rows; int ohw;  // pk == nullptr: plain EpiBiasRelu
+    __device__ __forceinline__ void stage(int tid, int bn, uint32_t sarea) const {
+        if (tid < bn) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sarea + 4u * tid), "f"(bias[tid]) : "memory");
+    }
+    template <int TN>
+    __device__ __forceinline__ void store_b(int m, int n, const float (&v)[TN], uint32_t sbias) const {
+        float* o = out + (size_t)m * ldo + n;
+        const int img = m / ohw, pix = m - img * ohw;
+        const int k0 = pix * ldo + n;  // first flat index of this run of TN channels (TN = 16, n % 16 == 0)
+        float* pt = pk ? pk + (size_t)(k0 >> 5) * (2 * pk_rows * 32) + (((img >> 3) * 1024 + ((k0 & 31) >> 2) * 128 + (img & 7) * 16) >> 2)
+                       : nullptr;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sbias + 4u * j));
+            const float4 r = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f), fmaxf(v[j + 3] + b.w, 0.f));
+            *reinterpret_cast<float4*>(o + j) = r;
+            if (pt) {
+                const float4 l = make_float4(r.x - __uint_as_float(__float_as_uint(r.x) & 0xFFFFE000u), r.y - __uint_as_float(__float_as_uint(r.y) & 0xFFFFE000u),
+                                             r.z - __uint_as_float(__float_as_uint(r.z) & 0xFFFFE000u), r.w - __uint_as_float(__float_as_uint(r.w) & 0xFFFFE000u));
+                *reinterpret_cast<float4*>(pt + (j >> 2) * 32) = r;                    // chunk (k0 % 32) / 4 + j / 4: 128 bytes apart
+                *reinterpret_cast<float4*>(pt + (j >> 2) * 32 + pk_rows * 32) = l;     // lo tile follows the hi tile
+            }
+        }
+    }
+};
+
 struct EpiGatePix {  // image-resident dgrad: out[pixel][n] = acc * (gate[pixel][n] > 0)
     float* out; const float* gate; int ldo;
     __device__ __forceinline__ void stage(int, int, uint32_t) const {}

@@ -67,6 +67,9 @@ struct dqn_learner {
                                   // slower than tensor-core wgrad + streaming Adam (instruction-bound: 61 us vs 17 + 45 us)
     bool fc_split_streams = true; // dense wgrad + optimizer per hidden stream on two side streams (pipelines HBM- and tensor-bound halves)
     int fc_tma_ctas = 0;          // > 0: the persistent form of that pass with this many CTAs (S-stage TMA ring of optimizer state)
+    float* act3_pk[2] = {nullptr, nullptr};  // conv3 output of the online (64 rows) / target (32 rows) tower as the dense layer's
+                                             // packed B tiles (EpiBiasReluPack -> fcfwd.cuh); valid for the launch that follows
+    bool act3_pk_valid[2] = {false, false};
     void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
     bool fc_tma_fwd = false;      // option: dense forward with TMA-streamed weights (fcfwd.cuh); measured equal to the tsgemm path (16 us)
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
@@ -176,6 +179,7 @@ struct dqn_learner {
     float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
     int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
+    bool merge_towers = true;   // option: conv layers of the online and the target tower in one launch each
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
@@ -245,6 +249,8 @@ void launch_tree_stats(dqn_learner* h, double per_b_override);
 // x_f32: the same rows as d_states already converted to f32 (used by the tcgen05 path; may be null in FP32 mode)
 void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts);
 void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows);
+bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
+void tower_fc_forward(dqn_learner* h, const float* params, int rows, TowerActs& acts);  // dense + heads after the conv stack
 void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of the packed conv weights
 void launch_pack_conv(dqn_learner* h, int tower);  // re-pack one tower's conv weights from its parameter slab
 void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n);

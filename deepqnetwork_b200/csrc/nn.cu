@@ -224,6 +224,7 @@ void alloc_packed_conv(dqn_learner* h) {
     for (int l = 0; l < 3; ++l) { h->pk_off[l] = off; off += (int64_t)cv::packed_floats(h->net.conv[l]); }
     h->pk_floats = off;
     for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->packed[t], (size_t)off * sizeof(float)));
+    for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->act3_pk[t], (size_t)(t == 0 ? 64 : 32) * h->net.flat * 2 * sizeof(float)));
     int64_t offd = 0;
     for (int l = 1; l < 3; ++l) { h->pkd_off[l] = offd; offd += (int64_t)cv::packed_floats(h->net.conv[l]); }
     DQN_CUDA_OK(cudaMalloc(&h->packed_dg, (size_t)offd * sizeof(float)));
@@ -260,6 +261,54 @@ static bool conv_image_resident(dqn_learner* h, const float* in, const float* pa
     return true;
 }
 
+static void tower_fc_heads(dqn_learner* h, const float* P, int rows, TowerActs& acts, bool tg);
+
+// Both towers' conv stacks as ONE launch per layer (grid = online images + target images): three launches instead of
+// six, and the target tower no longer trails the online one by a launch latency.  Returns false (nothing launched) if a
+// layer is outside the image-resident kernel's coverage.
+static bool g_pack_ok(const dqn_learner* h, int rows_on, int rows_tg) {
+    return rows_on == 64 && rows_tg == 32 && h->net.conv[2].cout == 64 && ff::supported(h, rows_on) && ff::supported(h, rows_tg);
+}
+
+bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg) {
+    const NetDesc& net = h->net;
+    if (h->cfg.math_mode == DQN_MATH_FP32 || !h->img_conv || !h->merge_towers) return false;
+    cv::ImgGeom q[3]; cv::Bands bd[3];
+    for (int l = 0; l < 3; ++l) {
+        if (!cv::img_geom(net.conv[l], q[l]) || q[l].nbands > 4) return false;
+        cv::forward_bands(q[l], bd[l]);
+    }
+    const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
+    const float *in_on = x_on, *in_tg = x_tg;
+    static const char* kName[3] = {"conv1_fwd", "conv2_fwd", "conv3_fwd"};
+    // conv3 also writes the dense layer's operand tiles when the TMA dense forward will consume them
+    const bool pack = h->fc_tma_fwd && g_pack_ok(h, rows_on, rows_tg);
+    h->act3_pk_valid[0] = h->act3_pk_valid[1] = false;
+    for (int l = 0; l < 3; ++l) {
+        const ConvGeom& g = net.conv[l];
+        prof_mark(h, kName[l]);
+        const bool pk = pack && l == 2;
+        EpiBiasReluPack e_on{h->acts_on.act[l], h->online + net.off_cb[l], g.cout, pk ? h->act3_pk[0] : nullptr, rows_on, g.oh * g.ow};
+        EpiBiasReluPack e_tg{h->acts_tg.act[l], h->target + net.off_cb[l], g.cout, pk ? h->act3_pk[1] : nullptr, rows_tg, g.oh * g.ow};
+        if (pk) h->act3_pk_valid[0] = h->act3_pk_valid[1] = true;
+        const float* pk_on = h->packed[0] + h->pk_off[l];
+        const float* pk_tg = h->packed[1] + h->pk_off[l];
+        if (g.cout == 64) {
+            if (x3) cv::launch_conv<64, 3>(h, in_on, pk_on, e_on, q[l], bd[l], rows_on, in_tg, pk_tg, &e_tg, rows_tg);
+            else cv::launch_conv<64, 1>(h, in_on, pk_on, e_on, q[l], bd[l], rows_on, in_tg, pk_tg, &e_tg, rows_tg);
+        } else {
+            if (x3) cv::launch_conv<32, 3>(h, in_on, pk_on, e_on, q[l], bd[l], rows_on, in_tg, pk_tg, &e_tg, rows_tg);
+            else cv::launch_conv<32, 1>(h, in_on, pk_on, e_on, q[l], bd[l], rows_on, in_tg, pk_tg, &e_tg, rows_tg);
+        }
+        in_on = h->acts_on.act[l]; in_tg = h->acts_tg.act[l];
+    }
+    return true;
+}
+
+void tower_fc_forward(dqn_learner* h, const float* P, int rows, TowerActs& acts) {
+    tower_fc_heads(h, P, rows, acts, h->prof_tag[0] == 't');
+}
+
 void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts) {
     const NetDesc& net = h->net;
     const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
@@ -279,6 +328,13 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
             gemm_auto<false>(h, a, b, e, rows * g.oh * g.ow, g.cout, g.k * g.k * g.cin, 1, 0);
         in = acts.act[l];
     }
+    tower_fc_heads(h, P, rows, acts, tg);
+}
+
+// dense hidden layer(s) (split-K partials) + bias / ReLU / heads / dueling combine of one tower
+static void tower_fc_heads(dqn_learner* h, const float* P, int rows, TowerActs& acts, bool tg) {
+    const NetDesc& net = h->net;
+    const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
     int kchunk = fc_kchunk();
     int splits = ceil_div(net.flat, kchunk);
     if (h->defer_start && P == h->online) {
@@ -288,7 +344,9 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
     }
     prof_mark(h, tg ? "tg_fc_fwd" : "on_fc_fwd");
     if (tcm && h->fc_tma_fwd && (P == h->online || P == h->target) && ff::supported(h, rows)) {
-        splits = ff::launch(h, P, acts.act[2], rows, acts.fc_part, h->fc_splits);
+        const int tw = P == h->online ? 0 : 1;
+        splits = ff::launch(h, P, acts.act[2], rows, acts.fc_part, h->fc_splits, h->act3_pk_valid[tw] ? h->act3_pk[tw] : nullptr);
+        h->act3_pk_valid[tw] = false;
     } else if (tcm && rows % 32 == 0) {
         // swap-AB: the 128-row MMA tile spans hidden units (weights stream as the A operand), the batch is N
         const int mt = ceil_div(net.NH, tc::BM);
@@ -312,9 +370,11 @@ void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, cons
     launch_fc_reduce_heads(h, P, splits, rows, acts);
 }
 
-// debug: conv layer `layer` of the online tower alone on `rows` images (dqn_debug_timeline, mode 16 + layer)
+// debug: conv layer `layer` of the online tower alone on `rows` images (dqn_debug_timeline, mode 16 + layer);
+// layer 3 = the dense forward + heads
 void debug_conv_layer(dqn_learner* h, int layer, int rows) {
     const NetDesc& net = h->net;
+    if (layer == 3) { tower_fc_heads(h, h->online, rows, h->acts_on, false); return; }
     const ConvGeom& g = net.conv[layer];
     const float* P = h->online;
     const void* in = layer == 0 ? (const void*)h->x_f32 : (const void*)h->acts_on.act[layer - 1];
