@@ -181,13 +181,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0;
+        bool ready = false;  // this block's barriers were already seen complete while the previous block's MMAs were issued
         for (int j = 0; j < nkb; ++j) {
-            mbar_wait(afull(s), ph);
+            if (!ready) {
+                mbar_wait(afull(s), ph);
+                if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
+                else mbar_wait(bfull(s), ph);
+            }
             FF_STAMP(lane == 0, j, 5);
-            if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
-            else { mbar_wait(bfull(s), ph); fence_proxy_async(); }  // B tile: generic -> async proxy
+            if (!PACKED) fence_proxy_async();  // B tile: generic -> async proxy
             FF_STAMP(lane == 0, j, 6);
             tc_fence_after();
+            {
+                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
+                ready = j + 1 < nkb && cv::mbar_test(afull(s1), ph1) && cv::mbar_test(PACKED ? wfull(s1) : bfull(s1), ph1);
+            }
             const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO), dbl = make_desc(stage_b(s) + B_TILE, cv::PK_LBO, cv::PK_SBO);
             const uint32_t ta = tmem_a(s);
 #pragma unroll
@@ -282,7 +290,8 @@ static int launch(dqn_learner* h, const float* P, const float* act, int rows, fl
     }
     const WMaps& maps = *static_cast<WMaps*>(h->ff_maps[tw]);
     const int mt = net.NH / BM, nkb = net.flat / BK;
-    int want = std::min(std::max(1, h->sm_count / mt), max_splits);
+    // the two towers' launches run side by side: half the SMs each, so that both fit in one wave
+    int want = std::min(std::max(1, h->sm_count / (2 * mt)), max_splits);
     if (const char* e = getenv("DQN_FC_SPLITS")) want = std::min(std::max(1, atoi(e)), max_splits);
     const int per = (nkb + want - 1) / want;
     const int splits = (nkb + per - 1) / per;

@@ -71,7 +71,7 @@ struct dqn_learner {
                                              // packed B tiles (EpiBiasReluPack -> fcfwd.cuh); valid for the launch that follows
     bool act3_pk_valid[2] = {false, false};
     void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
-    bool fc_tma_fwd = false;      // option: dense forward with TMA-streamed weights (fcfwd.cuh); measured equal to the tsgemm path (16 us)
+    bool fc_tma_fwd = true;       // dense forward with TMA-streamed weights and packed activation tiles (fcfwd.cuh)
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)

@@ -370,11 +370,19 @@ static void tower_fc_heads(dqn_learner* h, const float* P, int rows, TowerActs& 
     launch_fc_reduce_heads(h, P, splits, rows, acts);
 }
 
+bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
 // debug: conv layer `layer` of the online tower alone on `rows` images (dqn_debug_timeline, mode 16 + layer);
 // layer 3 = the dense forward + heads
 void debug_conv_layer(dqn_learner* h, int layer, int rows) {
     const NetDesc& net = h->net;
-    if (layer == 3) { tower_fc_heads(h, h->online, rows, h->acts_on, false); return; }
+    if (layer == 3) {
+        // conv stacks of both towers first (they write the packed activation tiles when the TMA dense forward is on), un-stamped
+        unsigned long long* dbg = h->tc_dbg; h->tc_dbg = nullptr;
+        towers_conv_forward_merged(h, h->x_f32, rows, h->x_f32 + (size_t)(rows / 2) * h->state_bytes, rows / 2);
+        h->tc_dbg = dbg;
+        tower_fc_heads(h, h->online, rows, h->acts_on, false);
+        return;
+    }
     const ConvGeom& g = net.conv[layer];
     const float* P = h->online;
     const void* in = layer == 0 ? (const void*)h->x_f32 : (const void*)h->acts_on.act[layer - 1];
