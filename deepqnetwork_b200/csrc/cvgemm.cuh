@@ -223,7 +223,7 @@ template <int BN, int NTERMS, class Epi>
 __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in_a, const float* __restrict__ packed_a,
                                                                const Epi epi_a, int images_a, const float* __restrict__ in_b,
                                                                const float* __restrict__ packed_b, const Epi epi_b,
-                                                               const ImgGeom g, const Bands bd,
+                                                               const ImgGeom g, const Bands bd, int bands_per_cta,
                                                                const float* __restrict__ zeros, unsigned long long* __restrict__ dbg) {
     using P = CvPlan<BN, NTERMS>;
     const bool cta0 = dbg && blockIdx.x == 0;  // in-kernel timeline (dqn_debug_timeline, mode >= 16)
@@ -251,9 +251,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
     const float* __restrict__ in = set_b ? in_b : in_a;
     const float* __restrict__ packed = set_b ? packed_b : packed_a;
     const Epi& epi = set_b ? epi_b : epi_a;
-    const int nsteps = bd.n * g.nkb;
+    // a CTA owns bands [band0, band0 + nb) of its image (blockIdx.y): bands are independent accumulators, so an image's
+    // bands can be spread over several CTAs (conv2 dgrad: 4 stride classes -> 2 CTAs) without any reduction
+    const int band0 = blockIdx.y * bands_per_cta;
+    const int nb = min(bd.n - band0, bands_per_cta);
+    const int nsteps = nb * g.nkb;
     constexpr int DCOLS_MIN = 32;
-    const int dcols = bd.n * BN < DCOLS_MIN ? DCOLS_MIN : bd.n * BN;  // accumulators: band b at column b*BN
+    const int dcols = nb * BN < DCOLS_MIN ? DCOLS_MIN : nb * BN;  // accumulators: band b at column b*BN
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -273,9 +277,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         const int off = (kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + c * 4;
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kbtab + 4u * tid), "r"(off) : "memory");
     }
-    for (int e = tid; e < bd.n * 128; e += CV_THREADS) {
+    for (int e = tid; e < nb * 128; e += CV_THREADS) {
         const int band = e >> 7, m = e & 127;
-        const Bands::B& c = bd.c[band];
+        const Bands::B& c = bd.c[band0 + band];
         const int ai = m / c.nb, bi = m - ai * c.nb;
         int off = 0, opix = -1;  // rows past the band: any finite data, never stored
         if (ai < c.na) {
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) choff[j] = g.cin >= 32 ? 16u * j : (uint32_t)(((j % g.s) * g.wps + j / g.s) * g.pitch);
         int step = cg;
-        for (int band = 0; band < bd.n; ++band) {
+        for (int band = 0; band < nb; ++band) {
             uint32_t roff;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(roff) : "r"(rowtab + 8u * (band * 128 + m)));
             const uint32_t base = img + roff;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         pdl_launch_dependents();
         // ---------------- epilogue: warp (grp, cg) owns TMEM lanes 32 grp.., columns [cg BN/2, +BN/2) of every band ----------------
         constexpr int HC = BN / 2;
-        for (int band = 0; band < bd.n; ++band) {
+        for (int band = 0; band < nb; ++band) {
             mbar_wait(accum_bar(band), 0);
             tc_fence_after();
             CV_STAMP(tid == 0 && band == 0, 63, 5);
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0, step = 0;
         bool ready = false;  // barriers of the current step already seen complete (tested during the previous step)
-        for (int band = 0; band < bd.n; ++band) {
+        for (int band = 0; band < nb; ++band) {
             const uint32_t tmem_d = tmem_base + (uint32_t)(band * BN);
             for (int kb = 0; kb < g.nkb; ++kb, ++step) {
                 if (!ready) {
@@ -424,8 +428,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         if (lane == 0) {
             pdl_wait();
             int s = 0, ph = 0, step = 0;
-            for (int band = 0; band < bd.n; ++band) {
-                const float* src = packed + (size_t)bd.c[band].pk_kb0 * (P::B_STAGE / 4);
+            for (int band = 0; band < nb; ++band) {
+                const float* src = packed + (size_t)bd.c[band0 + band].pk_kb0 * (P::B_STAGE / 4);
                 for (int kb = 0; kb < g.nkb; ++kb, ++step) {
                     if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
                     CV_STAMP(true, step, 5);
@@ -445,7 +449,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
 
 template <int BN, int NTERMS, class Epi>
 static void launch_conv(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ImgGeom& g, const Bands& bd, int images,
-                        const float* in_b = nullptr, const float* packed_b = nullptr, const Epi* e_b = nullptr, int images_b = 0) {
+                        const float* in_b = nullptr, const float* packed_b = nullptr, const Epi* e_b = nullptr, int images_b = 0,
+                        int bands_per_cta = 4) {
     using P = CvPlan<BN, NTERMS>;
     auto kern = cvconv_kernel<BN, NTERMS, Epi>;
     const size_t bytes = (size_t)P::S * P::B_STAGE + P::BAR_BYTES + g.img_bytes + 1024;
@@ -456,8 +461,9 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    launch_kernel(h->pdl, kern, dim3(images + images_b), dim3(CV_THREADS), bytes, h->stream, in, packed, e, images, in_b, packed_b,
-                  e_b ? *e_b : e, g, bd, (const float*)h->zeros16, h->tc_dbg);
+    if (bands_per_cta > bd.n) bands_per_cta = bd.n;
+    launch_kernel(h->pdl, kern, dim3(images + images_b, (bd.n + bands_per_cta - 1) / bands_per_cta), dim3(CV_THREADS), bytes, h->stream, in,
+                  packed, e, images, in_b, packed_b, e_b ? *e_b : e, g, bd, bands_per_cta, (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
 

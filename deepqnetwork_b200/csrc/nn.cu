@@ -623,8 +623,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
                 EpiGatePix e{h->d_act[l - 1], acts.act[l - 1], g.cin};
                 const float* pk = h->packed_dg + h->pkd_off[l];
                 const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
-                if (g.cin == 64) { if (x3) cv::launch_conv<64, 3>(h, h->d_act[l], pk, e, q, bd, rows); else cv::launch_conv<64, 1>(h, h->d_act[l], pk, e, q, bd, rows); }
-                else             { if (x3) cv::launch_conv<32, 3>(h, h->d_act[l], pk, e, q, bd, rows); else cv::launch_conv<32, 1>(h, h->d_act[l], pk, e, q, bd, rows); }
+                // the stride classes of one image are independent accumulators: two per CTA while that still fits one wave
+                const int bpc = (bd.n >= 4 && 2 * rows <= h->sm_count) ? 2 : 4;
+                if (g.cin == 64) { if (x3) cv::launch_conv<64, 3>(h, h->d_act[l], pk, e, q, bd, rows, nullptr, nullptr, (const EpiGatePix*)nullptr, 0, bpc); else cv::launch_conv<64, 1>(h, h->d_act[l], pk, e, q, bd, rows, nullptr, nullptr, (const EpiGatePix*)nullptr, 0, bpc); }
+                else             { if (x3) cv::launch_conv<32, 3>(h, h->d_act[l], pk, e, q, bd, rows, nullptr, nullptr, (const EpiGatePix*)nullptr, 0, bpc); else cv::launch_conv<32, 1>(h, h->d_act[l], pk, e, q, bd, rows, nullptr, nullptr, (const EpiGatePix*)nullptr, 0, bpc); }
             } else if (tcm && h->ts_gemm && 2 * ctas <= h->sm_count && Kd % 64 == 0 && g.cin % 32 == 0 &&
                 (int64_t)2 * rows * g.ih * g.iw * g.cin <= (int64_t)h->fc_splits * rows * net.NH) {
                 // too few tiles to fill the chip (conv3: 60): split K in two as well; the halves are added and gated by
