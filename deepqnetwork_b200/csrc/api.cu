@@ -221,6 +221,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
         cudaFree(t->fc_part); cudaFree(t->hid); cudaFree(t->q);
     }
     if (h->fa_maps) free(h->fa_maps);
+    if (h->fa_row_maps) free(h->fa_row_maps);
     for (int t = 0; t < 2; ++t) if (h->ff_maps[t]) free(h->ff_maps[t]);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_in_small) cudaFreeHost(h->h_in_small);
@@ -1173,6 +1174,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_split_streams") h->fc_split_streams = value != 0;
     else if (n == "fc_tma_fwd") h->fc_tma_fwd = value != 0;
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
+    else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels

@@ -406,6 +406,298 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fcwg_adam_persist_kernel(const 
     }
 }
 
+// ---- row-contiguous persistent variant -------------------------------------------------------------------------------
+// The tile is 16 rows x 256 columns of one hidden stream's kernel: every row segment is 1 KB of CONTIGUOUS parameters
+// and consecutive tiles of a CTA cover whole 2 KB rows, so the optimizer state streams through DRAM pages in order --
+// the 128 x 32 tiles above touch 128 rows x 128 bytes at a 2 KB pitch and lose most of the DRAM bandwidth to page
+// misses.  The product is formed transposed:
+//   D[n][kr] = sum_b dH[b][n] * act3[b][k0 + kr]     M = n (2 MMA tiles of 128 per 256-column tile), N = 16 rows
+//   A (TMEM): dH^T of the CTA's hidden stream, hi/lo, all 4 M tiles of the 512 columns resident (256 TMEM columns)
+//   B (smem): the 16 x 32 act3 slice of the tile, hi/lo (2 KB each), one warp per tile, double-buffered
+//   24 MMAs (N = 16) per tile into double-buffered accumulators (2 x 32 columns)
+// State ring: RS stages x {w, m, v} x 16 KB, one 2-D TMA box of 256 n x 16 rows per array (no swizzle: in the
+// epilogue thread == n, consecutive lanes read consecutive words).  16 epilogue warps (thread = one n, 8 of the 16
+// rows) apply the optimizer with approximate reciprocal / square root (2 ulp: the update term is lr * m / (sqrt(v) +
+// eps), so the weight sees < 1e-10 of it) -- with IEEE division and 8 warps the epilogue, not HBM, bound the pass.
+// A CTA walks a contiguous range of tiles (n-half fastest, then rows, then stream).
+constexpr int RS = 4, RT_THREADS = 576, RT_ROWS = 16, RT_N = 256;
+
+struct RowMaps { CUtensorMap w[2], m[2], v[2]; };  // box 256 (n) x 16 (k rows), SWIZZLE_NONE
+
+template <int NTERMS>
+__global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
+                                                                       int Bn, int flat, int NH, int hid,
+                                                                       const __grid_constant__ RowMaps maps,
+                                                                       float lr, float mom, int use_momentum,
+                                                                       const dqn_learner::Scalars* __restrict__ sc) {
+    constexpr uint32_t ARR = RT_ROWS * RT_N * 4, STAGE = 3 * ARR, B_TILE = 16 * 128;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t ring = sbase;
+    const uint32_t btiles = ring + RS * STAGE;                 // 2 x {hi, lo} x 2 KB
+    const uint32_t bars = btiles + 2 * 2 * B_TILE;
+    auto st_full = [&](int s) { return bars + 8u * s; };
+    auto computed = [&](int s) { return bars + 8u * (RS + s); };
+    auto b_full = [&](int b) { return bars + 8u * (2 * RS + b); };
+    auto b_empty = [&](int b) { return bars + 8u * (2 * RS + 2 + b); };
+    auto acc_full = [&](int b) { return bars + 8u * (2 * RS + 4 + b); };
+    auto acc_empty = [&](int b) { return bars + 8u * (2 * RS + 6 + b); };
+    const uint32_t a_full = bars + 8u * (2 * RS + 8), a_empty = bars + 8u * (2 * RS + 9), tmem_slot = bars + 8u * (2 * RS + 10);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int halves = hid / RT_N;                             // 2
+    const int tiles_per_stream = (flat / RT_ROWS) * halves, nstreams = NH / hid, total = tiles_per_stream * nstreams;
+    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+    const int ntiles = t1 - t0;
+    const int narr = use_momentum ? 2 : 3;
+    // tile t: stream = t / tiles_per_stream, then row block = (t % tiles_per_stream) / halves, n half = t % halves.  A CTA's
+    // range crosses the stream boundary at most once; i_sw = first local tile of the second stream (ntiles if none)
+    const int s_first = t0 / tiles_per_stream;
+    const int i_sw = min(ntiles, max(0, (s_first + 1) * tiles_per_stream - t0));
+    auto coords = [&](int i, int& strm, int& row0, int& nh) {
+        const int t = t0 + i; strm = t / tiles_per_stream;
+        const int r = t - strm * tiles_per_stream; row0 = (r / halves) * RT_ROWS; nh = r % halves;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < RS; ++s) { mbar_init(st_full(s), 1); mbar_init(computed(s), 16); }
+        for (int b = 0; b < 2; ++b) { mbar_init(b_full(b), 1); mbar_init(b_empty(b), 1); mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 16); }
+        mbar_init(a_full, 4); mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    // TMEM: accumulators [0,32), [32,64) (M tile j of the tile at +16 j); A of M tile mt (0..3): hi at 64 + 64 mt, lo at +32
+    auto tmem_a = [&](int mt) { return tmem_base + 64u + (uint32_t)mt * 64u; };
+
+    if (warp == 17) {
+        if (lane == 0 && ntiles > 0) {
+            auto issue_loads = [&](int i) {
+                int strm, row0, nh; coords(i, strm, row0, nh);
+                const int s = i % RS;
+                const uint32_t st = ring + s * STAGE;
+                cv::mbar_expect_tx(st_full(s), (uint32_t)(narr * ARR));
+                tma_load_2d(st, &maps.w[strm], nh * RT_N, row0, st_full(s));
+                tma_load_2d(st + ARR, &maps.m[strm], nh * RT_N, row0, st_full(s));
+                if (!use_momentum) tma_load_2d(st + 2 * ARR, &maps.v[strm], nh * RT_N, row0, st_full(s));
+            };
+            for (int j = 0; j < RS - 1 && j < ntiles; ++j) issue_loads(j);
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % RS;
+                mbar_wait(computed(s), (i / RS) & 1);
+                fence_proxy_async();  // the epilogue warps' shared-memory writes -> visible to the TMA stores
+                int strm, row0, nh; coords(i, strm, row0, nh);
+                const uint32_t st = ring + s * STAGE;
+                tma_store_2d(&maps.w[strm], nh * RT_N, row0, st);
+                tma_store_2d(&maps.m[strm], nh * RT_N, row0, st + ARR);
+                if (!use_momentum) tma_store_2d(&maps.v[strm], nh * RT_N, row0, st + 2 * ARR);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (i + RS - 1 < ntiles) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // stage (i - 1) % RS has been read by its stores
+                    issue_loads(i + RS - 1);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (warp == 16) {
+        // ---------------- MMA issue: 2 M tiles x 4 k-steps x NTERMS per tile ----------------
+        const uint32_t idesc = make_idesc(16, false, false);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        for (int i = 0; i < ntiles; ++i) {
+            const int bb = i & 1, use = i >> 1;
+            if (i == 0) mbar_wait(a_full, 0);
+            if (i == i_sw && i_sw > 0) mbar_wait(a_full, 1);  // dH^T of the second stream has replaced the first
+            mbar_wait(b_full(bb), use & 1);
+            if (use >= 1) mbar_wait(acc_empty(bb), (use - 1) & 1);
+            fence_proxy_async();  // B slice was written through the generic proxy
+            tc_fence_after();
+            int strm, row0, nh; coords(i, strm, row0, nh);
+            if (leader) {
+                const uint32_t bt = btiles + bb * 2 * B_TILE;
+                const uint64_t db = make_desc(bt, cv::PK_LBO, cv::PK_SBO), dbl = make_desc(bt + B_TILE, cv::PK_LBO, cv::PK_SBO);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t ta = tmem_a(nh * 2 + j), td = tmem_base + (uint32_t)(bb * 32 + j * 16);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2 * cv::PK_LBO) >> 4;
+                        if (NTERMS == 3) {
+                            ts::mma_tf32_ts(td, ta + ks * 8, dbl + o, idesc, ks != 0);
+                            ts::mma_tf32_ts(td, ta + 32u + ks * 8, db + o, idesc, 1);
+                            ts::mma_tf32_ts(td, ta + ks * 8, db + o, idesc, 1);
+                        } else {
+                            ts::mma_tf32_ts(td, ta + ks * 8, db + o, idesc, ks != 0);
+                        }
+                    }
+                }
+                mma_commit(b_empty(bb));
+                mma_commit(acc_full(bb));
+                if (i + 1 == i_sw && i_sw < ntiles) mma_commit(a_empty);  // last tile of the first stream: A may be replaced
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- warps 0-15 ----------------
+        const int q4 = warp & 3, grp = warp >> 2;                // grp: M tile of the tile (grp & 1), row half (grp >> 1)
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        auto convert_a = [&](int strm) {  // warps 0-3: dH^T of one stream, 4 M tiles, thread == n within the M tile
+            for (int mt = 0; mt < 4; ++mt) {
+                const int n = strm * hid + mt * 128 + q4 * 32 + lane;
+                float hi[32];
+#pragma unroll
+                for (int b = 0; b < 32; ++b) hi[b] = b < Bn ? __ldg(dhid + (size_t)b * NH + n) : 0.f;
+                const uint32_t ta = tmem_a(mt) + lane_base;
+                ts::tmem_st32(ta, hi);
+                if (NTERMS == 3) {
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
+                    ts::tmem_st32(ta + 32u, lo);
+                }
+            }
+            ts::tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        };
+        auto produce_b = [&](int i) {  // warp 4: act3[b][k0 .. k0+15] -> B(kr, b) hi/lo
+            const int bb = i & 1, use = i >> 1;
+            if (use >= 1) mbar_wait(b_empty(bb), (use - 1) & 1);
+            int strm, k0, nh; coords(i, strm, k0, nh);
+            const uint32_t bt = btiles + bb * 2 * B_TILE;
+            float v[16];
+            if (lane < Bn) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(act3 + (size_t)lane * flat + k0 + 4 * q));
+                    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int kr = 0; kr < 16; ++kr) {
+                const uint32_t a = bt + (uint32_t)((kr >> 3) * cv::PK_SBO + (lane >> 2) * cv::PK_LBO + (kr & 7) * 16 + (lane & 3) * 4);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[kr]) : "memory");
+                if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v[kr])) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full(bb));
+        };
+        if (warp < 4 && ntiles > 0) convert_a(s_first);
+        if (warp == 4 && ntiles > 0) produce_b(0);
+        const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+        const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
+        const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+        const int mj = grp & 1, rh = grp >> 1;                   // this warp: M tile mj of the tile, rows [8 rh, 8 rh + 8)
+        for (int i = 0; i < ntiles; ++i) {
+            if (warp == 4 && i + 1 < ntiles) produce_b(i + 1);
+            if (warp < 4 && i + 1 == i_sw && i_sw < ntiles) {
+                // the next tile belongs to the second stream: replace A once the MMAs of tile i have retired
+                mbar_wait(a_empty, 0);
+                tc_fence_after();
+                convert_a(s_first + 1);
+            }
+            const int ab = i & 1, s = i % RS;
+            mbar_wait(acc_full(ab), (i >> 1) & 1);
+            tc_fence_after();
+            float g[8];
+            tmem_ld8(tmem_base + lane_base + (uint32_t)(ab * 32 + mj * 16 + rh * 8), g);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(ab));
+            mbar_wait(st_full(s), (i / RS) & 1);
+            const uint32_t col = ring + s * STAGE + (uint32_t)((mj * 128 + q4 * 32 + lane) * 4 + rh * 8 * (RT_N * 4));
+#pragma unroll
+            for (int kr = 0; kr < 8; ++kr) {
+                const uint32_t sw = col + kr * (RT_N * 4), sm = sw + ARR, sv = sw + 2 * ARR;
+                float pp, mm, vv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pp) : "r"(sw));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mm) : "r"(sm));
+                const float gg = g[kr];
+                if (use_momentum) {
+                    mm = mm * mom + gg; pp = pp - (gg * lr + mm * mom * lr);
+                } else {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vv) : "r"(sv));
+                    mm = mm + (gg - mm) * omb1; vv = vv + (gg * gg - vv) * omb2;
+                    float rt, rc;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(vv));
+                    asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(rt + eps));
+                    pp = pp - (mm * lr_t) * rc;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sv), "f"(vv) : "memory");
+                }
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm), "f"(mm) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sw), "f"(pp) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(computed(s));  // release; the generic->async proxy fence runs once, on the TMA thread
+        }
+        pdl_launch_dependents();
+    }
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+static void encode_row_maps(dqn_learner* h, RowMaps& out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DQN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DQN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    const NetDesc& net = h->net;
+    float* slabs[3] = {h->online, h->slot_m, h->slot_v};
+    CUtensorMap* dst[3] = {out.w, out.m, out.v};
+    for (int a = 0; a < 3; ++a)
+        for (int st = 0; st < 2; ++st) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)net.hidden, (cuuint64_t)net.flat};
+            const cuuint64_t gstr[1] = {(cuuint64_t)net.hidden * 4};
+            const cuuint32_t box[2] = {RT_N, RT_ROWS}, estr[2] = {1, 1};
+            const CUresult r = ((EncodeFn)fn)(&dst[a][st], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, slabs[a] + net.off_fc_w[st], gdim, gstr, box,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            DQN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+        }
+}
+
+static inline bool rows_supported(const dqn_learner* h, int rows) {
+    const NetDesc& net = h->net;
+    return rows <= 32 && net.hidden == 2 * RT_N && net.flat % RT_ROWS == 0 && net.dueling && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;
+}
+
+static void launch_rows(dqn_learner* h, int rows, int ctas) {
+    const NetDesc& net = h->net;
+    if (!h->fa_row_maps) {
+        h->fa_row_maps = aligned_alloc(64, sizeof(RowMaps));
+        try { encode_row_maps(h, *static_cast<RowMaps*>(h->fa_row_maps)); } catch (...) { free(h->fa_row_maps); h->fa_row_maps = nullptr; throw; }
+    }
+    const RowMaps& maps = *static_cast<RowMaps*>(h->fa_row_maps);
+    const size_t bytes = (size_t)RS * 3 * RT_ROWS * RT_N * 4 + 2 * 2 * 16 * 128 + 256 + 1024;
+    auto go = [&](auto kern) {
+        DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        launch_kernel(h->pdl, kern, dim3(ctas), dim3(RT_THREADS), bytes, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid,
+                      rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum,
+                      (const dqn_learner::Scalars*)h->d_sc);
+    };
+    if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_rows_kernel<3>); else go(fcwg_adam_rows_kernel<1>);
+    h->launches++;
+}
+
 static inline bool supported(const dqn_learner* h, int rows) {
     const NetDesc& net = h->net;
     return rows <= 32 && net.flat % BM == 0 && net.hidden % FA_BN == 0 && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;

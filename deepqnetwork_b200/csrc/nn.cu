@@ -493,8 +493,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     };
     const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && rows <= 32 && fc_wgrad_adam_supported(h);
     // default for a whole step on one GPU: tcgen05 wgrad + optimizer in one pass with TMA-staged state (fcadam.cuh)
-    const bool tma_adam = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !h->fc_grads_needed && tcm && h->fc_tma_adam &&
-                          fa::supported(h, rows);
+    const bool rows_adam = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !h->fc_grads_needed && tcm && h->fc_rows_ctas > 0 &&
+                           fa::rows_supported(h, rows);
+    const bool tma_adam = rows_adam || (h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !h->fc_grads_needed && tcm &&
+                                        h->fc_tma_adam && fa::supported(h, rows));
     // unfused + optimizer inside backward: one wgrad launch per hidden stream, each on its own side stream, so that the
     // optimizer pass of stream 0 (HBM-bound) overlaps the weight gradient of stream 1 (tensor-bound)
     const bool split_fc = h->early_fc_adam && !h->fuse_fc_adam && !ffma_adam && !tma_adam && tcm && net.dueling && h->fc_split_streams;
@@ -551,7 +553,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         side_begin(h, saved, 0);
         if (tma_adam) {
             prof_mark(h, "fc_wgrad_adam");
-            fa::launch(h, rows);
+            if (rows_adam) fa::launch_rows(h, rows, h->fc_rows_ctas); else fa::launch(h, rows);
         } else if (ffma_adam) {
             prof_mark(h, "fc_wgrad_adam");
             launch_fc_wgrad_adam(h, rows, h->fc_grads_needed);
