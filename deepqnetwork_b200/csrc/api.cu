@@ -1175,6 +1175,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_tma_fwd") h->fc_tma_fwd = value != 0;
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
     else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
+    else if (n == "wg1_fit") h->wg1_fit = value != 0;
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels

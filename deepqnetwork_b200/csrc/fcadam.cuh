@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fcwg_adam_persist_kernel(const 
 // rows) apply the optimizer with approximate reciprocal / square root (2 ulp: the update term is lr * m / (sqrt(v) +
 // eps), so the weight sees < 1e-10 of it) -- with IEEE division and 8 warps the epilogue, not HBM, bound the pass.
 // A CTA walks a contiguous range of tiles (n-half fastest, then rows, then stream).
-constexpr int RS = 4, RT_THREADS = 576, RT_ROWS = 16, RT_N = 256;
+constexpr int RS = 4, RT_THREADS = 608, RT_ROWS = 16, RT_N = 256;  // 16 epilogue warps + MMA + TMA + B producer
 
 struct RowMaps { CUtensorMap w[2], m[2], v[2]; };  // box 256 (n) x 16 (k rows), SWIZZLE_NONE
 
@@ -507,6 +507,33 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
             }
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+    } else if (warp == 18) {
+        // ---------------- B producer: act3[b][k0 .. k0+15] -> B(kr, b) hi/lo; loads of the next tile are in flight while
+        // this one is stored (volatile asm keeps them where they are issued) ----------------
+        float v[16];
+        auto load_rows = [&](int i) {
+            int strm, k0, nh; coords(i < ntiles ? i : ntiles - 1, strm, k0, nh);
+            const float* p = act3 + (size_t)(lane < Bn ? lane : 0) * flat + k0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3]) : "l"(p + 4 * q));
+        };
+        if (ntiles > 0) load_rows(0);
+        for (int i = 0; i < ntiles; ++i) {
+            const int bb = i & 1, use = i >> 1;
+            if (use >= 1) mbar_wait(b_empty(bb), (use - 1) & 1);
+            const uint32_t bt = btiles + bb * 2 * B_TILE;
+#pragma unroll
+            for (int kr = 0; kr < 16; ++kr) {
+                const float x = lane < Bn ? v[kr] : 0.f;
+                const uint32_t a = bt + (uint32_t)((kr >> 3) * cv::PK_SBO + (lane >> 2) * cv::PK_LBO + (kr & 7) * 16 + (lane & 3) * 4);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+                if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(x)) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full(bb));
+            load_rows(i + 1);
+        }
     } else if (warp == 16) {
         // ---------------- MMA issue: 2 M tiles x 4 k-steps x NTERMS per tile ----------------
         const uint32_t idesc = make_idesc(16, false, false);
@@ -570,39 +597,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         };
-        auto produce_b = [&](int i) {  // warp 4: act3[b][k0 .. k0+15] -> B(kr, b) hi/lo
-            const int bb = i & 1, use = i >> 1;
-            if (use >= 1) mbar_wait(b_empty(bb), (use - 1) & 1);
-            int strm, k0, nh; coords(i, strm, k0, nh);
-            const uint32_t bt = btiles + bb * 2 * B_TILE;
-            float v[16];
-            if (lane < Bn) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(act3 + (size_t)lane * flat + k0 + 4 * q));
-                    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            }
-#pragma unroll
-            for (int kr = 0; kr < 16; ++kr) {
-                const uint32_t a = bt + (uint32_t)((kr >> 3) * cv::PK_SBO + (lane >> 2) * cv::PK_LBO + (kr & 7) * 16 + (lane & 3) * 4);
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[kr]) : "memory");
-                if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v[kr])) : "memory");
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_full(bb));
-        };
         if (warp < 4 && ntiles > 0) convert_a(s_first);
-        if (warp == 4 && ntiles > 0) produce_b(0);
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
         const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
         const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
         const int mj = grp & 1, rh = grp >> 1;                   // this warp: M tile mj of the tile, rows [8 rh, 8 rh + 8)
         for (int i = 0; i < ntiles; ++i) {
-            if (warp == 4 && i + 1 < ntiles) produce_b(i + 1);
             if (warp < 4 && i + 1 == i_sw && i_sw < ntiles) {
                 // the next tile belongs to the second stream: replace A once the MMAs of tile i have retired
                 mbar_wait(a_empty, 0);

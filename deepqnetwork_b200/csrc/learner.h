@@ -72,9 +72,10 @@ struct dqn_learner {
     bool act3_pk_valid[2] = {false, false};
     void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
     bool fc_tma_fwd = true;       // dense forward with TMA-streamed weights and packed activation tiles (fcfwd.cuh)
+    bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
     void* fa_row_maps = nullptr;  // fa::RowMaps
-    int fc_rows_ctas = 112;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
-                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  112 leaves 36 SMs to the conv chain (sweep: DESIGN.md)
+    int fc_rows_ctas = 100;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
+                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  100 leaves 48 SMs to the conv chain (sweep: DESIGN.md)
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)

@@ -575,7 +575,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             const int wstream = l == 2 ? 1 : l == 1 ? 3 : 4;
             side_begin(h, saved, wstream, 1);
             const int mt = ceil_div(mreal + 4, tcm ? tc::BM : 64);
-            int Z = ((tcm ? 1 : 2) * h->sm_count) / (mt * ceil_div(N, 64));
+            // conv1's wgrad runs last, next to the persistent dense wgrad+optimizer kernel: size it for the SMs that one leaves
+            int sms_avail = h->sm_count;
+            if (l == 0 && rows_adam && h->wg1_fit) sms_avail = std::max(32, h->sm_count - h->fc_rows_ctas);
+            int Z = ((tcm ? 1 : 2) * sms_avail) / (mt * ceil_div(N, 64));
             if (Z < 1) Z = 1; if (Z > 64) Z = 64;
             int kchunk = ceil_div(ceil_div(K, Z), 32) * 32;
             Z = ceil_div(K, kchunk);
