@@ -1057,7 +1057,7 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     h->prof_used = 0; h->prof_marks.clear();
     upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
     auto launches = [&]() {
-        h->early_fc_adam = true; h->fc_grads_needed = true;  // the seam-2 path keeps the full gradient slab readable
+        h->early_fc_adam = true; h->fc_grads_needed = h->keep_grads;  // option: keep the full gradient slab readable
         try {
             step_core(h, n, h->in_states, h->in_actions, h->in_rewards, h->in_cont, h->cfg.use_per ? h->in_isw : nullptr, 1, 1.0);
         } catch (...) { h->early_fc_adam = false; h->fc_grads_needed = false; throw; }
@@ -1176,6 +1176,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
     else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
     else if (n == "wg1_fit") h->wg1_fit = value != 0;
+    else if (n == "keep_grads") h->keep_grads = value != 0;  // dqn_train_batch: dense-kernel gradients stay readable (slot 3)
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels

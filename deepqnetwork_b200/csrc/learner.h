@@ -72,6 +72,8 @@ struct dqn_learner {
     bool act3_pk_valid[2] = {false, false};
     void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
     bool fc_tma_fwd = true;       // dense forward with TMA-streamed weights and packed activation tiles (fcfwd.cuh)
+    bool keep_grads = false;      // option: dqn_train_batch leaves the dense-kernel gradients in the slab (slot 3 read-back, parity
+                                  // tests); off: the fused dense wgrad+optimizer kernel runs there too and never writes them
     bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
     void* fa_row_maps = nullptr;  // fa::RowMaps
     int fc_rows_ctas = 100;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;

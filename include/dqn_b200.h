@@ -154,9 +154,11 @@ int dqn_train_steps(dqn_learner* h, int64_t n);
  * in the "grads" slab for an external all-reduce), phase 1 = optimizer + priority write-back.
  * grad_scale multiplies dL/dq (1/world_size for a global mean). */
 int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale);
-/* execution options (ablation / tests): "overlap" (fork independent kernels of a step onto a second stream, default 1),
- * "fuse_fc_adam" (apply the optimizer in the dense wgrad epilogue inside dqn_train_step(s); default 0: measured no
- * faster than the separate slab pass on B200 because the tile-wise read-modify-write loses DRAM page locality) */
+/* execution options (ablation / tests); the full table with defaults is in INTEGRATION.md section 4.  Every option keeps
+ * the results within the parity bars.  "keep_grads" (default 0): dqn_train_batch leaves the gradients of the dense
+ * hidden kernels readable through dqn_get_param(slot 3); with 0 they are consumed by the fused dense wgrad+optimizer
+ * kernel and slot 3 holds stale values for those two tensors.  "repack": call after writing weights through
+ * dqn_device_ptr. */
 int dqn_set_option(dqn_learner* h, const char* name, int32_t value);
 /* per-kernel launch counter since creation (bench.py reports gpu_launches from this) */
 int dqn_launch_count(const dqn_learner* h, int64_t* n);

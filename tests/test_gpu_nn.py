@@ -52,6 +52,7 @@ def make(cfg, batch=32, capacity=256, seed=0, math_mode='fp32'):
             if k.endswith('/bias'):
                 p[k] = (rng.normal(0, 0.05, p[k].shape)).astype(np.float32)
     L.set_tower(on, 0); L.set_tower(tg, 1)
+    L.set_option('keep_grads', 1)  # the parity tests read the gradient slab (slot 3) after train_batch
     return L, spec, shapes, on, tg
 
 
@@ -408,3 +409,24 @@ def test_kernel_variants_agree(name, opts):
         err = np.abs(ref[0][k] - got[0][k])
         assert float(np.mean(err > 1e-5 * scale + 2.5 * 0.00025 * 3)) == 0.0, k
         assert float(np.mean(err > 1e-5 * scale)) < 5e-2, k  # Adam turns a gradient within rounding of 0 into +-lr
+
+
+def test_train_batch_default_path_uses_fused_dense_kernel_and_agrees():
+    """dqn_train_batch without keep_grads (the default, what the e2e seam path runs) applies the dense-kernel update with
+    the fused row kernel; weights agree with the gradient-keeping path at the parity bar (1e-4 of the tensor scale; the two paths sum the 3xTF32
+    products in a different order and Adam amplifies gradients within rounding of 0), optimizer slots to 1e-3."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    out = []
+    for keep in (1, 0):
+        L, spec, shapes, on, tg = make(cfg, math_mode='tc3x')
+        L.set_option('keep_grads', keep)
+        for it in range(3):
+            b = rand_batch(cfg, 32, 100 + it)
+            w = np.random.default_rng(it).uniform(0.3, 1.0, 32).astype(np.float32)
+            L.train_batch(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'], w)
+        out.append((L.get_tower(0), L.get_tower(0, slot=1), L.get_tower(0, slot=2)))
+        L.close()
+    for slot, tol in ((0, 1e-4), (1, 1e-3), (2, 1e-3)):
+        for k in out[0][slot]:
+            scale = float(np.abs(out[0][slot][k]).max()) + 1e-20
+            assert float(np.abs(out[0][slot][k] - out[1][slot][k]).max()) <= tol * scale, (slot, k)
