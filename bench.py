@@ -168,7 +168,9 @@ def clocks_sampler_stop(handle, device_index):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind a profile name, from the ncu --set full
 # capture committed as profiles/r01c_top_kernels_raw.csv (adam_kernel: 62.9 MB read + 1.0-2.4 MB written per launch;
 # the stores are still dirty in L2 when the kernel ends)
-NCU_TRAFFIC = {'optimizer_fc': 62.92e6 + 0.92e6, 'optimizer_fc1': 62.92e6 + 2.35e6}
+NCU_TRAFFIC = {'optimizer_fc': 62.92e6 + 0.92e6, 'optimizer_fc1': 62.92e6 + 2.35e6,
+               # fcwg_adam_rows_kernel (profiles/r01d_fused_dense_kernel_raw.csv): 95.8 MB read + 36.7 MB written per launch
+               'fc_wgrad_adam': 95.77e6 + 36.72e6}
 
 
 def measured_peak_hbm():
