@@ -481,8 +481,11 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
 // converters and the MMA thread work on tile i+1.
 constexpr int WG_THREADS = 512;  // warps 0-7 converters, 8 MMA, 9 bias row, 10-11 idle, 12-15 epilogue
 
-template <int BN, int NTERMS>
-__global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+// U8IN (conv1): the layer input is the uint8 frame stack itself.  The image is staged as bytes (one pixel = 4 bytes, rows
+// zero-padded, NOT phase-split: the 32 lanes of a warp are the (kw, ci) of one kernel row and read 32 consecutive bytes)
+// and the converter applies cast / 255 (deep_q_model.py:226-227, exactly rounded) before the hi/lo split.
+template <int BN, int NTERMS, bool U8IN>
+__global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __restrict__ xin, const float* __restrict__ dy,
                                                                 float* __restrict__ part, const ImgGeom g, int mreal,
                                                                 int mtiles_per_cta, const float* __restrict__ zeros) {
     constexpr int S = 6, ACOLS = BK * (NTERMS == 3 ? 2 : 1), B_TILE = BN * 128, B_KB = B_TILE * 2;
@@ -513,14 +516,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __r
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    const int u8_row = ((g.ow - 1) * g.s + g.k) * g.cin;  // U8IN: bytes per padded image row
     for (int p = tid; p < nkb * 32; p += WG_THREADS) {
         const int oy = p / g.ow, ox = p - oy * g.ow;
-        const int off = p < npix ? (oy * g.s * g.wcols + ox) * g.pitch : 0;  // padding pixels: any finite data (B is 0 there)
+        // padding pixels: any finite data (B is 0 there)
+        const int off = p >= npix ? 0 : U8IN ? oy * g.s * u8_row + ox * g.s * g.cin : (oy * g.s * g.wcols + ox) * g.pitch;
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(pixtab + 4u * p), "r"(off) : "memory");
     }
     pdl_wait();
     // ---- stage the image and dY (all threads) ----
-    load_image_async(img, x + (size_t)image * g.ih * g.iw * g.cin, g, tid, WG_THREADS, zeros);
+    if constexpr (U8IN) {
+        // 8-byte cp.async chunks: a padded row = [pl pixels of zeros][iw pixels][zeros]; pl * cin and iw * cin are multiples of 8
+        const uint8_t* src_img = static_cast<const uint8_t*>(xin) + (size_t)image * g.ih * g.iw * g.cin;
+        const int cpr = u8_row / 8, first = g.pl * g.cin / 8, ncopy = g.iw * g.cin / 8;
+        for (int q = tid; q < g.hp * cpr; q += WG_THREADS) {
+            const int iyp = q / cpr, c = q - iyp * cpr;
+            const int iy = iyp - g.pt, cc = c - first;
+            const bool ok = (unsigned)iy < (unsigned)g.ih && (unsigned)cc < (unsigned)ncopy;
+            const void* src = ok ? (const void*)(src_img + (size_t)iy * g.iw * g.cin + cc * 8) : (const void*)zeros;
+            const uint32_t n = ok ? 8u : 0u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(img + (uint32_t)(iyp * u8_row + c * 8)), "l"(src), "r"(n) : "memory");
+        }
+    } else {
+        load_image_async(img, static_cast<const float*>(xin) + (size_t)image * g.ih * g.iw * g.cin, g, tid, WG_THREADS, zeros);
+    }
     {
         // dY[p][co] -> B(co, p): a warp covers 4 pixels x 8 channels per pass, lane = (p % 4) + 4 * (co % 8), so the
         // 32 scalar stores of a pass fall into 32 consecutive words of one core matrix (conflict-free)
@@ -558,7 +577,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __r
             if (m < mreal) {
                 const int tap = m / g.cin, ci = m - tap * g.cin;
                 const int kh = tap / g.k, kw = tap - kh * g.k;
-                base = img + (uint32_t)((kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + ci * 4);
+                base = img + (U8IN ? (uint32_t)(kh * u8_row + kw * g.cin + ci)
+                                   : (uint32_t)((kh * g.wcols + (kw % g.s) * g.wps + kw / g.s) * g.pitch + ci * 4));
             }
             const int step_end = (mt - mt0 + 1) * nkb;
             for (; step < step_end; step += 2) {
@@ -571,10 +591,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __r
                     uint32_t o0, o1, o2, o3;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3)
                                  : "r"(pixtab + 4u * (kb * 32 + q * 4)));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q]) : "r"(base + o0));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 1]) : "r"(base + o1));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 2]) : "r"(base + o2));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 3]) : "r"(base + o3));
+                    if constexpr (U8IN) {
+                        uint32_t b0, b1, b2, b3;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b0) : "r"(base + o0));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b1) : "r"(base + o1));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(base + o2));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b3) : "r"(base + o3));
+                        hi[4 * q] = u8_to_unit(b0); hi[4 * q + 1] = u8_to_unit(b1); hi[4 * q + 2] = u8_to_unit(b2); hi[4 * q + 3] = u8_to_unit(b3);
+                    } else {
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q]) : "r"(base + o0));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 1]) : "r"(base + o1));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 2]) : "r"(base + o2));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[4 * q + 3]) : "r"(base + o3));
+                    }
                 }
                 const uint32_t ta = tmem_a(s) + lane_base;
                 ts::tmem_st32(ta, hi);
@@ -682,24 +711,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const float* __r
     }
 }
 
-// true if launched: part[image][mreal + 4][N] holds the per-image partial sums (bias row at m = mreal)
+// true if launched: part[image][mreal + 4][N] holds the per-image partial sums (bias row at m = mreal).  u8_states: the
+// layer input is the uint8 batch (conv1)
 template <int BN, int NTERMS>
-static bool launch_wgrad(dqn_learner* h, const float* x, const float* dy, float* part, const ImgGeom& g, int images) {
+static bool launch_wgrad(dqn_learner* h, const void* x, bool u8_states, const float* dy, float* part, const ImgGeom& g, int images) {
     const int mreal = g.k * g.k * g.cin;
     const int npix = g.oh * g.ow, nkb = (npix + 31) / 32;
-    if (g.cin % 32 != 0 || npix > 128 || g.cout != BN) return false;
-    const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + g.img_bytes + 1024 + 128;
+    if (g.cout != BN) return false;
+    size_t img_bytes;
+    if (u8_states) {
+        if (g.cin != 4 || g.k != 8 || (g.pl * g.cin) % 8 != 0 || (g.iw * g.cin) % 8 != 0 || mreal % BM != 0) return false;
+        const int u8_row = ((g.ow - 1) * g.s + g.k) * g.cin;
+        if (u8_row % 8 != 0) return false;
+        img_bytes = (size_t)g.hp * u8_row + 64;
+    } else {
+        if (g.cin % 32 != 0 || npix > 128) return false;
+        img_bytes = g.img_bytes;
+    }
+    const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + img_bytes + 1024 + 128;
     if (bytes > 227 * 1024) return false;
     const int mtiles = (mreal + BM - 1) / BM;
     const int per_cta = mtiles >= 8 ? mtiles / 2 : mtiles;  // two CTAs per image once an image carries >= 8 M tiles
-    auto kern = cvwgrad_kernel<BN, NTERMS>;
-    static size_t configured = 0;
-    if (bytes > configured) {
+    auto go = [&](auto kern) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
-    }
-    launch_kernel(h->pdl, kern, dim3(images, (mtiles + per_cta - 1) / per_cta), dim3(WG_THREADS), bytes, h->stream, x, dy, part, g, mreal,
-                  per_cta, (const float*)h->zeros16);
+        launch_kernel(h->pdl, kern, dim3(images, (mtiles + per_cta - 1) / per_cta), dim3(WG_THREADS), bytes, h->stream, x, dy, part, g, mreal,
+                      per_cta, (const float*)h->zeros16);
+    };
+    if (u8_states) go(cvwgrad_kernel<BN, NTERMS, true>); else go(cvwgrad_kernel<BN, NTERMS, false>);
     h->launches++;
     return true;
 }

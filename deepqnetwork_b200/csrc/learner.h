@@ -185,6 +185,7 @@ struct dqn_learner {
     float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
     int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
+    bool img_wgrad1 = true;     // option: conv1 wgrad through the image-resident kernel on the uint8 frames
     bool merge_towers = true;   // option: conv layers of the online and the target tower in one launch each
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows

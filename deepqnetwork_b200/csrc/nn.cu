@@ -588,12 +588,14 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             const void* in0 = tcm ? (const void*)x_f32 : (const void*)d_states;
             bool done = false;
             cv::ImgGeom q;
-            if (tcm && h->img_conv && l > 0 && rows <= 64 && cv::img_geom(g, q)) {
-                // image-resident kernel: one partial per image (Z = rows), summed in image order by the reduce below
-                const float* xin = acts.act[l - 1];
+            if (tcm && h->img_conv && (l > 0 || h->img_wgrad1) && rows <= 64 && cv::img_geom(g, q)) {
+                // image-resident kernel: one partial per image (Z = rows), summed in image order by the reduce below;
+                // conv1 reads the uint8 frame stack itself
+                const void* xin = l == 0 ? (const void*)d_states : (const void*)acts.act[l - 1];
+                const bool u8 = l == 0;
                 const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
-                if (N == 64) done = x3 ? cv::launch_wgrad<64, 3>(h, xin, h->d_act[l], part, q, rows) : cv::launch_wgrad<64, 1>(h, xin, h->d_act[l], part, q, rows);
-                else if (N == 32) done = x3 ? cv::launch_wgrad<32, 3>(h, xin, h->d_act[l], part, q, rows) : cv::launch_wgrad<32, 1>(h, xin, h->d_act[l], part, q, rows);
+                if (N == 64) done = x3 ? cv::launch_wgrad<64, 3>(h, xin, u8, h->d_act[l], part, q, rows) : cv::launch_wgrad<64, 1>(h, xin, u8, h->d_act[l], part, q, rows);
+                else if (N == 32) done = x3 ? cv::launch_wgrad<32, 3>(h, xin, u8, h->d_act[l], part, q, rows) : cv::launch_wgrad<32, 1>(h, xin, u8, h->d_act[l], part, q, rows);
                 if (done) Z = rows;
             }
             if (!done) {
