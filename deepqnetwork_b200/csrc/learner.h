@@ -76,8 +76,8 @@ struct dqn_learner {
                                   // tests); off: the fused dense wgrad+optimizer kernel runs there too and never writes them
     bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
     void* fa_row_maps = nullptr;  // fa::RowMaps
-    int fc_rows_ctas = 100;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
-                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  100 leaves 48 SMs to the conv chain (sweep: DESIGN.md)
+    int fc_rows_ctas = 148;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
+                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  clamped to the SM count; sweep after conv1's wgrad moved to the image-resident kernel: 108 -> 5913, 124 -> 6027, 148 -> 6081 steps/s
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)

@@ -553,7 +553,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
         side_begin(h, saved, 0);
         if (tma_adam) {
             prof_mark(h, "fc_wgrad_adam");
-            if (rows_adam) fa::launch_rows(h, rows, h->fc_rows_ctas); else fa::launch(h, rows);
+            if (rows_adam) fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count)); else fa::launch(h, rows);
         } else if (ffma_adam) {
             prof_mark(h, "fc_wgrad_adam");
             launch_fc_wgrad_adam(h, rows, h->fc_grads_needed);
