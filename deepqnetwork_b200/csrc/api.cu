@@ -168,9 +168,9 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             wg_total += need;
         }
         dmalloc(h->wg_part, (size_t)wg_total);
-        dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4); dmalloc(h->opt_ticket, 1);
+        dmalloc(h->zeros16, 4); dmalloc(h->ones_row, 4); dmalloc(h->opt_ticket, 4); h->fa_tile_ctr = h->opt_ticket + 1;
         DQN_CUDA_OK(cudaMemsetAsync(h->zeros16, 0, 16, h->stream));
-        DQN_CUDA_OK(cudaMemsetAsync(h->opt_ticket, 0, 4, h->stream));
+        DQN_CUDA_OK(cudaMemsetAsync(h->opt_ticket, 0, 16, h->stream));
         {
             const float one[4] = {1.f, 0.f, 0.f, 0.f};
             DQN_CUDA_OK(cudaMemcpyAsync(h->ones_row, one, 16, cudaMemcpyHostToDevice, h->stream));

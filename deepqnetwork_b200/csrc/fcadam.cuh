@@ -429,7 +429,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                                                                        int Bn, int flat, int NH, int hid,
                                                                        const __grid_constant__ RowMaps maps,
                                                                        float lr, float mom, int use_momentum,
-                                                                       const dqn_learner::Scalars* __restrict__ sc) {
+                                                                       const dqn_learner::Scalars* __restrict__ sc,
+                                                                       unsigned int* __restrict__ tile_ctr) {
+    // Tiles are claimed DYNAMICALLY (atomic counter, stream-major order, so a CTA sees at most one switch of stream): the CTAs of this low-priority
+    // kernel get their SMs at different times -- whenever the conv chain of the backward pass leaves some free -- and
+    // with a static partition the late starters, each still holding a full share, ended the kernel ~15 us late.
     constexpr uint32_t ARR = RT_ROWS * RT_N * 4, STAGE = 3 * ARR, B_TILE = 16 * 128;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
@@ -443,24 +447,18 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
     auto acc_full = [&](int b) { return bars + 8u * (2 * RS + 4 + b); };
     auto acc_empty = [&](int b) { return bars + 8u * (2 * RS + 6 + b); };
     const uint32_t a_full = bars + 8u * (2 * RS + 8), a_empty = bars + 8u * (2 * RS + 9), tmem_slot = bars + 8u * (2 * RS + 10);
+    const uint32_t tile_ids = bars + 8u * (2 * RS + 12);      // int[RS]: tile claimed for ring slot s, -1 = no more tiles
+    auto id_full = [&](int s) { return bars + 8u * (2 * RS + 14 + s); };  // tile id of slot s published (at claim time, before its data lands)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int halves = hid / RT_N;                             // 2
-    const int tiles_per_stream = (flat / RT_ROWS) * halves, nstreams = NH / hid, total = tiles_per_stream * nstreams;
-    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
-    const int ntiles = t1 - t0;
+    const int per_stream = (flat / RT_ROWS) * halves;          // tile t: stream t / per_stream, rows [16 ((t % per_stream) / halves), +16), n half t % halves
+    const int ntotal = per_stream * (NH / hid);
     const int narr = use_momentum ? 2 : 3;
-    // tile t: stream = t / tiles_per_stream, then row block = (t % tiles_per_stream) / halves, n half = t % halves.  A CTA's
-    // range crosses the stream boundary at most once; i_sw = first local tile of the second stream (ntiles if none)
-    const int s_first = t0 / tiles_per_stream;
-    const int i_sw = min(ntiles, max(0, (s_first + 1) * tiles_per_stream - t0));
-    auto coords = [&](int i, int& strm, int& row0, int& nh) {
-        const int t = t0 + i; strm = t / tiles_per_stream;
-        const int r = t - strm * tiles_per_stream; row0 = (r / halves) * RT_ROWS; nh = r % halves;
-    };
+    auto tile_of = [&](int s) { int t; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t) : "r"(tile_ids + 4u * s)); return t; };
 
     if (tid == 0) {
-        for (int s = 0; s < RS; ++s) { mbar_init(st_full(s), 1); mbar_init(computed(s), 16); }
+        for (int s = 0; s < RS; ++s) { mbar_init(st_full(s), 1); mbar_init(computed(s), 16); mbar_init(id_full(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(b_full(b), 1); mbar_init(b_empty(b), 1); mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 16); }
         mbar_init(a_full, 4); mbar_init(a_empty, 1);
         fence_barrier_init();
@@ -479,47 +477,55 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
     auto tmem_a = [&](int mt) { return tmem_base + 64u + (uint32_t)mt * 64u; };
 
     if (warp == 17) {
-        if (lane == 0 && ntiles > 0) {
-            auto issue_loads = [&](int i) {
-                int strm, row0, nh; coords(i, strm, row0, nh);
+        if (lane == 0) {
+            // claim a tile for ring slot i % RS and start its loads; past the last tile publish -1 (the barrier still completes)
+            auto publish = [&](int i) {
                 const int s = i % RS;
+                const int t = (int)atomicAdd(tile_ctr, 1u);
+                const int tt = t < ntotal ? t : -1;
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_ids + 4u * s), "r"(tt) : "memory");
+                mbar_arrive(id_full(s));  // release: the B producer and the MMA warp may look at the id now
+                if (tt < 0) { mbar_arrive(st_full(s)); return; }
+                const int strm = tt / per_stream, r = tt - strm * per_stream;
+                const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
                 const uint32_t st = ring + s * STAGE;
                 cv::mbar_expect_tx(st_full(s), (uint32_t)(narr * ARR));
                 tma_load_2d(st, &maps.w[strm], nh * RT_N, row0, st_full(s));
                 tma_load_2d(st + ARR, &maps.m[strm], nh * RT_N, row0, st_full(s));
                 if (!use_momentum) tma_load_2d(st + 2 * ARR, &maps.v[strm], nh * RT_N, row0, st_full(s));
             };
-            for (int j = 0; j < RS - 1 && j < ntiles; ++j) issue_loads(j);
-            for (int i = 0; i < ntiles; ++i) {
+            for (int j = 0; j < RS - 1; ++j) publish(j);
+            for (int i = 0;; ++i) {
                 const int s = i % RS;
+                const int tt = tile_of(s);
+                if (tt < 0) break;
                 mbar_wait(computed(s), (i / RS) & 1);
                 fence_proxy_async();  // the epilogue warps' shared-memory writes -> visible to the TMA stores
-                int strm, row0, nh; coords(i, strm, row0, nh);
+                const int strm = tt / per_stream, r = tt - strm * per_stream;
+                const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
                 const uint32_t st = ring + s * STAGE;
                 tma_store_2d(&maps.w[strm], nh * RT_N, row0, st);
                 tma_store_2d(&maps.m[strm], nh * RT_N, row0, st + ARR);
                 if (!use_momentum) tma_store_2d(&maps.v[strm], nh * RT_N, row0, st + 2 * ARR);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (i + RS - 1 < ntiles) {
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // stage (i - 1) % RS has been read by its stores
-                    issue_loads(i + RS - 1);
-                }
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // stage (i - 1) % RS has been read by its stores
+                publish(i + RS - 1);
             }
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     } else if (warp == 18) {
-        // ---------------- B producer: act3[b][k0 .. k0+15] -> B(kr, b) hi/lo; loads of the next tile are in flight while
-        // this one is stored (volatile asm keeps them where they are issued) ----------------
-        float v[16];
-        auto load_rows = [&](int i) {
-            int strm, k0, nh; coords(i < ntiles ? i : ntiles - 1, strm, k0, nh);
+        // ---------------- B producer: act3[b][k0 .. k0+15] -> B(kr, b) hi/lo ----------------
+        for (int i = 0;; ++i) {
+            const int s = i % RS;
+            mbar_wait(id_full(s), (i / RS) & 1);
+            const int tt = tile_of(s);
+            if (tt < 0) break;
+            const int k0 = ((tt % per_stream) / halves) * RT_ROWS;
+            float v[16];
             const float* p = act3 + (size_t)(lane < Bn ? lane : 0) * flat + k0;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3]) : "l"(p + 4 * q));
-        };
-        if (ntiles > 0) load_rows(0);
-        for (int i = 0; i < ntiles; ++i) {
             const int bb = i & 1, use = i >> 1;
             if (use >= 1) mbar_wait(b_empty(bb), (use - 1) & 1);
             const uint32_t bt = btiles + bb * 2 * B_TILE;
@@ -532,22 +538,31 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full(bb));
-            load_rows(i + 1);
         }
     } else if (warp == 16) {
         // ---------------- MMA issue: 2 M tiles x 4 k-steps x NTERMS per tile ----------------
         const uint32_t idesc = make_idesc(16, false, false);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        for (int i = 0; i < ntiles; ++i) {
+        int a_strm = -1, a_gen = 0;  // stream whose dH^T is in tensor memory, number of conversions seen
+        for (int i = 0;; ++i) {
+            const int s = i % RS;
+            mbar_wait(id_full(s), (i / RS) & 1);
+            const int tt = tile_of(s);
+            if (tt < 0) break;
+            const int strm = tt / per_stream, nh = tt % halves;
+            if (strm != a_strm) {
+                // first tile of a stream: (after the first) let the converters replace A once every MMA issued so far has retired
+                if (a_strm >= 0 && leader) mma_commit(a_empty);
+                __syncwarp();
+                mbar_wait(a_full, a_gen & 1);
+                ++a_gen; a_strm = strm;
+            }
             const int bb = i & 1, use = i >> 1;
-            if (i == 0) mbar_wait(a_full, 0);
-            if (i == i_sw && i_sw > 0) mbar_wait(a_full, 1);  // dH^T of the second stream has replaced the first
             mbar_wait(b_full(bb), use & 1);
             if (use >= 1) mbar_wait(acc_empty(bb), (use - 1) & 1);
             fence_proxy_async();  // B slice was written through the generic proxy
             tc_fence_after();
-            int strm, row0, nh; coords(i, strm, row0, nh);
             if (leader) {
                 const uint32_t bt = btiles + bb * 2 * B_TILE;
                 const uint64_t db = make_desc(bt, cv::PK_LBO, cv::PK_SBO), dbl = make_desc(bt + B_TILE, cv::PK_LBO, cv::PK_SBO);
@@ -568,7 +583,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                 }
                 mma_commit(b_empty(bb));
                 mma_commit(acc_full(bb));
-                if (i + 1 == i_sw && i_sw < ntiles) mma_commit(a_empty);  // last tile of the first stream: A may be replaced
             }
             __syncwarp();
         }
@@ -597,19 +611,21 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         };
-        if (warp < 4 && ntiles > 0) convert_a(s_first);
+        int a_strm = -1;
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
         const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
         const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
         const int mj = grp & 1, rh = grp >> 1;                   // this warp: M tile mj of the tile, rows [8 rh, 8 rh + 8)
-        for (int i = 0; i < ntiles; ++i) {
-            if (warp < 4 && i + 1 == i_sw && i_sw < ntiles) {
-                // the next tile belongs to the second stream: replace A once the MMAs of tile i have retired
-                mbar_wait(a_empty, 0);
-                tc_fence_after();
-                convert_a(s_first + 1);
-            }
+        for (int i = 0;; ++i) {
             const int ab = i & 1, s = i % RS;
+            mbar_wait(st_full(s), (i / RS) & 1);
+            const int tt = tile_of(s);
+            if (tt < 0) break;
+            if (warp < 4 && tt / per_stream != a_strm) {
+                if (a_strm >= 0) { mbar_wait(a_empty, 0); tc_fence_after(); }  // MMAs of the previous stream have retired
+                a_strm = tt / per_stream;
+                convert_a(a_strm);
+            }
             mbar_wait(acc_full(ab), (i >> 1) & 1);
             tc_fence_after();
             float g[8];
@@ -617,7 +633,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(ab));
-            mbar_wait(st_full(s), (i / RS) & 1);
             const uint32_t col = ring + s * STAGE + (uint32_t)((mj * 128 + q4 * 32 + lane) * 4 + rh * 8 * (RT_N * 4));
 #pragma unroll
             for (int kr = 0; kr < 8; ++kr) {
@@ -688,11 +703,12 @@ static void launch_rows(dqn_learner* h, int rows, int ctas) {
     }
     const RowMaps& maps = *static_cast<RowMaps*>(h->fa_row_maps);
     const size_t bytes = (size_t)RS * 3 * RT_ROWS * RT_N * 4 + 2 * 2 * 16 * 128 + 256 + 1024;
+    // (the tile counter is zeroed by optimizer_tail_kernel at the end of every step: no memset node in front of this launch)
     auto go = [&](auto kern) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(ctas), dim3(RT_THREADS), bytes, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid,
                       rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum,
-                      (const dqn_learner::Scalars*)h->d_sc);
+                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr);
     };
     if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_rows_kernel<3>); else go(fcwg_adam_rows_kernel<1>);
     h->launches++;

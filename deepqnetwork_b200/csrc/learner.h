@@ -75,6 +75,7 @@ struct dqn_learner {
     bool keep_grads = false;      // option: dqn_train_batch leaves the dense-kernel gradients in the slab (slot 3 read-back, parity
                                   // tests); off: the fused dense wgrad+optimizer kernel runs there too and never writes them
     bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
+    unsigned int* fa_tile_ctr = nullptr;  // dynamic tile counter of the fused dense kernel (= opt_ticket + 1, zeroed by the optimizer tail)
     void* fa_row_maps = nullptr;  // fa::RowMaps
     int fc_rows_ctas = 148;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
                                   // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  clamped to the SM count; sweep after conv1's wgrad moved to the image-resident kernel: 108 -> 5913, 124 -> 6027, 148 -> 6081 steps/s

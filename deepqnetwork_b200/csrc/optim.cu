@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
         __threadfence();
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             *ticket = 0;
+            ticket[1] = 0;  // tile counter of the fused dense wgrad+optimizer kernel (fcadam.cuh): ready for the next step
             sc->step += 1;
             sc->b1p_prev = sc->b1p; sc->b2p_prev = sc->b2p;
             if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
