@@ -26,6 +26,7 @@ CONFIGS = {
     'c3_mspacman_ddp': dict(h=86, w=80, a=9, dueling=True, double=True, per=True),
     'double_only_momentum': dict(h=89, w=80, a=6, dueling=False, double=True, per=False, momentum=True),
     'dueling_only': dict(h=86, w=80, a=9, dueling=True, double=False, per=False),
+    'c2_momentum': dict(h=89, w=80, a=4, dueling=True, double=True, per=True, momentum=True),
     'nature84': dict(h=84, w=84, a=4, dueling=False, double=False, per=False, variant='nature'),
     'nature84_ddp': dict(h=84, w=84, a=4, dueling=True, double=True, per=True, variant='nature'),
 }
@@ -376,6 +377,17 @@ def test_scheduling_options_are_bit_identical(opts):
         for k in ref[slot]:
             assert np.array_equal(ref[slot][k], got[slot][k]), (slot, k)
     assert np.array_equal(ref[3], got[3])
+
+
+def test_fused_row_kernel_momentum_matches_split_path():
+    """Same comparison for the Nesterov-momentum optimizer (MomentumOptimizer, deep_q_model.py:385): no division, so the two
+    paths differ only by the summation order of the gradient."""
+    ref = _run_steps('c2_momentum', dict(fc_rows_ctas=0))
+    got = _run_steps('c2_momentum', dict(fc_rows_ctas=148))
+    for slot in (0, 1):
+        for k in ref[slot]:
+            scale = float(np.abs(ref[slot][k]).max()) + 1e-20
+            assert float(np.abs(ref[slot][k] - got[slot][k]).max()) <= 1e-5 * scale, (slot, k)
 
 
 @pytest.mark.parametrize('ctas', [112, 148, 61])
