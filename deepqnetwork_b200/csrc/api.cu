@@ -1184,6 +1184,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
+    else if (n == "pack_in_tail") h->pack_in_tail = value != 0;
     else if (n == "img_wgrad1") h->img_wgrad1 = value != 0;
     else if (n == "merge_towers") h->merge_towers = value != 0;
     else if (n == "prefetch") h->prefetch = value != 0;

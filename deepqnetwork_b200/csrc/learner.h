@@ -186,6 +186,7 @@ struct dqn_learner {
     float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
     int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
+    bool pack_in_tail = true;   // option: optimizer_tail_kernel re-packs the conv weights it updates (no separate pack launch)
     bool img_wgrad1 = true;     // option: conv1 wgrad through the image-resident kernel on the uint8 frames
     bool merge_towers = true;   // option: conv layers of the online and the target tower in one launch each
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
@@ -260,7 +261,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
 bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
 void tower_fc_forward(dqn_learner* h, const float* params, int rows, TowerActs& acts);  // dense + heads after the conv stack
 void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of the packed conv weights
-void launch_pack_conv(dqn_learner* h, int tower);  // re-pack one tower's conv weights from its parameter slab
+void launch_pack_conv(dqn_learner* h, int tower);
+bool dgrad_pack_ok(const dqn_learner* h, int layer);  // nn.cu: layer has a packed dgrad operand (cv::dgrad_geom)  // re-pack one tower's conv weights from its parameter slab
 void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n);
 int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, int b_kcontig, const float* dA, const float* dB, float* dC);
 

@@ -230,6 +230,11 @@ void alloc_packed_conv(dqn_learner* h) {
     DQN_CUDA_OK(cudaMalloc(&h->packed_dg, (size_t)offd * sizeof(float)));
 }
 
+bool dgrad_pack_ok(const dqn_learner* h, int layer) {
+    cv::ImgGeom q; cv::Bands bd;
+    return cv::dgrad_geom(h->net.conv[layer], q, bd);
+}
+
 void launch_pack_conv(dqn_learner* h, int tower) {
     if (h->cfg.math_mode == DQN_MATH_FP32 || !h->packed[tower]) return;
     const float* P = tower ? h->target : h->online;

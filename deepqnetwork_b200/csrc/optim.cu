@@ -205,10 +205,48 @@ void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g) {
 // read by every CTA before its ticket is taken, so the update cannot race with them.
 struct OptRanges { long long beg4[3], n4[3]; int count; };
 
+// The conv kernels this launch updates are re-packed on the spot for the image-resident conv kernels (cvgemm.cuh:
+// [k-block][hi, lo][rows x 32 k] tiles in the dense K-major UMMA layout; dgrad: per stride class, flipped / transposed),
+// which saves the separate pack launch at the very end of every step.
+struct TailPack {
+    int n;
+    struct L { long long w0; int KN, N, k, s, cin, cout; float* fwd; float* dg; } l[3];
+};
+__device__ __forceinline__ void tail_pack4(const TailPack::L& q, int e, const float4& w) {
+    const float v[4] = {w.x, w.y, w.z, w.w};
+    const int kk = e / q.N, n = e - kk * q.N;  // HWIO: e = kk * cout + n, the four values are n .. n+3 of one kk
+    {
+        const int kb = kk >> 5, kin = kk & 31;
+        const size_t tile = (size_t)q.N * 32;
+        float* o = q.fwd + (size_t)kb * 2 * tile + (((n >> 3) * 1024 + (kin >> 2) * 128 + (n & 7) * 16 + (kin & 3) * 4) >> 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[4 * j] = v[j];
+            o[4 * j + tile] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+        }
+    }
+    if (q.dg) {
+        const int tap = kk / q.cin, ci = kk - tap * q.cin;
+        const int kh = tap / q.k, kw = tap - kh * q.k;
+        const int kt = q.k / q.s, Kc = kt * kt * q.cout;
+        const int cls = (kh % q.s) * q.s + (kw % q.s);
+        const int th = kt - 1 - kh / q.s, tw = kt - 1 - kw / q.s;
+        const int k2 = (th * kt + tw) * q.cout + n;  // co = n .. n+3 -> four consecutive k of the dgrad operand
+        const int kb = cls * (Kc >> 5) + (k2 >> 5), kin = k2 & 31;
+        const size_t tile = (size_t)q.cin * 32;
+        float* o = q.dg + (size_t)kb * 2 * tile + (((ci >> 3) * 1024 + (kin >> 2) * 128 + (ci & 7) * 16) >> 2);
+        *reinterpret_cast<float4*>(o) = w;
+        *reinterpret_cast<float4*>(o + tile) = make_float4(v[0] - __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u),
+                                                           v[1] - __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u),
+                                                           v[2] - __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u),
+                                                           v[3] - __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u));
+    }
+}
+
 __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                              const float4* __restrict__ g, OptRanges rg, float lr, float mom,
                                                              int use_momentum, dqn_learner::Scalars* sc,
-                                                             unsigned int* __restrict__ ticket) {
+                                                             unsigned int* __restrict__ ticket, const TailPack tp) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -230,6 +268,9 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
                 v[o + i] = vv;
             }
             m[o + i] = mm; p[o + i] = pp;
+            const long long e = (long long)(o + i) * 4;
+            for (int l = 0; l < tp.n; ++l)
+                if (e >= tp.l[l].w0 && e < tp.l[l].w0 + tp.l[l].KN) tail_pack4(tp.l[l], (int)(e - tp.l[l].w0), pp);
         }
     }
     __syncthreads();
@@ -261,14 +302,24 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
         if (net.dueling) { add(net.off_fc_w[0] + fcw, net.off_fc_w[1]); add(net.off_fc_w[1] + fcw, net.slab); }
         else add(net.off_fc_w[0] + fcw, net.slab);
     }
+    TailPack tp; tp.n = 0;
+    if (h->pack_in_tail && h->cfg.math_mode != DQN_MATH_FP32 && h->packed[0]) {
+        for (int l = 0; l < 3; ++l) {
+            const ConvGeom& g = net.conv[l];
+            const int K = g.k * g.k * g.cin, N = g.cout;
+            if (K % 32 != 0 || N % 4 != 0) { tp.n = 0; break; }
+            tp.l[tp.n++] = {net.off_cw[l], K * N, N, g.k, g.s, g.cin, g.cout, h->packed[0] + h->pk_off[l],
+                            (l > 0 && h->packed_dg && dgrad_pack_ok(h, l)) ? h->packed_dg + h->pkd_off[l] : nullptr};
+        }
+    }
     long long most = 1;
     for (int q = 0; q < rg.count; ++q) most = std::max(most, rg.n4[q]);
     const int blocks = (int)std::min<long long>((most + 255) / 256, (long long)h->sm_count * 8);
     launch_kernel(false, optimizer_tail_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online, (float4*)h->slot_m,
                   (float4*)h->slot_v, (const float4*)h->grads, rg, (float)h->cfg.learning_rate, (float)h->cfg.momentum,
-                  h->cfg.use_momentum, h->d_sc, h->opt_ticket);
+                  h->cfg.use_momentum, h->d_sc, h->opt_ticket, tp);
     h->launches++;
-    launch_pack_conv(h, 0);  // the image-resident conv kernels read the online conv weights pre-split and pre-tiled
+    if (!tp.n) launch_pack_conv(h, 0);  // (option off: separate pack launch) the conv kernels read the weights pre-split and pre-tiled
 }
 
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
