@@ -740,9 +740,17 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         tower_forward(h, h->online, states2, xf, rows_on, h->acts_on);
     }
     main_wait_side(h);
-    prof_mark(h, "td_epilogue");
-    launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
-                       grad_scale);
+    const bool fuse_td = train && h->fuse_td;
+    TdFuse tf{h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, rewards, cont, isw, grad_scale};
+    if (fuse_td) {
+        // the TD epilogue rides in the head backward kernel: one launch less on the critical chain
+        prof_mark(h, "head_backward");
+        launch_head_backward(h, n, actions, &tf);
+    } else {
+        prof_mark(h, "td_epilogue");
+        launch_td_epilogue(h, n, h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, actions, rewards, cont, isw, train,
+                           grad_scale);
+    }
     if (train && (per_update || h->pf_capture)) {
         // replay_sampler.update_sum_tree(tree_idxes, _make_priority(losses)) (deep_q_agent.py:341-347): it only needs
         // the TD errors, so it runs on a side stream underneath the whole backward pass ...
@@ -766,8 +774,10 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         side_end(h, sv);
     }
     if (train) {
-        prof_mark(h, "head_backward");
-        launch_head_backward(h, n, actions);
+        if (!fuse_td) {
+            prof_mark(h, "head_backward");
+            launch_head_backward(h, n, actions);
+        }
         tower_backward(h, states2, xf, n);
         if (h->pf_capture) main_wait_side(h, 2);  // the look-ahead batch is complete before the counters are bumped
     }
@@ -1184,6 +1194,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
+    else if (n == "fuse_td") h->fuse_td = value != 0;
     else if (n == "pack_in_tail") h->pack_in_tail = value != 0;
     else if (n == "img_wgrad1") h->img_wgrad1 = value != 0;
     else if (n == "merge_towers") h->merge_towers = value != 0;

@@ -7,66 +7,96 @@
 //   rl/deep_q_agent.py:527-534  _make_priority: min(|delta| + 0.01, 1.0) ** per_a  (float32)
 // and the autodiff of the loss w.r.t. the head inputs (dueling combine, the two tiny head matmuls, hidden ReLU).
 #include "learner.h"
+#include <string.h>
 
-// one thread per sample; a single CTA so the scalar loss is reduced in a fixed order
-__global__ void __launch_bounds__(1024) td_epilogue_kernel(
-    int n, int A, int use_double, int use_per, double gamma, float per_a, double grad_scale, int train,
-    const float* __restrict__ q_on, const float* __restrict__ q_on_next, const float* __restrict__ q_tg_next,
-    const uint8_t* __restrict__ actions, const uint8_t* __restrict__ rewards, const uint8_t* __restrict__ cont,
-    const float* __restrict__ isw, float* __restrict__ o_y, float* __restrict__ o_maxq, float* __restrict__ o_losses,
-    float* __restrict__ o_dq, float* __restrict__ o_newprio, dqn_learner::Scalars* sc) {
+struct TdArgs {
+    int n, A, use_double, use_per, train;
+    double gamma, grad_scale;
+    float per_a;
+    const float *q_on, *q_on_next, *q_tg_next;
+    const uint8_t *actions, *rewards, *cont;
+    const float* isw;
+    float *o_y, *o_maxq, *o_losses, *o_dq, *o_newprio;
+    dqn_learner::Scalars* sc;
+};
+
+// TD target, loss and dL/dq of sample i (the arithmetic of deep_q_model.py:247-255,106-114,361-378)
+__device__ __forceinline__ void td_sample(const TdArgs& t, int i, float& y, float& maxq, float& out_l, float& dq, float& newprio, float& li) {
+    const int A = t.A;
+    const float* qt = t.q_tg_next + (size_t)i * A;
+    if (t.use_double) {
+        const float* qo = t.q_on_next + (size_t)i * A;
+        int best = 0;
+        float bv = qo[0];
+        for (int a = 1; a < A; ++a) if (qo[a] > bv) { bv = qo[a]; best = a; }  // tf.argmax: first maximum
+        // reduce_max over {target_q[a*] * 1, target_q[a] * 0 ...}: the masked zeros take part in the max
+        maxq = qt[best];
+        if (A > 1) maxq = fmaxf(maxq, 0.f);
+    } else {
+        maxq = qt[0];
+        for (int a = 1; a < A; ++a) maxq = fmaxf(maxq, qt[a]);
+    }
+    const double y64 = (double)t.rewards[i] + ((t.cont[i] ? 1.0 : 0.0) * t.gamma) * (double)maxq;
+    y = (float)y64;  // fed through a tf.float32 placeholder (deep_q_model.py:206)
+    const float qa = t.q_on[(size_t)i * A + t.actions[i]];
+    const float delta = y - qa;
+    const float ad = fabsf(delta);
+    if (t.use_per) {
+        const float w = t.isw[i];
+        li = w * (delta * delta);  // is_weights * squared_difference (deep_q_model.py:374)
+        out_l = ad;                // self.losses = abs_losses (:375)
+        dq = (float)(-2.0 * (double)w * (double)delta * t.grad_scale / (double)t.n);
+    } else {
+        const float quad = fminf(ad, 1.0f);  // tf.losses.huber_loss, delta=1
+        li = 0.5f * quad * quad + (ad - quad);
+        out_l = li;
+        const float e = -delta;  // predictions - labels
+        dq = (float)((double)fminf(fmaxf(e, -1.0f), 1.0f) * t.grad_scale / (double)t.n);
+    }
+    newprio = t.use_per ? powf(fminf(ad + 0.01f, 1.0f), t.per_a) : 0.f;
+}
+
+// outputs + scalar loss, by ONE CTA (fixed reduction order): thread i handles samples i, i + blockDim, ...
+__device__ __forceinline__ void td_block(const TdArgs& t, float* s_dq_out) {
     __shared__ double s_red[32];
     double lsum = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float* qt = q_tg_next + (size_t)i * A;
-        float maxq;
-        if (use_double) {
-            const float* qo = q_on_next + (size_t)i * A;
-            int best = 0;
-            float bv = qo[0];
-            for (int a = 1; a < A; ++a) if (qo[a] > bv) { bv = qo[a]; best = a; }  // tf.argmax: first maximum
-            // reduce_max over {target_q[a*] * 1, target_q[a] * 0 ...}: the masked zeros take part in the max
-            maxq = qt[best];
-            if (A > 1) maxq = fmaxf(maxq, 0.f);
-        } else {
-            maxq = qt[0];
-            for (int a = 1; a < A; ++a) maxq = fmaxf(maxq, qt[a]);
+    for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
+        float y, maxq, out_l, dq, newprio, li;
+        td_sample(t, i, y, maxq, out_l, dq, newprio, li);
+        t.o_y[i] = y; t.o_maxq[i] = maxq; t.o_losses[i] = out_l;
+        if (t.train) {
+            t.o_dq[i] = dq;
+            if (t.use_per) t.o_newprio[i] = newprio;
         }
-        const double y64 = (double)rewards[i] + ((cont[i] ? 1.0 : 0.0) * gamma) * (double)maxq;
-        const float y = (float)y64;  // fed through a tf.float32 placeholder (deep_q_model.py:206)
-        const float qa = q_on[(size_t)i * A + actions[i]];
-        const float delta = y - qa;
-        const float ad = fabsf(delta);
-        float li, out_l, dq;
-        if (use_per) {
-            const float w = isw[i];
-            li = w * (delta * delta);  // is_weights * squared_difference (deep_q_model.py:374)
-            out_l = ad;                // self.losses = abs_losses (:375)
-            dq = (float)(-2.0 * (double)w * (double)delta * grad_scale / (double)n);
-        } else {
-            const float quad = fminf(ad, 1.0f);  // tf.losses.huber_loss, delta=1
-            li = 0.5f * quad * quad + (ad - quad);
-            out_l = li;
-            const float e = -delta;  // predictions - labels
-            dq = (float)((double)fminf(fmaxf(e, -1.0f), 1.0f) * grad_scale / (double)n);
-        }
-        o_y[i] = y; o_maxq[i] = maxq; o_losses[i] = out_l;
-        if (train) {
-            o_dq[i] = dq;
-            if (use_per) o_newprio[i] = powf(fminf(ad + 0.01f, 1.0f), per_a);
-        }
+        if (s_dq_out) s_dq_out[i] = dq;
         lsum += (double)li;
     }
     for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = lsum;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-        const float loss = (float)(t / (double)n);
-        sc->loss = loss;
-        if (train) sc->loss_sum += loss;
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+        const float loss = (float)(tot / (double)t.n);
+        t.sc->loss = loss;
+        if (t.train) t.sc->loss_sum += loss;
     }
+}
+
+// one thread per sample; a single CTA so the scalar loss is reduced in a fixed order
+__global__ void __launch_bounds__(1024) td_epilogue_kernel(const TdArgs t) { td_block(t, nullptr); }
+
+static TdArgs make_td_args(dqn_learner* h, int n, const float* q_on, const float* q_on_next, const float* q_tg_next,
+                           const uint8_t* actions, const uint8_t* rewards, const uint8_t* cont, const float* isw, int train,
+                           double grad_scale) {
+    TdArgs t;
+    t.n = n; t.A = h->net.A; t.use_double = h->cfg.use_double; t.use_per = h->cfg.use_per; t.train = train;
+    t.gamma = h->cfg.discount_rate; t.grad_scale = grad_scale; t.per_a = (float)h->cfg.per_a;
+    t.q_on = q_on; t.q_on_next = q_on_next; t.q_tg_next = q_tg_next;
+    t.actions = actions; t.rewards = rewards; t.cont = cont; t.isw = isw;
+    t.o_y = h->b_y; t.o_maxq = h->b_maxq; t.o_losses = h->b_losses_out; t.o_dq = h->b_dq; t.o_newprio = h->b_newprio;
+    t.sc = h->d_sc;
+    return t;
 }
 
 void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q_on_next, const float* q_tg_next,
@@ -74,9 +104,8 @@ void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q
                         int train, double grad_scale) {
     int threads = ((n + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
-    launch_kernel(false, td_epilogue_kernel, dim3(1), dim3(threads), 0, h->stream, n, h->net.A, h->cfg.use_double, h->cfg.use_per,
-                  h->cfg.discount_rate, (float)h->cfg.per_a, grad_scale, train, q_on, q_on_next, q_tg_next, actions, rewards, cont,
-                  isw, h->b_y, h->b_maxq, h->b_losses_out, h->b_dq, h->b_newprio, h->d_sc);
+    const TdArgs t = make_td_args(h, n, q_on, q_on_next, q_tg_next, actions, rewards, cont, isw, train, grad_scale);
+    launch_kernel(false, td_epilogue_kernel, dim3(1), dim3(threads), 0, h->stream, t);
     h->launches++;
 }
 
@@ -92,13 +121,28 @@ __global__ void __launch_bounds__(1024) head_backward_kernel(int n, int NH, int 
                                                              float* __restrict__ d_hid, float* __restrict__ g_hw0,
                                                              float* __restrict__ g_hb0, float* __restrict__ g_hw1,
                                                              float* __restrict__ g_hb1, float* __restrict__ g_fb0,
-                                                             float* __restrict__ g_fb1) {
+                                                             float* __restrict__ g_fb1, const TdArgs td) {
     extern __shared__ float sm[];
     float* s_dh = sm;                 // [32][33]
     float* s_hv = sm + 32 * 33;       // [32][33]
     float* s_dq = sm + 2 * 32 * 33;   // [n]
     uint8_t* s_act = reinterpret_cast<uint8_t*>(s_dq + n);  // [n]
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { s_dq[i] = dq[i]; s_act[i] = actions[i]; }
+    if (td.n > 0) {
+        // fused TD epilogue: every CTA derives dL/dq of all samples itself (a few hundred flops) instead of waiting for a
+        // separate one-CTA kernel; CTA 0 also publishes the targets / losses / priorities and the scalar loss
+        if (blockIdx.x == 0) {
+            td_block(td, s_dq);
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                float y, maxq, out_l, dqi, newprio, li;
+                td_sample(td, i, y, maxq, out_l, dqi, newprio, li);
+                s_dq[i] = dqi;
+            }
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_act[i] = actions[i];
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { s_dq[i] = dq[i]; s_act[i] = actions[i]; }
+    }
     __syncthreads();
     const float invA = 1.0f / (float)A;
     const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
@@ -170,7 +214,9 @@ __global__ void __launch_bounds__(1024) head_backward_kernel(int n, int NH, int 
     }
 }
 
-void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions) {
+void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions, const TdFuse* fuse) {
+    TdArgs td; memset(&td, 0, sizeof(td));
+    if (fuse) td = make_td_args(h, n, fuse->q_on, fuse->q_on_next, fuse->q_tg_next, actions, fuse->rewards, fuse->cont, fuse->isw, 1, fuse->grad_scale);
     const NetDesc& net = h->net;
     const float* P = h->online;
     float* G = h->grads;
@@ -180,7 +226,7 @@ void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions) {
     launch_kernel(false, head_backward_kernel<AMAX>, dim3(net.NH / 32), dim3(1024), smem, h->stream,                    \
         n, net.NH, net.hidden, net.A, net.dueling, h->acts_on.hid, h->b_dq, actions, P + net.off_hd_w[0],              \
         P + net.off_hd_w[1], h->d_hid, G + net.off_hd_w[0], G + net.off_hd_b[0], G + net.off_hd_w[1],                  \
-        G + net.off_hd_b[1], G + net.off_fc_b[0], G + net.off_fc_b[1])
+        G + net.off_hd_b[1], G + net.off_fc_b[0], G + net.off_fc_b[1], td)
     if (net.A <= 4) HEAD_BWD(4);
     else if (net.A <= 8) HEAD_BWD(8);
     else if (net.A <= 16) HEAD_BWD(16);

@@ -186,6 +186,7 @@ struct dqn_learner {
     float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
     int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
+    bool fuse_td = true;        // option: TD epilogue inside the head backward kernel (training steps)
     bool pack_in_tail = true;   // option: optimizer_tail_kernel re-packs the conv weights it updates (no separate pack launch)
     bool img_wgrad1 = true;     // option: conv1 wgrad through the image-resident kernel on the uint8 frames
     bool merge_towers = true;   // option: conv layers of the online and the target tower in one launch each
@@ -270,7 +271,9 @@ int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, 
 void launch_td_epilogue(dqn_learner* h, int n, const float* q_on, const float* q_on_next, const float* q_tg_next,
                         const uint8_t* actions, const uint8_t* rewards, const uint8_t* cont, const float* isw,
                         int train, double grad_scale);
-void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions);
+// fuse != nullptr: the TD epilogue of a training step is computed inside the head backward kernel (no separate launch)
+struct TdFuse { const float *q_on, *q_on_next, *q_tg_next; const uint8_t *rewards, *cont; const float* isw; double grad_scale; };
+void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions, const TdFuse* fuse = nullptr);
 
 // optim.cu
 void launch_optimizer(dqn_learner* h, bool skip_fc);
