@@ -107,7 +107,15 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
 
         // parameters + optimizer slots + gradient slab
         const size_t P = (size_t)net.slab;
-        dmalloc(h->online, P); dmalloc(h->target, P); dmalloc(h->slot_m, P); dmalloc(h->slot_v, P); dmalloc(h->grads, P);
+        {
+            // the five parameter-sized slabs come from ONE allocation at a fixed relative placement
+            const size_t stride = (((size_t)P * 4 + (2u << 20) - 1) / (2u << 20)) * (2u << 20);  // bytes
+            float* base = nullptr;
+            dmalloc(base, 5 * stride / 4);
+            h->slab_base = base;
+            h->online = base; h->target = base + stride / 4; h->slot_m = base + 2 * (stride / 4); h->slot_v = base + 3 * (stride / 4);
+            h->grads = base + 4 * (stride / 4);
+        }
         for (float* p : {h->online, h->target, h->slot_m, h->slot_v, h->grads}) DQN_CUDA_OK(cudaMemsetAsync(p, 0, P * 4, h->stream));
         dmalloc(h->d_sc, 1); dmalloc(h->d_dev, 1);
         DQN_CUDA_OK(cudaMemsetAsync(h->d_sc, 0, sizeof(dqn_learner::Scalars), h->stream));
@@ -209,7 +217,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->sets[0].states) select_set(h, 0);  // the b_* aliases freed below must be set 0 (set 1 is freed separately)
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
     if (h->prof_graph) cudaGraphExecDestroy(h->prof_graph);
-    void* ptrs[] = {h->online, h->target, h->slot_m, h->slot_v, h->grads, h->d_sc, h->d_dev, h->r_states, h->r_next,
+    void* ptrs[] = {h->slab_base, h->d_sc, h->d_dev, h->r_states, h->r_next,
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,

@@ -77,8 +77,11 @@ struct dqn_learner {
     bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
     unsigned int* fa_tile_ctr = nullptr;  // dynamic tile counter of the fused dense kernel (= opt_ticket + 1, zeroed by the optimizer tail)
     void* fa_row_maps = nullptr;  // fa::RowMaps
-    int fc_rows_ctas = 148;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
-                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  clamped to the SM count; sweep after conv1's wgrad moved to the image-resident kernel: 108 -> 5913, 124 -> 6027, 148 -> 6081 steps/s
+    int fc_rows_ctas = 100;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
+                                  // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  clamped to the SM count.  With 148 the step time is BIMODAL (5400-5600 vs 6150 steps/s per learner instance): the kernel
+                                  // becomes ready at the same instant as conv3's dgrad + wgrad (96 CTAs); if its persistent CTAs are dispatched first
+                                  // they hold every SM and the critical conv chain waits 40 us (CUPTI traces of both modes).  With <= 100 CTAs the
+                                  // chain always finds SMs and dynamic tile claims keep the pass balanced: 84-100 -> 6030-6180 in both modes
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)
@@ -88,6 +91,7 @@ struct dqn_learner {
 
     // parameters
     float *online = nullptr, *target = nullptr, *slot_m = nullptr, *slot_v = nullptr, *grads = nullptr;
+    float* slab_base = nullptr;  // the five slabs above are carved from this one allocation
     // device scalars: [0]=step (int64), game_count, beta powers, PER stats
     struct Scalars {
         long long step;
