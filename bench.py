@@ -125,7 +125,7 @@ def clocks_sampler_start():
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
     try:
         f = open(path, 'w')
-        p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', os.environ.get('DQN_BENCH_CLOCKS_MS', '100')],
+        p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
                              stdout=f, stderr=subprocess.DEVNULL)
         return p, f, path
     except OSError:

@@ -292,7 +292,6 @@ static int launch(dqn_learner* h, const float* P, const float* act, int rows, fl
     const int mt = net.NH / BM, nkb = net.flat / BK;
     // the two towers' launches run side by side: half the SMs each, so that both fit in one wave
     int want = std::min(std::max(1, h->sm_count / (2 * mt)), max_splits);
-    if (const char* e = getenv("DQN_FC_SPLITS")) want = std::min(std::max(1, atoi(e)), max_splits);
     const int per = (nkb + want - 1) / want;
     const int splits = (nkb + per - 1) / per;
     auto go = [&](auto kern, int bn) {

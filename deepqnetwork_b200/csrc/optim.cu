@@ -186,7 +186,6 @@ void launch_fc_wgrad_adam(dqn_learner* h, int rows, bool write_g) {
     float *W = h->online, *M = h->slot_m, *V = h->slot_v, *G = h->grads;
     const int ntiles = net.NH / 256;
     int per_tile = (2 * h->sm_count) / ntiles;  // two resident CTAs per SM, split evenly over the n tiles
-    if (const char* e = getenv("DQN_FCW_CTAS")) per_tile = atoi(e);
     if (per_tile < 1) per_tile = 1;
     if (per_tile > net.flat / 16) per_tile = net.flat / 16;
     dim3 grid(per_tile, ntiles);
