@@ -4,7 +4,7 @@
 // At batch 32-64 this layer is a stream of the 31.5 MB weight matrix through the tensor core.  One thread issues 2-D TMA
 // tensor copies of 128 (n) x 32 (k) boxes of W into a 6-stage ring (16 KB each, 96 KB in flight per CTA), and the
 // converters read their column of the box from shared memory (conflict-free: consecutive lanes are consecutive n),
-// split hi/lo and feed the MMA through tensor memory.  What the in-kernel timeline (scratch/fftl.py) taught:
+// split hi/lo and feed the MMA through tensor memory.  What the in-kernel timeline (tools/dense_fwd_timeline.py) taught:
 //   * the activation tile must not be produced by threads with row-scattered global loads: those LDGs (8 lines per
 //     instruction) share the L1tex wavefront queue with the converters' LDS and doubled the k-block time; the compiler
 //     also sank the prefetch loads to their use (volatile asm keeps them early), and a select on a just-loaded value
