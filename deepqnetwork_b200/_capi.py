@@ -103,12 +103,21 @@ def lib():
     return _lib
 
 
+_from_buffer = C.c_char.from_buffer
+
+
 def ptr(a):
-    """Host pointer of a C-contiguous numpy array (or None)."""
+    """Host pointer of a C-contiguous numpy array (or None).
+
+    Through the buffer protocol (0.3 us) rather than ndarray.ctypes (3-4 us per pointer, ~13 pointers per host-fed
+    train step); read-only and empty arrays take the slow way."""
     if a is None:
         return None
-    assert a.flags['C_CONTIGUOUS'], 'array must be C-contiguous'
-    return a.ctypes.data_as(_P)
+    assert a.flags.c_contiguous, 'array must be C-contiguous'
+    try:
+        return C.byref(_from_buffer(a))
+    except (TypeError, ValueError, BufferError):
+        return a.ctypes.data_as(_P)
 
 
 def as_u8(a, shape=None):
