@@ -47,6 +47,8 @@ static void push_sizes(dqn_learner* h) {
     set_ll(h, &h->d_dev->tree_size, h->tree_size);
     set_ll(h, &h->d_dev->ring_len, h->ring_size);
 }
+constexpr size_t SC_BLOCK = 128;  // Scalars, padded; the losses of the last step follow (device block and pinned mirror)
+
 static void read_scalars(dqn_learner* h) {
     DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(dqn_learner::Scalars), cudaMemcpyDeviceToHost, h->stream));
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -117,10 +119,18 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             h->grads = base + 4 * (stride / 4);
         }
         for (float* p : {h->online, h->target, h->slot_m, h->slot_v, h->grads}) DQN_CUDA_OK(cudaMemsetAsync(p, 0, P * 4, h->stream));
-        dmalloc(h->d_sc, 1); dmalloc(h->d_dev, 1);
+        // scalars and the per-sample losses of a step share one block, so that dqn_train_batch reads both with one copy
+        static_assert(sizeof(dqn_learner::Scalars) <= SC_BLOCK, "scalar block");
+        {
+            void* blk = nullptr;
+            DQN_CUDA_OK(cudaMalloc(&blk, SC_BLOCK + 4 * (size_t)h->max_rows));
+            h->d_sc = static_cast<dqn_learner::Scalars*>(blk);
+            h->b_losses_out = reinterpret_cast<float*>(static_cast<char*>(blk) + SC_BLOCK);
+        }
+        dmalloc(h->d_dev, 1);
         DQN_CUDA_OK(cudaMemsetAsync(h->d_sc, 0, sizeof(dqn_learner::Scalars), h->stream));
         DQN_CUDA_OK(cudaMemsetAsync(h->d_dev, 0, sizeof(dqn_learner::DevSizes), h->stream));
-        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, sizeof(dqn_learner::Scalars), cudaHostAllocDefault));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, SC_BLOCK + 4 * (size_t)h->max_rows, cudaHostAllocDefault));
         set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, 0.9f, &h->d_sc->b2p, 0.999f);
 
         // replay ring + tree
@@ -158,7 +168,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         dmalloc(h->b_isw, R);
         DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2, 64 * R, cudaHostAllocDefault));
         DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage2_ev, cudaEventDisableTiming));
-        dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_losses_out, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
+        dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
         dmalloc(h->b_rows, R);
 
         // activations
@@ -221,7 +231,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,
-                    h->b_losses_out, h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
+                    h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
                     h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg, h->act3_pk[0], h->act3_pk[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
@@ -609,9 +619,10 @@ extern "C" int dqn_per_sample(dqn_learner* h, const double* u, int32_t refresh, 
     memcpy(hs, u, B * 8);
     DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, hs, B * 8, cudaMemcpyHostToDevice, h->stream));
     launch_tree_sample(h, h->B, 0, per_b);
-    launch_gather(h, h->b_mem_idx, h->B);
     DQN_CUDA_OK(cudaMemcpyAsync(hs + 8 * R, h->b_tree_idx, 3 * R * 8, cudaMemcpyDeviceToHost, h->stream));
-    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    DQN_CUDA_OK(cudaEventRecord(h->stage2_ev, h->stream));
+    launch_gather(h, h->b_mem_idx, h->B);  // stream-ordered behind the read-back: the host does not wait for it
+    DQN_CUDA_OK(cudaEventSynchronize(h->stage2_ev));
     if (t_idx) memcpy(t_idx, hs + 8 * R, B * 8);
     if (prio) memcpy(prio, hs + 16 * R, B * 8);
     if (isw) memcpy(isw, hs + 24 * R, B * 8);
@@ -1108,12 +1119,11 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
         h->launches += h->batch_graph_launches;
         h->host_step++;
     }
-    // per-sample losses through the pinned staging block (a copy into pageable memory is staged by the driver and costs
-    // a second synchronisation), scalars through their pinned mirror: one stream synchronisation for both
-    float* hl = reinterpret_cast<float*>(h->h_stage2 + 32 * (size_t)h->max_rows);
-    if (losses) DQN_CUDA_OK(cudaMemcpyAsync(hl, h->b_losses_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-    read_scalars(h);
-    if (losses) memcpy(losses, hl, (size_t)n * 4);
+    // scalars and per-sample losses sit in one device block with a pinned mirror: one copy, one synchronisation (a copy
+    // into the caller's pageable memory would be staged by the driver and cost a second one)
+    DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, SC_BLOCK + (losses ? (size_t)n * 4 : 0), cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (losses) memcpy(losses, reinterpret_cast<const char*>(h->h_sc) + SC_BLOCK, (size_t)n * 4);
     if (step) *step = h->h_sc->step;
     if (loss) *loss = h->h_sc->loss;
     API_END(h)

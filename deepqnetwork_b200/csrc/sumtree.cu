@@ -157,8 +157,10 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(float* tree, const ui
             float v = 0.f;
             if (lead) v = tree[node];
             const int maxcnt = __reduce_max_sync(FULL, part ? cnt : 0);
+            unsigned rem = grp;  // group members in ascending lane (= update) order, one per round
             for (int r = 0; r < maxcnt; ++r) {
-                const int src = (r < cnt) ? (int)__fns(grp, 0, r + 1) : lane;
+                const int src = rem ? __ffs(rem) - 1 : lane;
+                rem &= rem - 1u;
                 const float cr = __shfl_sync(FULL, c, src);
                 if (lead && r < cnt) v = __fadd_rn(v, cr);  // sum_tree.py:107
             }
