@@ -1057,8 +1057,13 @@ extern "C" int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_s
     API_END(h)
 }
 
+static void upload_small(dqn_learner* h) {
+    DQN_CUDA_OK(cudaMemcpyAsync(h->in_actions, h->h_in_small, h->in_small_bytes, cudaMemcpyHostToDevice, h->stream));
+}
+
+// copy_small = false: the staging block is filled but its H2D copy is left to the caller (a node of the replayed graph)
 static void upload_batch(dqn_learner* h, int n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw, const uint8_t* ct,
-                         const uint8_t* ns, const float* isw) {
+                         const uint8_t* ns, const float* isw, bool copy_small = true) {
     const size_t S = h->state_bytes;
     // s on the main stream, s' on a side stream: two copy engines share the upload
     DQN_CUDA_OK(cudaEventRecord(h->fork_ev[22], h->stream));
@@ -1074,8 +1079,8 @@ static void upload_batch(dqn_learner* h, int n, const uint8_t* st, const uint8_t
     memcpy(hs + (h->in_rewards - h->in_actions), rw, n);
     memcpy(hs + (h->in_cont - h->in_actions), ct, n);
     if (isw) memcpy(hs + (reinterpret_cast<uint8_t*>(h->in_isw) - h->in_actions), isw, (size_t)n * 4);
-    DQN_CUDA_OK(cudaMemcpyAsync(h->in_actions, hs, h->in_small_bytes, cudaMemcpyHostToDevice, h->stream));
-    DQN_CUDA_OK(cudaEventRecord(h->stage_ev, h->stream));
+    if (copy_small) upload_small(h);
+    DQN_CUDA_OK(cudaEventRecord(h->stage_ev, h->stream));  // (graph path: the caller synchronises the stream before returning)
 }
 
 extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, const uint8_t* ac, const uint8_t* rw,
@@ -1084,7 +1089,9 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     DQN_REQUIRE(n >= 1 && n <= h->max_rows, "n exceeds max_rows");
     DQN_REQUIRE(!h->cfg.use_per || isw, "use_per: is_weights are required");
     h->prof_used = 0; h->prof_marks.clear();
-    upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr);
+    const bool use_graph = !h->profile && h->batch_graph_enabled;
+    upload_batch(h, n, st, ac, rw, ct, ns, h->cfg.use_per ? isw : nullptr, !use_graph);
+    const size_t readback = SC_BLOCK + (size_t)n * 4;
     auto launches = [&]() {
         h->early_fc_adam = true; h->fc_grads_needed = h->keep_grads;  // option: keep the full gradient slab readable
         try {
@@ -1093,8 +1100,9 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
         h->early_fc_adam = false; h->fc_grads_needed = false;
         finish_step(h, 0);  // priorities are written back by the caller (sampler.update_sum_tree), as in the reference
     };
-    if (h->profile || !h->batch_graph_enabled) {
+    if (!use_graph) {
         launches();
+        DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, readback, cudaMemcpyDeviceToHost, h->stream));
     } else {
         // the ~28 launches of one host-fed step replayed as one graph (inputs/outputs sit in fixed device buffers);
         // re-captured when the batch size or an option changes
@@ -1102,7 +1110,13 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches, s0 = h->host_step;
             DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            try { launches(); } catch (...) {
+            // the small-input upload and the scalar/loss read-back have fixed pinned addresses: they ride the graph as
+            // its first and last nodes (no stream-level launch latency in front of / behind the kernels)
+            try {
+                upload_small(h);
+                launches();
+                DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, readback, cudaMemcpyDeviceToHost, h->stream));
+            } catch (...) {
                 cudaStreamEndCapture(h->stream, &g);
                 if (g) cudaGraphDestroy(g);
                 throw;
@@ -1121,7 +1135,6 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
     }
     // scalars and per-sample losses sit in one device block with a pinned mirror: one copy, one synchronisation (a copy
     // into the caller's pageable memory would be staged by the driver and cost a second one)
-    DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, SC_BLOCK + (losses ? (size_t)n * 4 : 0), cudaMemcpyDeviceToHost, h->stream));
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     if (losses) memcpy(losses, reinterpret_cast<const char*>(h->h_sc) + SC_BLOCK, (size_t)n * 4);
     if (step) *step = h->h_sc->step;
