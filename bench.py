@@ -247,7 +247,24 @@ def cpu_reference_run(cfg, steps, warmup, replay_rows, time_budget_s, threads=No
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Only the JSON line may reach stdout: fd 1 is pointed at stderr for the whole run (NCCL prints its version banner to
+# stdout, subprocesses inherit fd 1) and the line is written to the saved descriptor.
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2000)
@@ -295,7 +312,7 @@ def main():
                     cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind='port',
                                       sample='%d consecutive train steps, 20000-row host replay (sampler cost is O(log N))' % done),
                     e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---- B200 arm ---------------------------------------------------------------------------------------------------
@@ -446,7 +463,7 @@ def main():
                     dtype={'fp32': 'f32', 'tc3x': 'f32 (tf32x3 on tcgen05)', 'tc1x': 'tf32'}[args.math],
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
                     cpu_baseline=cpu)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
