@@ -1223,15 +1223,15 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "pdl") h->pdl = value != 0;             // programmatic dependent launch between consecutive kernels
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
-    else if (n == "img_conv") h->img_conv = value != 0;
+    else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "fuse_td") h->fuse_td = value != 0;
     else if (n == "pack_in_tail") h->pack_in_tail = value != 0;
     else if (n == "img_wgrad1") h->img_wgrad1 = value != 0;
     else if (n == "merge_towers") h->merge_towers = value != 0;
-    else if (n == "prefetch") h->prefetch = value != 0;
+    else if (n == "prefetch") h->prefetch = value != 0;   // dqn_train_steps samples the next batch inside the current step
     else if (n == "defer_adam") h->defer_adam = value != 0;  // dense-kernel optimizer pass of step i under the conv forward of step i+1
-    else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels   // dqn_train_steps samples the next batch inside the current step   // conv layers through the image-resident kernel (cvgemm.cuh)
+    else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels
     else throw std::string("unknown option: ") + n;
     h->graph_valid = false; h->graph_valid_batch = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }

@@ -119,7 +119,9 @@ int dqn_tree_read(dqn_learner* h, float* h_tree /*2N-1*/, uint32_t* h_data /*N*/
 /* ---- samplers (seam 3): fill the device-resident train batch --------- */
 /* ReplaySamplerPriority.sample_memories (replay_sampler_priority.py:27-43) + the IS-weight maths of
  * DeepQAgent._sample_memories (deep_q_agent.py:500-524). refresh_stats!=0 recomputes avg/min/max and
- * last_max_weight first. */
+ * last_max_weight first.  Returns once tree_idx / priorities / is_weights are on the host; the gather of the sampled
+ * rows into the device batch is stream-ordered behind that (every later call on this handle sees it; code that reads
+ * the batch through dqn_device_ptr on another stream calls dqn_sync first). */
 int dqn_per_sample(dqn_learner* h, const double* h_u, int32_t refresh_stats, double per_b,
                    int64_t* h_tree_idx, double* h_priorities, double* h_is_weights);
 /* ReplaySampler.sample_memories (replay_sampler.py:21-32) with the caller's randint draws */
