@@ -154,7 +154,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
             uint8_t* blk = nullptr;
             dmalloc(blk, h->in_small_bytes);
             h->in_actions = blk; h->in_rewards = blk + Rp; h->in_cont = blk + 2 * Rp; h->in_isw = reinterpret_cast<float*>(blk + 3 * Rp);
-            DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_in_small, std::max<size_t>(h->in_small_bytes, 16 * R), cudaHostAllocDefault));
+            DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_in_small, std::max<size_t>(h->in_small_bytes, 16 * R), cudaHostAllocMapped));
             DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
         }
         auto carve = [&](dqn_learner::BatchSet& b) {
@@ -166,7 +166,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         h->b_tree_idx = h->sets[0].tree_idx; h->b_data_idx = h->sets[0].data_idx; h->b_mem_idx = h->sets[0].mem_idx;
         h->b_prio = h->sets[0].prio; h->b_isw64 = h->sets[0].isw64; h->b_u = h->sets[0].u;
         dmalloc(h->b_isw, R);
-        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2, 64 * R, cudaHostAllocDefault));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2, 64 * R, cudaHostAllocMapped));
         DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage2_ev, cudaEventDisableTiming));
         dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
         dmalloc(h->b_rows, R);
@@ -537,17 +537,16 @@ extern "C" int dqn_tree_update(dqn_learner* h, int64_t n, const int64_t* idx, co
     API_BEGIN(h)
     for (int64_t j = 0; j < n; ++j) DQN_REQUIRE(idx[j] >= h->cap - 1 && idx[j] < 2 * h->cap - 1, "tree_idx is not a leaf");
     if (n <= h->max_rows) {
-        // the per-step write-back (B rows): indices and scores ride one pinned staging copy, no host sync -- the
+        // the per-step write-back (B rows): indices and scores ride one pinned staging block, no host sync -- the
         // update is ordered on the handle's stream like every later call
         DQN_CUDA_OK(cudaEventSynchronize(h->stage_ev));
         uint8_t* hs = h->h_in_small;
         memcpy(hs, idx, (size_t)n * 8);
         memcpy(hs + (size_t)n * 8, scores, (size_t)n * 4);
-        long long* d_i = (long long*)h->dev_stage;
-        float* d_s = (float*)(h->dev_stage + (size_t)n * 8);
-        DQN_CUDA_OK(cudaMemcpyAsync(d_i, hs, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+        // the kernel reads both columns from the pinned, device-mapped block over PCIe (no copy operation in front of it)
+        launch_tree_update(h, (int)n, reinterpret_cast<const long long*>(hs), reinterpret_cast<const float*>(hs + (size_t)n * 8),
+                           store_losses);
         DQN_CUDA_OK(cudaEventRecord(h->stage_ev, h->stream));
-        launch_tree_update(h, (int)n, d_i, d_s, store_losses);
         return 0;
     }
     const int64_t max_chunk = (int64_t)(h->dev_stage_bytes / 16);
@@ -613,13 +612,12 @@ extern "C" int dqn_per_sample(dqn_learner* h, const double* u, int32_t refresh, 
     DQN_REQUIRE(h->cfg.use_per, "handle was created without use_per");
     DQN_REQUIRE(u != nullptr, "uniform draws are required");
     if (refresh) launch_tree_stats(h, per_b);
-    // uniforms in and {tree_idx, prio, is_w} out ride one pinned staging block: one H2D, one D2H
+    // uniforms in and {tree_idx, prio, is_w} out ride one pinned, device-mapped staging block: the sampling kernel reads
+    // the draws from it and writes the three columns into it over PCIe -- no copy operations on the stream
     const size_t R = (size_t)h->max_rows, B = (size_t)h->B;
     uint8_t* hs = h->h_stage2;
     memcpy(hs, u, B * 8);
-    DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, hs, B * 8, cudaMemcpyHostToDevice, h->stream));
-    launch_tree_sample(h, h->B, 0, per_b);
-    DQN_CUDA_OK(cudaMemcpyAsync(hs + 8 * R, h->b_tree_idx, 3 * R * 8, cudaMemcpyDeviceToHost, h->stream));
+    launch_tree_sample(h, h->B, 0, per_b, reinterpret_cast<const double*>(hs), hs + 8 * R);
     DQN_CUDA_OK(cudaEventRecord(h->stage2_ev, h->stream));
     launch_gather(h, h->b_mem_idx, h->B);  // stream-ordered behind the read-back: the host does not wait for it
     DQN_CUDA_OK(cudaEventSynchronize(h->stage2_ev));

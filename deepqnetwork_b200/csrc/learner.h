@@ -254,7 +254,10 @@ void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
 
 // sumtree.cu
-void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b);
+// u_src: uniforms read from there instead of b_u (may be pinned host memory); host_out: pinned host block that also
+// receives the {tree_idx | priority | is_weight} columns (stride max_rows, 8-byte entries)
+void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b, const double* u_src = nullptr,
+                        void* host_out = nullptr);
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
 void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uint32_t* d_data, int64_t write0);
 void launch_tree_stats(dqn_learner* h, double per_b_override);

@@ -67,7 +67,7 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
                                    long long* __restrict__ o_tree_idx, long long* __restrict__ o_data_idx,
                                    long long* __restrict__ o_mem_idx, double* __restrict__ o_prio,
                                    double* __restrict__ o_isw64, float* __restrict__ o_isw, double* __restrict__ o_u,
-                                   int ahead) {
+                                   int ahead, long long* host_out, int host_stride) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= batch) return;
@@ -105,6 +105,12 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
             if (o_isw64) o_isw64[i] = w;
             if (o_isw) o_isw[i] = (float)w;
             if (i == 0) sc->per_b = (float)per_b;
+            if (host_out) reinterpret_cast<double*>(host_out)[2 * host_stride + i] = w;
+        }
+        // seam-3 callers: {tree_idx | priority | is_weight} columns straight into the pinned host block (no D2H copy op)
+        if (host_out) {
+            host_out[i] = leaf;
+            reinterpret_cast<double*>(host_out)[host_stride + i] = (double)p;
         }
     }
 }
@@ -244,12 +250,12 @@ static PerParams make_pp(const dqn_learner* h, double override_b) {
 
 long long* tree_size_ptr(dqn_learner* h);  // api.cu: device mirror of tree_size
 
-void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b) {
+void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b, const double* u_src, void* host_out) {
     const int wpb = 8;
     launch_kernel(false, tree_sample_kernel, dim3(ceil_div(batch, wpb)), dim3(wpb * 32), 0, h->stream,
-        h->tree, h->tree_data, h->cap, tree_size_ptr(h), batch, h->b_u, device_rng, h->cfg.seed, h->d_sc,
+        h->tree, h->tree_data, h->cap, tree_size_ptr(h), batch, u_src ? u_src : (const double*)h->b_u, device_rng, h->cfg.seed, h->d_sc,
         make_pp(h, per_b), h->cfg.use_per, h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64,
-        h->b_isw, device_rng ? h->b_u : (double*)nullptr, h->sample_ahead);
+        h->b_isw, device_rng ? h->b_u : (double*)nullptr, h->sample_ahead, (long long*)host_out, h->max_rows);
     h->launches++;
 }
 
