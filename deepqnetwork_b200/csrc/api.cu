@@ -130,7 +130,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         dmalloc(h->d_dev, 1);
         DQN_CUDA_OK(cudaMemsetAsync(h->d_sc, 0, sizeof(dqn_learner::Scalars), h->stream));
         DQN_CUDA_OK(cudaMemsetAsync(h->d_dev, 0, sizeof(dqn_learner::DevSizes), h->stream));
-        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, SC_BLOCK + 4 * (size_t)h->max_rows, cudaHostAllocDefault));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, SC_BLOCK + 4 * (size_t)h->max_rows, cudaHostAllocMapped));
         set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, 0.9f, &h->d_sc->b2p, 0.999f);
 
         // replay ring + tree
@@ -1108,13 +1108,15 @@ extern "C" int dqn_train_batch(dqn_learner* h, int32_t n, const uint8_t* st, con
             cudaGraph_t g = nullptr;
             const int64_t l0 = h->launches, s0 = h->host_step;
             DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            // the small-input upload and the scalar/loss read-back have fixed pinned addresses: they ride the graph as
-            // its first and last nodes (no stream-level launch latency in front of / behind the kernels)
+            // the small-input upload has a fixed pinned address: it rides the graph as its first node; the scalar/loss
+            // read-back is done by the step's last kernel (optimizer tail) into the pinned, device-mapped mirror
+            h->tail_mirror = reinterpret_cast<float*>(h->h_sc); h->tail_mirror_words = (int)(readback / 4);
             try {
                 upload_small(h);
                 launches();
-                DQN_CUDA_OK(cudaMemcpyAsync(h->h_sc, h->d_sc, readback, cudaMemcpyDeviceToHost, h->stream));
+                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
             } catch (...) {
+                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
                 cudaStreamEndCapture(h->stream, &g);
                 if (g) cudaGraphDestroy(g);
                 throw;

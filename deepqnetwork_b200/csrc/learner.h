@@ -109,6 +109,8 @@ struct dqn_learner {
     unsigned int* opt_ticket = nullptr;  // last-CTA-done counter of optimizer_tail_kernel
     Scalars* d_sc = nullptr;
     Scalars* h_sc = nullptr;  // pinned mirror for reads
+    float* tail_mirror = nullptr;  // set while dqn_train_batch captures its graph: optimizer tail writes scalars+losses to h_sc
+    int tail_mirror_words = 0;
     // host-owned sizes mirrored on the device so that captured graphs see current values
     struct DevSizes { long long tree_size; long long ring_len; };
     DevSizes* d_dev = nullptr;

@@ -245,7 +245,8 @@ __device__ __forceinline__ void tail_pack4(const TailPack::L& q, int e, const fl
 __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                              const float4* __restrict__ g, OptRanges rg, float lr, float mom,
                                                              int use_momentum, dqn_learner::Scalars* sc,
-                                                             unsigned int* __restrict__ ticket, const TailPack tp) {
+                                                             unsigned int* __restrict__ ticket, const TailPack tp,
+                                                             float* host_mirror, int mirror_words) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -282,6 +283,14 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
             sc->b1p_prev = sc->b1p; sc->b2p_prev = sc->b2p;
             if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
             sc->rng_counter += 1;
+            // host-fed step (dqn_train_batch): the scalar block and the per-sample losses behind it go straight into their
+            // pinned, device-mapped mirror -- the step needs no read-back copy operation after its last kernel
+            if (host_mirror) {
+                __threadfence();
+                const volatile float* src = reinterpret_cast<const volatile float*>(sc);
+                for (int i = 0; i < mirror_words; ++i) host_mirror[i] = src[i];
+                __threadfence_system();
+            }
         }
     }
 }
@@ -316,7 +325,7 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
     const int blocks = (int)std::min<long long>((most + 255) / 256, (long long)h->sm_count * 8);
     launch_kernel(false, optimizer_tail_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online, (float4*)h->slot_m,
                   (float4*)h->slot_v, (const float4*)h->grads, rg, (float)h->cfg.learning_rate, (float)h->cfg.momentum,
-                  h->cfg.use_momentum, h->d_sc, h->opt_ticket, tp);
+                  h->cfg.use_momentum, h->d_sc, h->opt_ticket, tp, h->tail_mirror, h->tail_mirror_words);
     h->launches++;
     if (!tp.n) launch_pack_conv(h, 0);  // (option off: separate pack launch) the conv kernels read the weights pre-split and pre-tiled
 }
