@@ -7,7 +7,6 @@
 static std::string g_create_error;
 
 // launchers living in other translation units
-void launch_tree_stats(dqn_learner* h, double per_b_override);
 void debug_conv_layer(dqn_learner* h, int layer, int rows);
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
 
@@ -209,11 +208,11 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         launch_pack_conv(h, 0); launch_pack_conv(h, 1);
         h->dev_stage_bytes = 8u << 20;
         dmalloc(h->dev_stage, h->dev_stage_bytes);
-        dmalloc(h->stats_scratch, 8192);
+        dmalloc(h->stats_scratch, 16384);
         DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     } catch (const std::string& e) {
         g_create_error = e;
-        if (h) { cudaDeviceSynchronize(); delete h; }
+        if (h) dqn_destroy(h);  // frees whatever was allocated before the failure (every pointer starts out null)
         return 1;
     }
     *out = h;
@@ -586,12 +585,16 @@ extern "C" int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* u, i
 
 extern "C" int dqn_tree_stats(dqn_learner* h, float* mn, float* mx, float* avg, float* total) {
     API_BEGIN(h)
-    launch_tree_stats(h, -1.0);
-    read_scalars(h);
-    if (mn) *mn = h->h_sc->stat_min;
-    if (mx) *mx = h->h_sc->stat_max;
-    if (avg) *avg = h->h_sc->stat_avg;
-    if (total) *total = h->h_sc->stat_total;
+    // read-only: results land in a scratch block, the PER normaliser / report statistics keep their own cadence
+    float* d_out = reinterpret_cast<float*>(h->stats_scratch + 8192);  // behind the 296 partials
+    launch_tree_stats(h, -1.0, d_out);
+    float v[4];
+    DQN_CUDA_OK(cudaMemcpyAsync(v, d_out, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (mn) *mn = v[0];
+    if (mx) *mx = v[1];
+    if (avg) *avg = v[2];
+    if (total) *total = v[3];
     API_END(h)
 }
 
@@ -892,6 +895,11 @@ static void after_step_host(dqn_learner* h) {
 extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* rows, int64_t* step, float* losses, float* loss) {
     API_BEGIN(h)
     DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+    // the draws must match the sampler this handle was created with (a mismatched argument used to be ignored silently)
+    DQN_REQUIRE(!(u && !h->cfg.use_per), "uniform draws were given but the handle samples uniformly (pass h_rows)");
+    DQN_REQUIRE(!(rows && h->cfg.use_per), "rows were given but the handle samples by priority (pass h_u)");
+    if (u) for (int i = 0; i < h->B; ++i) DQN_REQUIRE(u[i] >= 0.0 && u[i] < 1.0, "uniform draw outside [0,1)");
+    if (rows) for (int i = 0; i < h->B; ++i) DQN_REQUIRE(rows[i] >= 0 && rows[i] < h->ring_size, "row out of range");
     h->prof_used = 0; h->prof_marks.clear();
     maybe_refresh_stats(h);
     fused_step_launches(h, u, rows, 1.0, 3);
@@ -1273,7 +1281,10 @@ struct CkptHeader {
     int64_t slab, step, game_count;
     float b1p, b2p;
     int32_t H, W, C, A, hidden, dueling, variant, pad;
+    uint64_t rng_counter;  // version >= 2: device Philox counter, so that a resumed device_rng run continues its draw sequence
+    uint64_t reserved[3];
 };
+constexpr size_t CKPT_V1_HEADER = 80;  // sizeof(CkptHeader) of version 1 (everything up to and including `pad`)
 
 extern "C" int dqn_save(dqn_learner* h, const char* prefix) {
     API_BEGIN(h)
@@ -1282,15 +1293,17 @@ extern "C" int dqn_save(dqn_learner* h, const char* prefix) {
     FILE* f = fopen((path + ".tmp").c_str(), "wb");
     DQN_REQUIRE(f != nullptr, "cannot open checkpoint for writing");
     CkptHeader hd; memset(&hd, 0, sizeof(hd));
-    memcpy(hd.magic, "DQNB200", 8); hd.version = 1; hd.n_tensors = (int32_t)h->net.tensors.size();
+    memcpy(hd.magic, "DQNB200", 8); hd.version = 2; hd.n_tensors = (int32_t)h->net.tensors.size();
     hd.slab = h->net.slab; hd.step = h->h_sc->step; hd.game_count = h->h_sc->game_count;
     hd.b1p = h->h_sc->b1p; hd.b2p = h->h_sc->b2p;
     hd.H = h->net.H; hd.W = h->net.W; hd.C = h->net.C; hd.A = h->net.A; hd.hidden = h->net.hidden;
     hd.dueling = h->net.dueling; hd.variant = h->cfg.conv_variant;
+    hd.rng_counter = h->h_sc->rng_counter;
     bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
     std::vector<float> buf((size_t)h->net.slab);
     for (float* slab : {h->online, h->target, h->slot_m, h->slot_v}) {
-        DQN_CUDA_OK(cudaMemcpy(buf.data(), slab, buf.size() * 4, cudaMemcpyDeviceToHost));
+        DQN_CUDA_OK(cudaMemcpyAsync(buf.data(), slab, buf.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
         ok = ok && fwrite(buf.data(), 4, buf.size(), f) == buf.size();
     }
     fclose(f);
@@ -1299,6 +1312,8 @@ extern "C" int dqn_save(dqn_learner* h, const char* prefix) {
     API_END(h)
 }
 
+__global__ void set_rng_kernel(dqn_learner::Scalars* sc, unsigned long long v) { sc->rng_counter = v; }
+
 extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
     if (!h) return 2;
     const std::string path = std::string(prefix) + ".dqnb200";
@@ -1306,21 +1321,32 @@ extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
     if (!f) return 3;  // "model does not exist" (rl/model/model.py:76-78)
     try {
         DQN_CUDA_OK(cudaSetDevice(h->device));
-        CkptHeader hd;
-        DQN_REQUIRE(fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "DQNB200", 8) == 0, "not a dqn_b200 checkpoint");
-        DQN_REQUIRE(hd.slab == h->net.slab && hd.H == h->net.H && hd.W == h->net.W && hd.A == h->net.A &&
-                        hd.hidden == h->net.hidden && hd.dueling == h->net.dueling && hd.variant == h->cfg.conv_variant,
+        // steps may still be in flight (dqn_train_steps returns after enqueueing); the look-ahead batch was sampled for the
+        // old weights' step counter
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        h->pf_valid = false;
+        CkptHeader hd; memset(&hd, 0, sizeof(hd));
+        DQN_REQUIRE(fread(&hd, CKPT_V1_HEADER, 1, f) == 1 && memcmp(hd.magic, "DQNB200", 8) == 0, "not a dqn_b200 checkpoint");
+        DQN_REQUIRE(hd.version == 1 || hd.version == 2, "unsupported dqn_b200 checkpoint version");
+        if (hd.version >= 2)
+            DQN_REQUIRE(fread(reinterpret_cast<char*>(&hd) + CKPT_V1_HEADER, sizeof(hd) - CKPT_V1_HEADER, 1, f) == 1, "truncated checkpoint header");
+        DQN_REQUIRE(hd.slab == h->net.slab && hd.H == h->net.H && hd.W == h->net.W && hd.C == h->net.C && hd.A == h->net.A &&
+                        hd.hidden == h->net.hidden && hd.dueling == h->net.dueling && hd.variant == h->cfg.conv_variant &&
+                        hd.n_tensors == (int32_t)h->net.tensors.size(),
                     "checkpoint was written for a different network configuration");
         std::vector<float> buf((size_t)h->net.slab);
         for (float* slab : {h->online, h->target, h->slot_m, h->slot_v}) {
             DQN_REQUIRE(fread(buf.data(), 4, buf.size(), f) == buf.size(), "truncated checkpoint");
-            DQN_CUDA_OK(cudaMemcpy(slab, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+            DQN_CUDA_OK(cudaMemcpyAsync(slab, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, h->stream));
+            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));  // buf is reused
         }
         fclose(f); f = nullptr;
         set_ll(h, &h->d_sc->step, hd.step);
         set_ll(h, &h->d_sc->game_count, hd.game_count);
         set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, hd.b1p, &h->d_sc->b2p, hd.b2p);
+        if (hd.version >= 2) set_rng_kernel<<<1, 1, 0, h->stream>>>(h->d_sc, hd.rng_counter);
         h->host_step = hd.step;
+        h->has_max_weight = false;  // PER normaliser: recomputed by the first sample, as after a reference restart (:505 "is None")
         launch_pack_conv(h, 0); launch_pack_conv(h, 1);
         DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     } catch (const std::string& e) {

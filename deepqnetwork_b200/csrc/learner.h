@@ -262,7 +262,9 @@ void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b,
                         void* host_out = nullptr);
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
 void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uint32_t* d_data, int64_t write0);
-void launch_tree_stats(dqn_learner* h, double per_b_override);
+// d_out4 == nullptr: refresh the handle's PER state (stat_*, last_max_weight; deep_q_agent.py:505-510 cadence);
+// otherwise {min, max, avg, total} go to d_out4 and the handle's state is left alone (read-only getters)
+void launch_tree_stats(dqn_learner* h, double per_b_override, float* d_out4 = nullptr);
 
 // nn.cu
 // x_f32: the same rows as d_states already converted to f32 (used by the tcgen05 path; may be null in FP32 mode)

@@ -215,7 +215,7 @@ __global__ void tree_stats_partial(const float* __restrict__ leaves, long long n
 
 __global__ void tree_stats_final(const float* pmin, const float* pmax, const double* psum, int parts,
                                  const float* __restrict__ tree, const long long* p_size, int batch, PerParams pp,
-                                 dqn_learner::Scalars* sc) {
+                                 dqn_learner::Scalars* sc, float* out4) {
     float mn = INFINITY, mx = -INFINITY;
     double sm = 0.0;
     for (int i = threadIdx.x; i < parts; i += 32) { mn = fminf(mn, pmin[i]); mx = fmaxf(mx, pmax[i]); sm += psum[i]; }
@@ -227,8 +227,15 @@ __global__ void tree_stats_final(const float* pmin, const float* pmax, const dou
     if (threadIdx.x == 0) {
         const long long n = *p_size;
         const float total = tree[0];
+        const float avg = n > 0 ? (float)(sm / (double)n) : 0.f;
+        if (out4) {
+            // read-only getters (SumTree.get_min/get_max/get_average/total): the handle's PER state keeps the cadence of
+            // DeepQAgent._sample_memories (step % per_calculate_steps == 0, deep_q_agent.py:505)
+            out4[0] = mn; out4[1] = mx; out4[2] = avg; out4[3] = total;
+            return;
+        }
         sc->stat_min = mn; sc->stat_max = mx; sc->stat_total = total;
-        sc->stat_avg = n > 0 ? (float)(sm / (double)n) : 0.f;
+        sc->stat_avg = avg;
         // deep_q_agent.py:508-510: last_min = max(min, 0.01); last_max_weight = pow(B*(last_min/total), -per_b)
         const float last_min = fmaxf(mn, 0.01f);
         const float x = __fmul_rn((float)batch, __fdiv_rn(last_min, total));
@@ -273,7 +280,7 @@ void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uin
     h->launches += 2;
 }
 
-void launch_tree_stats(dqn_learner* h, double per_b_override) {
+void launch_tree_stats(dqn_learner* h, double per_b_override, float* d_out4) {
     const int parts = 296;
     float* pmin = (float*)h->stats_scratch;
     float* pmax = pmin + parts;
@@ -281,7 +288,7 @@ void launch_tree_stats(dqn_learner* h, double per_b_override) {
     const long long n = h->tree_size;
     tree_stats_partial<<<parts, 256, 0, h->stream>>>(h->tree + (h->cap - 1), n, pmin, pmax, psum);
     tree_stats_final<<<1, 32, 0, h->stream>>>(pmin, pmax, psum, parts, h->tree, tree_size_ptr(h), h->B,
-                                               make_pp(h, per_b_override), h->d_sc);
+                                               make_pp(h, per_b_override), h->d_sc, d_out4);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches += 2;
 }

@@ -10,6 +10,8 @@ import torch
 
 from oracle import nn_ref
 from tests.gpu_util import need_gpu, rel_err
+from tests.parity_util import (DENSE_KERNELS, check_step_against_oracle, oracle_state_from_gpu,
+                               oracle_step_with_device_gates, snapshot)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -32,13 +34,13 @@ CONFIGS = {
 }
 
 
-def make(cfg, batch=32, capacity=256, seed=0, math_mode='fp32'):
+def make(cfg, batch=32, capacity=256, seed=0, math_mode='fp32', keep_grads=1, **learner_kw):
     from deepqnetwork_b200.learner import Learner
     from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
     variant = cfg.get('variant', 'reference')
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
                 use_per=cfg['per'], use_momentum=cfg.get('momentum', False), batch_size=batch, replay_capacity=capacity,
-                conv_variant=variant, math_mode=math_mode)
+                conv_variant=variant, math_mode=math_mode, **learner_kw)
     spec = nn_ref.NetSpec(cfg['h'], cfg['w'], 4, cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
                           use_per=cfg['per'], use_momentum=cfg.get('momentum', False), variant=variant)
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], variant)
@@ -53,22 +55,17 @@ def make(cfg, batch=32, capacity=256, seed=0, math_mode='fp32'):
             if k.endswith('/bias'):
                 p[k] = (rng.normal(0, 0.05, p[k].shape)).astype(np.float32)
     L.set_tower(on, 0); L.set_tower(tg, 1)
-    L.set_option('keep_grads', 1)  # the parity tests read the gradient slab (slot 3) after train_batch
+    # keep_grads=1: dqn_train_batch leaves every gradient readable in slot 3 (split dense wgrad + streaming optimizer);
+    # keep_grads=0 is what ships: the fused dense wgrad+optimizer kernel, whose gradient the tests recover from the m slot
+    L.set_option('keep_grads', keep_grads)
     return L, spec, shapes, on, tg
 
 
-def gate_flips(L, aux, n=32):
-    """Number of ReLU units whose on/off state differs between the device step and the fp64 truth (and check the
-    activations themselves at TOL).  A pre-activation below fp32 resolution can land on either side of zero; the
-    forward is unaffected but that unit's gradient path is switched, and Adam's first steps (update ~ lr*sign(g))
-    amplify it.  Parity of gradients / optimizer slots / weights at 1e-4 is therefore asserted for runs whose gates
-    all agree; after a flipped gate those tensors are held to 2e-2 instead (Q-values, targets, losses stay at 1e-4)."""
-    flips = 0
-    for nm, a_ref in zip(('act1_online', 'act2_online', 'act3_online', 'hid_online'), aux['acts']):
-        a_gpu = L.debug_read(nm, (2 * n,) + a_ref.shape[1:] if L.cfg.use_double else a_ref.shape)[:n]
-        flips += int(np.sum((a_gpu > 0) != (a_ref > 0)))
-        assert rel_err(a_gpu, a_ref) < TOL, nm
-    return flips
+def slab_grad_names(L, shapes, mode, keep_grads):
+    """Tensors whose gradient is in the gradient slab after a step."""
+    if mode == 'fp32' or keep_grads:
+        return None
+    return [k for k in shapes if k not in DENSE_KERNELS]
 
 
 def rand_batch(cfg, n, seed):
@@ -99,74 +96,34 @@ def test_predict_matches_oracle(name, mode):
     L.close()
 
 
-def oracle_state_from_gpu(L, shapes, spec):
-    """fp64 oracle state (weights, optimizer slots, beta powers, step) equal to the device's current state, so that
-    every step is compared from identical inputs instead of letting two chaotic trajectories drift apart."""
-    o = nn_ref.to_torch({k: L.get_param(k).reshape(shapes[k]) for k in shapes}, torch.float64)
-    t = nn_ref.to_torch({k: L.get_param(k, tower=1).reshape(shapes[k]) for k in shapes}, torch.float64)
-    opt = nn_ref.OptState(o, spec, torch.float64)
-    opt.m = nn_ref.to_torch({k: L.get_param(k, slot=1).reshape(shapes[k]) for k in shapes}, torch.float64)
-    opt.v = nn_ref.to_torch({k: L.get_param(k, slot=2).reshape(shapes[k]) for k in shapes}, torch.float64)
-    b1p, b2p = L.get_beta_powers()
-    opt.beta1_power = torch.tensor(b1p, dtype=torch.float64); opt.beta2_power = torch.tensor(b2p, dtype=torch.float64)
-    opt.step = L.get_step()
-    return o, t, opt
+PATHS = [('fp32', 1), ('tc3x', 1), ('tc3x', 0)]  # (math mode, keep_grads); ('tc3x', 0) is the shipped default
 
 
-def check_optimizer_given_grads(L, shapes, spec, o_before, opt_before):
-    """Optimizer parity in isolation: apply the oracle's Adam/Momentum to the DEVICE's gradient and compare weights
-    and slots tightly.  (End-to-end, Adam's early steps behave like lr*sign(g), so an element whose gradient is
-    within fp32 noise of zero legitimately moves by up to ~2*lr in either direction; that is bounded separately.)"""
-    g = {k: torch.as_tensor(L.get_param(k, slot=3).reshape(shapes[k])).to(torch.float64) for k in shapes}
-    nn_ref.apply_optimizer(o_before, g, opt_before, spec, torch.float64)
-    for k in shapes:
-        assert rel_err(L.get_param(k), o_before[k].numpy().reshape(-1)) < 2e-6, ('opt weight', k)
-        assert rel_err(L.get_param(k, slot=1), opt_before.m[k].numpy().reshape(-1)) < 2e-6, ('opt m', k)
-        if not spec.use_momentum:
-            assert rel_err(L.get_param(k, slot=2), opt_before.v[k].numpy().reshape(-1)) < 2e-6, ('opt v', k)
-
-
-def check_weights_end_to_end(L, shapes, spec, o_after, flipped):
-    """Updated weights vs the fp64 truth: 1e-4 relative per tensor, except for elements whose update sign is decided
-    by a gradient inside fp32 noise (|dw| then differs by at most ~2*lr); those must be rare."""
-    lr = spec.learning_rate
-    for k in shapes:
-        got = L.get_param(k).astype(np.float64); ref = o_after[k].numpy().reshape(-1)
-        scale = max(np.max(np.abs(ref)), 1e-30)
-        bad = np.abs(got - ref) > TOL * scale
-        assert np.max(np.abs(got - ref)) <= TOL * scale + 2.5 * lr, ('e2e weight bound', k)
-        assert bad.mean() <= (1e-3 if not flipped else 5e-2), ('e2e weight outliers', k, float(bad.mean()))
-
-
-@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('mode,keep', PATHS, ids=['fp32', 'tc3x-keep_grads', 'tc3x-shipped'])
 @pytest.mark.parametrize('name', list(CONFIGS))
-def test_train_batch_matches_oracle(name, mode):
-    """DeepQModel.train (two runs + host target) for three consecutive steps on fresh batches.  Each step starts
-    the fp64 oracle from the device's own state.  Both arithmetic modes that claim fp32-grade results are held to
-    the same 1e-4: FFMA fp32 and tcgen05 TF32 x3."""
+def test_train_batch_matches_oracle(name, mode, keep):
+    """DeepQModel.train (two runs + host target) for consecutive steps on fresh batches, each step starting the fp64
+    oracle from the device's own state.  FFMA fp32 and tcgen05 TF32 x3 are held to the same 1e-4; the shipped path
+    (fused dense wgrad+optimizer kernel, no gradient round trip) runs 5 steps and has its m / v slots and delta-w
+    compared with the oracle like the others (tests/parity_util.py)."""
     import copy
     cfg = CONFIGS[name]
-    L, spec, shapes, on, tg = make(cfg, math_mode=mode)
-    for it in range(3):
+    L, spec, shapes, on, tg = make(cfg, math_mode=mode, keep_grads=keep)
+    tag = 'train_batch[%s-%s-%d]' % (name, mode, keep)
+    for it in range(3 if keep else 5):
         b = rand_batch(cfg, 32, 100 + it)
         w = np.random.default_rng(it).random(32).astype(np.float32) + 0.1 if cfg['per'] else None
         o, t, opt = oracle_state_from_gpu(L, shapes, spec)
-        o2, opt2 = copy.deepcopy(o), copy.deepcopy(opt)
+        before = snapshot(o, opt)
         step, losses, loss = L.train_batch(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'], w)
-        rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, b, w, spec, torch.float64)
+        rstep, rlosses, rloss, aux = oracle_step_with_device_gates(L, spec, o, t, opt, b, w, 32, tag, it)
         assert step == rstep == it + 1
         A = cfg['a']
-        flipped = gate_flips(L, aux) > 0
-        gtol = TOL if not flipped else 2e-2
         assert rel_err(L.debug_read('q_online', (32, A)), aux['q']) < TOL
         assert rel_err(L.debug_read('max_q', (32,)), aux['max_q']) < TOL
         assert rel_err(L.debug_read('y', (32,)), aux['y']) < TOL
         assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
-        for k in shapes:
-            g = L.get_param(k, slot=3)
-            assert rel_err(g, aux['grads'][k].reshape(-1)) < gtol, (name, it, 'grad', k, flipped, rel_err(g, aux['grads'][k].reshape(-1)))
-        check_optimizer_given_grads(L, shapes, spec, o2, opt2)
-        check_weights_end_to_end(L, shapes, spec, o, flipped)
+        check_step_against_oracle(L, spec, shapes, before, aux, o, opt, tag, it, slab_grad_names(L, shapes, mode, keep))
         for k in shapes:  # the target tower only changes through copy_network (SURVEY Q8)
             assert np.array_equal(L.get_param(k, tower=1), tg[k].reshape(-1))
     L.copy_network()
@@ -191,11 +148,12 @@ def test_double_dqn_masked_max_clamps_negative_targets():
     L.close()
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('name', ['c1_vanilla', 'c2_breakout_ddp'])
-def test_get_losses_matches_oracle(name):
+def test_get_losses_matches_oracle(name, mode):
     """DeepQModel.get_losses on the 128-row PER insert batch (deep_q_agent.py:481-485)."""
     cfg = CONFIGS[name]
-    L, spec, shapes, on, tg = make(cfg)
+    L, spec, shapes, on, tg = make(cfg, math_mode=mode)
     b = rand_batch(cfg, 128, 9)
     got = L.get_losses(b['states'], b['actions'], b['rewards'], b['continues'], b['next_states'])
     ref = nn_ref.losses_only(nn_ref.to_torch(on, torch.float64), nn_ref.to_torch(tg, torch.float64), b, spec, torch.float64)
@@ -204,46 +162,55 @@ def test_get_losses_matches_oracle(name):
     L.close()
 
 
-@pytest.mark.parametrize('mode', MODES)
-@pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c1_vanilla', 'c3_mspacman_ddp'])
-def test_fused_train_steps_match_reference_loop(name, mode):
-    """DeepQAgent._train_run_train for 4 consecutive steps, fully on device, vs the oracle loop fed the same
-    random.random()/randint draws: sampled indices and gathered rows bit-exact, IS weights / losses / weights
-    within tolerance, priority write-back bit-exact given the device priorities."""
+def fused_loop_vs_oracle(name, mode, steps, draws, tag, N=2000, per_b_start=0.4, per_b_end=1.0, **learner_kw):
+    """DeepQAgent._train_run_train + _train_save_model's target sync, `steps` times, fully on device (dqn_train_step fed
+    the draws), each step against the oracle restatement of rl/deep_q_agent.py:326-360,500-534: sampled rows and gathered
+    bytes bit-exact, IS weights (with the per_calculate_steps refresh cadence and the beta anneal) 1e-6, losses 1e-4,
+    gradients / slots / delta-w per tests/parity_util.py, priority write-back and f16 loss column bit-exact given the
+    device priorities, target tower equal to the online one exactly when step % copy_network_steps == 0.
+    Returns the learner (caller closes)."""
     from oracle.sumtree_c import SumTreeC
-    from oracle.sumtree_ref import uniform_rows
     cfg = CONFIGS[name]
-    N, B = 2000, 32
-    L, spec, shapes, on, tg = make(cfg, capacity=N, math_mode=mode)
+    B = 32
+    L, spec, shapes, on, tg = make(cfg, capacity=N, math_mode=mode, keep_grads=0, per_b_start=per_b_start,
+                                   per_b_end=per_b_end, **learner_kw)
     L.replay_fill_synthetic(N, seed=77)
     ref_tree = SumTreeC(N)
-    rnd = random.Random(0)
+    anneal = learner_kw.get('use_per_annealing', False)
+    calc = learner_kw.get('per_calculate_steps', 5000)
+    copy_steps = learner_kw.get('copy_network_steps', 10000)
     max_w = None
-    ever_flipped = False
-    for it in range(4):
+    for it in range(steps):
         o, t, opt = oracle_state_from_gpu(L, shapes, spec)
+        before = snapshot(o, opt)
+        tg_before = {k: v.numpy().reshape(-1).astype(np.float32) for k, v in t.items()}
+        assert opt.step == it
         if cfg['per']:
             tree, data, size, write = L.tree_read()
             ref_tree.load(tree, data, size, write)
-            u = np.array([rnd.random() for _ in range(B)])
+            u = draws(it, B, N)
             step, losses, loss = L.train_step(uniforms=u)
             ti, di, p, mi = ref_tree.sample(u)
-            if max_w is None:  # step % per_calculate_steps == 0 or first (deep_q_agent.py:505-510)
+            # deep_q_agent.py:445-450: per_b follows the step counter; :505-510: normaliser every per_calculate_steps
+            per_b = nn_ref.per_beta(it, per_b_start, per_b_end, learner_kw.get('per_anneal_steps', 2000000)) if anneal else per_b_start
+            if max_w is None or it % calc == 0:
                 leaves = tree[N - 1:N - 1 + size]
-                max_w = nn_ref.max_weight(leaves.min(), tree[0], B, 0.4)
-            isw = nn_ref.is_weights(p, tree[0], B, 0.4, max_w)
-            assert rel_err(L.debug_read('is_weights', (B,)), isw) < 1e-6
+                max_w = nn_ref.max_weight(leaves.min(), tree[0], B, per_b)
+            isw = nn_ref.is_weights(p, tree[0], B, per_b, max_w)
+            assert rel_err(L.debug_read('is_weights', (B,)), isw) < 1e-6, (tag, it, 'is_weights')
+            st = L.get_stats()
+            assert abs(st['per_b'] - per_b) < 1e-6 and abs(st['last_max_weight'] - max_w) <= 1e-6 * max_w, (tag, it, st, per_b, max_w)
         else:
-            mi = uniform_rows(N, B, rnd)
+            mi = draws(it, B, N)
             step, losses, loss = L.train_step(rows=mi)
             isw = None
         got = L.batch_read(); rows = L.replay_read(mi)
         for k in ('states', 'next_states', 'actions', 'rewards', 'continues'):
             assert np.array_equal(got[k], rows[k]), k
-        rstep, rlosses, rloss, aux = nn_ref.train_step(o, t, opt, rows, isw, spec, torch.float64)
-        assert step == rstep
+        rstep, rlosses, rloss, aux = oracle_step_with_device_gates(L, spec, o, t, opt, rows, isw, B, tag, it)
+        assert step == rstep == it + 1
         assert rel_err(losses, rlosses) < TOL and abs(float(loss) - rloss) <= TOL * abs(rloss)
-        check_weights_end_to_end(L, shapes, spec, o, gate_flips(L, aux) > 0)
+        check_step_against_oracle(L, spec, shapes, before, aux, o, opt, tag, it, slab_grad_names(L, shapes, mode, 0))
         if cfg['per']:
             newp = L.debug_read('new_priorities', (B,))
             assert rel_err(newp, nn_ref.make_priority(losses)) < 1e-6  # powf vs np.power, float tolerance
@@ -253,6 +220,99 @@ def test_fused_train_steps_match_reference_loop(name, mode):
             for r, v in zip(mi.tolist(), newp.astype(np.float16)):
                 last[r] = v  # later duplicates win, as the sequential loop does
             assert all(L.replay_read([r], ('losses',))['losses'][0] == v for r, v in last.items())
+        # deep_q_agent.py:358-360: target <- online when the post-increment step is a multiple of copy_network_steps
+        for k in shapes:
+            tgt = L.get_param(k, tower=1)
+            if copy_steps > 0 and step % copy_steps == 0:
+                assert np.array_equal(tgt, L.get_param(k, tower=0)), (tag, it, 'target sync missing', k)
+            else:
+                assert np.array_equal(tgt, tg_before[k]), (tag, it, 'target tower changed without a sync', k)
+    return L, shapes
+
+
+def host_random_draws(per):
+    from oracle.sumtree_ref import uniform_rows
+    rnd = random.Random(0)
+    if per:
+        return lambda it, B, N: np.array([rnd.random() for _ in range(B)])
+    return lambda it, B, N: uniform_rows(N, B, rnd)
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c1_vanilla', 'c3_mspacman_ddp'])
+def test_fused_train_steps_match_reference_loop(name, mode):
+    """4 consecutive fused steps fed CPython random.random() / randint draws, as the reference's samplers make them."""
+    L, _ = fused_loop_vs_oracle(name, mode, 4, host_random_draws(CONFIGS[name]['per']), 'fused[%s-%s]' % (name, mode))
+    L.close()
+
+
+CADENCE = dict(copy_network_steps=3, per_calculate_steps=2, use_per_annealing=True, per_anneal_steps=10)
+
+
+@pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c1_vanilla'])
+def test_cadences_inside_train_steps_match_oracle_loop(name):
+    """Target sync every copy_network_steps, PER normaliser refresh every per_calculate_steps and the beta anneal, all
+    crossed several times inside ONE dqn_train_steps(9) call (CUDA-graph replay, look-ahead sampling, device Philox).
+    Leg 1: the same nine steps issued one by one with the device's own draws restated on the host
+    (oracle/philox_ref.py), every step checked against the oracle loop.  Leg 2: dqn_train_steps(9) must end bit-identical
+    to leg 1 -- online and target towers, both optimizer slots, sum tree, step, beta powers, PER statistics."""
+    from oracle import philox_ref
+    cfg = CONFIGS[name]
+    seed = 7
+    if cfg['per']:
+        draws = lambda it, B, N: philox_ref.per_uniforms(B, it, seed)
+    else:
+        draws = lambda it, B, N: philox_ref.uniform_rows(B, N, it, seed)
+    steps = 9
+    L1, shapes = fused_loop_vs_oracle(name, 'tc3x', steps, draws, 'cadence[%s]' % name, **CADENCE)
+    L2, *_ = make(cfg, capacity=2000, math_mode='tc3x', keep_grads=0, **CADENCE)
+    L2.replay_fill_synthetic(2000, seed=77)
+    L2.train_steps(steps); L2.sync()
+    assert L1.get_step() == L2.get_step() == steps
+    assert L1.get_beta_powers() == L2.get_beta_powers()
+    for tower, slot in ((0, 0), (1, 0), (0, 1), (0, 2)):
+        for k in shapes:
+            assert np.array_equal(L1.get_param(k, tower=tower, slot=slot), L2.get_param(k, tower=tower, slot=slot)), (tower, slot, k)
+    if cfg['per']:
+        assert np.array_equal(L1.tree_read()[0], L2.tree_read()[0])
+        s1, s2 = L1.get_stats(), L2.get_stats()
+        for key in ('min', 'max', 'avg', 'total', 'last_max_weight', 'per_b'):
+            assert s1[key] == s2[key], (key, s1, s2)
+    b1, b2 = L1.batch_read(), L2.batch_read()  # the last trained batch
+    for k in b1:
+        assert np.array_equal(b1[k], b2[k]), k
+    L1.close(); L2.close()
+
+
+def test_tree_stats_getter_leaves_the_per_normaliser_alone():
+    """SumTree.get_min/get_max/get_average/total are read-only in the reference (sum_tree.py:139-165); the [train] report
+    line reads `total` every train_report_interval steps (deep_q_agent.py:391).  The normaliser last_max_weight must keep
+    the per_calculate_steps cadence however often the getters run (dqn_tree_stats used to overwrite it)."""
+    cfg = CONFIGS['c2_breakout_ddp']
+    L, spec, shapes, on, tg = make(cfg, capacity=2000, math_mode='tc3x', keep_grads=0, per_calculate_steps=1000)
+    L.replay_fill_synthetic(2000, seed=77)
+    L.train_step(fetch=False)
+    st0 = L.get_stats()
+    for _ in range(3):
+        L.tree_stats()
+        L.train_step(fetch=False)
+    mn, mx, avg, total = L.tree_stats()
+    st1 = L.get_stats()
+    assert st1['last_max_weight'] == st0['last_max_weight'] and st1['min'] == st0['min'] and st1['total'] == st0['total']
+    tree = L.tree_read()[0]
+    assert mn == tree[1999:].min() and mx == tree[1999:].max() and total == tree[0] and total != st0['total']
+    L.close()
+
+
+def test_per_stats_getters_match_numpy():
+    cfg = CONFIGS['c2_breakout_ddp']
+    L, *_ = make(cfg, capacity=2000, math_mode='tc3x', keep_grads=0)
+    L.replay_fill_synthetic(1500, seed=3)
+    tree = L.tree_read()[0]
+    leaves = tree[1999:1999 + 1500]
+    mn, mx, avg, total = L.tree_stats()
+    assert mn == leaves.min() and mx == leaves.max() and total == tree[0]
+    assert abs(avg - np.average(leaves)) <= 2e-6 * abs(np.average(leaves))
     L.close()
 
 

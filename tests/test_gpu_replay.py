@@ -203,3 +203,42 @@ def test_synthetic_fill_tree_is_sequential_add_semantics():
     assert rows['actions'].max() < 4 and set(np.unique(rows['rewards'])) <= {0, 1, 4, 7}
     assert 0.2 < rows['states'].mean() / 255 < 0.8
     L.close()
+
+
+def test_gather_beyond_4gib_offsets_at_benchmark_capacity():
+    """BASELINE C2 geometry at full size: 1M-transition ring of 89x80x4 rows (2 x 28.5 GB in HBM).  Rows are sampled from
+    the whole ring, most of them beyond the 4 GiB byte offset (row 150,796 and up), through BOTH samplers' gathers
+    (dqn_uniform_sample with explicit rows; the fused step's PER gather) and compared with the bytes the synthetic fill
+    defines for those rows, restated on the host (oracle/philox_ref.synthetic_state_rows) -- so neither the fill's nor
+    the gather's 64-bit row arithmetic can hide an overflow behind the other."""
+    from deepqnetwork_b200.learner import Learner
+    from oracle import philox_ref
+    from oracle.sumtree_c import SumTreeC
+    H, W, N, B, seed = 89, 80, 1000000, 32, 1234
+    L = Learner(H, W, 4, num_actions=4, num_hidden=512, use_dueling=True, use_double=True, use_per=True, batch_size=B,
+                replay_capacity=N, math_mode='tc3x')
+    L.replay_fill_synthetic(N, seed=seed)
+    S = H * W * 4
+    rng = np.random.default_rng(0)
+    size = N / B
+    rows = np.array([rng.integers(int(i * size), int((i + 1) * size)) for i in range(B)], np.int64)
+    rows[0], rows[1], rows[-1] = 0, 150796, N - 1  # first row, first row whose bytes start beyond 4 GiB, last row
+    assert rows[1] * S > (1 << 32) > (rows[1] - 1) * S
+    L.uniform_sample(rows)
+    got = L.batch_read()
+    assert np.array_equal(got['states'].reshape(B, S), philox_ref.synthetic_state_rows(rows, S, seed))
+    assert np.array_equal(got['next_states'].reshape(B, S), philox_ref.synthetic_state_rows(rows, S, seed, next_states=True))
+    direct = L.replay_read(rows)  # cudaMemcpy path
+    for k in ('states', 'next_states', 'actions', 'rewards', 'continues', 'losses'):
+        assert np.array_equal(got[k], direct[k]), k
+    # the fused step's own sampling + gather at this size: rows from the C oracle fed the same draws
+    tree, data, tsize, write = L.tree_read()
+    ref = SumTreeC(N); ref.load(tree, data, tsize, write)
+    u = rng.random(B)
+    L.train_step(uniforms=u, fetch=False)
+    ti, di, p, mi = ref.sample(u)
+    assert (mi * S > (1 << 32)).sum() >= B // 2
+    got = L.batch_read()
+    assert np.array_equal(got['states'].reshape(B, S), philox_ref.synthetic_state_rows(mi, S, seed))
+    assert np.array_equal(got['next_states'].reshape(B, S), philox_ref.synthetic_state_rows(mi, S, seed, next_states=True))
+    L.close()
