@@ -53,8 +53,11 @@ _SIGS = {
     'dqn_tree_add': [_P, C.c_int64, _P, _P],
     'dqn_tree_update': [_P, C.c_int64, _P, _P, C.c_int32],
     'dqn_tree_sample': [_P, C.c_int32, _P, _P, _P, _P, _P],
+    'dqn_tree_retrieve': [_P, C.c_int32, _P, _P, _P, _P, _P],
     'dqn_tree_stats': [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)],
     'dqn_tree_read': [_P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    'dqn_tree_info': [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)],
+    'dqn_tree_get': [_P, C.c_int64, _P, _P, _P],
     'dqn_per_sample': [_P, _P, C.c_int32, C.c_double, _P, _P, _P],
     'dqn_uniform_sample': [_P, _P],
     'dqn_batch_read': [_P, _P, _P, _P, _P, _P, _P],

@@ -567,19 +567,32 @@ static void d2h(dqn_learner* h, T* dst, const T* src, size_t n) {
     if (dst) DQN_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
 }
 
-extern "C" int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* u, int64_t* t_idx, int64_t* d_idx,
-                               double* prio, int64_t* m_idx) {
-    API_BEGIN(h)
+static void tree_probe(dqn_learner* h, int32_t batch, const double* u, bool raw, int64_t* t_idx, int64_t* d_idx, double* prio,
+                       int64_t* m_idx) {
     DQN_REQUIRE(batch >= 1 && batch <= h->max_rows, "batch exceeds max_rows");
-    DQN_REQUIRE(u != nullptr, "uniform draws are required");
+    DQN_REQUIRE(u != nullptr, "draws are required");
+    DQN_REQUIRE(h->tree_size >= 1, "sum tree is empty");
     DQN_CUDA_OK(cudaMemcpyAsync(h->b_u, u, batch * 8, cudaMemcpyHostToDevice, h->stream));
     const int saved = h->cfg.use_per;
     h->cfg.use_per = 0;  // indices only: no IS weights
-    launch_tree_sample(h, batch, 0, -1.0);
+    try { launch_tree_sample(h, batch, 0, -1.0, nullptr, nullptr, raw); } catch (...) { h->cfg.use_per = saved; throw; }
     h->cfg.use_per = saved;
     d2h(h, (long long*)t_idx, h->b_tree_idx, batch); d2h(h, (long long*)d_idx, h->b_data_idx, batch);
     d2h(h, prio, h->b_prio, batch); d2h(h, (long long*)m_idx, h->b_mem_idx, batch);
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+
+extern "C" int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* u, int64_t* t_idx, int64_t* d_idx,
+                               double* prio, int64_t* m_idx) {
+    API_BEGIN(h)
+    tree_probe(h, batch, u, false, t_idx, d_idx, prio, m_idx);
+    API_END(h)
+}
+
+extern "C" int dqn_tree_retrieve(dqn_learner* h, int32_t n, const double* scores, int64_t* t_idx, int64_t* d_idx,
+                                 double* prio, int64_t* m_idx) {
+    API_BEGIN(h)
+    tree_probe(h, n, scores, true, t_idx, d_idx, prio, m_idx);
     API_END(h)
 }
 
@@ -605,6 +618,32 @@ extern "C" int dqn_tree_read(dqn_learner* h, float* tree, uint32_t* data, int64_
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     if (size) *size = h->tree_size;
     if (write) *write = h->tree_write;
+    API_END(h)
+}
+
+extern "C" int dqn_tree_info(dqn_learner* h, int64_t* size, int64_t* write, float* total) {
+    API_BEGIN(h)
+    if (size) *size = h->tree_size;
+    if (write) *write = h->tree_write;
+    if (total) {
+        DQN_CUDA_OK(cudaMemcpyAsync(total, h->tree, 4, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    API_END(h)
+}
+
+extern "C" int dqn_tree_get(dqn_learner* h, int64_t n, const int64_t* idx, float* scores, uint32_t* data) {
+    API_BEGIN(h)
+    for (int64_t j = 0; j < n; ++j) {
+        DQN_REQUIRE(idx[j] >= 0 && idx[j] < 2 * h->cap - 1, "tree_idx out of range");
+        if (scores) DQN_CUDA_OK(cudaMemcpyAsync(scores + j, h->tree + idx[j], 4, cudaMemcpyDeviceToHost, h->stream));
+        if (data) {
+            const int64_t d = idx[j] - (h->cap - 1);
+            if (d >= 0) DQN_CUDA_OK(cudaMemcpyAsync(data + j, h->tree_data + d, 4, cudaMemcpyDeviceToHost, h->stream));
+            else data[j] = 0;
+        }
+    }
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     API_END(h)
 }
 

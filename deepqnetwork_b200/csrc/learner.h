@@ -258,8 +258,9 @@ void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t se
 // sumtree.cu
 // u_src: uniforms read from there instead of b_u (may be pinned host memory); host_out: pinned host block that also
 // receives the {tree_idx | priority | is_weight} columns (stride max_rows, 8-byte entries)
+// raw_probe: the "uniforms" are the probes themselves (SumTree.get_with_info(s))
 void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b, const double* u_src = nullptr,
-                        void* host_out = nullptr);
+                        void* host_out = nullptr, bool raw_probe = false);
 void launch_tree_update(dqn_learner* h, int n, const long long* d_tree_idx, const float* d_scores, int store_losses);
 void launch_tree_add(dqn_learner* h, int64_t n, const float* d_scores, const uint32_t* d_data, int64_t write0);
 // d_out4 == nullptr: refresh the handle's PER state (stat_*, last_max_weight; deep_q_agent.py:505-510 cadence);

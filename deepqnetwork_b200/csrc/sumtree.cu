@@ -67,7 +67,7 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
                                    long long* __restrict__ o_tree_idx, long long* __restrict__ o_data_idx,
                                    long long* __restrict__ o_mem_idx, double* __restrict__ o_prio,
                                    double* __restrict__ o_isw64, float* __restrict__ o_isw, double* __restrict__ o_u,
-                                   int ahead, long long* host_out, int host_stride) {
+                                   int ahead, long long* host_out, int host_stride, int raw_probe) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= batch) return;
@@ -85,7 +85,8 @@ __global__ void tree_sample_kernel(const float* __restrict__ tree, const uint32_
     // replay_sampler_priority.py:30,33 under NEP 50: every operand is rounded to f32 first
     const float total = __ldcg(tree);
     const float seg = __fdiv_rn(total, (float)batch);
-    const float s = __fadd_rn(__fmul_rn(__double2float_rn(u), seg), __fmul_rn((float)i, seg));
+    // raw_probe: u already is the probe (SumTree.get_with_info(s) called directly, sum_tree.py:76-83)
+    const float s = raw_probe ? __double2float_rn(u) : __fadd_rn(__fmul_rn(__double2float_rn(u), seg), __fmul_rn((float)i, seg));
     long long leaf = tree_descend(tree, n_nodes, s, lane);
     long long d = leaf - (N - 1);
     const long long over = d - size + 1;  // sum_tree.py:121-123 "float rounding bug" clamp
@@ -257,12 +258,12 @@ static PerParams make_pp(const dqn_learner* h, double override_b) {
 
 long long* tree_size_ptr(dqn_learner* h);  // api.cu: device mirror of tree_size
 
-void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b, const double* u_src, void* host_out) {
+void launch_tree_sample(dqn_learner* h, int batch, int device_rng, double per_b, const double* u_src, void* host_out, bool raw_probe) {
     const int wpb = 8;
     launch_kernel(false, tree_sample_kernel, dim3(ceil_div(batch, wpb)), dim3(wpb * 32), 0, h->stream,
         h->tree, h->tree_data, h->cap, tree_size_ptr(h), batch, u_src ? u_src : (const double*)h->b_u, device_rng, h->cfg.seed, h->d_sc,
         make_pp(h, per_b), h->cfg.use_per, h->b_tree_idx, h->b_data_idx, h->b_mem_idx, h->b_prio, h->b_isw64,
-        h->b_isw, device_rng ? h->b_u : (double*)nullptr, h->sample_ahead, (long long*)host_out, h->max_rows);
+        h->b_isw, device_rng ? h->b_u : (double*)nullptr, h->sample_ahead, (long long*)host_out, h->max_rows, raw_probe ? 1 : 0);
     h->launches++;
 }
 

@@ -58,7 +58,7 @@ class ReplayMemory:
         if learner is None:
             from ..learner import Learner
             learner = Learner(input_height, input_width, input_channels, num_hidden=8, replay_capacity=self.max_size,
-                              batch_size=min(32, self.max_size))
+                              batch_size=min(32, self.max_size), math_mode='fp32')  # ring only
             self._owns = True
         if learner.capacity != self.max_size or learner.state_shape != self.shape:
             raise ValueError('learner ring geometry does not match this ReplayMemory')

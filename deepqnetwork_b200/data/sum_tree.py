@@ -16,7 +16,7 @@ class SumTree:
         if learner is None:
             from ..learner import Learner
             learner = Learner(8, 8, 4, num_hidden=8, replay_capacity=self.capacity, batch_size=32, use_per=True,
-                              max_rows=4096)
+                              max_rows=4096, math_mode='fp32')  # ring/tree only: the tiny network is never run
         if learner.capacity != self.capacity:
             raise ValueError('learner capacity does not match this SumTree')
         self.learner = learner
@@ -47,23 +47,25 @@ class SumTree:
 
     @property
     def tree(self):
+        """The whole heap array (device -> host copy; parity / debug)."""
         return self.learner.tree_read()[0]
 
     @property
     def data(self):
         return self.learner.tree_read()[1]
 
+    # size / write are host-side bookkeeping and total is the 4-byte root: none of them moves the tree
     @property
     def size(self):
-        return self.learner.tree_read()[2]
+        return self.learner.tree_info()[0]
 
     @property
     def write(self):
-        return self.learner.tree_read()[3]
+        return self.learner.tree_info()[1]
 
     @property
     def total(self):
-        return self.learner.tree_stats()[3]
+        return self.learner.tree_info(with_total=True)[2]
 
     def get_min(self):
         return self.learner.tree_stats()[0]
@@ -74,8 +76,19 @@ class SumTree:
     def get_average(self):
         return self.learner.tree_stats()[2]
 
+    def get_score(self, tree_idx):
+        return self.learner.tree_get([tree_idx])[0][0]
+
     def get_data(self, tree_idx):
-        return self.data[self.get_data_idx(tree_idx)]
+        return self.learner.tree_get([tree_idx])[1][0]
+
+    def get_with_info(self, score):
+        """(tree_idx, data_idx, score, data) of the leaf a probe lands on (sum_tree.py:76-83)."""
+        t, d, p, m = self.learner.tree_retrieve([score])
+        return int(t[0]), int(d[0]), np.float32(p[0]), np.uint32(m[0])
+
+    def get(self, score):
+        return self.get_with_info(score)[3]
 
     def __len__(self):
         return self.size

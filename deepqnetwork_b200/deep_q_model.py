@@ -129,7 +129,7 @@ class DeepQModel:
             per_a=c.get('per_a', 0.6), per_b_start=c.get('per_b_start', 0.4), per_b_end=c.get('per_b_end', 1),
             per_anneal_steps=c.get('per_anneal_steps', 2000000), use_per_annealing=c.get('use_per_annealing', False),
             per_calculate_steps=c.get('per_calculate_steps', 5000), copy_network_steps=0,
-            conv_variant=self.CONV_VARIANT, math_mode=c.get('math_mode', 'fp32'), seed=c.get('device_seed', 7),
+            conv_variant=self.CONV_VARIANT, math_mode=c.get('math_mode', 'tc3x'), seed=c.get('device_seed', 7),
             device=c.get('device', 0))
         loaded = False
         prefix = self.conf.get('save_path_prefix')

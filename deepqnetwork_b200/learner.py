@@ -17,7 +17,7 @@ class Learner:
                  use_double=False, use_per=False, use_momentum=False, learning_rate=0.00025, momentum=0.95,
                  discount_rate=0.99, batch_size=32, replay_capacity=10000, per_a=0.6, per_b_start=0.4,
                  per_b_end=1.0, per_anneal_steps=2000000, use_per_annealing=False, per_calculate_steps=5000,
-                 copy_network_steps=10000, max_rows=0, conv_variant='reference', math_mode='fp32', seed=7,
+                 copy_network_steps=10000, max_rows=0, conv_variant='reference', math_mode='tc3x', seed=7,
                  device=0):
         self._lib = _capi.lib()
         cfg = _capi.DqnConfig()
@@ -197,6 +197,14 @@ class Learner:
         self._c(self._lib.dqn_tree_sample(self._h, b, ptr(u), ptr(t), ptr(d), ptr(p), ptr(m)))
         return t, d, p, m
 
+    def tree_retrieve(self, scores):
+        """SumTree.get_with_info for caller-computed probes -> (tree_idx, data_idx, priority, mem_idx) arrays."""
+        sc = np.ascontiguousarray(np.atleast_1d(scores), dtype=np.float64)
+        b = sc.size
+        t = np.empty(b, np.int64); d = np.empty(b, np.int64); p = np.empty(b, np.float64); m = np.empty(b, np.int64)
+        self._c(self._lib.dqn_tree_retrieve(self._h, b, ptr(sc), ptr(t), ptr(d), ptr(p), ptr(m)))
+        return t, d, p, m
+
     def tree_stats(self):
         v = [C.c_float() for _ in range(4)]
         self._c(self._lib.dqn_tree_stats(self._h, *[C.byref(x) for x in v]))
@@ -207,6 +215,19 @@ class Learner:
         s = C.c_int64(); w = C.c_int64()
         self._c(self._lib.dqn_tree_read(self._h, ptr(tree), ptr(data), C.byref(s), C.byref(w)))
         return tree, data, s.value, w.value
+
+    def tree_info(self, with_total=False):
+        """(size, write[, total]) -- host bookkeeping plus, on request, the 4-byte root; the tree is not moved."""
+        s = C.c_int64(); w = C.c_int64(); t = C.c_float()
+        self._c(self._lib.dqn_tree_info(self._h, C.byref(s), C.byref(w), C.byref(t) if with_total else None))
+        return (s.value, w.value, np.float32(t.value)) if with_total else (s.value, w.value)
+
+    def tree_get(self, tree_idx):
+        """(scores f32[n], data u32[n]) of individual tree nodes."""
+        t = np.ascontiguousarray(np.atleast_1d(tree_idx), dtype=np.int64)
+        sc = np.empty(t.size, np.float32); d = np.empty(t.size, np.uint32)
+        self._c(self._lib.dqn_tree_get(self._h, t.size, ptr(t), ptr(sc), ptr(d)))
+        return sc, d
 
     # -- samplers ---------------------------------------------------------------------
     def per_sample(self, uniforms, refresh_stats, per_b):

@@ -113,8 +113,19 @@ int dqn_tree_update(dqn_learner* h, int64_t n, const int64_t* h_tree_idx, const 
  * (replay_sampler_priority.py:30-35); u are the B uniform draws (random.random()). Outputs may be NULL. */
 int dqn_tree_sample(dqn_learner* h, int32_t batch, const double* h_u, int64_t* h_tree_idx, int64_t* h_data_idx,
                     double* h_priorities, int64_t* h_mem_idx);
+/* SumTree.get_with_info(s) (sum_tree.py:76-83) for n caller-computed probes s (rounded to f32 like the reference's
+ * NumPy-2 arithmetic): same outputs as dqn_tree_sample */
+int dqn_tree_retrieve(dqn_learner* h, int32_t n, const double* h_scores, int64_t* h_tree_idx, int64_t* h_data_idx,
+                      double* h_priorities, int64_t* h_mem_idx);
+/* read-only (does not touch the PER normaliser or the report statistics of the handle) */
 int dqn_tree_stats(dqn_learner* h, float* mn, float* mx, float* avg, float* total);               /* :139-165 */
 int dqn_tree_read(dqn_learner* h, float* h_tree /*2N-1*/, uint32_t* h_data /*N*/, int64_t* size, int64_t* write);
+/* SumTree.size / .write / .total (sum_tree.py:18-21,139-141) without moving the tree: size and write are host-side
+ * bookkeeping, total is the 4-byte root; any pointer may be NULL */
+int dqn_tree_info(dqn_learner* h, int64_t* size, int64_t* write, float* total);
+/* SumTree.tree[tree_idx] and SumTree.get_data(tree_idx) (sum_tree.py:62-73) for n nodes; h_data entries of inner
+ * nodes are 0; either output may be NULL */
+int dqn_tree_get(dqn_learner* h, int64_t n, const int64_t* h_tree_idx, float* h_scores, uint32_t* h_data);
 
 /* ---- samplers (seam 3): fill the device-resident train batch --------- */
 /* ReplaySamplerPriority.sample_memories (replay_sampler_priority.py:27-43) + the IS-weight maths of

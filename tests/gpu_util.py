@@ -23,6 +23,6 @@ def rel_err(a, b):
 def small_learner(capacity, batch=32, use_per=True, **kw):
     from deepqnetwork_b200.learner import Learner
     args = dict(height=8, width=8, channels=4, num_actions=4, num_hidden=64, batch_size=batch,
-                replay_capacity=capacity, use_per=use_per, max_rows=max(batch, 128))
+                replay_capacity=capacity, use_per=use_per, max_rows=max(batch, 128), math_mode='fp32')
     args.update(kw)
     return Learner(**args)
