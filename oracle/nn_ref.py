@@ -214,7 +214,7 @@ def apply_optimizer(params, grads, opt, spec, dtype):
     opt.step += 1
 
 
-def train_step(online, target, opt, batch, is_weights, spec, dtype=torch.float32, gates=None):
+def train_step(online, target, opt, batch, is_weights, spec, dtype=torch.float32, gates=None, dq_override=None):
     """DeepQModel.train (deep_q_model.py:75-103): returns (step, losses, loss); updates `online`, `opt` in place.
 
     online/target: dict name -> torch tensor of `dtype`.  batch: dict of numpy arrays
@@ -238,13 +238,21 @@ def train_step(online, target, opt, batch, is_weights, spec, dtype=torch.float32
     else:
         loss = hub.mean()
         losses = hub
-    grads = torch.autograd.grad(loss, list(leaf.values()))
+    # dL/dq_a per sample, the vector the backward pass starts from (aux['dq']).  dq_override: evaluate the backward pass
+    # from a caller-supplied vector instead (the device's own TD-error gradient), so that a test can hold the backward
+    # arithmetic to its tolerance separately from the forward error that |y - q_a| << |q_a| amplifies.
+    dq_ref = torch.autograd.grad(loss, qa, retain_graph=True)[0]
+    if dq_override is None:
+        grads = torch.autograd.grad(loss, list(leaf.values()))
+    else:
+        up = torch.as_tensor(np.asarray(dq_override, np.float64)).to(dtype)
+        grads = torch.autograd.grad(qa, list(leaf.values()), grad_outputs=up)
     grads = dict(zip(leaf.keys(), grads))
     with torch.no_grad():
         apply_optimizer(online, grads, opt, spec, dtype)
     return opt.step, losses.detach().numpy(), float(loss.detach()), dict(q=q.detach().numpy(), y=y.numpy(),
                                                                         grads={k: g.numpy() for k, g in grads.items()},
-                                                                        max_q=mq.numpy(), acts=acts)
+                                                                        max_q=mq.numpy(), acts=acts, dq=dq_ref.detach().numpy())
 
 
 def to_torch(params_np, dtype=torch.float32):

@@ -72,7 +72,18 @@ def oracle_step_with_device_gates(L, spec, o, t, opt, batch, isw, n, tag, it):
     FLIP_LOG.append((tag, it, flips, int(sum(g.size for g in gates))))
     for nm, a_dev, a_ref in zip(('act1', 'act2', 'act3', 'hid'), acts_dev, free):
         assert rel_err(a_dev, a_ref) < TOL, (tag, it, nm, rel_err(a_dev, a_ref))
-    return nn_ref.train_step(o, t, opt, batch, isw, spec, torch.float64, gates=gates)
+    # The backward pass is evaluated from the DEVICE's TD-error gradient dL/dq_a, which is itself held to the forward bar:
+    # dq = 2 w (q_a - y) / B (PER) or clip(q_a - y, +-1) / B, so an error of 1e-4 of the Q / y scale in the forward pass
+    # is an error of 1e-4 * max(|q|, |y|) * dq/d(q_a) in dq -- however small |q_a - y| itself is.  Comparing gradients
+    # against a backward pass started from the oracle's own dq would instead amplify the forward error by |q| / |q - y|
+    # (measured: all tensors of a step off by the same 3e-5 .. 2e-3 when the batch's TD errors nearly cancel).
+    dq_dev = L.debug_read('dq', (n,)).astype(np.float64)
+    out = nn_ref.train_step(o, t, opt, batch, isw, spec, torch.float64, gates=gates, dq_override=dq_dev)
+    aux = out[3]
+    qscale = max(float(np.max(np.abs(aux['q']))), float(np.max(np.abs(aux['y']))), 1.0)
+    slope = (2.0 * float(np.max(np.asarray(isw))) if spec.use_per else 1.0) / n
+    assert float(np.max(np.abs(dq_dev - aux['dq']))) <= TOL * qscale * slope, (tag, it, 'dq', float(np.max(np.abs(dq_dev - aux['dq']))) / (qscale * slope))
+    return out
 
 
 def _consts(spec):

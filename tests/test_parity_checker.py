@@ -24,7 +24,7 @@ class Fp32Device:
 
     def train_batch(self, b, w):
         step, losses, loss, aux = nn_ref.train_step(self.o, self.t, self.opt, b, w, self.spec, torch.float32)
-        self.grads, self.acts = aux['grads'], aux['acts']
+        self.grads, self.acts, self.dq = aux['grads'], aux['acts'], aux['dq']
         return step, losses, loss
 
     def get_param(self, k, tower=0, slot=0):
@@ -34,6 +34,8 @@ class Fp32Device:
         return src[k].numpy().astype(np.float32).reshape(-1)
 
     def debug_read(self, name, shape):
+        if name == 'dq':
+            return np.asarray(self.dq, np.float32).reshape(shape)
         a = self.acts[('act1_online', 'act2_online', 'act3_online', 'hid_online').index(name)]
         out = np.zeros(shape, np.float32)
         out[:a.shape[0]] = a
