@@ -1263,6 +1263,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_tma_fwd") h->fc_tma_fwd = value != 0;
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
     else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
+    else if (n == "l2_keep") h->l2_keep = value;          // L2 residency hints (learner.h)
     else if (n == "wg1_fit") h->wg1_fit = value != 0;
     else if (n == "keep_grads") h->keep_grads = value != 0;  // dqn_train_batch: dense-kernel gradients stay readable (slot 3)
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state

@@ -33,6 +33,29 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
                  ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
 }
 
+// L2 residency control (createpolicy + .L2::cache_hint on the TMA copies).  The optimizer state of the two dense kernels
+// (m, v: 63 MB) plus the online dense weights (31.5 MB) fit in the 126 MB L2: loaded and stored "evict_last" they stay
+// resident from one step to the next, and the pass that bounds the step stops going to HBM for them; streams that are
+// read once per step (the target tower's dense weights) go "evict_first" so that they do not push the state out.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, int x, int y, uint32_t src, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 ::"l"(map), "r"(x), "r"(y), "r"(src), "l"(pol) : "memory");
+}
+
 template <int NTERMS>
 __global__ void __launch_bounds__(FA_THREADS, 3) fcwg_adam_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
                                                                   int Bn, int flat, int NH, int hid,
@@ -430,7 +453,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                                                                        const __grid_constant__ RowMaps maps,
                                                                        float lr, float mom, int use_momentum,
                                                                        const dqn_learner::Scalars* __restrict__ sc,
-                                                                       unsigned int* __restrict__ tile_ctr) {
+                                                                       unsigned int* __restrict__ tile_ctr, int l2_keep) {
     // Tiles are claimed DYNAMICALLY (atomic counter, stream-major order, so a CTA sees at most one switch of stream): the CTAs of this low-priority
     // kernel get their SMs at different times -- whenever the conv chain of the backward pass leaves some free -- and
     // with a static partition the late starters, each still holding a full share, ended the kernel ~15 us late.
@@ -478,6 +501,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
 
     if (warp == 17) {
         if (lane == 0) {
+            const uint64_t pol_keep = l2_policy_evict_last();
+            const bool keep_mv = (l2_keep & 1) != 0, keep_w = (l2_keep & 2) != 0;
+            auto ld = [&](uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, bool keep) {
+                if (keep) tma_load_2d_hint(dst, map, x, y, bar, pol_keep); else tma_load_2d(dst, map, x, y, bar);
+            };
+            auto stg = [&](const CUtensorMap* map, int x, int y, uint32_t src, bool keep) {
+                if (keep) tma_store_2d_hint(map, x, y, src, pol_keep); else tma_store_2d(map, x, y, src);
+            };
             // claim a tile for ring slot i % RS and start its loads; past the last tile publish -1 (the barrier still completes)
             auto publish = [&](int i) {
                 const int s = i % RS;
@@ -490,9 +521,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                 const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
                 const uint32_t st = ring + s * STAGE;
                 cv::mbar_expect_tx(st_full(s), (uint32_t)(narr * ARR));
-                tma_load_2d(st, &maps.w[strm], nh * RT_N, row0, st_full(s));
-                tma_load_2d(st + ARR, &maps.m[strm], nh * RT_N, row0, st_full(s));
-                if (!use_momentum) tma_load_2d(st + 2 * ARR, &maps.v[strm], nh * RT_N, row0, st_full(s));
+                ld(st, &maps.w[strm], nh * RT_N, row0, st_full(s), keep_w);
+                ld(st + ARR, &maps.m[strm], nh * RT_N, row0, st_full(s), keep_mv);
+                if (!use_momentum) ld(st + 2 * ARR, &maps.v[strm], nh * RT_N, row0, st_full(s), keep_mv);
             };
             for (int j = 0; j < RS - 1; ++j) publish(j);
             for (int i = 0;; ++i) {
@@ -504,9 +535,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                 const int strm = tt / per_stream, r = tt - strm * per_stream;
                 const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
                 const uint32_t st = ring + s * STAGE;
-                tma_store_2d(&maps.w[strm], nh * RT_N, row0, st);
-                tma_store_2d(&maps.m[strm], nh * RT_N, row0, st + ARR);
-                if (!use_momentum) tma_store_2d(&maps.v[strm], nh * RT_N, row0, st + 2 * ARR);
+                stg(&maps.w[strm], nh * RT_N, row0, st, keep_w);
+                stg(&maps.m[strm], nh * RT_N, row0, st + ARR, keep_mv);
+                if (!use_momentum) stg(&maps.v[strm], nh * RT_N, row0, st + 2 * ARR, keep_mv);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // stage (i - 1) % RS has been read by its stores
                 publish(i + RS - 1);
@@ -708,7 +739,7 @@ static void launch_rows(dqn_learner* h, int rows, int ctas) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(ctas), dim3(RT_THREADS), bytes, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid,
                       rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum,
-                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr);
+                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr, h->l2_keep);
     };
     if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_rows_kernel<3>); else go(fcwg_adam_rows_kernel<1>);
     h->launches++;

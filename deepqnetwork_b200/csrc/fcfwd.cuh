@@ -30,7 +30,7 @@ constexpr int FF_S = 6, FF_THREADS = 320;
 // converter group instead of B producers
 template <int BN, int NTERMS, bool PACKED>
 __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __restrict__ act, const float* __restrict__ act_pk, int rows, int flat, int NH, int hid,
-                                                              const __grid_constant__ WMaps maps, float* __restrict__ part,
+                                                              const __grid_constant__ WMaps maps, float* __restrict__ part, int w_policy,
                                                               int kb_per_split, unsigned long long* __restrict__ dbg) {
     constexpr int S = FF_S, ACOLS = BK * (NTERMS == 3 ? 2 : 1);
     const bool cta0 = dbg && blockIdx.x == 0 && blockIdx.y == 0;
@@ -77,11 +77,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         if (lane == 0) {
             if (PACKED) pdl_wait();  // the packed activation tiles are the stream predecessor's output
             int s = 0, ph = 0;
+            // w_policy: 1 = evict_last (online weights: re-read by the dgrad and the optimizer pass), 2 = evict_first (target
+            // weights: read once per step), 0 = no hint
+            const uint64_t pol = w_policy == 1 ? fa::l2_policy_evict_last() : fa::l2_policy_evict_first();
             for (int j = 0; j < nkb; ++j) {
                 if (j >= S) mbar_wait(empty(s), ph ^ 1);
                 FF_STAMP(true, j, 0);
                 cv::mbar_expect_tx(wfull(s), PACKED ? W_TILE + 2 * B_TILE : W_TILE);
-                fa::tma_load_2d(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s));
+                if (w_policy) fa::tma_load_2d_hint(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s), pol);
+                else fa::tma_load_2d(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s));
                 if (PACKED) cv::tma_bulk_g2s(stage_b(s), act_pk + (size_t)(kb0 + j) * (2 * BN * 32), 2 * B_TILE, wfull(s));
                 if (++s == S) { s = 0; ph ^= 1; }
             }
@@ -298,8 +302,9 @@ static int launch(dqn_learner* h, const float* P, const float* act, int rows, fl
         const size_t bytes = (size_t)FF_S * (BM * BK * 4 + 2 * bn * 128) + 512 + 1024;
         // (no static "configured" flag here: both BN instantiations share one function-pointer type, hence one lambda body)
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        const int w_policy = tw == 0 ? ((h->l2_keep & 2) ? 1 : 0) : ((h->l2_keep & 4) ? 2 : 0);
         launch_kernel(h->pdl, kern, dim3(mt, splits), dim3(FF_THREADS), bytes, h->stream, act, act_pk, rows, net.flat, net.NH, net.hidden, maps,
-                      part, per, h->tc_dbg);
+                      part, w_policy, per, h->tc_dbg);
     };
     const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
     if (act_pk) {

@@ -82,6 +82,8 @@ struct dqn_learner {
                                   // becomes ready at the same instant as conv3's dgrad + wgrad (96 CTAs); if its persistent CTAs are dispatched first
                                   // they hold every SM and the critical conv chain waits 40 us (CUPTI traces of both modes).  With <= 100 CTAs the
                                   // chain always finds SMs and dynamic tile claims keep the pass balanced: 84-100 -> 6030-6180 in both modes
+    int l2_keep = 0;              // L2 residency hints on the TMA copies (fcadam.cuh): bit 0 = dense-kernel m, v evict_last; bit 1 = online dense
+                                  // weights evict_last (optimizer pass + dense forward); bit 2 = target dense weights evict_first
     void* fa_maps = nullptr;      // fa::StateMaps (TMA tensor maps of w/m/v of the dense kernels), built on first use
     bool fc_tma_adam = false;     // option: tcgen05 dense wgrad + optimizer in one pass, optimizer state staged by TMA (fcadam.cuh);
                                   // measured 67 us alone vs 23 + 40 us for wgrad + streaming Adam (too few bytes in flight per CTA)
