@@ -68,6 +68,8 @@ _SIGS = {
     'dqn_train_step': [_P, _P, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_float)],
     'dqn_train_steps': [_P, C.c_int64],
     'dqn_train_step_phase': [_P, C.c_int32, C.c_double],
+    'dqn_phase_wait': [_P, C.c_char_p, _P],
+    'dqn_set_per_normaliser': [_P, C.c_float],
     'dqn_set_option': [_P, C.c_char_p, C.c_int32],
     'dqn_launch_count': [_P, C.POINTER(C.c_int64)],
     'dqn_set_profile': [_P, C.c_int32],

@@ -96,6 +96,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side5_stream, cudaStreamNonBlocking));
         DQN_CUDA_OK(cudaStreamCreateWithFlags(&h->side6_stream, cudaStreamNonBlocking));
         for (auto& e : h->fork_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : h->phase_ev) DQN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         net_describe(h->net, h->cfg);
         const NetDesc& net = h->net;
         h->state_bytes = (size_t)net.H * net.W * net.C;
@@ -247,6 +248,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     for (auto& e : h->fork_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->phase_ev) if (e) cudaEventDestroy(e);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->side2_stream) cudaStreamDestroy(h->side2_stream);
     if (h->side3_stream) cudaStreamDestroy(h->side3_stream);
@@ -910,7 +912,7 @@ static void fused_step_launches(dqn_learner* h, const double* u, const int64_t* 
     h->fuse_fc_adam = (phases == 3) && h->fuse_enabled;
     h->early_fc_adam = (phases == 3) && !h->fuse_fc_adam;
     if (phases & 1) {
-        sample_into_batch(h, u, rows);
+        if (!(phases & 4)) sample_into_batch(h, u, rows);  // bit 2: train on the batch already in the device buffers
         step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1, grad_scale,
                   h->cfg.use_per);
     }
@@ -1091,14 +1093,39 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
 extern "C" int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale) {
     API_BEGIN(h)
     h->prof_used = 0; h->prof_marks.clear();
-    if (phase == 0) {
+    if (phase == 0 || phase == 4) {
         DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
-        maybe_refresh_stats(h);
-        fused_step_launches(h, nullptr, nullptr, grad_scale, 1);
-    } else {
+        if (phase == 0) maybe_refresh_stats(h);
+        h->phase_ev_armed = true;
+        try {
+            fused_step_launches(h, nullptr, nullptr, grad_scale, phase == 0 ? 1 : 5);
+        } catch (...) { h->phase_ev_armed = false; throw; }
+        h->phase_ev_armed = false;
+        DQN_CUDA_OK(cudaEventRecord(h->phase_ev[1], h->stream));
+    } else if (phase == 1) {
+        // (the priority write-back of the local samples ran inside phase 0: it only needs the TD errors)
         fused_step_launches(h, nullptr, nullptr, grad_scale, 2);
         after_step_host(h);
+    } else {
+        throw std::string("phase must be 0 (sample + forward + backward), 4 (the same on the current device batch) or 1 (optimizer)");
     }
+    API_END(h)
+}
+
+extern "C" int dqn_phase_wait(dqn_learner* h, const char* what, void* cuda_stream) {
+    API_BEGIN_KEEP(h)
+    const std::string w = what;
+    DQN_REQUIRE(w == "fc_grads" || w == "grads", "dqn_phase_wait: what must be \"fc_grads\" or \"grads\"");
+    DQN_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->phase_ev[w == "grads" ? 1 : 0], 0));
+    API_END(h)
+}
+
+extern "C" int dqn_set_per_normaliser(dqn_learner* h, float last_max_weight) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->cfg.use_per && last_max_weight > 0.f, "dqn_set_per_normaliser needs use_per and a positive weight");
+    set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->last_max_weight, last_max_weight, &h->d_sc->last_max_weight, last_max_weight);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->has_max_weight = true;
     API_END(h)
 }
 

@@ -52,6 +52,11 @@ struct dqn_learner {
     // parallel branches
     cudaStream_t side_stream = nullptr, side2_stream = nullptr, side3_stream = nullptr, side4_stream = nullptr, side5_stream = nullptr, side6_stream = nullptr;
     cudaEvent_t fork_ev[24] = {};
+    // data-parallel split step: recorded inside phase 0 -- [0] the dense-kernel gradients (98.6 % of the slab) are complete,
+    // [1] the whole gradient slab is complete -- so that an external all-reduce can start on the big bucket while the conv
+    // backward chain is still running (dqn_phase_wait)
+    cudaEvent_t phase_ev[2] = {nullptr, nullptr};
+    bool phase_ev_armed = false;  // set while phase 0 of a split step is being issued
     int fork_used = 0;
     bool overlap = true;
     int prio_hi = 0, prio_lo = 0;  // device stream-priority range (hi is numerically lower)

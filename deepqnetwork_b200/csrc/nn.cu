@@ -494,6 +494,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             EpiFcWgrad e{G + net.off_fc_w[0], G + net.off_fc_w[1], net.hidden};
             gemm_auto<false>(h, a, b, e, net.flat, net.NH, rows, 1, 0);
         }
+        // split (data-parallel) step: the dense-kernel gradients are final here, long before the conv chain is done
+        if (h->phase_ev_armed) DQN_CUDA_OK(cudaEventRecord(h->phase_ev[0], h->stream));
         side_end(h, saved);
     };
     const bool ffma_adam = h->early_fc_adam && !h->fuse_fc_adam && h->fc_ffma_adam && rows <= 32 && fc_wgrad_adam_supported(h);

@@ -7,9 +7,12 @@ Two partitionings (the reference itself is single-process, rl/deep
                steps (`aggregate_throughput`).
 * data-parallel -- C5 (new capability): every rank samples B/N transitions from its own replay shard and runs the
                forward/backward (`dqn_train_step_phase(0)`), the flat fp32 gradient slab (P floats, one contiguous
-               buffer: `dqn_device_ptr("grads")`) is all-reduced and averaged, then every rank applies the same
-               optimizer step (`dqn_train_step_phase(1)`), so the weights stay identical on all ranks.  The one
-               exchange step of the path is that all-reduce.
+               buffer: `dqn_device_ptr("grads")`) is summed over the ranks (each rank scaled its loss by 1/N, so the sum
+               is the gradient of the global-batch mean), then every rank applies the same optimizer step
+               (`dqn_train_step_phase(1)`), so the weights stay identical on all ranks.  The one exchange step of the
+               path is that all-reduce; it is issued in two buckets on a communication stream: the two dense hidden
+               kernels (98.6 % of the bytes, complete first in the backward pass: `dqn_phase_wait("fc_grads")`) go
+               while the conv backward chain is still running, the remaining 0.4 MB follow when the slab is complete.
 """
 import numpy as np
 
@@ -63,25 +66,94 @@ def shard_capacity(total_transitions, rank, world):
     return start, n
 
 
+def gradient_buckets(tensors):
+    """Split the gradient slab into the exchange buckets.  tensors: [(name, count, offset)] (Learner.tensors()).
+    Returns (big, small): big = [(offset, count)] of the dense hidden kernels ('dense/kernel', 'dense_2/kernel'), each one
+    contiguous range; small = [(offset, count)] of everything else, coalesced into maximal contiguous ranges (tensor
+    starts are 16-byte aligned, so the ranges include the zero padding between tensors)."""
+    big = [(off, cnt) for name, cnt, off in tensors if name in ('dense/kernel', 'dense_2/kernel')]
+    end = max(off + (cnt + 3) // 4 * 4 for _, cnt, off in tensors)
+    small, cur = [], 0
+    for off, cnt in sorted(big):
+        if off > cur:
+            small.append((cur, off - cur))
+        cur = off + (cnt + 3) // 4 * 4
+    if end > cur:
+        small.append((cur, end - cur))
+    return big, small
+
+
 class DataParallelLearner:
     """Large-batch data-parallel step over `world` learners (global batch = world x per-rank batch).
 
     `learner` needs train_step_phase(phase, grad_scale) and a gradient tensor (default: the device slab of
-    deepqnetwork_b200.learner.Learner); tests drive it with a CPU stand-in over gloo."""
+    deepqnetwork_b200.learner.Learner); tests drive it with a CPU stand-in over gloo.
 
-    def __init__(self, learner, group=None, grads=None, stream_sync=None):
+    overlap=True (device learners): the learner must run on a torch stream (Learner.set_stream(torch stream)); the
+    collectives are issued on a second torch stream that waits for events recorded INSIDE phase 0, so the 31.5 MB
+    dense-kernel bucket is on the wire while the conv backward chain still runs, and phase 1 waits for both buckets on
+    the device (no host synchronisation anywhere in the step)."""
+
+    def __init__(self, learner, group=None, grads=None, stream_sync=None, overlap=False, learner_stream=None):
+        import torch.distributed as dist
         self.learner = learner
         self.group = group
         self._grads = grads if grads is not None else grads_tensor(learner)
         self._sync = stream_sync if stream_sync is not None else getattr(learner, 'sync', lambda: None)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = bool(overlap) and self.world > 1
+        self.steps = 0
+        if self.overlap:
+            import torch
+            self._stream = learner_stream
+            assert learner_stream is not None, 'overlap needs the torch stream the learner runs on'
+            self._comm = torch.cuda.Stream()
+            big, small = gradient_buckets(learner.tensors())
+            self._big = [self._grads[o:o + c] for o, c in big]
+            self._small = [self._grads[o:o + c] for o, c in small]
+            self._small_flat = torch.empty(sum(c for _, c in small), dtype=torch.float32, device=self._grads.device)
+
+    def sync_per_normaliser(self):
+        """One scale for the importance weights of all shards: the maximum of the ranks' last_max_weight (the rank whose
+        shard holds the globally smallest sampling probability), deep_q_agent.py:506-510."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        mw = torch.tensor([self.learner.get_stats()['last_max_weight']], dtype=torch.float32, device=self._grads.device)
+        dist.all_reduce(mw, op=dist.ReduceOp.MAX, group=self.group)
+        self.learner.set_per_normaliser(float(mw.item()))
 
     def train_step(self):
-        # phase 0: sample the local shard, forward, backward -> local mean gradient in the slab
-        self.learner.train_step_phase(0, 1.0)
-        self._sync()  # the learner runs on its own stream; the collective runs on torch's
-        allreduce_mean_(self._grads, self.group)  # mean over ranks == gradient of the global-batch mean loss
         import torch
-        if self._grads.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        # phase 1: identical optimizer step on every rank
-        self.learner.train_step_phase(1, 1.0)
+        import torch.distributed as dist
+        scale = 1.0 / self.world
+        if not self.overlap:
+            # phase 0: sample the local shard, forward, backward -> local gradient (already scaled by 1/world) in the slab
+            self.learner.train_step_phase(0, scale)
+            if self.world > 1:
+                self._sync()  # the learner runs on its own stream; the collective runs on torch's
+                dist.all_reduce(self._grads, op=dist.ReduceOp.SUM, group=self.group)
+                if self._grads.is_cuda:
+                    torch.cuda.current_stream().synchronize()
+            self.learner.train_step_phase(1, scale)  # identical optimizer step on every rank
+            self.steps += 1
+            return
+        L = self.learner
+        L.train_step_phase(0, scale)
+        works = []
+        with torch.cuda.stream(self._comm):
+            L.phase_wait('fc_grads', self._comm.cuda_stream)      # the two dense kernels: ready early in the backward pass
+            for t in self._big:
+                works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            L.phase_wait('grads', self._comm.cuda_stream)          # conv / heads / biases: ready when phase 0 ends
+            torch.cat(self._small, out=self._small_flat)
+            works.append(dist.all_reduce(self._small_flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        with torch.cuda.stream(self._stream):
+            for w in works:
+                w.wait()                                           # the learner's stream waits on the device
+            off = 0
+            for t in self._small:
+                t.copy_(self._small_flat[off:off + t.numel()]); off += t.numel()
+            L.train_step_phase(1, scale)
+        self.steps += 1

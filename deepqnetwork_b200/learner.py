@@ -300,6 +300,13 @@ class Learner:
     def train_step_phase(self, phase, grad_scale=1.0):
         self._c(self._lib.dqn_train_step_phase(self._h, int(phase), float(grad_scale)))
 
+    def phase_wait(self, what, cuda_stream_ptr):
+        """Make a CUDA stream wait for 'fc_grads' / 'grads' of the phase 0 just issued."""
+        self._c(self._lib.dqn_phase_wait(self._h, what.encode(), C.c_void_p(cuda_stream_ptr)))
+
+    def set_per_normaliser(self, last_max_weight):
+        self._c(self._lib.dqn_set_per_normaliser(self._h, float(last_max_weight)))
+
     def set_option(self, name, value):
         self._c(self._lib.dqn_set_option(self._h, name.encode(), int(value)))
 

@@ -163,10 +163,19 @@ int dqn_train_step(dqn_learner* h, const double* h_u, const int64_t* h_rows, int
 /* n back-to-back fused steps (device RNG), target sync every copy_network_steps and PER stats
  * refresh every per_calculate_steps included; returns after enqueueing (call dqn_sync). */
 int dqn_train_steps(dqn_learner* h, int64_t n);
-/* data-parallel split step (new capability): phase 0 = sample..backward (gradient left
- * in the "grads" slab for an external all-reduce), phase 1 = optimizer + priority write-back.
- * grad_scale multiplies dL/dq (1/world_size for a global mean). */
+/* data-parallel split step (new capability; the reference is single-device).  phase 0 = sample the
+ * local replay shard, forward, backward, priority write-back of the sampled rows: the gradient of (grad_scale x the local mean loss) is left in the "grads" slab
+ * (dqn_device_ptr) for an external all-reduce; phase 4 = the same on the batch already in the device buffers (after
+ * dqn_uniform_sample / dqn_per_sample: equivalence tests); phase 1 = optimizer on the (reduced) slab + target sync cadence.  grad_scale = 1 / world_size with a SUM all-reduce gives the
+ * gradient of the global-batch mean. */
 int dqn_train_step_phase(dqn_learner* h, int32_t phase, double grad_scale);
+/* make a caller's CUDA stream wait for a point inside the phase 0 just issued: "fc_grads" = the gradients of the two
+ * dense hidden kernels (98.6 % of the slab) are complete -- they are produced first, so their all-reduce can overlap
+ * the conv backward chain -- or "grads" = the whole slab is complete */
+int dqn_phase_wait(dqn_learner* h, const char* what, void* cuda_stream);
+/* overwrite the PER normaliser last_max_weight (rl/deep_q_agent.py:510) -- data-parallel ranks install the maximum
+ * over all shards so that importance weights share one scale */
+int dqn_set_per_normaliser(dqn_learner* h, float last_max_weight);
 /* execution options (ablation / tests); the full table with defaults is in INTEGRATION.md section 4.  Every option keeps
  * the results within the parity bars.  "keep_grads" (default 0): dqn_train_batch leaves the gradients of the dense
  * hidden kernels readable through dqn_get_param(slot 3); with 0 they are consumed by the fused dense wgrad+optimizer

@@ -28,7 +28,8 @@ class FakeLearner:
     def train_step_phase(self, phase, scale):
         self.calls.append(phase)
         if phase == 0:
-            self.g.copy_(torch.arange(self.g.numel(), dtype=torch.float32) * (self.rank + 1))
+            # the local gradient arrives scaled by grad_scale = 1/world: the SUM over ranks is the global-batch mean
+            self.g.copy_(torch.arange(self.g.numel(), dtype=torch.float32) * (self.rank + 1) * scale)
         else:
             self.w.sub_(0.5 * self.g)
 
@@ -79,3 +80,21 @@ def test_replay_shards_are_disjoint_and_cover(total, world):
         assert seen == list(range(total))
     else:
         assert sum(n for _, n in seen) == total and all(seen[i][0] + seen[i][1] == seen[i + 1][0] for i in range(world - 1))
+
+
+def test_gradient_buckets_cover_the_slab_once():
+    """The exchange buckets of the data-parallel step: the two dense hidden kernels as one contiguous range each (sent
+    first, while the conv backward still runs), everything else coalesced -- together every slab element exactly once."""
+    tensors, off = [], 0
+    for name, cnt in (('conv2d/kernel', 8192), ('conv2d/bias', 32), ('conv2d_1/kernel', 32768), ('conv2d_1/bias', 64),
+                      ('conv2d_2/kernel', 65536), ('conv2d_2/bias', 64), ('dense/kernel', 7680 * 512), ('dense/bias', 512),
+                      ('dense_1/kernel', 2048), ('dense_1/bias', 4), ('dense_2/kernel', 7680 * 512), ('dense_2/bias', 512),
+                      ('dense_3/kernel', 512), ('dense_3/bias', 1)):
+        tensors.append((name, cnt, off)); off += (cnt + 3) // 4 * 4
+    big, small = D.gradient_buckets(tensors)
+    assert [c for _, c in big] == [7680 * 512] * 2
+    cover = np.zeros(off, np.int32)
+    for o, c in big + small:
+        cover[o:o + c] += 1
+    assert (cover == 1).all() and len(small) == 3
+    assert sum(c for _, c in small) * 4 < 500000  # the late bucket is < 0.5 MB
