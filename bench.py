@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput benchmark: DQN train steps/sec (batch 32, PER, reference Q-network) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c1|c2|c3|nature] [--capacity R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c1|c2|c3|nature|c5] [--capacity R]
 
 A *step* is one DeepQAgent._train_run_train equivalent (rl/deep_q_agent.py:326-349): PER sum-tree sample ->
 replay gather -> target/online forward -> TD loss -> backward -> Adam -> priority write-back, with the
@@ -10,6 +10,9 @@ target sync every copy_network_steps and the PER stats refresh every per_calcula
 N=1 workload = BASELINE.json configs[1] (C2): Breakout double+dueling+PER, 89x80x4 uint8, batch 32, 1M-transition
 replay resident in HBM, synthetic data.  N>1 (torchrun, one rank per GPU) = configs[3] (C4):
 N independent learners, no data-path collective, value = total steps of all ranks / max-over-ranks time.
+`--config c5` under torchrun = configs[4] (C5): ONE learner with a global batch of 2048 split over the ranks, replay and
+sum tree sharded, the 31.9 MB gradient all-reduced with NCCL in two buckets overlapped with the backward pass
+(deepqnetwork_b200/distributed.py); value = global-batch steps/s, "scaling": "strong".
 
 Printed JSON (one line, rank 0): the driver contract keys plus
   roofline     -- the dominant kernel (largest CUDA-event time in a per-kernel profile pass of the same step),
@@ -17,9 +20,11 @@ Printed JSON (one line, rank 0): the driver contract keys plus
                   HBM peak of MEASURED_PEAKS.json;
   cpu_baseline -- the oracle's CPU restatement of the reference step (NumPy/Python replay+PER exactly as the
                   reference structures it, torch-CPU fp32 network) timed on this box's host cores;
-  e2e          -- the same step driven through the reference-facing seams with HOST buffers: tree sample (seam 3),
-                  DeepQModel.train with pinned host states/next_states (seam 2, H2D inside the timed region),
-                  priority write-back, losses read back every step.
+  e2e          -- the step as the drop-in DeepQAgent runs it (deepqnetwork_b200/deep_q_agent.py:_train_run_train): one
+                  dqn_train_step call per step fed the step's host inputs -- the B random.random() draws, pinned -- and
+                  returning step / per-sample losses / loss to the host; the replay stays where the design keeps it, in
+                  HBM (it is appended as frames arrive, not per train step).  `e2e.host_batch` is the other integration:
+                  seams 3 + 2 + 3 with the sampled rows gathered on the HOST from a host replay and uploaded every step.
 `--impl reference` times the CPU restatement of the reference alone (TensorFlow cannot be installed here; see
 DESIGN.md) and prints the same line shape with "impl": "reference".
 """
@@ -42,6 +47,8 @@ CONFIGS = {
     'c2': dict(name='C2 Breakout double+dueling+PER', h=89, w=80, a=4, dueling=True, double=True, per=True, variant='reference'),
     'c3': dict(name='C3 MsPacman double+dueling+PER', h=86, w=80, a=9, dueling=True, double=True, per=True, variant='reference'),
     'nature': dict(name='canonical Nature-84 vanilla (labelled extra)', h=84, w=84, a=4, dueling=False, double=False, per=False, variant='nature'),
+    'c5': dict(name='C5 large-batch data-parallel DQN (global batch 2048), Breakout double+dueling+PER', h=89, w=80, a=4, dueling=True,
+               double=True, per=True, variant='reference', global_batch=2048),
 }
 METRIC = 'DQN train steps/sec (batch 32, PER, Nature CNN) per B200 and at 1/2/4/8 GPUs'
 UNIT = 'train steps/s'
@@ -64,7 +71,7 @@ def net_numbers(cfg):
     flops = 2 * BATCH * (n_fwd * F + F + (F - conv_macs[0]))
     S = cfg['h'] * cfg['w'] * 4
     step_bytes = 8 * 4 * P + 2 * BATCH * S + 15 * BATCH
-    return dict(P=P, F=F, flops=flops, step_bytes=step_bytes, S=S, flat=flat, geo=geo, streams=streams, n_fwd=n_fwd)
+    return dict(P=P, F=F, F1=conv_macs[0], flops=flops, step_bytes=step_bytes, S=S, flat=flat, geo=geo, streams=streams, n_fwd=n_fwd)
 
 
 def kernel_bytes(name, cfg, nn):
@@ -119,50 +126,60 @@ def kernel_bytes(name, cfg, nn):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def clocks_sampler_start():
-    path = tempfile.mktemp(prefix='clocks_', suffix='.csv')
-    q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-    try:
-        f = open(path, 'w')
-        p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
-                             stdout=f, stderr=subprocess.DEVNULL)
-        return p, f, path
-    except OSError:
-        return None, None, path
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every few milliseconds
+    (a 100 ms nvidia-smi poll cannot see a region of a few hundred milliseconds)."""
 
+    def __init__(self, device_index, period_s=0.004):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[device_index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else device_index
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+            return
+        self._period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
 
-def clocks_sampler_stop(handle, device_index):
-    p, f, path = handle
-    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-    if p is None:
-        return out
-    p.terminate()
-    try:
-        p.wait(timeout=5)
-    except Exception:
-        p.kill()
-    f.close()
-    sm, mx, reasons = [], [], set()
-    try:
-        for line in open(path):
-            c = [x.strip() for x in line.split(',')]
-            if len(c) < 9 or c[0] != str(device_index):
-                continue
+    def _run(self):
+        nv, h = self._nv, self._h
+        names = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap),
+                 ('hw_power_brake', nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        while not self._stop.is_set():
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        os.unlink(path)
-    except OSError:
-        pass
-    if sm:
-        out['sm_mhz'] = statistics.median(sm); out['sm_max_mhz'] = max(mx); out['samples'] = len(sm)
-    out['reasons'] = sorted(reasons)
-    return out
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def start(self):
+        if self._thread:
+            self._thread.start()
+        return self
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[])
+        if self._thread:
+            self._stop.set(); self._thread.join(timeout=2)
+        if self.samples:
+            out['sm_mhz'] = statistics.median(self.samples); out['sm_min_mhz'] = min(self.samples); out['samples'] = len(self.samples)
+            out['power_w_max'] = max(self.power) if self.power else None
+        out['reasons'] = sorted(self.reasons)
+        out['how'] = 'in-process NVML, %.0f ms period, over the timed region' % (1000 * getattr(self, '_period', 0))
+        return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind a profile name, from the ncu --set full
@@ -182,7 +199,7 @@ def measured_peak_hbm():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, steps, warmup, replay_rows, time_budget_s, threads=None):
+def cpu_reference_run(cfg, steps, warmup, replay_rows, time_budget_s, threads=None, BATCH=BATCH):
     """The reference's CPU path, restated (oracle/): NumPy/Python replay ring + sum tree structured exactly like
     rl/data/*.py, torch-CPU fp32 network + TF-formula Adam like rl/deep_q_model.py, driven like
     DeepQAgent._train_run_train.  Returns (steps_per_s, steps_timed, threads)."""
@@ -305,7 +322,10 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        v, done, threads = cpu_reference_run(cfg, args.steps, min(args.warmup, 5), 20000, 150.0)
+        gb = cfg.get('global_batch', BATCH)
+        v, done, threads = cpu_reference_run(cfg, args.steps, min(args.warmup, 5) if gb == BATCH else 1, 20000, 150.0, BATCH=gb)
+        if gb != BATCH:
+            config.update(batch=gb, workload='%s, %dx%dx4 uint8, global batch %d on the host cores, 20000-row replay' % (cfg['name'], cfg['h'], cfg['w'], gb))
         line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=done, warmup=min(args.warmup, 5),
                     ms_per_step=1000.0 / v, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                     data='synthetic', impl='reference', config=config, gpu_launches=0,
@@ -323,17 +343,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    import __graft_entry__ as ge
     if rank == 0:
-        ge.build()
+        from deepqnetwork_b200 import build as lib_build  # the CUDA library only: this arm never touches oracle/
+        lib_build.build()
     if world > 1:
         dist.barrier()
     from deepqnetwork_b200.learner import Learner
     from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
 
+    dp = args.config == 'c5'
+    batch = cfg['global_batch'] // world if dp else BATCH
+    capacity = args.capacity // world if dp else args.capacity
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
-                use_per=cfg['per'], batch_size=BATCH, replay_capacity=args.capacity, conv_variant=cfg['variant'],
-                math_mode=args.math, seed=7 + rank, device=local_rank)
+                use_per=cfg['per'], batch_size=batch, replay_capacity=capacity, conv_variant=cfg['variant'],
+                math_mode=args.math, seed=7 + rank, device=local_rank, max_rows=max(batch, 256))
     # a real (non-default) stream: stream capture is illegal on the legacy stream; high priority, because the learner's
     # own side streams (weight gradients, optimizer, look-ahead sampling) only carry work with slack
     stream = torch.cuda.Stream(priority=-1)
@@ -350,9 +373,11 @@ def main():
         L.set_option('pdl', 0)
     if args.ffma_adam:
         L.set_option('fc_ffma_adam', 1)
-    L.set_tower(init_tower_params(shapes, 42 + 2 * rank), 0)
-    L.set_tower(init_tower_params(shapes, 43 + 2 * rank), 1)
-    L.replay_fill_synthetic(args.capacity, seed=1234 + rank)
+    # replicas: every learner has its own weights; data-parallel: all ranks start from the same weights
+    wseed = 42 if dp else 42 + 2 * rank
+    L.set_tower(init_tower_params(shapes, wseed), 0)
+    L.set_tower(init_tower_params(shapes, wseed + 1), 1)
+    L.replay_fill_synthetic(capacity, seed=1234 + rank)
     L.sync()
 
     def barrier():
@@ -360,20 +385,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if dp:
+        from deepqnetwork_b200.distributed import DataParallelLearner, grads_tensor
+        D = DataParallelLearner(L, overlap=not args.no_overlap, learner_stream=stream)
+        run_steps = lambda n: [D.train_step() for _ in range(n)]
+        L.train_step_phase(0, 1.0 / world); L.sync()      # first sample computes the local PER statistics
+        D.sync_per_normaliser()                            # one importance-weight scale for all shards
+        L.train_step_phase(1, 1.0 / world); L.sync()
+        args.warmup = max(args.warmup - 1, 3)
+    else:
+        run_steps = L.train_steps
+
     # warm-up (also captures the CUDA graph of the fused step)
-    L.train_steps(args.warmup)
+    step_before = L.get_step()
+    run_steps(args.warmup)
     barrier()
-    clk = clocks_sampler_start() if rank == 0 else None
+    clk = ClockSampler(local_rank).start() if rank == 0 else None
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    L.train_steps(args.steps)
+    run_steps(args.steps)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = L.launch_count() - l0
-    clocks = clocks_sampler_stop(clk, local_rank) if rank == 0 else None
+    clocks = clk.stop() if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([ms], device='cuda', dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -381,13 +418,52 @@ def main():
         lsum = torch.tensor([launches], device='cuda', dtype=torch.int64)
         dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
         launches = int(lsum.item())
-    value = world * args.steps / (ms / 1000.0)
+    value = (1 if dp else world) * args.steps / (ms / 1000.0)
     step_now = L.get_step()
-    assert step_now == args.warmup + args.steps, 'step counter does not match the steps requested'
+    assert step_now == step_before + args.warmup + args.steps, 'step counter does not match the steps requested'
+
+    if dp:
+        # every rank must hold the same weights after the same number of exchanged steps
+        chk = torch.tensor([float(np.float64(L.get_param('dense/kernel').astype(np.float64).sum()))], device='cuda', dtype=torch.float64)
+        lo, hi = chk.clone(), chk.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float(lo.item()) == float(hi.item()), 'data-parallel ranks diverged'
+        # the exchange step alone: the same two buckets, back to back, nothing else on the GPU
+        coll = None
+        if world > 1:
+            g = grads_tensor(L)
+            from deepqnetwork_b200.distributed import gradient_buckets
+            big, small = gradient_buckets(L.tensors())
+            tb = [g[o:o + c] for o, c in big]
+            nbytes = sum(c for _, c in big) * 4
+            for _ in range(5):
+                for t in tb:
+                    dist.all_reduce(t)
+            torch.cuda.synchronize(); dist.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            iters = 50
+            for _ in range(iters):
+                for t in tb:
+                    dist.all_reduce(t)
+            c1.record(stream); torch.cuda.synchronize()
+            us = c0.elapsed_time(c1) * 1000.0 / iters
+            tm = torch.tensor([us], device='cuda', dtype=torch.float64); dist.all_reduce(tm, op=dist.ReduceOp.MAX); us = float(tm.item())
+            coll = dict(what='NCCL all-reduce (sum, fp32) of the two dense-kernel gradient buckets', bytes=nbytes, us=us,
+                        bus_gb_s=2.0 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9, ranks=world,
+                        exposed='overlapped with the conv backward chain (dqn_phase_wait "fc_grads"); the 0.4 MB bucket follows the backward pass')
+        config.update(parallelism='data-parallel x%d (global batch %d = %d per GPU, replay and sum tree sharded, gradient all-reduce)' % (
+            world, cfg['global_batch'], batch), batch=cfg['global_batch'], per_gpu_batch=batch, samples_per_s=value * cfg['global_batch'],
+            collective=coll, replay_transitions=args.capacity)
+        gf = 2 * batch * (nn['n_fwd'] * nn['F'] + nn['F'] + (nn['F'] - nn['F1']))  # SURVEY.md 8d, per GPU
+        config['gflop_per_step'] = round(gf * world / 1e9, 2)
+        config['workload'] = '%s, %dx%dx4 uint8, global batch %d over %d GPU(s), %d-transition replay sharded in HBM' % (
+            cfg['name'], cfg['h'], cfg['w'], cfg['global_batch'], world, args.capacity)
 
     # ---- per-kernel profile pass (CUDA events around every launch, un-graphed) -> roofline of the dominant kernel
     roofline = None
-    if rank == 0:
+    if rank == 0 and not dp:
         prof_steps = max(20, min(200, args.steps // 10))
         L.set_profile(True)
         L.train_steps(prof_steps)
@@ -408,58 +484,123 @@ def main():
                         kernel_share_of_step=per_kernel[dom] / total_us,
                         step_frac_of_hbm_roofline=(nn['step_bytes'] / (ms / args.steps * 1e-3) / 1e9) / peak,
                         per_kernel_us={k: round(v, 2) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])})
+    elif rank == 0:
+        # C5 at per-GPU batch >= 256 is tensor-bound: whole-step FLOP/s against the measured bf16 peak
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peak_tf, how = float(json.load(f)['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        except Exception:
+            peak_tf, how = 1400.0, 'fallback (B200_PROFILING.md sustained bf16)'
+        ach = config['gflop_per_step'] / world / (ms / args.steps * 1e-3) / 1e3
+        roofline = dict(bound='tensor', kernel='whole data-parallel step (per GPU)', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf,
+                        traffic=None, peak_source=how, note='fp32-grade arithmetic = 3 tf32 MMAs per product; FLOPs counted once')
 
-    # ---- e2e: through the reference-facing seams with pinned HOST buffers -------------------------------------------
+    # ---- e2e ------------------------------------------------------------------------------------------------------------
     e2e = None
-    if not args.no_e2e:
-        S = nn['S']
-        pool = 8
-        hs = [torch.randint(0, 256, (BATCH, cfg['h'], cfg['w'], 4), dtype=torch.uint8).pin_memory() for _ in range(2 * pool)]
-        ha = np.random.default_rng(0).integers(0, cfg['a'], BATCH).astype(np.uint8)
-        hr = np.zeros(BATCH, np.uint8); hc = np.ones(BATCH, np.uint8)
+    if not args.no_e2e and not dp:
+        import random as pyrandom
         from deepqnetwork_b200.deep_q_agent import make_priority as host_make_priority
+        S = nn['S']
         e2e_steps = max(50, min(args.steps, 500))
-        rs = np.random.default_rng(5)
+        pyrandom.seed(5)
+        u_pin = torch.empty(BATCH, dtype=torch.float64).pin_memory()  # the step's host input: B random.random() draws
+        u_np = u_pin.numpy()
 
-        def e2e_step(i):
-            st, ns = hs[2 * (i % pool)].numpy(), hs[2 * (i % pool) + 1].numpy()
+        def draw_rows():
+            size = capacity / BATCH
+            return np.array([pyrandom.randint(int(i * size), int((i + 1) * size - 1)) for i in range(BATCH)], np.int64)
+
+        def agent_step(i):
+            # DeepQAgent._train_run_train (deepqnetwork_b200/deep_q_agent.py): host draws in, step / losses / loss out
             if cfg['per']:
-                t, p, w = L.per_sample(rs.random(BATCH), i % 5000 == 0, 0.4)        # seam 3: H2D u, D2H idx/prio/is_w
-                step, losses, loss = L.train_batch(st, ha, hr, hc, ns, w)           # seam 2: H2D batch, D2H losses/loss
-                L.tree_update(t, host_make_priority(losses), store_losses=True)    # seam 3: H2D idx/prio
-            else:
-                step, losses, loss = L.train_batch(st, ha, hr, hc, ns, None)
-            return loss
+                for k in range(BATCH):
+                    u_np[k] = pyrandom.random()
+                return L.train_step(uniforms=u_np)
+            return L.train_step(rows=draw_rows())
 
         for i in range(10):
-            e2e_step(i)
+            agent_step(i)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            e2e_step(i)
+            agent_step(i)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             tm = torch.tensor([dt], device='cuda', dtype=torch.float64)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dt = float(tm.item())
-        h2d = 2 * BATCH * S + 3 * BATCH + (BATCH * (8 + 4 + 8 + 4) if cfg['per'] else 0)
-        d2h = BATCH * 4 + 12 + (BATCH * 32 if cfg['per'] else 0)
-        e2e = dict(value=world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
-                   path='seam 3 dqn_per_sample -> seam 2 dqn_train_batch (pinned host batch) -> seam 3 dqn_tree_update')
+        e2e = dict(value=world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 8, d2h_bytes_per_step=BATCH * 4 + 8 + 4,
+                   steps=e2e_steps, path='DeepQAgent._train_run_train as the drop-in agent runs it: dqn_train_step(h_u = B host draws) -> '
+                   '(step, losses[B], loss) on the host every step; replay, sum tree and batch stay in HBM',
+                   excluded='replay append (actor side, once per environment step, not per train step)')
+
+        # the other integration: seams 3 + 2 + 3 with a HOST replay -- the sampled rows are gathered on the host from a pinned
+        # host ring and uploaded every step (ReplayMemory.copy x B, rl/data/replay_memory.py:113-122, paid on the host)
+        R_host = 20000
+        rng = np.random.default_rng(0)
+        ring_s = torch.from_numpy(rng.integers(0, 256, (R_host, cfg['h'], cfg['w'], 4), dtype=np.uint8)).pin_memory().numpy()
+        ring_n = torch.from_numpy(rng.integers(0, 256, (R_host, cfg['h'], cfg['w'], 4), dtype=np.uint8)).pin_memory().numpy()
+        ring_a = rng.integers(0, cfg['a'], R_host).astype(np.uint8); ring_r = rng.choice([0, 1, 4, 7], R_host).astype(np.uint8)
+        ring_c = (rng.random(R_host) < 0.99)
+        bs = torch.empty((2, BATCH, cfg['h'], cfg['w'], 4), dtype=torch.uint8).pin_memory().numpy()  # s and s' in one pinned block
+        rs = np.random.default_rng(5)
+
+        def seam_step(i):
+            if cfg['per']:
+                t, p, w = L.per_sample(rs.random(BATCH), i % 5000 == 0, 0.4)        # seam 3: H2D u, D2H idx/prio/is_w
+                rows = (t - (capacity - 1)) % R_host                                # the host ring stands in for the 1M-row one
+            else:
+                rows = draw_rows() % R_host; w = None
+            np.take(ring_s, rows, axis=0, out=bs[0]); np.take(ring_n, rows, axis=0, out=bs[1])   # host gather of the 2B rows
+            step, losses, loss = L.train_batch(bs[0], ring_a[rows], ring_r[rows], ring_c[rows], bs[1], w)  # seam 2: H2D batch, D2H losses
+            if cfg['per']:
+                L.tree_update(t, host_make_priority(losses), store_losses=True)     # seam 3: H2D idx/prio
+            return loss
+
+        hb_steps = max(50, min(args.steps, 300))
+        for i in range(10):
+            seam_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(hb_steps):
+            seam_step(i)
+        torch.cuda.synchronize()
+        dth = time.perf_counter() - t0
+        e2e['host_batch'] = dict(value=hb_steps / dth, unit=UNIT, steps=hb_steps,
+                                 h2d_bytes_per_step=2 * BATCH * S + 3 * BATCH + (BATCH * (8 + 4 + 8 + 4) if cfg['per'] else 0),
+                                 d2h_bytes_per_step=BATCH * 4 + 12 + (BATCH * 32 if cfg['per'] else 0),
+                                 path='seam 3 dqn_per_sample -> host gather of the sampled rows from a pinned %d-row host ring -> seam 2 '
+                                      'dqn_train_batch (H2D of the batch) -> seam 3 dqn_tree_update' % R_host)
+    elif dp and not args.no_e2e:
+        # the data-parallel step is driven from the host every step already (phase 0, collectives, phase 1): its wall-clock
+        # rate, with the scalar loss read back every step, is the end-to-end number
+        e2e_steps = max(20, min(args.steps, 200))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            D.train_step()
+            L.get_stats()  # device -> host read of the step's scalars (loss, PER statistics)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tm = torch.tensor([dt], device='cuda', dtype=torch.float64); dist.all_reduce(tm, op=dist.ReduceOp.MAX); dt = float(tm.item())
+        e2e = dict(value=e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=64, steps=e2e_steps,
+                   path='DataParallelLearner.train_step (device Philox draws, replay shards in HBM) + scalar read-back, wall clock')
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not dp:
         v, done, threads = cpu_reference_run(cfg, 10 ** 9, 3, 20000, args.cpu_seconds)
-        cpu = dict(value=v, unit=UNIT, cores=threads, kind='port',
-                   sample='%d consecutive train steps (%.0f s), 20000-row host replay; NumPy/Python replay+PER as in '
-                          'rl/data/*.py, torch-CPU fp32 network (stand-in for TF 1.x CPU)' % (done, args.cpu_seconds))
+        v1, done1, _ = cpu_reference_run(cfg, 10 ** 9, 1, 20000, min(8.0, args.cpu_seconds), threads=1)
+        cpu = dict(value=v, unit=UNIT, cores=threads, kind='port', value_1_thread=v1,
+                   sample='%d consecutive train steps (%.0f s) on %d threads, %d steps on 1 thread; 20000-row host replay; NumPy/Python '
+                          'replay+PER as in rl/data/*.py, torch-CPU fp32 network (stand-in for TF 1.x CPU)' % (done, args.cpu_seconds, threads, done1))
 
     L.close()
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='strong' if dp else 'weak', vs_baseline=None,
                     dtype={'fp32': 'f32', 'tc3x': 'f32 (tf32x3 on tcgen05)', 'tc1x': 'tf32'}[args.math],
                     data='synthetic', config=config, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
                     cpu_baseline=cpu)

