@@ -389,10 +389,6 @@ def main():
         from deepqnetwork_b200.distributed import DataParallelLearner, grads_tensor
         D = DataParallelLearner(L, overlap=not args.no_overlap, learner_stream=stream)
         run_steps = lambda n: [D.train_step() for _ in range(n)]
-        L.train_step_phase(0, 1.0 / world); L.sync()      # first sample computes the local PER statistics
-        D.sync_per_normaliser()                            # one importance-weight scale for all shards
-        L.train_step_phase(1, 1.0 / world); L.sync()
-        args.warmup = max(args.warmup - 1, 3)
     else:
         run_steps = L.train_steps
 

@@ -23,6 +23,7 @@ class DqnConfig(C.Structure):
         ('per_anneal_steps', C.c_int64), ('use_per_annealing', C.c_int32),
         ('per_calculate_steps', C.c_int64), ('copy_network_steps', C.c_int64),
         ('max_rows', C.c_int32), ('math_mode', C.c_int32), ('seed', C.c_uint64),
+        ('frame_dedup', C.c_int32), ('frame_capacity', C.c_int64),
     ]
 
 
@@ -49,6 +50,9 @@ _SIGS = {
     'dqn_replay_read': [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P],
     'dqn_replay_info': [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)],
     'dqn_replay_clear': [_P],
+    'dqn_frames_append': [_P, C.c_int64, _P, C.POINTER(C.c_int64)],
+    'dqn_frames_info': [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    'dqn_replay_append_indexed': [_P, C.c_int64, _P, _P, _P, _P, _P],
     'dqn_replay_fill_synthetic': [_P, C.c_int64, C.c_uint64],
     'dqn_tree_add': [_P, C.c_int64, _P, _P],
     'dqn_tree_update': [_P, C.c_int64, _P, _P, C.c_int32],

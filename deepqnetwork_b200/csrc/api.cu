@@ -136,7 +136,18 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         // replay ring + tree
         h->cap = cfg->replay_capacity;
         const size_t N = (size_t)h->cap;
-        dmalloc(h->r_states, N * h->state_bytes); dmalloc(h->r_next, N * h->state_bytes);
+        h->dedup = cfg->frame_dedup != 0;
+        h->frame_bytes = (size_t)net.H * net.W;
+        if (h->dedup) {
+            DQN_REQUIRE(h->frame_bytes % 16 == 0, "frame_dedup: H*W must be a multiple of 16 bytes");
+            h->fcap = cfg->frame_capacity > 0 ? cfg->frame_capacity : h->cap + h->cap / 16 + 64;
+            DQN_REQUIRE(h->fcap >= 8 && h->fcap < (int64_t)1 << 32, "frame_capacity out of range");
+            dmalloc(h->r_frames, (size_t)h->fcap * h->frame_bytes);
+            dmalloc(h->r_fidx, N * 8);
+            DQN_CUDA_OK(cudaMemsetAsync(h->r_fidx, 0, N * 8 * sizeof(uint32_t), h->stream));
+        } else {
+            dmalloc(h->r_states, N * h->state_bytes); dmalloc(h->r_next, N * h->state_bytes);
+        }
         dmalloc(h->r_actions, N); dmalloc(h->r_rewards, N); dmalloc(h->r_cont, N); dmalloc(h->r_losses, N);
         DQN_CUDA_OK(cudaMemsetAsync(h->r_losses, 0, N * sizeof(__half), h->stream));
         dmalloc(h->tree, 2 * N - 1); dmalloc(h->tree_data, N);
@@ -227,7 +238,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->sets[0].states) select_set(h, 0);  // the b_* aliases freed below must be set 0 (set 1 is freed separately)
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
     if (h->prof_graph) cudaGraphExecDestroy(h->prof_graph);
-    void* ptrs[] = {h->slab_base, h->d_sc, h->d_dev, h->r_states, h->r_next,
+    void* ptrs[] = {h->slab_base, h->d_sc, h->d_dev, h->r_states, h->r_next, h->r_frames, h->r_fidx,
                     h->r_actions, h->r_rewards, h->r_cont, h->r_losses, h->tree, h->tree_data, h->b_states, h->in_states,
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,
@@ -346,6 +357,7 @@ extern "C" int dqn_device_ptr(dqn_learner* h, const char* what, void** ptr, int6
     else if (w == "adam_m") { p = h->slot_m; b = P4; }
     else if (w == "adam_v") { p = h->slot_v; b = P4; }
     else if (w == "tree") { p = h->tree; b = (2 * h->cap - 1) * 4; }
+    else if (w == "replay_frames") { p = h->r_frames; b = h->fcap * (int64_t)h->frame_bytes; }
     else if (w == "replay_states") { p = h->r_states; b = h->cap * (int64_t)h->state_bytes; }
     else if (w == "replay_next_states") { p = h->r_next; b = h->cap * (int64_t)h->state_bytes; }
     else if (w == "batch_states") { p = h->b_states; b = 2 * (int64_t)h->max_rows * h->state_bytes; }
@@ -424,6 +436,7 @@ extern "C" int dqn_replay_append(dqn_learner* h, int64_t n, const uint8_t* st, c
                                  const uint8_t* ns, const uint8_t* ct, const float* losses) {
     API_BEGIN(h)
     DQN_REQUIRE(!(h->cfg.use_per && !losses), "use_per: losses (priorities) are required on append");
+    DQN_REQUIRE(!h->dedup, "frame_dedup layout: append frames with dqn_frames_append and rows with dqn_replay_append_indexed");
     int64_t done = 0;
     const int64_t max_chunk = std::min<int64_t>(h->cap, (int64_t)(h->dev_stage_bytes / 4));
     while (done < n) {
@@ -459,9 +472,89 @@ extern "C" int dqn_replay_append(dqn_learner* h, int64_t n, const uint8_t* st, c
     API_END(h)
 }
 
+extern "C" int dqn_frames_append(dqn_learner* h, int64_t n, const uint8_t* frames, int64_t* first_slot) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->dedup, "handle was created without frame_dedup");
+    DQN_REQUIRE(n >= 0 && n <= h->fcap, "more frames than the frame ring holds");
+    const int64_t slot0 = h->f_written % h->fcap;
+    if (first_slot) *first_slot = slot0;
+    const int64_t first = std::min<int64_t>(n, h->fcap - slot0);
+    DQN_CUDA_OK(cudaMemcpyAsync(h->r_frames + (size_t)slot0 * h->frame_bytes, frames, (size_t)first * h->frame_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (n > first)
+        DQN_CUDA_OK(cudaMemcpyAsync(h->r_frames, frames + (size_t)first * h->frame_bytes, (size_t)(n - first) * h->frame_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->f_written += n;
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));  // caller memory is reusable on return
+    API_END(h)
+}
+
+extern "C" int dqn_frames_info(dqn_learner* h, int64_t* frame_capacity, int64_t* frames_written) {
+    if (!h) return 2;
+    if (frame_capacity) *frame_capacity = h->fcap;
+    if (frames_written) *frames_written = h->f_written;
+    return 0;
+}
+
+extern "C" int dqn_replay_append_indexed(dqn_learner* h, int64_t n, const uint32_t* slots, const uint8_t* ac, const uint8_t* rw,
+                                         const uint8_t* ct, const float* losses) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->dedup, "handle was created without frame_dedup");
+    DQN_REQUIRE(!(h->cfg.use_per && !losses), "use_per: losses (priorities) are required on append");
+    for (int64_t i = 0; i < n * 8; ++i) DQN_REQUIRE((int64_t)slots[i] < h->fcap, "frame slot out of range");
+    int64_t done = 0;
+    const int64_t max_chunk = std::min<int64_t>(h->cap, (int64_t)(h->dev_stage_bytes / 4));
+    while (done < n) {
+        const int64_t m = std::min(n - done, max_chunk);
+        const int64_t cur = h->ring_cur;
+        if (losses) {
+            float* d_sc = (float*)h->dev_stage;
+            DQN_CUDA_OK(cudaMemcpyAsync(d_sc, losses + done, m * 4, cudaMemcpyHostToDevice, h->stream));
+            if (h->cfg.use_per) {  // ReplaySamplerPriority.append (replay_sampler_priority.py:22-24)
+                DQN_REQUIRE(h->tree_write == cur, "sum tree write pointer out of step with the ring");
+                launch_tree_add(h, m, d_sc, nullptr, h->tree_write);
+                if (h->tree_write + m >= h->cap) h->tree_max_reached = true;
+                h->tree_size = h->tree_max_reached ? h->cap : h->tree_write + m;
+                h->tree_write = (h->tree_write + m) % h->cap;
+            }
+            store_losses_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, h->stream>>>(h->r_losses, h->cap, cur, m, d_sc);
+            DQN_CUDA_OK(cudaGetLastError());
+        }
+        ring_copy(h, reinterpret_cast<uint8_t*>(h->r_fidx), reinterpret_cast<const uint8_t*>(slots + (size_t)done * 8), cur, m, 32);
+        ring_copy(h, h->r_actions, ac + done, cur, m, 1);
+        ring_copy(h, h->r_rewards, rw + done, cur, m, 1);
+        ring_copy(h, h->r_cont, ct + done, cur, m, 1);
+        if (cur + m >= h->cap) h->ring_full = true;
+        h->ring_cur = (cur + m) % h->cap;
+        h->ring_size = h->ring_full ? h->cap : h->ring_cur;
+        done += m;
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    push_sizes(h);
+    API_END(h)
+}
+
 extern "C" int dqn_replay_read(dqn_learner* h, int64_t n, const int64_t* rows, uint8_t* st, uint8_t* ac, uint8_t* rw,
                                uint8_t* ns, uint8_t* ct, uint16_t* ls) {
     API_BEGIN(h)
+    if (h->dedup && (st || ns)) {
+        // stacked states are assembled from the frame ring on the device (the gather the training step uses), max_rows at a time
+        const size_t S = h->state_bytes;
+        for (int64_t done = 0; done < n;) {
+            const int m = (int)std::min<int64_t>(n - done, h->max_rows);
+            for (int j = 0; j < m; ++j) DQN_REQUIRE(rows[done + j] >= 0 && rows[done + j] < h->cap, "row out of range");
+            DQN_CUDA_OK(cudaMemcpyAsync(h->b_rows, rows + done, (size_t)m * 8, cudaMemcpyHostToDevice, h->stream));
+            if (st) {
+                launch_gather_states(h, h->b_rows, m, false, h->in_states);
+                DQN_CUDA_OK(cudaMemcpyAsync(st + (size_t)done * S, h->in_states, (size_t)m * S, cudaMemcpyDeviceToHost, h->stream));
+            }
+            if (ns) {
+                launch_gather_states(h, h->b_rows, m, true, h->in_states + (size_t)h->max_rows * S);
+                DQN_CUDA_OK(cudaMemcpyAsync(ns + (size_t)done * S, h->in_states + (size_t)h->max_rows * S, (size_t)m * S, cudaMemcpyDeviceToHost, h->stream));
+            }
+            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+            done += m;
+        }
+        st = nullptr; ns = nullptr;
+    }
     for (int64_t j = 0; j < n; ++j) {
         const int64_t r = rows[j];
         DQN_REQUIRE(r >= 0 && r < h->cap, "row out of range");
@@ -488,7 +581,7 @@ extern "C" int dqn_replay_info(dqn_learner* h, int64_t* size, int64_t* cur, int3
 extern "C" int dqn_replay_clear(dqn_learner* h) {
     API_BEGIN(h)
     h->ring_cur = 0; h->ring_full = false; h->ring_size = 0;
-    push_sizes(h);
+    push_sizes(h);  // (the frame ring of the frame_dedup layout keeps running: slots are reused by age, not by row)
     API_END(h)
 }
 
@@ -862,7 +955,8 @@ static void maybe_refresh_stats_noprof(dqn_learner* h) {
 }
 static bool maybe_refresh_stats(dqn_learner* h) {
     // deep_q_agent.py:505: step % per_calculate_steps == 0 or last_max_weight is None
-    if (h->cfg.use_per && (!h->has_max_weight || h->host_step % h->cfg.per_calculate_steps == 0)) {
+    // (external_normaliser: data-parallel ranks install the maximum over all shards themselves, dqn_set_per_normaliser)
+    if (h->cfg.use_per && !h->external_normaliser && (!h->has_max_weight || h->host_step % h->cfg.per_calculate_steps == 0)) {
         launch_tree_stats(h, -1.0);
         h->has_max_weight = true;
         return true;
@@ -1290,6 +1384,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "fc_tma_fwd") h->fc_tma_fwd = value != 0;
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
     else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
+    else if (n == "external_normaliser") h->external_normaliser = value != 0;  // the caller owns last_max_weight (data-parallel)
     else if (n == "l2_keep") h->l2_keep = value;          // L2 residency hints (learner.h)
     else if (n == "wg1_fit") h->wg1_fit = value != 0;
     else if (n == "keep_grads") h->keep_grads = value != 0;  // dqn_train_batch: dense-kernel gradients stay readable (slot 3)

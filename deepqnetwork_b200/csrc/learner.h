@@ -123,6 +123,7 @@ struct dqn_learner {
     DevSizes* d_dev = nullptr;
     int64_t host_step = 0;     // host mirror of Scalars::step (cadence decisions without a device read)
     bool has_max_weight = false;
+    bool external_normaliser = false;  // option: dqn_set_per_normaliser is the only writer of last_max_weight
 
     // replay ring (SoA, HBM)
     int64_t cap = 0, ring_size = 0, ring_cur = 0;
@@ -130,6 +131,12 @@ struct dqn_learner {
     size_t state_bytes = 0;
     uint8_t *r_states = nullptr, *r_next = nullptr, *r_actions = nullptr, *r_rewards = nullptr, *r_cont = nullptr;
     __half* r_losses = nullptr;
+    // frame-de-duplicated layout (cfg.frame_dedup): frames stored once, transitions hold 8 frame slots
+    bool dedup = false;
+    int64_t fcap = 0, f_written = 0;   // frame ring slots, frames appended so far (slot = count % fcap)
+    size_t frame_bytes = 0;            // H * W
+    uint8_t* r_frames = nullptr;       // [fcap][H][W]
+    uint32_t* r_fidx = nullptr;        // [cap][8]: s channels 0..3, s' channels 0..3
 
     // sum tree
     float* tree = nullptr;       // 2*cap-1
@@ -261,6 +268,8 @@ void net_describe(NetDesc& net, const dqn_config& cfg);
 // with_f32: also write the batch as f32/255 (the fused step feeds the tensor-core loaders from it)
 void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32 = false);
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio);
+// stacked [n][H][W][4] states of ring rows -> dst (frame_dedup: assembled from the frame ring); next: the s' stacks
+void launch_gather_states(dqn_learner* h, const long long* d_rows, int n, bool next, uint8_t* dst);
 
 // sumtree.cu
 // u_src: uniforms read from there instead of b_u (may be pinned host memory); host_out: pinned host block that also

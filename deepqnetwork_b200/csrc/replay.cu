@@ -59,7 +59,76 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ states, const uin
     }
 }
 
+// Frame-de-duplicated layout: state[h][w][c] = frame[slot[c]][h][w].  A thread assembles 4 pixels (16 output bytes): one
+// 4-byte load from each of the 4 frames of the stack, a 4 x 4 byte transpose (prmt), one 16-byte store.  Reads are 4-byte
+// coalesced per frame (a warp reads 128 contiguous bytes of each), writes 16-byte coalesced.
+__global__ void gather_frames_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ fidx,
+                                     const uint8_t* __restrict__ actions, const uint8_t* __restrict__ rewards,
+                                     const uint8_t* __restrict__ cont, const __half* __restrict__ losses,
+                                     const long long* __restrict__ rows, int n, size_t frame_bytes, int only_next,
+                                     uint8_t* __restrict__ b_states, uint8_t* __restrict__ b_actions,
+                                     uint8_t* __restrict__ b_rewards, uint8_t* __restrict__ b_cont,
+                                     __half* __restrict__ b_losses, float4* __restrict__ x_f32) {
+    // only_next < 0: slots [0,n) = s, [n,2n) = s' (the train batch); only_next = 0 / 1: n slots of s / s' (read-back)
+    const int slot = blockIdx.y;
+    const int j = only_next < 0 ? (slot < n ? slot : slot - n) : slot;
+    const int half = only_next < 0 ? (slot < n ? 0 : 1) : only_next;
+    const long long row = rows[j];
+    const uint32_t* fi = fidx + (size_t)row * 8 + half * 4;
+    const uint32_t* f0 = reinterpret_cast<const uint32_t*>(frames + (size_t)fi[0] * frame_bytes);
+    const uint32_t* f1 = reinterpret_cast<const uint32_t*>(frames + (size_t)fi[1] * frame_bytes);
+    const uint32_t* f2 = reinterpret_cast<const uint32_t*>(frames + (size_t)fi[2] * frame_bytes);
+    const uint32_t* f3 = reinterpret_cast<const uint32_t*>(frames + (size_t)fi[3] * frame_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(b_states + (size_t)slot * frame_bytes * 4);
+    const int nq = (int)(frame_bytes >> 2);  // groups of 4 pixels
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const uint32_t a = __ldg(f0 + q), b = __ldg(f1 + q), c = __ldg(f2 + q), d = __ldg(f3 + q);
+        // pixel p of the group: bytes {a.p, b.p, c.p, d.p}
+        const uint32_t ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);  // a0 b0 a1 b1 | a2 b2 a3 b3
+        const uint32_t cd_lo = __byte_perm(c, d, 0x5140), cd_hi = __byte_perm(c, d, 0x7362);
+        uint4 o;
+        o.x = __byte_perm(ab_lo, cd_lo, 0x5410); o.y = __byte_perm(ab_lo, cd_lo, 0x7632);
+        o.z = __byte_perm(ab_hi, cd_hi, 0x5410); o.w = __byte_perm(ab_hi, cd_hi, 0x7632);
+        dst[q] = o;
+        if (x_f32) {
+            float4* xd = x_f32 + ((size_t)slot * frame_bytes) + (size_t)q * 4;
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                xd[k] = make_float4(u8_to_unit(w[k] & 255u), u8_to_unit((w[k] >> 8) & 255u), u8_to_unit((w[k] >> 16) & 255u), u8_to_unit(w[k] >> 24));
+        }
+    }
+    if (only_next < 0 && blockIdx.x == 0 && threadIdx.x == 0 && slot < n) {
+        b_actions[j] = actions[row];
+        b_rewards[j] = rewards[row];
+        b_cont[j] = cont[row];
+        b_losses[j] = losses[row];
+    }
+}
+
+void launch_gather_states(dqn_learner* h, const long long* d_rows, int n, bool next, uint8_t* dst) {
+    if (h->dedup) {
+        launch_kernel(false, gather_frames_kernel, dim3(ceil_div((int)(h->frame_bytes >> 2), 256), n), dim3(256), 0, h->stream,
+                      (const uint8_t*)h->r_frames, (const uint32_t*)h->r_fidx, (const uint8_t*)nullptr, (const uint8_t*)nullptr,
+                      (const uint8_t*)nullptr, (const __half*)nullptr, d_rows, n, h->frame_bytes, next ? 1 : 0, dst, (uint8_t*)nullptr,
+                      (uint8_t*)nullptr, (uint8_t*)nullptr, (__half*)nullptr, (float4*)nullptr);
+        h->launches++;
+        return;
+    }
+    throw std::string("launch_gather_states is the frame_dedup read-back path");
+}
+
 void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32) {
+    if (h->dedup) {
+        const bool f32 = with_f32 && h->cfg.math_mode != DQN_MATH_FP32;
+        launch_kernel(false, gather_frames_kernel, dim3(ceil_div((int)(h->frame_bytes >> 2), 256), 2 * n), dim3(256), 0, h->stream,
+                      (const uint8_t*)h->r_frames, (const uint32_t*)h->r_fidx, (const uint8_t*)h->r_actions, (const uint8_t*)h->r_rewards,
+                      (const uint8_t*)h->r_cont, (const __half*)h->r_losses, d_rows, n, h->frame_bytes, -1, h->b_states, h->b_actions,
+                      h->b_rewards, h->b_cont, h->b_losses, f32 ? reinterpret_cast<float4*>(h->x_f32) : (float4*)nullptr);
+        h->launches++;
+        h->xf_from_gather = f32;
+        return;
+    }
     const int threads = 256;
     const int nvec = (int)(h->state_bytes >> 4);
     dim3 grid(ceil_div(nvec, threads * 4), 2 * n);
@@ -104,7 +173,31 @@ __global__ void fill_scalars_kernel(uint8_t* actions, uint8_t* rewards, uint8_t*
     prio_out[j] = p;
 }
 
+// frame_dedup synthetic fill: transition t holds frames {t .. t+3} (s) and {t+1 .. t+4} (s'), slots modulo the frame ring
+__global__ void fill_fidx_kernel(uint32_t* __restrict__ fidx, long long start, long long n, long long fcap) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n * 8) return;
+    const long long t = start + (i >> 3);
+    const int c = (int)(i & 7);
+    fidx[(size_t)t * 8 + c] = (uint32_t)((t + (c & 3) + (c >> 2)) % fcap);
+}
+
 void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t seed, float* d_prio) {
+    if (h->dedup) {
+        // frames [start, start + n) of the stream (+ the 4 trailing ones once, with the first chunk's successor frames)
+        const int blocks = h->sm_count * 16;
+        const int64_t f0 = start == 0 ? 0 : start + 4, f1 = start + n + 4;  // transition t needs frames up to t + 4
+        DQN_REQUIRE(f1 <= h->fcap, "synthetic fill: frame ring too small (needs replay rows + 4)");
+        const size_t nvec = (size_t)(f1 - f0) * (h->frame_bytes >> 4), vec0 = (size_t)f0 * (h->frame_bytes >> 4);
+        fill_states_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<uint4*>(h->r_frames + (size_t)f0 * h->frame_bytes), nvec, vec0, seed, 1u);
+        fill_fidx_kernel<<<(unsigned)ceil_div64(n * 8, 256), 256, 0, h->stream>>>(h->r_fidx, start, n, h->fcap);
+        fill_scalars_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, h->stream>>>(h->r_actions, h->r_rewards, h->r_cont, h->r_losses, d_prio,
+                                                                                 start, n, h->cfg.num_actions, seed);
+        DQN_CUDA_OK(cudaGetLastError());
+        if (f1 > h->f_written) h->f_written = f1;
+        h->launches += 3;
+        return;
+    }
     const size_t nvec = (size_t)n * (h->state_bytes >> 4);
     const int blocks = h->sm_count * 16;
     const size_t vec0 = (size_t)start * (h->state_bytes >> 4);

@@ -33,6 +33,77 @@ class _RingField:
         return a.astype(dtype) if dtype is not None else a
 
 
+class _FrameDedup:
+    """Host side of the frame-de-duplicated ring (dqn_config.frame_dedup): turns the stacked states the agent seam hands
+    over (H x W x 4, built by GameRunner from its 4-frame deque, rl/game_runner.py:139-148,236-244) back into single
+    frames.  Frames are content-addressed through a small cache of the most recent ones, so the 3 frames a stack shares
+    with its predecessor -- and the s == s' transition the runner emits after a life loss (SURVEY Q5) -- are stored once;
+    only frames not seen among the last CACHE appended ones are uploaded.  Nothing is assumed about HOW stacks overlap:
+    a stack whose frames are all new simply costs four uploads, so episode and game boundaries need no special case.
+
+    The frame ring reuses a slot after frame_capacity appends.  A monotonic queue over the live transitions tracks the
+    oldest frame any of them references; overwriting a referenced slot raises instead of corrupting the replay."""
+    CACHE = 16
+
+    def __init__(self, learner, max_size):
+        from collections import OrderedDict, deque
+        self.learner = learner
+        self.fcap = learner.frames_info()[0]
+        self.cache = OrderedDict()      # frame bytes -> append count of the frame
+        self.count = learner.frames_info()[1]
+        self.max_size = max_size
+        self.rows = 0                   # transitions appended so far
+        self.window = deque()           # (row number, oldest frame count of that row), increasing in both: sliding minimum
+
+    def append_rows(self, states, actions, rewards, next_states, continues, losses):
+        n = len(actions)
+        H, W = self.learner.height, self.learner.width
+        new_frames, slots = [], np.empty((n, 8), np.uint32)
+        count0 = self.count
+        oldest = []
+        for i in range(n):
+            row_oldest = None
+            for c in range(8):
+                src = states[i] if c < 4 else next_states[i]
+                key = np.ascontiguousarray(src[..., c & 3]).tobytes()
+                k = self.cache.get(key)
+                if k is not None and self.count + len(new_frames) - k >= self.fcap // 2:
+                    k = None  # too old to be trusted to outlive this transition: store it again
+                if k is None:
+                    k = count0 + len(new_frames)
+                    new_frames.append(np.frombuffer(key, np.uint8).reshape(H, W))
+                self.cache[key] = k
+                self.cache.move_to_end(key)
+                while len(self.cache) > self.CACHE:
+                    self.cache.popitem(last=False)
+                slots[i, c] = k % self.fcap
+                row_oldest = k if row_oldest is None else min(row_oldest, k)
+            oldest.append(row_oldest)
+        # slots about to be reused must not be referenced by a transition that is still in the ring after this append
+        end = count0 + len(new_frames)
+        first_live = self.rows + n - self.max_size
+        while self.window and self.window[0][0] < first_live:
+            self.window.popleft()
+        live = [o for r, o in zip(range(self.rows, self.rows + n), oldest) if r >= first_live]
+        if self.window:
+            live.append(self.window[0][1])  # front of the monotonic queue = oldest frame among the earlier live rows
+        live_min = min(live) if live else end
+        if end - live_min > self.fcap:
+            raise RuntimeError('frame ring too small: a live transition references a frame %d appends old but frame_capacity '
+                               'is %d; create the learner with a larger frame_capacity' % (end - live_min, self.fcap))
+        if new_frames:
+            got = self.learner.frames_append(np.stack(new_frames))
+            assert int(got[0]) == count0 % self.fcap
+        self.count = end
+        self.learner.replay_append_indexed(slots, _as_u8_store(actions), _as_u8_store(rewards), np.asarray(continues, dtype=bool), losses)
+        for r, o in zip(range(self.rows, self.rows + n), oldest):
+            while self.window and self.window[-1][1] >= o:
+                self.window.pop()
+            self.window.append((r, o))
+        self.rows += n
+        return len(new_frames)
+
+
 class ReplayMemory:
     MAX_SIZE = 10000
     STATE_TYPE = 'uint8'
@@ -63,6 +134,8 @@ class ReplayMemory:
         if learner.capacity != self.max_size or learner.state_shape != self.shape:
             raise ValueError('learner ring geometry does not match this ReplayMemory')
         self.learner = learner
+        self._dedup = _FrameDedup(learner, self.max_size) if getattr(learner, 'frame_dedup', False) else None
+        self.frames_uploaded = 0
         for name in ('states', 'next_states', 'actions', 'rewards', 'continues', 'losses'):
             setattr(self, name, _RingField(self, name))
 
@@ -108,6 +181,9 @@ class ReplayMemory:
             for i in range(len(actions)):
                 self.append(states[i], actions[i], rewards[i], next_states[i], continues[i],
                             None if losses is None else losses[i])
+            return
+        if self._dedup is not None:
+            self.frames_uploaded += self._dedup.append_rows(np.asarray(states), actions, rewards, np.asarray(next_states), continues, losses)
             return
         self.learner.replay_append(states, _as_u8_store(actions), _as_u8_store(rewards), next_states,
                                    np.asarray(continues, dtype=bool), losses)

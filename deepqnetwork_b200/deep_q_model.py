@@ -130,7 +130,7 @@ class DeepQModel:
             per_anneal_steps=c.get('per_anneal_steps', 2000000), use_per_annealing=c.get('use_per_annealing', False),
             per_calculate_steps=c.get('per_calculate_steps', 5000), copy_network_steps=0,
             conv_variant=self.CONV_VARIANT, math_mode=c.get('math_mode', 'tc3x'), seed=c.get('device_seed', 7),
-            device=c.get('device', 0))
+            device=c.get('device', 0), frame_dedup=c.get('frame_dedup', False), frame_capacity=c.get('frame_capacity', 0) or 0)
         loaded = False
         prefix = self.conf.get('save_path_prefix')
         if self.load_model and prefix:

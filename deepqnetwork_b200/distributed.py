@@ -103,6 +103,9 @@ class DataParallelLearner:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.overlap = bool(overlap) and self.world > 1
         self.steps = 0
+        self._per = bool(getattr(learner, 'use_per', False)) and hasattr(learner, 'set_per_normaliser')
+        if self._per:
+            learner.set_option('external_normaliser', 1)
         if self.overlap:
             import torch
             self._stream = learner_stream
@@ -114,20 +117,31 @@ class DataParallelLearner:
             self._small_flat = torch.empty(sum(c for _, c in small), dtype=torch.float32, device=self._grads.device)
 
     def sync_per_normaliser(self):
-        """One scale for the importance weights of all shards: the maximum of the ranks' last_max_weight (the rank whose
-        shard holds the globally smallest sampling probability), deep_q_agent.py:506-510."""
+        """One scale for the importance weights of all shards (deep_q_agent.py:506-510 evaluated per shard, then the
+        maximum over the ranks: the shard that holds the globally smallest sampling probability sets the scale).  The
+        learner's own refresh is switched off (option external_normaliser); this runs at the reference's cadence."""
         import torch
         import torch.distributed as dist
-        if self.world == 1:
-            return
-        mw = torch.tensor([self.learner.get_stats()['last_max_weight']], dtype=torch.float32, device=self._grads.device)
-        dist.all_reduce(mw, op=dist.ReduceOp.MAX, group=self.group)
-        self.learner.set_per_normaliser(float(mw.item()))
+        from .deep_q_agent import max_weight
+        L = self.learner
+        mn, mx, avg, total = L.tree_stats()
+        per_b = L.cfg.per_b_start
+        if L.cfg.use_per_annealing:
+            per_b = min(L.cfg.per_b_end, per_b + self.steps * ((L.cfg.per_b_end - L.cfg.per_b_start) / L.cfg.per_anneal_steps))
+        mw = float(max_weight(float(mn), float(total), L.batch_size, per_b))
+        if self.world > 1:
+            t = torch.tensor([mw], dtype=torch.float64, device=self._grads.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            mw = float(t.item())
+        L.set_per_normaliser(mw)
+        return mw
 
     def train_step(self):
         import torch
         import torch.distributed as dist
         scale = 1.0 / self.world
+        if self._per and self.steps % max(int(self.learner.cfg.per_calculate_steps), 1) == 0:
+            self.sync_per_normaliser()
         if not self.overlap:
             # phase 0: sample the local shard, forward, backward -> local gradient (already scaled by 1/world) in the slab
             self.learner.train_step_phase(0, scale)

@@ -18,7 +18,7 @@ class Learner:
                  discount_rate=0.99, batch_size=32, replay_capacity=10000, per_a=0.6, per_b_start=0.4,
                  per_b_end=1.0, per_anneal_steps=2000000, use_per_annealing=False, per_calculate_steps=5000,
                  copy_network_steps=10000, max_rows=0, conv_variant='reference', math_mode='tc3x', seed=7,
-                 device=0):
+                 device=0, frame_dedup=False, frame_capacity=0):
         self._lib = _capi.lib()
         cfg = _capi.DqnConfig()
         cfg.struct_size = C.sizeof(_capi.DqnConfig)
@@ -36,6 +36,8 @@ class Learner:
         cfg.max_rows = max_rows
         cfg.math_mode = {'fp32': _capi.DQN_MATH_FP32, 'tc3x': _capi.DQN_MATH_TC3X, 'tc1x': _capi.DQN_MATH_TC1X}[math_mode]
         cfg.seed = seed
+        cfg.frame_dedup, cfg.frame_capacity = int(bool(frame_dedup)), int(frame_capacity)
+        self.frame_dedup = bool(frame_dedup)
         self.cfg = cfg
         self.height, self.width, self.channels = height, width, channels
         self.num_actions, self.batch_size, self.capacity = num_actions, batch_size, replay_capacity
@@ -149,6 +151,28 @@ class Learner:
         assert ns.shape[0] == n and ac.size == n and rw.size == n and ct.size == n
         ls = None if losses is None else np.ascontiguousarray(np.atleast_1d(losses), dtype=np.float32)
         self._c(self._lib.dqn_replay_append(self._h, n, ptr(st), ptr(ac), ptr(rw), ptr(ns), ptr(ct), ptr(ls)))
+
+    def frames_append(self, frames):
+        """frame_dedup layout: store n new [H,W] uint8 frames; returns their slots in the frame ring."""
+        f = as_u8(np.asarray(frames)).reshape((-1, self.height, self.width))
+        first = C.c_int64()
+        self._c(self._lib.dqn_frames_append(self._h, f.shape[0], ptr(f), C.byref(first)))
+        cap, _ = self.frames_info()
+        return (first.value + np.arange(f.shape[0], dtype=np.int64)) % cap
+
+    def frames_info(self):
+        c = C.c_int64(); w = C.c_int64()
+        self._c(self._lib.dqn_frames_info(self._h, C.byref(c), C.byref(w)))
+        return c.value, w.value
+
+    def replay_append_indexed(self, frame_slots, actions, rewards, continues, losses=None):
+        """frame_dedup layout: n transitions whose s / s' stacks are the given frame slots ([n, 8] = s0..s3, s'0..s'3)."""
+        sl = np.ascontiguousarray(frame_slots, dtype=np.uint32).reshape(-1, 8)
+        n = sl.shape[0]
+        ac = as_u8(np.atleast_1d(actions)); rw = as_u8(np.atleast_1d(rewards)); ct = as_u8(np.atleast_1d(continues))
+        assert ac.size == n and rw.size == n and ct.size == n
+        ls = None if losses is None else np.ascontiguousarray(np.atleast_1d(losses), dtype=np.float32)
+        self._c(self._lib.dqn_replay_append_indexed(self._h, n, ptr(sl), ptr(ac), ptr(rw), ptr(ct), ptr(ls)))
 
     def replay_read(self, rows, fields=('states', 'actions', 'rewards', 'next_states', 'continues', 'losses')):
         rows = np.ascontiguousarray(np.atleast_1d(rows), dtype=np.int64)

@@ -55,6 +55,13 @@ typedef struct dqn_config {
     int32_t max_rows;         /* largest n for predict/get_losses/train_batch (0 -> max(2*batch,256)) */
     int32_t math_mode;        /* DQN_MATH_* */
     uint64_t seed;            /* device Philox seed for throughput-mode sampling */
+    /* Replay layout.  0: the reference's layout, full stacked s and s' per transition (rl/data/replay_memory.py:26-39,
+     * 2 x H*W*4 bytes per row).  1: frame-de-duplicated -- every H x W frame is stored once in a frame ring and a
+     * transition holds the 8 frame slots of its s / s' stacks (the 4-frame deque of rl/game_runner.py:139-148,236-244
+     * re-uses 3 of 4 frames from one step to the next): H*W + 32 bytes per transition, so that the 10M-transition replay
+     * of BASELINE.json configs[2] fits HBM.  The gathered batch, and everything downstream of it, is byte-identical. */
+    int32_t frame_dedup;
+    int64_t frame_capacity;   /* frame ring slots (frame_dedup only); 0 -> replay_capacity * 17/16 + 64 */
 } dqn_config;
 
 /* ---- lifecycle ------------------------------------------------------- */
@@ -100,6 +107,15 @@ int dqn_replay_append(dqn_learner* h, int64_t n, const uint8_t* h_states, const 
 int dqn_replay_read(dqn_learner* h, int64_t n, const int64_t* h_rows, uint8_t* h_states, uint8_t* h_actions,
                     uint8_t* h_rewards, uint8_t* h_next_states, uint8_t* h_continues, uint16_t* h_losses_f16);
 int dqn_replay_info(dqn_learner* h, int64_t* size, int64_t* cur_idx, int32_t* is_full); /* __len__, cur_idx, is_full */
+/* frame_dedup layout: store n new H x W frames ([n,H,W] u8) in the frame ring; *first_slot receives the slot of the first
+ * one, the others follow consecutively modulo frame_capacity.  A frame slot is reused after frame_capacity appends: the
+ * caller keeps frame_capacity >= replay_capacity + the frames a transition can lag behind the newest one. */
+int dqn_frames_append(dqn_learner* h, int64_t n, const uint8_t* h_frames, int64_t* first_slot);
+/* frame_dedup layout: ReplayMemory.append x n with states given as frame slots: h_frame_slots is [n][8] u32 =
+ * {s channel 0..3, s' channel 0..3}.  Same tree / loss-column semantics as dqn_replay_append. */
+int dqn_replay_append_indexed(dqn_learner* h, int64_t n, const uint32_t* h_frame_slots, const uint8_t* h_actions,
+                              const uint8_t* h_rewards, const uint8_t* h_continues, const float* h_losses);
+int dqn_frames_info(dqn_learner* h, int64_t* frame_capacity, int64_t* frames_written);
 int dqn_replay_clear(dqn_learner* h);                                                    /* replay_memory.py:46-52 */
 /* bench/test fill on the device (SURVEY.md 8d "synthetic inputs"): n rows from Philox(seed);
  * when use_per the tree is built with the semantics of n sequential SumTree.add calls. */

@@ -28,8 +28,9 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_matches_header_layout():
     from deepqnetwork_b200 import _capi
     # field-by-field natural alignment of the header's struct
-    assert ctypes.sizeof(_capi.DqnConfig) == 160
+    assert ctypes.sizeof(_capi.DqnConfig) == 176
     assert _capi.DqnConfig.learning_rate.offset == 48 and _capi.DqnConfig.seed.offset == 152
+    assert _capi.DqnConfig.frame_dedup.offset == 160 and _capi.DqnConfig.frame_capacity.offset == 168
 
 
 def test_create_without_gpu_fails_loudly():
