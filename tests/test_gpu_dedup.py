@@ -38,7 +38,8 @@ def transitions_from_runner(n_calls, h=86, w=80, seed=3, episode_len=23, lives=2
     calls = drive(_Recorder(9), StubEnvironment(h, w, 9, seed=seed, episode_len=episode_len, lives=lives), n_calls)
     tr = [c for c in calls if c['old_state'] is not None]
     assert any(np.array_equal(c['old_state'], c['state']) for c in tr)  # the s == s' transition after a life loss (Q5)
-    return tr
+    games = sum(1 for c in calls if c['old_state'] is None)             # first call of a game: no transition yet
+    return tr, games
 
 
 def make_pair(cap, h=86, w=80, a=9, per=True, **kw):
@@ -57,7 +58,7 @@ def make_pair(cap, h=86, w=80, a=9, per=True, **kw):
 @pytest.mark.parametrize('cap,n_calls', [(600, 420), (200, 520)], ids=['partial-ring', 'wrapped-ring'])
 def test_dedup_ring_is_byte_identical_to_the_stacked_ring(cap, n_calls):
     from deepqnetwork_b200.data.replay_memory import ReplayMemory
-    tr = transitions_from_runner(n_calls)
+    tr, games = transitions_from_runner(n_calls)
     Ls, Ld = make_pair(cap, frame_capacity=cap + 96)
     mems = [ReplayMemory(86, 80, 4, max_size=cap, learner=L) for L in (Ls, Ld)]
     rng = np.random.default_rng(0)
@@ -69,8 +70,8 @@ def test_dedup_ring_is_byte_identical_to_the_stacked_ring(cap, n_calls):
                           np.stack([c['state'] for c in chunk]), [c['cont'] for c in chunk], pri)
     n = min(len(tr), cap)
     assert len(mems[0]) == len(mems[1]) == n and mems[0].cur_idx == mems[1].cur_idx
-    # one new frame per environment step (+3 per game start): ~4x fewer bytes uploaded, ~8x fewer stored
-    assert mems[1].frames_uploaded <= len(tr) + 4 * 8
+    # one new frame per environment step (+3 when a game starts with an empty deque): 8x fewer frames than 2 x 4 per row
+    assert mems[1].frames_uploaded <= len(tr) + 4 * (games + 1)
     rows = np.arange(n)
     a, b = Ls.replay_read(rows), Ld.replay_read(rows)
     for k in a:
@@ -95,7 +96,7 @@ def test_dedup_ring_is_byte_identical_to_the_stacked_ring(cap, n_calls):
 
 def test_frame_ring_overrun_is_an_error_not_corruption():
     from deepqnetwork_b200.data.replay_memory import ReplayMemory
-    tr = transitions_from_runner(300)
+    tr, _ = transitions_from_runner(300)
     Ls, Ld = make_pair(200, frame_capacity=64)  # far fewer frame slots than live transitions need
     mem = ReplayMemory(86, 80, 4, max_size=200, learner=Ld)
     with pytest.raises(RuntimeError, match='frame ring too small'):
