@@ -288,7 +288,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c2', choices=list(CONFIGS))
-    ap.add_argument('--capacity', type=int, default=1000000, help='replay transitions resident in HBM')
+    ap.add_argument('--capacity', type=int, default=None, help='replay transitions resident in HBM (default 1M; c3: 10M)')
+    ap.add_argument('--layout', default=None, choices=['stacked', 'frames'],
+                    help="replay layout: the reference's stacked s/s' rows, or frame-de-duplicated (default for c3: 10M transitions = 69 GB)")
     ap.add_argument('--math', default='tc3x', choices=['fp32', 'tc3x', 'tc1x'],
                     help='fp32: FFMA; tc3x: tcgen05 TF32 3-term split (fp32-grade, default); tc1x: single-pass TF32')
     ap.add_argument('--no-fuse', action='store_true', help='ablation: optimizer as a separate pass over the gradient slab')
@@ -308,13 +310,19 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     cfg = CONFIGS[args.config]
     nn = net_numbers(cfg)
-    workload = '%s, %dx%dx4 uint8, batch %d, %d-transition replay in HBM' % (cfg['name'], cfg['h'], cfg['w'], BATCH, args.capacity)
+    if args.capacity is None:
+        args.capacity = 10000000 if args.config == 'c3' else 1000000
+    if args.layout is None:
+        args.layout = 'frames' if args.config == 'c3' else 'stacked'
+    replay_gb = args.capacity * ((nn['S'] // 4 + 32) if args.layout == 'frames' else 2 * nn['S']) / 1e9
+    workload = '%s, %dx%dx4 uint8, batch %d, %d-transition replay in HBM (%s layout, %.1f GB)' % (
+        cfg['name'], cfg['h'], cfg['w'], BATCH, args.capacity, "frame-de-duplicated" if args.layout == 'frames' else "stacked s/s'", replay_gb)
     if world > 1:
         workload = 'C4 %d independent learners (one per GPU, no collectives), each: ' % world + workload
     config = dict(workload=workload, batch=BATCH, replay_transitions=args.capacity, parallelism='replicas x%d' % world,
                   params=nn['P'], gflop_per_step=round(nn['flops'] / 1e9, 3), algorithmic_mb_per_step=round(nn['step_bytes'] / 1e6, 1),
                   l2='no flush: steady-state step; per-step working set (5 parameter-sized slabs = %.0f MB + random replay rows '
-                     'out of %.1f GB) exceeds the 126 MB L2' % (5 * 4 * nn['P'] / 1e6, 2 * args.capacity * nn['S'] / 1e9),
+                     'out of %.1f GB) exceeds the 126 MB L2' % (5 * 4 * nn['P'] / 1e6, replay_gb),
                   math={'fp32': 'fp32 FFMA (DQN_MATH_FP32)', 'tc3x': 'tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (DQN_MATH_TC3X; parity-tested at 1e-4 like fp32)',
                         'tc1x': 'tcgen05 kind::tf32 single pass (DQN_MATH_TC1X; NOT fp32-grade, ~1e-3)'}[args.math])
 
@@ -356,7 +364,7 @@ def main():
     capacity = args.capacity // world if dp else args.capacity
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
                 use_per=cfg['per'], batch_size=batch, replay_capacity=capacity, conv_variant=cfg['variant'],
-                math_mode=args.math, seed=7 + rank, device=local_rank, max_rows=max(batch, 256))
+                math_mode=args.math, seed=7 + rank, device=local_rank, max_rows=max(batch, 256), frame_dedup=args.layout == 'frames')
     # a real (non-default) stream: stream capture is illegal on the legacy stream; high priority, because the learner's
     # own side streams (weight gradients, optimizer, look-ahead sampling) only carry work with slack
     stream = torch.cuda.Stream(priority=-1)

@@ -273,6 +273,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
         for (void* p : p2) if (p) cudaFree(p);
     }
     if (h->batch_graph) cudaGraphExecDestroy(h->batch_graph);
+    if (h->ustep_graph) cudaGraphExecDestroy(h->ustep_graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -290,7 +291,7 @@ extern "C" int dqn_set_stream(dqn_learner* h, void* s) {
     API_BEGIN(h)
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     h->stream = s ? (cudaStream_t)s : h->own_stream;
-    h->graph_valid = false; h->graph_valid_batch = false;
+    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }
@@ -1037,6 +1038,52 @@ extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* ro
     if (rows) for (int i = 0; i < h->B; ++i) DQN_REQUIRE(rows[i] >= 0 && rows[i] < h->ring_size, "row out of range");
     h->prof_used = 0; h->prof_marks.clear();
     maybe_refresh_stats(h);
+    const bool host_draws = u != nullptr || rows != nullptr;
+    if (host_draws && !h->profile && h->batch_graph_enabled) {
+        // The drop-in agent's call (DeepQAgent._train_run_train): ~35 launches replayed as ONE graph.  The draws are copied
+        // into a pinned staging block with a fixed address (first node of the graph: H2D of that block); scalars and
+        // per-sample losses are written into their pinned mirror by the step's last kernel, so a caller that wants them
+        // pays one stream synchronisation and no copy operation.
+        const size_t readback = SC_BLOCK + (size_t)h->B * 4;
+        DQN_CUDA_OK(cudaEventSynchronize(h->stage2_ev));  // the previous launch has consumed the staging block
+        memcpy(h->h_stage2, u ? (const void*)u : (const void*)rows, (size_t)h->B * 8);
+        select_set(h, 0);
+        if (!h->ustep_graph || !h->graph_valid_u) {
+            cudaGraph_t g = nullptr;
+            const int64_t l0 = h->launches, s0 = h->host_step;
+            DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            h->tail_mirror = reinterpret_cast<float*>(h->h_sc); h->tail_mirror_words = (int)(readback / 4);
+            try {
+                fused_step_launches(h, u ? reinterpret_cast<const double*>(h->h_stage2) : nullptr,
+                                    rows ? reinterpret_cast<const int64_t*>(h->h_stage2) : nullptr, 1.0, 3);
+                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
+            } catch (...) {
+                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
+                cudaStreamEndCapture(h->stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+            h->ustep_graph_launches = h->launches - l0;
+            h->launches = l0; h->host_step = s0;
+            if (h->ustep_graph) { cudaGraphExecDestroy(h->ustep_graph); h->ustep_graph = nullptr; }
+            DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->ustep_graph, g, cudaGraphInstantiateFlagUseNodePriority));
+            DQN_CUDA_OK(cudaGraphDestroy(g));
+            h->graph_valid_u = true;
+        }
+        DQN_CUDA_OK(cudaGraphLaunch(h->ustep_graph, h->stream));
+        DQN_CUDA_OK(cudaEventRecord(h->stage2_ev, h->stream));
+        h->launches += h->ustep_graph_launches;
+        h->host_step++;
+        after_step_host(h);
+        if (step || losses || loss) {
+            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+            if (losses) memcpy(losses, reinterpret_cast<const char*>(h->h_sc) + SC_BLOCK, (size_t)h->B * 4);
+            if (step) *step = h->h_sc->step;
+            if (loss) *loss = h->h_sc->loss;
+        }
+        return 0;
+    }
     fused_step_launches(h, u, rows, 1.0, 3);
     after_step_host(h);
     if (step || losses || loss) {
@@ -1403,7 +1450,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "defer_adam") h->defer_adam = value != 0;  // dense-kernel optimizer pass of step i under the conv forward of step i+1
     else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels
     else throw std::string("unknown option: ") + n;
-    h->graph_valid = false; h->graph_valid_batch = false;
+    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }

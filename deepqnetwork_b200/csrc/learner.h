@@ -233,6 +233,11 @@ struct dqn_learner {
     cudaGraphExec_t batch_graph = nullptr;
     int batch_graph_n = 0;
     bool graph_valid_batch = false, batch_graph_enabled = true;
+    // graph of one fused step fed HOST draws (dqn_train_step with h_u / h_rows: the drop-in agent's call): the draws ride a
+    // pinned staging block (fixed address -> memcpy node), scalars + losses come back through the optimizer tail's mirror
+    cudaGraphExec_t ustep_graph = nullptr;
+    bool graph_valid_u = false;
+    int64_t ustep_graph_launches = 0;
     int64_t batch_graph_launches = 0;
     int64_t graph_launches = 0;
 
