@@ -218,6 +218,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         }
         alloc_packed_conv(h);
         launch_pack_conv(h, 0); launch_pack_conv(h, 1);
+        if (net.dueling) dmalloc(h->w_scratch, (size_t)2 * net.flat * net.hidden);
         h->dev_stage_bytes = 8u << 20;
         dmalloc(h->dev_stage, h->dev_stage_bytes);
         dmalloc(h->stats_scratch, 16384);
@@ -243,7 +244,7 @@ extern "C" int dqn_destroy(dqn_learner* h) {
                     h->b_actions, h->b_rewards, h->b_cont, h->b_losses, h->in_actions,
                     h->sets[0].blk, h->sets[1].blk, h->b_isw, h->b_y, h->b_maxq,
                     h->b_dq, h->b_newprio, h->b_rows, h->d_hid, h->d_act[0], h->d_act[1], h->d_act[2],
-                    h->wg_part, h->dev_stage, h->stats_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg, h->act3_pk[0], h->act3_pk[1]};
+                    h->wg_part, h->dev_stage, h->stats_scratch, h->w_scratch, h->zeros16, h->ones_row, h->x_f32, h->opt_ticket, h->packed[0], h->packed[1], h->packed_dg, h->act3_pk[0], h->act3_pk[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (TowerActs* t : {&h->acts_on, &h->acts_tg}) {
         for (int l = 0; l < 3; ++l) cudaFree(t->act[l]);
@@ -788,7 +789,7 @@ extern "C" int dqn_batch_read(dqn_learner* h, uint8_t* st, uint8_t* ac, uint8_t*
 bool overlap_enabled(const dqn_learner* h) { return h->overlap && !h->profile; }
 
 static cudaEvent_t next_fork_event(dqn_learner* h) {
-    DQN_REQUIRE(h->fork_used < 22, "fork event pool exhausted");  // [22], [23] belong to upload_batch
+    DQN_REQUIRE(h->fork_used < 21, "fork event pool exhausted");  // [21]: dense dgrad done (nn.cu); [22], [23] belong to upload_batch
     return h->fork_ev[h->fork_used++];
 }
 
@@ -1429,8 +1430,13 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "batch_graph") h->batch_graph_enabled = value != 0;  // dqn_train_batch replays a captured graph
     else if (n == "fc_split_streams") h->fc_split_streams = value != 0;
     else if (n == "fc_tma_fwd") h->fc_tma_fwd = value != 0;
+    else if (n == "fc_fwd_share") h->fc_fwd_share = value;
     else if (n == "fc_tma_ctas") h->fc_tma_ctas = value;
     else if (n == "fc_rows_ctas") h->fc_rows_ctas = value;
+    else if (n == "w_scratch") {  // fused dense kernel writes the new dense weights to a scratch copy (starts before the dense dgrad)
+        h->w_scratch_on = value != 0;
+        if (h->fa_row_maps) { free(h->fa_row_maps); h->fa_row_maps = nullptr; }  // the store maps point somewhere else now
+    }
     else if (n == "external_normaliser") h->external_normaliser = value != 0;  // the caller owns last_max_weight (data-parallel)
     else if (n == "l2_keep") h->l2_keep = value;          // L2 residency hints (learner.h)
     else if (n == "wg1_fit") h->wg1_fit = value != 0;

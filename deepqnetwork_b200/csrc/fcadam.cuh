@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) fcwg_adam_persist_kernel(const 
 // A CTA walks a contiguous range of tiles (n-half fastest, then rows, then stream).
 constexpr int RS = 4, RT_THREADS = 608, RT_ROWS = 16, RT_N = 256;  // 16 epilogue warps + MMA + TMA + B producer
 
-struct RowMaps { CUtensorMap w[2], m[2], v[2]; };  // box 256 (n) x 16 (k rows), SWIZZLE_NONE
+struct RowMaps { CUtensorMap w[2], m[2], v[2], wout[2]; };  // box 256 (n) x 16 (k rows), SWIZZLE_NONE; wout: where the updated weights go
 
 template <int NTERMS>
 __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const float* __restrict__ act3, const float* __restrict__ dhid,
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                 const int strm = tt / per_stream, r = tt - strm * per_stream;
                 const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
                 const uint32_t st = ring + s * STAGE;
-                stg(&maps.w[strm], nh * RT_N, row0, st, keep_w);
+                stg(&maps.wout[strm], nh * RT_N, row0, st, keep_w);
                 stg(&maps.m[strm], nh * RT_N, row0, st + ARR, keep_mv);
                 if (!use_momentum) stg(&maps.v[strm], nh * RT_N, row0, st + 2 * ARR, keep_mv);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
     }
 }
 
-static void encode_row_maps(dqn_learner* h, RowMaps& out) {
+static void encode_row_maps(dqn_learner* h, RowMaps& out, float* wout_base) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -707,14 +707,17 @@ static void encode_row_maps(dqn_learner* h, RowMaps& out) {
     DQN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     DQN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
     const NetDesc& net = h->net;
-    float* slabs[3] = {h->online, h->slot_m, h->slot_v};
-    CUtensorMap* dst[3] = {out.w, out.m, out.v};
-    for (int a = 0; a < 3; ++a)
+    // wout: the in-place slab, or (w_scratch) a scratch copy of the two dense kernels [2][flat][hidden] that is copied over
+    // the slab once the dense dgrad has read the old weights -- the pass can then start before that dgrad
+    float* slabs[4] = {h->online, h->slot_m, h->slot_v, h->online};
+    CUtensorMap* dst[4] = {out.w, out.m, out.v, out.wout};
+    for (int a = 0; a < 4; ++a)
         for (int st = 0; st < 2; ++st) {
+            float* base = (a == 3 && wout_base) ? wout_base + (size_t)st * net.flat * net.hidden : slabs[a] + net.off_fc_w[st];
             const cuuint64_t gdim[2] = {(cuuint64_t)net.hidden, (cuuint64_t)net.flat};
             const cuuint64_t gstr[1] = {(cuuint64_t)net.hidden * 4};
             const cuuint32_t box[2] = {RT_N, RT_ROWS}, estr[2] = {1, 1};
-            const CUresult r = ((EncodeFn)fn)(&dst[a][st], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, slabs[a] + net.off_fc_w[st], gdim, gstr, box,
+            const CUresult r = ((EncodeFn)fn)(&dst[a][st], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box,
                                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             DQN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
@@ -730,7 +733,7 @@ static void launch_rows(dqn_learner* h, int rows, int ctas) {
     const NetDesc& net = h->net;
     if (!h->fa_row_maps) {
         h->fa_row_maps = aligned_alloc(64, sizeof(RowMaps));
-        try { encode_row_maps(h, *static_cast<RowMaps*>(h->fa_row_maps)); } catch (...) { free(h->fa_row_maps); h->fa_row_maps = nullptr; throw; }
+        try { encode_row_maps(h, *static_cast<RowMaps*>(h->fa_row_maps), h->w_scratch_on ? h->w_scratch : nullptr); } catch (...) { free(h->fa_row_maps); h->fa_row_maps = nullptr; throw; }
     }
     const RowMaps& maps = *static_cast<RowMaps*>(h->fa_row_maps);
     const size_t bytes = (size_t)RS * 3 * RT_ROWS * RT_N * 4 + 2 * 2 * 16 * 128 + 256 + 1024;

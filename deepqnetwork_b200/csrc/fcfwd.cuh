@@ -294,8 +294,12 @@ static int launch(dqn_learner* h, const float* P, const float* act, int rows, fl
     }
     const WMaps& maps = *static_cast<WMaps*>(h->ff_maps[tw]);
     const int mt = net.NH / BM, nkb = net.flat / BK;
-    // the two towers' launches run side by side: half the SMs each, so that both fit in one wave
-    int want = std::min(std::max(1, h->sm_count / (2 * mt)), max_splits);
+    // the two towers' launches run side by side and must fit in one wave together.  A k-block costs the online tower
+    // (64 batch columns per MMA) ~1.7x what it costs the target tower (32), so the SMs are shared 2 : 1 (fc_fwd_share = 0:
+    // half each) -- both launches then end at about the same time instead of the online one trailing
+    int share_num = 1, share_den = 2;
+    if (h->fc_fwd_share && (rows == 64 || rows == 32)) { share_num = rows == 64 ? 2 : 1; share_den = 3; }
+    int want = std::min(std::max(1, (h->sm_count * share_num) / (share_den * mt)), max_splits);
     const int per = (nkb + want - 1) / want;
     const int splits = (nkb + per - 1) / per;
     auto go = [&](auto kern, int bn) {

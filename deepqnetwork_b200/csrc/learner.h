@@ -76,12 +76,19 @@ struct dqn_learner {
                                              // packed B tiles (EpiBiasReluPack -> fcfwd.cuh); valid for the launch that follows
     bool act3_pk_valid[2] = {false, false};
     void* ff_maps[2] = {nullptr, nullptr};  // ff::WMaps of the online / target dense kernels (fcfwd.cuh), built on first use
+    int fc_fwd_share = 0;         // option: dense forward CTAs split 2 : 1 between the online (64 rows) and the target (32 rows) launch
+                                  // (measured: no difference, 5925 steps/s either way inside the +-4 % instance-to-instance spread)
     bool fc_tma_fwd = true;       // dense forward with TMA-streamed weights and packed activation tiles (fcfwd.cuh)
     bool keep_grads = false;      // option: dqn_train_batch leaves the dense-kernel gradients in the slab (slot 3 read-back, parity
                                   // tests); off: the fused dense wgrad+optimizer kernel runs there too and never writes them
     bool wg1_fit = false;         // option: conv1 wgrad split count sized for the SMs the persistent dense kernel leaves free (measured -4 %)
     unsigned int* fa_tile_ctr = nullptr;  // dynamic tile counter of the fused dense kernel (= opt_ticket + 1, zeroed by the optimizer tail)
     void* fa_row_maps = nullptr;  // fa::RowMaps
+    float* w_scratch = nullptr;   // [2][flat][hidden]: the fused dense kernel writes the updated dense weights here ...
+    bool w_scratch_on = false;    // ... (option w_scratch) so that it can start BEFORE the dense dgrad has read the old ones; copied over the slab
+                                  // afterwards.  Measured (profiles/r02_trace_w_scratch.txt): the pass then runs 82-135 us instead of 101-157, but its
+                                  // 100 persistent CTAs starve the conv wgrads (conv3 wgrad 18 -> 55 us) and the two 15.7 MB copies run as SM kernels
+                                  // (30 us) in front of the optimizer tail: 5780 vs 5950-6060 steps/s.  Off.
     int fc_rows_ctas = 100;       // dense wgrad + optimizer as the row-contiguous persistent kernel (fcadam.cuh) on this many SMs;
                                   // 0: tcgen05 wgrad into the gradient slab + streaming Adam.  clamped to the SM count.  With 148 the step time is BIMODAL (5400-5600 vs 6150 steps/s per learner instance): the kernel
                                   // becomes ready at the same instant as conv3's dgrad + wgrad (96 CTAs); if its persistent CTAs are dispatched first

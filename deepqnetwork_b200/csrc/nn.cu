@@ -518,6 +518,12 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     };
     if (split_fc) { fc_wgrad_stream(0); fc_wgrad_stream(1); }
     else if (!h->fuse_fc_adam && !ffma_adam && !tma_adam) fc_wgrad();  // unfused: independent of the dgrad below, start it first
+    // fused dense wgrad+optimizer writing to the scratch copy: it only needs dH and act3, so its side stream forks HERE, in front
+    // of the dense dgrad; the kernel itself is issued right behind the dgrad launch (both become ready at the same instant and
+    // the high-priority dgrad grid is dispatched first, the persistent low-priority grid takes the SMs that are left)
+    const bool rows_early = rows_adam && h->w_scratch_on && h->w_scratch != nullptr && overlap_enabled(h);
+    cudaStream_t early_saved = nullptr;
+    if (rows_early) { side_begin(h, early_saved, 0); side_end(h, early_saved); }
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
     {
         prof_mark(h, "fc_dgrad");
@@ -554,13 +560,38 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             side_end(h, saved);
         }
         h->fc_adam_done = true;
+    } else if (rows_early) {
+        // side stream 0 already waits for the head backward only (fork above): launch there, then, once the dense dgrad on the
+        // main stream has read the old weights, copy the updated dense kernels from the scratch over the slab
+        cudaStream_t main_s = h->stream;
+        const int sp = g_launch_priority;
+        h->stream = h->side_stream; g_launch_priority = h->prio_lo;
+        prof_mark(h, "fc_wgrad_adam");
+        fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count));
+        h->stream = main_s; g_launch_priority = sp;
+        cudaEvent_t e = h->fork_ev[21];  // dgrad (+ its reduce) done
+        DQN_CUDA_OK(cudaEventRecord(e, main_s));
+        DQN_CUDA_OK(cudaStreamWaitEvent(h->side_stream, e, 0));
+        const size_t fcw = (size_t)net.flat * net.hidden * sizeof(float);
+        for (int st = 0; st < 2; ++st)
+            DQN_CUDA_OK(cudaMemcpyAsync(h->online + net.off_fc_w[st], h->w_scratch + (size_t)st * net.flat * net.hidden, fcw,
+                                        cudaMemcpyDeviceToDevice, h->side_stream));
+        h->fc_adam_done = true;
     } else if (h->early_fc_adam && !h->fuse_fc_adam) {
         // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
         // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
         side_begin(h, saved, 0);
         if (tma_adam) {
             prof_mark(h, "fc_wgrad_adam");
-            if (rows_adam) fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count)); else fa::launch(h, rows);
+            if (rows_adam) {
+                fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count));
+                if (h->w_scratch_on && h->w_scratch) {  // (not forked early: single-stream / profile mode) the copy follows at once
+                    const size_t fcw = (size_t)net.flat * net.hidden * sizeof(float);
+                    for (int st = 0; st < 2; ++st)
+                        DQN_CUDA_OK(cudaMemcpyAsync(h->online + net.off_fc_w[st], h->w_scratch + (size_t)st * net.flat * net.hidden, fcw,
+                                                    cudaMemcpyDeviceToDevice, h->stream));
+                }
+            } else fa::launch(h, rows);
         } else if (ffma_adam) {
             prof_mark(h, "fc_wgrad_adam");
             launch_fc_wgrad_adam(h, rows, h->fc_grads_needed);
