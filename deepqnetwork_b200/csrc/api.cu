@@ -1439,6 +1439,19 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     }
     else if (n == "external_normaliser") h->external_normaliser = value != 0;  // the caller owns last_max_weight (data-parallel)
     else if (n == "l2_keep") h->l2_keep = value;          // L2 residency hints (learner.h)
+    else if (n == "w_scratch") {  // fused dense kernel writes the new dense weights to a scratch copy (starts before the dense dgrad)
+        h->w_scratch_on = value != 0;
+        if (h->fa_row_maps) { free(h->fa_row_maps); h->fa_row_maps = nullptr; }  // the store maps point somewhere else now
+    }
+    else if (n == "external_normaliser") h->external_normaliser = value != 0;  // the caller owns last_max_weight (data-parallel)
+    else if (n == "l2_keep") h->l2_keep = value;          // L2 residency hints (learner.h)
+    else if (n == "l2_persist_mb") {                      // experiment: size of the persisting L2 carve-out
+        cudaDeviceProp prop; DQN_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+        size_t want = (size_t)value << 20;
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        DQN_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        fprintf(stderr, "[dqn_b200] persisting L2: max %d MB, set %zu MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
+    }
     else if (n == "wg1_fit") h->wg1_fit = value != 0;
     else if (n == "keep_grads") h->keep_grads = value != 0;  // dqn_train_batch: dense-kernel gradients stay readable (slot 3)
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
