@@ -52,6 +52,7 @@ _SIGS = {
     'dqn_replay_clear': [_P],
     'dqn_frames_append': [_P, C.c_int64, _P, C.POINTER(C.c_int64)],
     'dqn_frames_info': [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    'dqn_preprocess': [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int64)],
     'dqn_replay_append_indexed': [_P, C.c_int64, _P, _P, _P, _P, _P],
     'dqn_replay_fill_synthetic': [_P, C.c_int64, C.c_uint64],
     'dqn_tree_add': [_P, C.c_int64, _P, _P],

@@ -534,6 +534,41 @@ extern "C" int dqn_replay_append_indexed(dqn_learner* h, int64_t n, const uint32
     API_END(h)
 }
 
+// GameEnvironment.preprocess_observation for n raw observations (actor side): crop, take every stride-th pixel, "grey",
+// uint8.  to_frame_ring != 0 (frame_dedup handles): the frames are appended to the frame ring on the device and
+// *first_slot receives the slot of the first one; h_frames (may be NULL then) also receives them.
+extern "C" int dqn_preprocess(dqn_learner* h, int64_t n, const uint8_t* h_obs, int32_t raw_h, int32_t raw_w, int32_t top,
+                              int32_t bottom, int32_t stride, uint8_t* h_frames, int32_t to_frame_ring, int64_t* first_slot) {
+    API_BEGIN(h)
+    DQN_REQUIRE(n >= 1 && stride >= 1 && top >= 0 && bottom >= 0 && raw_h - bottom > top, "dqn_preprocess: bad geometry");
+    const int oh = (raw_h - bottom - top + stride - 1) / stride, ow = (raw_w + stride - 1) / stride;
+    const size_t in_b = (size_t)raw_h * raw_w * 3, out_b = (size_t)oh * ow;
+    if (to_frame_ring) {
+        DQN_REQUIRE(h->dedup, "to_frame_ring needs a frame_dedup handle");
+        DQN_REQUIRE(oh == h->net.H && ow == h->net.W, "preprocessed frame size differs from the model input");
+    }
+    const int64_t max_chunk = std::max<int64_t>(1, (int64_t)(h->dev_stage_bytes / (in_b + out_b)));
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min(n - done, max_chunk);
+        uint8_t* d_in = h->dev_stage;
+        uint8_t* d_out = h->dev_stage + (size_t)m * in_b;
+        DQN_CUDA_OK(cudaMemcpyAsync(d_in, h_obs + (size_t)done * in_b, (size_t)m * in_b, cudaMemcpyHostToDevice, h->stream));
+        launch_preprocess(h, d_in, raw_h, raw_w, top, stride, oh, ow, m, d_out);
+        if (to_frame_ring) {
+            for (int64_t j = 0; j < m; ++j) {  // ring slots may wrap: one copy per frame
+                const int64_t slot = (h->f_written + j) % h->fcap;
+                if (done == 0 && j == 0 && first_slot) *first_slot = slot;
+                DQN_CUDA_OK(cudaMemcpyAsync(h->r_frames + (size_t)slot * h->frame_bytes, d_out + (size_t)j * out_b, out_b, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            h->f_written += m;
+        }
+        if (h_frames) DQN_CUDA_OK(cudaMemcpyAsync(h_frames + (size_t)done * out_b, d_out, (size_t)m * out_b, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        done += m;
+    }
+    API_END(h)
+}
+
 extern "C" int dqn_replay_read(dqn_learner* h, int64_t n, const int64_t* rows, uint8_t* st, uint8_t* ac, uint8_t* rw,
                                uint8_t* ns, uint8_t* ct, uint16_t* ls) {
     API_BEGIN(h)

@@ -283,6 +283,9 @@ void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t se
 // stacked [n][H][W][4] states of ring rows -> dst (frame_dedup: assembled from the frame ring); next: the s' stacks
 void launch_gather_states(dqn_learner* h, const long long* d_rows, int n, bool next, uint8_t* dst);
 
+void launch_preprocess(dqn_learner* h, const uint8_t* d_obs, int raw_h, int raw_w, int top, int stride, int oh, int ow, int64_t n,
+                       uint8_t* d_out);
+
 // sumtree.cu
 // u_src: uniforms read from there instead of b_u (may be pinned host memory); host_out: pinned host block that also
 // receives the {tree_idx | priority | is_weight} columns (stride max_rows, 8-byte entries)

@@ -6,6 +6,7 @@
 //   rl/data/replay_memory.py:54-67,94-110  append/set            == ring copies in api.cu (dqn_replay_append)
 // Pure byte movement: 16-byte vector loads/stores, rows are 16-byte aligned (H*W*C % 16 == 0 is required).
 #include "learner.h"
+#include <algorithm>
 
 // grid: (chunks, 2*n). slot j<n copies states[row_j] -> dst[j]; slot n+j copies next_states[row_j] -> dst[n+j]
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ states, const uint8_t* __restrict__ next_states,
@@ -210,4 +211,32 @@ void launch_fill_synthetic(dqn_learner* h, int64_t start, int64_t n, uint64_t se
                                                                              h->cfg.num_actions, seed);
     DQN_CUDA_OK(cudaGetLastError());
     h->launches += 3;
+}
+
+
+// ---- frame preprocessing (actor side; rl/game_environment.py:110-116,134-140,154-160) -----------------------------------
+//   obs[top : raw_h - bottom : stride, ::stride] -> np.dot(rgb, [0.299, 0.587, 0.144]) -> astype(uint8)
+// in float64 with the contraction the reference's np.dot performs on the [H, W, 3] view (pinned by executing it over all
+// 2^24 colours, oracle/preprocess_ref.py): fl(r * .299), then two fused multiply-adds; the C cast truncates and wraps
+// (white = 262.65 -> 6).  One thread per output pixel; a warp reads 32 pixels x 3 bytes at a 2-pixel stride.
+__global__ void preprocess_kernel(const uint8_t* __restrict__ obs, int raw_h, int raw_w, int top, int stride, int oh, int ow,
+                                  long long n, uint8_t* __restrict__ out) {
+    const long long total = n * oh * ow;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long img = i / (oh * ow);
+        const int p = (int)(i - img * oh * ow), y = p / ow, x = p - y * ow;
+        const uint8_t* px = obs + ((size_t)img * raw_h * raw_w + (size_t)(top + y * stride) * raw_w + (size_t)x * stride) * 3;
+        const double r = (double)px[0], g = (double)px[1], b = (double)px[2];
+        const double v = fma(b, 0.144, fma(g, 0.587, __dmul_rn(r, 0.299)));
+        out[i] = (uint8_t)((long long)v & 255);
+    }
+}
+
+void launch_preprocess(dqn_learner* h, const uint8_t* d_obs, int raw_h, int raw_w, int top, int stride, int oh, int ow, int64_t n,
+                       uint8_t* d_out) {
+    const long long total = (long long)n * oh * ow;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    preprocess_kernel<<<blocks, 256, 0, h->stream>>>(d_obs, raw_h, raw_w, top, stride, oh, ow, (long long)n, d_out);
+    DQN_CUDA_OK(cudaGetLastError());
+    h->launches++;
 }

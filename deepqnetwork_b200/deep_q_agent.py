@@ -183,6 +183,18 @@ class DeepQAgent(GameAgent):
             return self._epsilon_greedy(q_values, self.step)
         return np.argmax(q_values)
 
+    def get_actions(self, states):
+        """Vectorised actors: the states of n environments -> n actions with ONE batched forward pass
+        (DeepQModel.predict on [n, H, W, 4]) and the reference's per-call epsilon-greedy rule (deep_q_agent.py:559-592)
+        applied per environment."""
+        q_values = self.model.predict(np.asarray(states))
+        greedy = np.argmax(q_values, axis=1)
+        if not (self.is_training or self.use_epsilon):
+            return greedy
+        eps = self._get_epsilon(self.step)
+        explore = np.random.rand(len(greedy)) < eps
+        return np.where(explore, np.random.randint(self.model.num_outputs, size=len(greedy)), greedy)
+
     # -- one training step -------------------------------------------------------------------------------------
     def _train_step(self):
         self._train_run_train()

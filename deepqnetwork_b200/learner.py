@@ -174,6 +174,25 @@ class Learner:
         ls = None if losses is None else np.ascontiguousarray(np.atleast_1d(losses), dtype=np.float32)
         self._c(self._lib.dqn_replay_append_indexed(self._h, n, ptr(sl), ptr(ac), ptr(rw), ptr(ct), ptr(ls)))
 
+    PREPROCESS = {'Breakout': (16, 16), 'SpaceInvaders': (20, 12), 'MsPacman': (0, 38)}  # rows cropped top / bottom
+
+    def preprocess(self, obs, game=None, top=None, bottom=None, stride=2, to_frame_ring=False):
+        """GameEnvironment.preprocess_observation for a batch of raw RGB observations [n, raw_h, raw_w, 3] -> uint8 frames
+        [n, oh, ow] (and, with to_frame_ring on a frame_dedup learner, their slots in the frame ring)."""
+        o = as_u8(np.asarray(obs))
+        o = o.reshape((-1,) + o.shape[-3:])
+        if game is not None:
+            top, bottom = self.PREPROCESS[game]
+        n, rh, rw, _ = o.shape
+        oh, ow = -(-(rh - bottom - top) // stride), -(-rw // stride)
+        out = np.empty((n, oh, ow), np.uint8)
+        first = C.c_int64(-1)
+        self._c(self._lib.dqn_preprocess(self._h, n, ptr(o), rh, rw, int(top), int(bottom), int(stride), ptr(out), int(bool(to_frame_ring)), C.byref(first)))
+        if to_frame_ring:
+            cap, _ = self.frames_info()
+            return out, (first.value + np.arange(n, dtype=np.int64)) % cap
+        return out
+
     def replay_read(self, rows, fields=('states', 'actions', 'rewards', 'next_states', 'continues', 'losses')):
         rows = np.ascontiguousarray(np.atleast_1d(rows), dtype=np.int64)
         n = rows.size

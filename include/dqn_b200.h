@@ -116,6 +116,13 @@ int dqn_frames_append(dqn_learner* h, int64_t n, const uint8_t* h_frames, int64_
 int dqn_replay_append_indexed(dqn_learner* h, int64_t n, const uint32_t* h_frame_slots, const uint8_t* h_actions,
                               const uint8_t* h_rewards, const uint8_t* h_continues, const float* h_losses);
 int dqn_frames_info(dqn_learner* h, int64_t* frame_capacity, int64_t* frames_written);
+/* GameEnvironment.preprocess_observation (rl/game_environment.py:110-116,134-140,154-160) for n raw RGB observations
+ * ([n, raw_h, raw_w, 3] u8): rows top .. raw_h - bottom and all columns at the given stride, "grey" = dot(rgb, [0.299,
+ * 0.587, 0.144]) in float64 with the reference's contraction, C cast to uint8 (values above 255 wrap).  h_frames
+ * ([n, oh, ow] u8) may be NULL when to_frame_ring != 0: the frames then go straight into the frame ring of a frame_dedup
+ * handle (*first_slot = slot of the first one).  SURVEY.md 8f-2. */
+int dqn_preprocess(dqn_learner* h, int64_t n, const uint8_t* h_obs, int32_t raw_h, int32_t raw_w, int32_t top, int32_t bottom,
+                   int32_t stride, uint8_t* h_frames, int32_t to_frame_ring, int64_t* first_slot);
 int dqn_replay_clear(dqn_learner* h);                                                    /* replay_memory.py:46-52 */
 /* bench/test fill on the device (SURVEY.md 8d "synthetic inputs"): n rows from Philox(seed);
  * when use_per the tree is built with the semantics of n sequential SumTree.add calls. */

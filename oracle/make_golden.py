@@ -249,6 +249,37 @@ def agent_math():
     return out
 
 
+def preprocess_cases():
+    """Frames pushed through the reference environments' own preprocess_observation (rl/game_environment.py:110-160;
+    instances made with __new__: the constructor only wraps gym), plus the CRC of the full RGB cube through Breakout's."""
+    import zlib
+    from rl.game_environment import BreakoutEnvironment, SpaceInvadersEnvironment, MsPacmanEnvironment
+    rng = np.random.default_rng(7)
+    out = {}
+    for name, cls in (('Breakout', BreakoutEnvironment), ('SpaceInvaders', SpaceInvadersEnvironment), ('MsPacman', MsPacmanEnvironment)):
+        env = cls.__new__(cls)
+        obs = rng.integers(0, 256, (2, 210, 160, 3), dtype=np.uint8)
+        obs[1] = 255                      # saturated frame: 262.65 -> wraps to 6
+        obs[1, ::7, ::5] = (0, 0, 255); obs[1, 1::7, ::3] = (255, 255, 0); obs[1, 2::9] = np.arange(160)[:, None]
+        out[name + '_obs'] = obs
+        out[name + '_out'] = np.stack([env.preprocess_observation(o) for o in obs])
+    # every (r, g, b) triple through Breakout's method, 7120 triples per call, r-major order
+    env = BreakoutEnvironment.__new__(BreakoutEnvironment)
+    r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing='ij')
+    cube = np.stack([r, g, b], axis=-1).reshape(-1, 3)
+    per = 89 * 80
+    crc = 0
+    for i0 in range(0, len(cube), per):
+        chunk = cube[i0:i0 + per]
+        pad = np.zeros((per, 3), np.uint8); pad[:len(chunk)] = chunk
+        obs = np.zeros((210, 160, 3), np.uint8)
+        obs[16:-16:2, ::2] = pad.reshape(89, 80, 3)
+        res = env.preprocess_observation(obs).reshape(-1)[:len(chunk)]
+        crc = zlib.crc32(res.tobytes(), crc)
+    out['cube_crc'] = np.array(crc, np.uint64)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     SumTree, ReplayMemory, ReplaySampler, ReplaySamplerPriority = _import_reference()
@@ -276,6 +307,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'per_trace_%02d.npz' % k),
                             **per_trace(SumTree, cap, n_add, bsz, rounds, seed, zf, dup))
     np.savez_compressed(os.path.join(OUT, 'agent_math.npz'), **agent_math())
+    np.savez_compressed(os.path.join(OUT, 'preprocess_cases.npz'), **preprocess_cases())
     print('wrote', sorted(os.listdir(OUT)))
 
 

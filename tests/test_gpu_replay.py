@@ -243,3 +243,33 @@ def test_gather_beyond_4gib_offsets_at_benchmark_capacity():
     assert np.array_equal(got['states'].reshape(B, S), philox_ref.synthetic_state_rows(mi, S, seed))
     assert np.array_equal(got['next_states'].reshape(B, S), philox_ref.synthetic_state_rows(mi, S, seed, next_states=True))
     L.close()
+
+
+def test_preprocess_kernel_matches_reference_execution():
+    """dqn_preprocess (crop / stride-2 / grey / uint8 wrap) against frames the reference environments' own
+    preprocess_observation produced (tests/golden/preprocess_cases.npz) and, over all 2^24 colours, against the CRC of the
+    reference's output; bit-exact."""
+    import zlib
+    g = np.load(os.path.join(G, 'preprocess_cases.npz'))
+    L = small_learner(64)
+    for game in ('Breakout', 'SpaceInvaders', 'MsPacman'):
+        out = L.preprocess(g[game + '_obs'], game)
+        assert np.array_equal(out[..., None], g[game + '_out']), game
+    r, gg, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing='ij')
+    cube = np.stack([r, gg, b], axis=-1).reshape(256, 65536, 3)  # 256 "observations" of 1 x 65536 pixels
+    out = L.preprocess(cube[:, None], top=0, bottom=0, stride=1)
+    assert out.shape == (256, 1, 65536) and zlib.crc32(out.tobytes()) == int(g['cube_crc'])
+    L.close()
+
+
+def test_preprocess_straight_into_the_frame_ring():
+    from deepqnetwork_b200.learner import Learner
+    from oracle import preprocess_ref
+    L = Learner(89, 80, 4, num_actions=4, num_hidden=512, batch_size=32, replay_capacity=64, frame_dedup=True, math_mode='fp32')
+    obs = np.random.default_rng(0).integers(0, 256, (5, 210, 160, 3), dtype=np.uint8)
+    frames, slots = L.preprocess(obs, 'Breakout', to_frame_ring=True)
+    assert np.array_equal(frames[..., None], preprocess_ref.preprocess(obs, 'Breakout')) and slots.tolist() == [0, 1, 2, 3, 4]
+    L.replay_append_indexed(np.array([[0, 1, 2, 3, 1, 2, 3, 4]], np.uint32), [1], [0], [True])
+    row = L.replay_read([0])
+    assert np.array_equal(row['states'][0], np.stack(list(frames[0:4]), axis=2)) and np.array_equal(row['next_states'][0], np.stack(list(frames[1:5]), axis=2))
+    L.close()
