@@ -85,6 +85,8 @@ _SIGS = {
     'dqn_debug_timeline': [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P],
     'dqn_save': [_P, C.c_char_p],
     'dqn_restore': [_P, C.c_char_p],
+    'dqn_save_replay': [_P, C.c_char_p],
+    'dqn_restore_replay': [_P, C.c_char_p, C.POINTER(C.c_int64)],
 }
 
 _lib = None

@@ -1621,6 +1621,132 @@ extern "C" int dqn_restore(dqn_learner* h, const char* prefix) {
 }
 
 
+// ---- replay persistence ----------------------------------------------------------------------------------------------
+// The reference writes its RAM replay to <prefix>_replay_memory.hdf5 at exit and reloads it at the next start
+// (rl/deep_q_agent.py:410-432, :211-222): rows 0 .. len-1 in INDEX order, all six columns; the sum tree is not stored, it is
+// rebuilt from the float16 `losses` column by ReplaySamplerPriority.add_losses (rl/data/replay_sampler_priority.py:57-59).
+// Same contents and the same reload semantics here, in this library's own container (<prefix>_replay_memory.dqnb200;
+// HDF5 itself cannot be produced or checked in this environment).
+struct ReplayHeader {
+    char magic[8];                 // "DQNRPLY"
+    int32_t version, layout;       // layout 0 = stacked s / s', 1 = frame ring + 8 slots per row
+    int32_t H, W, C, pad;
+    int64_t max_size, rows, cur_idx, is_full;
+    int64_t frame_capacity, frames_written;
+};
+
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __half2float(src[i]);
+}
+
+static void stream_out(dqn_learner* h, FILE* f, const void* d_src, size_t bytes, std::vector<uint8_t>& buf) {
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t m = std::min(buf.size(), bytes - off);
+        DQN_CUDA_OK(cudaMemcpyAsync(buf.data(), static_cast<const uint8_t*>(d_src) + off, m, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        DQN_REQUIRE(fwrite(buf.data(), 1, m, f) == m, "short write on replay file");
+    }
+}
+static void stream_in(dqn_learner* h, FILE* f, void* d_dst, size_t bytes, std::vector<uint8_t>& buf) {
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t m = std::min(buf.size(), bytes - off);
+        DQN_REQUIRE(fread(buf.data(), 1, m, f) == m, "truncated replay file");
+        DQN_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, buf.data(), m, cudaMemcpyHostToDevice, h->stream));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+}
+
+extern "C" int dqn_save_replay(dqn_learner* h, const char* prefix) {
+    API_BEGIN(h)
+    DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+    const std::string path = std::string(prefix) + "_replay_memory.dqnb200";
+    FILE* f = fopen((path + ".tmp").c_str(), "wb");
+    DQN_REQUIRE(f != nullptr, "cannot open replay file for writing");
+    try {
+        ReplayHeader hd; memset(&hd, 0, sizeof(hd));
+        memcpy(hd.magic, "DQNRPLY", 8); hd.version = 1; hd.layout = h->dedup ? 1 : 0;
+        hd.H = h->net.H; hd.W = h->net.W; hd.C = h->net.C;
+        hd.max_size = h->cap; hd.rows = h->ring_size; hd.cur_idx = h->ring_cur; hd.is_full = h->ring_full ? 1 : 0;
+        hd.frame_capacity = h->fcap; hd.frames_written = h->f_written;
+        DQN_REQUIRE(fwrite(&hd, sizeof(hd), 1, f) == 1, "short write on replay file");
+        std::vector<uint8_t> buf(64u << 20);
+        const size_t n = (size_t)h->ring_size;
+        stream_out(h, f, h->r_actions, n, buf); stream_out(h, f, h->r_rewards, n, buf); stream_out(h, f, h->r_cont, n, buf);
+        stream_out(h, f, h->r_losses, n * sizeof(__half), buf);
+        if (h->dedup) {
+            stream_out(h, f, h->r_fidx, n * 8 * sizeof(uint32_t), buf);
+            stream_out(h, f, h->r_frames, (size_t)std::min<int64_t>(h->f_written, h->fcap) * h->frame_bytes, buf);
+        } else {
+            stream_out(h, f, h->r_states, n * h->state_bytes, buf);
+            stream_out(h, f, h->r_next, n * h->state_bytes, buf);
+        }
+    } catch (...) { fclose(f); remove((path + ".tmp").c_str()); throw; }
+    fclose(f);
+    DQN_REQUIRE(rename((path + ".tmp").c_str(), path.c_str()) == 0, "cannot move replay file into place");
+    API_END(h)
+}
+
+// returns 3 when the file does not exist.  The ring must be empty (a freshly created handle): rows are appended from index 0
+// like ReplayMemory.extend does, the sum tree is rebuilt by add(losses[i], i) in index order.
+extern "C" int dqn_restore_replay(dqn_learner* h, const char* prefix, int64_t* rows_loaded) {
+    if (!h) return 2;
+    const std::string path = std::string(prefix) + "_replay_memory.dqnb200";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return 3;
+    try {
+        DQN_CUDA_OK(cudaSetDevice(h->device));
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        h->pf_valid = false;
+        DQN_REQUIRE(h->ring_size == 0 && h->tree_size == 0, "replay restore needs an empty ring");
+        ReplayHeader hd;
+        DQN_REQUIRE(fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "DQNRPLY", 8) == 0 && hd.version == 1, "not a dqn_b200 replay file");
+        DQN_REQUIRE(hd.H == h->net.H && hd.W == h->net.W && hd.C == h->net.C, "replay file holds frames of another geometry");
+        DQN_REQUIRE(hd.layout == (h->dedup ? 1 : 0), "replay file layout (stacked / frame ring) differs from this handle's");
+        DQN_REQUIRE(hd.rows <= h->cap, "replay file holds more rows than this handle's capacity");
+        DQN_REQUIRE(!h->dedup || hd.frame_capacity == h->fcap, "frame ring capacity differs from the file's");
+        std::vector<uint8_t> buf(64u << 20);
+        const size_t n = (size_t)hd.rows;
+        stream_in(h, f, h->r_actions, n, buf); stream_in(h, f, h->r_rewards, n, buf); stream_in(h, f, h->r_cont, n, buf);
+        stream_in(h, f, h->r_losses, n * sizeof(__half), buf);
+        if (h->dedup) {
+            stream_in(h, f, h->r_fidx, n * 8 * sizeof(uint32_t), buf);
+            stream_in(h, f, h->r_frames, (size_t)std::min<int64_t>(hd.frames_written, hd.frame_capacity) * h->frame_bytes, buf);
+            h->f_written = hd.frames_written;
+        } else {
+            stream_in(h, f, h->r_states, n * h->state_bytes, buf);
+            stream_in(h, f, h->r_next, n * h->state_bytes, buf);
+        }
+        fclose(f); f = nullptr;
+        // ReplayMemory.extend: n appends from index 0 (rl/data/replay_memory.py:70-75)
+        h->ring_cur = hd.rows % h->cap; h->ring_full = hd.rows >= h->cap; h->ring_size = hd.rows;
+        if (h->cfg.use_per && n > 0) {
+            // ReplaySamplerPriority.add_losses: sum_tree.add(losses[i], i) for i in range(len) -- the priorities are the stored
+            // float16 values (rl/data/replay_sampler_priority.py:57-59)
+            const int64_t chunk = (int64_t)(h->dev_stage_bytes / 4);
+            for (int64_t s0 = 0; s0 < hd.rows; s0 += chunk) {
+                const int64_t m = std::min(chunk, hd.rows - s0);
+                float* d_sc = (float*)h->dev_stage;
+                half_to_float_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, h->stream>>>(h->r_losses + s0, d_sc, m);
+                launch_tree_add(h, m, d_sc, nullptr, s0);
+                DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+            }
+            h->tree_max_reached = hd.rows >= h->cap;
+            h->tree_size = hd.rows; h->tree_write = hd.rows % h->cap;
+        }
+        h->has_max_weight = false;
+        push_sizes(h);
+        DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (rows_loaded) *rows_loaded = hd.rows;
+    } catch (const std::string& e) {
+        if (f) fclose(f);
+        h->err = e;
+        return 1;
+    }
+    return 0;
+}
+
+
 // GEMM engine self-test (tests/test_gpu_tcgemm.py): C[M,N] = A * B with host matrices, through the FFMA kernel
 // (mode 0) or the tcgen05 kernel (mode 1: TF32 x3, mode 2: TF32 x1)
 extern "C" int dqn_selftest_gemm(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32_t K, int32_t a_kcontig,

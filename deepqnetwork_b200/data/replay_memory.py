@@ -52,8 +52,12 @@ class _FrameDedup:
         self.cache = OrderedDict()      # frame bytes -> append count of the frame
         self.count = learner.frames_info()[1]
         self.max_size = max_size
-        self.rows = 0                   # transitions appended so far
+        self.rows = learner.replay_info()[0]  # transitions in the ring (non-zero after a replay restore)
         self.window = deque()           # (row number, oldest frame count of that row), increasing in both: sliding minimum
+        if self.rows:
+            # restored rows: their frame references are not re-read; assume the density of a runner stream (one new frame per
+            # transition plus a few per game) so that the overrun check stays meaningful for them
+            self.window.append((self.rows - 1, max(0, self.count - (self.rows + self.rows // 16 + 32))))
 
     def append_rows(self, states, actions, rewards, next_states, continues, losses):
         n = len(actions)

@@ -134,6 +134,11 @@ class DeepQAgent(GameAgent):
         learner = m.learner
         # the replay ring lives in the model's device learner (HBM); the reference's RAM/HDF5 choice (--memory /
         # --disk) only decides where the *reference* keeps it, so both map to the HBM ring here
+        if c.get('use_memory', True) and os.path.exists(self._get_replay_memory_path()):
+            # deep_q_agent.py:218-222: reload the replay written at the last exit (before the sampler is built: under PER its
+            # tree is rebuilt from the stored float16 losses, as ReplaySamplerPriority.add_losses does)
+            log('loading old memories from', self._get_replay_memory_path())
+            log('found', learner.restore_replay(self.save_path_prefix))
         self.memories = ReplayMemory(m.INPUT_HEIGHT, m.INPUT_WIDTH, m.INPUT_CHANNELS, max_size=self.replay_max_memory_length,
                                      state_type=m.STATE_TYPE, learner=learner)
         self.train_batch = None  # the B-row batch is device resident (learner.batch_read() for inspection)
@@ -249,8 +254,11 @@ class DeepQAgent(GameAgent):
 
     def _train_finish(self):
         log('train finish')
-        # the reference streams its RAM replay into <prefix>_replay_memory.hdf5 here (h5py; SURVEY 8f-3: next row)
-        log('replay persistence is not part of this build; saving the model only')
+        if self.conf.get('use_memory', True):
+            # deep_q_agent.py:416-432: the replay goes to disk at exit (own container instead of HDF5, same contents)
+            log('saving', len(self.memories), 'memories to disk')
+            self.model.learner.save_replay(self.save_path_prefix)
+            log('saved memory to disk')
         self.model.save(self.save_path_prefix)
         elapsed = time.time() - self.train_start_time
         log('train finished in {:0.1f} seconds / {:0.1f} mins / {:0.1f} hours'.format(elapsed, elapsed / 60, elapsed / 3600))
@@ -273,7 +281,7 @@ class DeepQAgent(GameAgent):
         return make_priority(losses, self.per_a)
 
     def _get_replay_memory_path(self):
-        return '{}_replay_memory.hdf5'.format(self.save_path_prefix)
+        return '{}_replay_memory.dqnb200'.format(self.save_path_prefix)
 
     # -- epsilon-greedy -----------------------------------------------------------------------------------------------
     def _get_epsilon(self, step):

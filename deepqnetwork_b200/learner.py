@@ -399,3 +399,15 @@ class Learner:
             return False
         self._c(rc)
         return True
+
+    def save_replay(self, prefix):
+        self._c(self._lib.dqn_save_replay(self._h, str(prefix).encode()))
+
+    def restore_replay(self, prefix):
+        """-> number of rows loaded, or None when <prefix>_replay_memory.dqnb200 does not exist."""
+        n = C.c_int64()
+        rc = self._lib.dqn_restore_replay(self._h, str(prefix).encode(), C.byref(n))
+        if rc == 3:
+            return None
+        self._c(rc)
+        return n.value

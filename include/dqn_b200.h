@@ -228,7 +228,14 @@ int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32_t N, int32
 
 /* ---- persistence (own container format; TF-bundle compatibility is SURVEY.md 8f-3) -- */
 int dqn_save(dqn_learner* h, const char* prefix);     /* Model.save, rl/model/model.py:60-68 */
-int dqn_restore(dqn_learner* h, const char* prefix);  /* Model.restore :71-83; returns 1 if absent */
+int dqn_restore(dqn_learner* h, const char* prefix);  /* Model.restore :71-83; returns 3 if absent */
+/* replay persistence: what DeepQAgent._train_finish / _train_init_memory do with <prefix>_replay_memory.hdf5
+ * (rl/deep_q_agent.py:410-432, :211-222) -- rows 0 .. len-1 in index order, six columns, no tree; on restore the rows are
+ * appended from index 0 and the sum tree is rebuilt from the float16 losses column (ReplaySamplerPriority.add_losses,
+ * rl/data/replay_sampler_priority.py:57-59).  Own container <prefix>_replay_memory.dqnb200 (either layout).
+ * dqn_restore_replay returns 3 if the file is absent. */
+int dqn_save_replay(dqn_learner* h, const char* prefix);
+int dqn_restore_replay(dqn_learner* h, const char* prefix, int64_t* rows_loaded);
 
 #ifdef __cplusplus
 }

@@ -131,3 +131,45 @@ def test_synthetic_fill_and_gather_in_the_dedup_layout():
     L.train_steps(5); L.sync()
     assert L.get_step() == 5
     L.close()
+
+
+@pytest.mark.parametrize('dedup', [False, True], ids=['stacked', 'frames'])
+def test_replay_save_restore_follows_the_reference_reload(tmp_path, dedup):
+    """DeepQAgent._train_finish / _train_init_memory (rl/deep_q_agent.py:410-432, :211-222): the replay is written at exit,
+    rows 0 .. len-1 in index order; at the next start the rows are appended from index 0 and the sum tree is rebuilt from the
+    float16 losses column (ReplaySamplerPriority.add_losses).  Rows byte-identical, tree bit-identical to the oracle's
+    rebuild, and training continues identically on both layouts."""
+    from deepqnetwork_b200.data.replay_memory import ReplayMemory
+    from oracle.sumtree_c import SumTreeC
+    tr, _ = transitions_from_runner(330)
+    cap = 400
+    L = make_pair(cap, frame_capacity=cap + 96)[1 if dedup else 0]
+    mem = ReplayMemory(86, 80, 4, max_size=cap, learner=L)
+    rng = np.random.default_rng(0)
+    pri = (rng.random(len(tr)) * 0.9 + 0.05).astype(np.float32)
+    mem.append_rows(np.stack([c['old_state'] for c in tr]), [c['action'] for c in tr], [c['reward'] for c in tr],
+                    np.stack([c['state'] for c in tr]), [c['cont'] for c in tr], pri)
+    rnd = random.Random(1)
+    for _ in range(3):
+        L.train_step(uniforms=np.array([rnd.random() for _ in range(32)]), fetch=False)  # priority write-back changes losses + tree
+    n = len(tr)
+    before = L.replay_read(np.arange(n))
+    prefix = str(tmp_path / 'rl.game_environment.MsPacmanEnvironment')
+    L.save_replay(prefix)
+    L2 = make_pair(cap, frame_capacity=cap + 96)[1 if dedup else 0]
+    assert L2.restore_replay(str(tmp_path / 'missing')) is None
+    assert L2.restore_replay(prefix) == n
+    assert L2.replay_info() == (n, n % cap, False)
+    after = L2.replay_read(np.arange(n))
+    for k in before:
+        assert np.array_equal(before[k], after[k]), k
+    ref = SumTreeC(cap)
+    ref.add(before['losses'].astype(np.float32), np.arange(n).astype(np.uint32))  # add(losses[i], i), float16 values
+    tree, data, size, write = L2.tree_read()
+    assert np.array_equal(tree, ref.tree) and np.array_equal(data, ref.data) and (size, write) == (n, n % cap)
+    u = np.array([rnd.random() for _ in range(32)])
+    t, d, p, m = ref.sample(u)
+    L2.train_step(uniforms=u, fetch=False)
+    got = L2.batch_read()
+    assert np.array_equal(got['states'], before['states'][m]) and np.array_equal(got['next_states'], before['next_states'][m])
+    L.close(); L2.close()
