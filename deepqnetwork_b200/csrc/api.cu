@@ -896,13 +896,18 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     const int A = h->net.A;
     const float* xf = nullptr;
     g_launch_priority = prio_of(h, 2);  // everything issued on the main stream of a step is the critical chain
+    // the fused conv tower (cvtower.cuh) and the image-resident conv1 wgrad read the uint8 batch themselves: no f32 copy
+    const bool fused_tower = tower_fused_ready(h);
     if (h->cfg.math_mode != DQN_MATH_FP32) {
-        if (!(h->xf_from_gather && states2 == h->b_states)) {  // host-fed batch: convert here; sampled batch: gather did
+        bool have = h->xf_from_gather && states2 == h->b_states;  // sampled batch: the gather may have written it
+        if (!have && !fused_tower) {                               // host-fed batch: convert here
             prof_mark(h, "u8_to_f32");
             launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S);
+            have = true;
         }
         h->xf_from_gather = false;
-        xf = h->x_f32;
+        h->xf_valid = have;
+        xf = h->x_f32;  // contents valid only if xf_valid (tower_backward converts lazily if a fallback kernel needs them)
     }
     h->fork_used = 0;
     if (h->defer_start) {
@@ -915,7 +920,8 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
     const int rows_on = h->cfg.use_double ? 2 * n : n;  // double DQN: s and s' share one pass of the online tower
-    if (xf && towers_conv_forward_merged(h, xf, rows_on, xf + (size_t)n * S, n)) {
+    if ((fused_tower && towers_conv_forward_fused(h, h->online, states2, rows_on, h->acts_on, states2 + (size_t)n * S, n)) ||
+        (xf && h->xf_valid && towers_conv_forward_merged(h, xf, rows_on, xf + (size_t)n * S, n))) {
         side_begin(h, saved, 0, 2);
         h->prof_tag = "tg_";
         tower_fc_forward(h, h->target, n, h->acts_tg);
@@ -923,6 +929,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         h->prof_tag = "on_";
         tower_fc_forward(h, h->online, rows_on, h->acts_on);
     } else {
+        if (xf && !h->xf_valid) { launch_u8_to_f32(h, states2, h->x_f32, 2 * (size_t)n * S); h->xf_valid = true; }
         side_begin(h, saved, 0, 2);
         h->prof_tag = "tg_";
         tower_forward(h, h->target, states2 + (size_t)n * S, xf ? xf + (size_t)n * S : nullptr, n, h->acts_tg);
@@ -1191,7 +1198,7 @@ extern "C" int dqn_train_steps(dqn_learner* h, int64_t n) {
                 h->defer_capture = can_defer; h->defer_start = v == 1;
                 try {
                     h->fuse_fc_adam = h->fuse_enabled; h->early_fc_adam = !h->fuse_fc_adam;
-                    h->xf_from_gather = true;  // the look-ahead gather of the previous step wrote x_f32 of this set
+                    h->xf_from_gather = !tower_fused_ready(h);  // the look-ahead gather of the previous step wrote x_f32 of this set
                     step_core(h, h->B, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->cfg.use_per ? h->b_isw : nullptr, 1,
                               1.0, h->cfg.use_per);
                     finish_step(h, 0);
@@ -1495,6 +1502,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "ts_gemm") h->ts_gemm = value != 0;     // A operand through tensor memory (tsgemm.cuh) vs all-smem (tcgemm.cuh)
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
+    else if (n == "tower_fused") h->tower_fused = value != 0;  // conv1..conv3 of both towers as one kernel on the uint8 batch (cvtower.cuh)
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "fuse_td") h->fuse_td = value != 0;
     else if (n == "pack_in_tail") h->pack_in_tail = value != 0;
@@ -1807,14 +1815,16 @@ extern "C" int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32
     float *dA = nullptr, *dB = nullptr, *dC = nullptr;
     unsigned long long* dT = nullptr;
     if (mode >= 16) {  // conv layer (mode - 16) of the online tower over M images, in place on the tower's buffers
-        DQN_REQUIRE(mode - 16 < 4 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
-        dmalloc(dT, 512);
-        DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 512 * 8, h->stream));
+        // mode 20: the fused conv tower (cvtower.cuh) of the online tower over M images of the sampled batch; 1024 marks
+        DQN_REQUIRE(mode - 16 <= 4 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
+        const int marks = mode == 20 ? 1024 : 512;
+        dmalloc(dT, 1024);
+        DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 1024 * 8, h->stream));
         debug_conv_layer(h, mode - 16, M);
         h->tc_dbg = dT;
         try { debug_conv_layer(h, mode - 16, M); } catch (...) { h->tc_dbg = nullptr; throw; }
         h->tc_dbg = nullptr;
-        DQN_CUDA_OK(cudaMemcpyAsync(out512, dT, 512 * 8, cudaMemcpyDeviceToHost, h->stream));
+        DQN_CUDA_OK(cudaMemcpyAsync(out512, dT, marks * 8, cudaMemcpyDeviceToHost, h->stream));
         DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
         cudaFree(dT);
         return 0;

@@ -219,6 +219,8 @@ struct dqn_learner {
     bool merge_towers = true;   // option: conv layers of the online and the target tower in one launch each
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
+    bool tower_fused = true;    // option: the conv stack of both towers as one fused kernel on the uint8 batch (cvtower.cuh)
+    bool xf_valid = false;      // x_f32 holds the f32 copy of the batch the current step trains on
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
     // staging
     uint8_t* dev_stage = nullptr;
@@ -303,6 +305,9 @@ void launch_tree_stats(dqn_learner* h, double per_b_override, float* d_out4 = nu
 void tower_forward(dqn_learner* h, const float* params, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts);
 void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32, int rows);
 bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
+bool tower_fused_ready(const dqn_learner* h);
+bool towers_conv_forward_fused(dqn_learner* h, const float* P_on, const uint8_t* s_on, int rows_on, TowerActs& acts_on,
+                               const uint8_t* s_tg, int rows_tg);
 void tower_fc_forward(dqn_learner* h, const float* params, int rows, TowerActs& acts);  // dense + heads after the conv stack
 void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of the packed conv weights
 void launch_pack_conv(dqn_learner* h, int tower);

@@ -6,6 +6,7 @@
 // the TF layouts, so tensors copy 1:1 to/from checkpoints.
 #include "tsgemm.cuh"
 #include "cvgemm.cuh"
+#include "cvtower.cuh"
 #include "fcadam.cuh"
 #include "fcfwd.cuh"
 #include <algorithm>
@@ -310,6 +311,38 @@ bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, 
     return true;
 }
 
+// Conv stacks of both towers (or of one: rows_tg == 0) as ONE launch of the fused tower kernel (cvtower.cuh), reading the
+// uint8 batch itself.  Returns false (nothing launched) if the option is off or a layer is outside its coverage.
+bool tower_fused_ready(const dqn_learner* h) {
+    if (h->cfg.math_mode == DQN_MATH_FP32 || !h->img_conv || !h->tower_fused || !h->packed[0]) return false;
+    cv::TowerArgs t; size_t bytes;
+    return cv::tower_plan(h->net.conv, t, bytes);
+}
+
+bool towers_conv_forward_fused(dqn_learner* h, const float* P_on, const uint8_t* s_on, int rows_on, TowerActs& acts_on,
+                               const uint8_t* s_tg, int rows_tg) {
+    const NetDesc& net = h->net;
+    if (!tower_fused_ready(h)) return false;
+    if (P_on != h->online && P_on != h->target) return false;  // packed weights exist for the handle's two towers only
+    cv::TowerArgs t; size_t bytes;
+    if (!cv::tower_plan(net.conv, t, bytes)) return false;
+    const bool pack = rows_tg > 0 && h->fc_tma_fwd && g_pack_ok(h, rows_on, rows_tg);
+    h->act3_pk_valid[0] = h->act3_pk_valid[1] = false;
+    const int tw = P_on == h->online ? 0 : 1;
+    t.a.in = s_on; t.b.in = s_tg; t.images_a = rows_on;
+    for (int l = 0; l < 3; ++l) {
+        t.a.packed[l] = h->packed[tw] + h->pk_off[l]; t.a.bias[l] = P_on + net.off_cb[l]; t.a.act[l] = acts_on.act[l];
+        t.b.packed[l] = h->packed[1] + h->pk_off[l]; t.b.bias[l] = h->target + net.off_cb[l]; t.b.act[l] = h->acts_tg.act[l];
+    }
+    t.a.pk = pack ? h->act3_pk[0] : nullptr; t.a.pk_rows = rows_on;
+    t.b.pk = pack ? h->act3_pk[1] : nullptr; t.b.pk_rows = rows_tg;
+    if (pack) h->act3_pk_valid[0] = h->act3_pk_valid[1] = true;
+    prof_mark(h, "conv_tower_fwd");
+    if (h->cfg.math_mode == DQN_MATH_TC3X) cv::launch_tower<3>(h, t, bytes, rows_on + rows_tg);
+    else cv::launch_tower<1>(h, t, bytes, rows_on + rows_tg);
+    return true;
+}
+
 void tower_fc_forward(dqn_learner* h, const float* P, int rows, TowerActs& acts) {
     tower_fc_heads(h, P, rows, acts, h->prof_tag[0] == 't');
 }
@@ -375,7 +408,6 @@ static void tower_fc_heads(dqn_learner* h, const float* P, int rows, TowerActs& 
     launch_fc_reduce_heads(h, P, splits, rows, acts);
 }
 
-bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
 // debug: conv layer `layer` of the online tower alone on `rows` images (dqn_debug_timeline, mode 16 + layer);
 // layer 3 = the dense forward + heads
 void debug_conv_layer(dqn_learner* h, int layer, int rows) {
@@ -386,6 +418,10 @@ void debug_conv_layer(dqn_learner* h, int layer, int rows) {
         towers_conv_forward_merged(h, h->x_f32, rows, h->x_f32 + (size_t)(rows / 2) * h->state_bytes, rows / 2);
         h->tc_dbg = dbg;
         tower_fc_heads(h, h->online, rows, h->acts_on, false);
+        return;
+    }
+    if (layer == 4) {
+        DQN_REQUIRE(towers_conv_forward_fused(h, h->online, h->b_states, rows, h->acts_on, nullptr, 0), "fused conv tower not available");
         return;
     }
     const ConvGeom& g = net.conv[layer];
@@ -637,6 +673,10 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
                 if (done) Z = rows;
             }
             if (!done) {
+                if (l == 0 && tcm && !h->xf_valid) {  // the fused tower did not need the f32 copy of the batch; this kernel does
+                    launch_u8_to_f32(h, d_states, h->x_f32, (size_t)rows * h->state_bytes);
+                    h->xf_valid = true;
+                }
                 OpConvWgradABias a{OpConvWgradA{l == 0 ? in0 : (const void*)acts.act[l - 1], g, (l == 0 && !tcm) ? 1 : 0}, mreal, h->ones_row};
                 OpColContig b{h->d_act[l], N};
                 EpiPartial e{part, mreal + 4, N};

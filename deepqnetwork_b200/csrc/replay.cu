@@ -121,7 +121,7 @@ void launch_gather_states(dqn_learner* h, const long long* d_rows, int n, bool n
 
 void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32) {
     if (h->dedup) {
-        const bool f32 = with_f32 && h->cfg.math_mode != DQN_MATH_FP32;
+        const bool f32 = with_f32 && h->cfg.math_mode != DQN_MATH_FP32 && !tower_fused_ready(h);
         launch_kernel(false, gather_frames_kernel, dim3(ceil_div((int)(h->frame_bytes >> 2), 256), 2 * n), dim3(256), 0, h->stream,
                       (const uint8_t*)h->r_frames, (const uint32_t*)h->r_fidx, (const uint8_t*)h->r_actions, (const uint8_t*)h->r_rewards,
                       (const uint8_t*)h->r_cont, (const __half*)h->r_losses, d_rows, n, h->frame_bytes, -1, h->b_states, h->b_actions,
@@ -134,11 +134,13 @@ void launch_gather(dqn_learner* h, const long long* d_rows, int n, bool with_f32
     const int nvec = (int)(h->state_bytes >> 4);
     dim3 grid(ceil_div(nvec, threads * 4), 2 * n);
     // the batch buffer keeps s in rows [0,n) and s' in rows [n,2n): one contiguous [2n,S] input for the online tower
+    // (the fused conv tower reads the uint8 rows themselves: no f32 copy, the gather moves 2 x 2 x B x S bytes and nothing else)
+    const bool f32 = with_f32 && h->cfg.math_mode != DQN_MATH_FP32 && !tower_fused_ready(h);
     launch_kernel(false, gather_rows_kernel, grid, dim3(threads), 0, h->stream, h->r_states, h->r_next, h->r_actions, h->r_rewards,
                   h->r_cont, h->r_losses, d_rows, n, h->state_bytes, h->b_states, h->b_actions, h->b_rewards, h->b_cont, h->b_losses,
-                  with_f32 && h->cfg.math_mode != DQN_MATH_FP32 ? reinterpret_cast<float4*>(h->x_f32) : (float4*)nullptr);
+                  f32 ? reinterpret_cast<float4*>(h->x_f32) : (float4*)nullptr);
     h->launches++;
-    h->xf_from_gather = with_f32 && h->cfg.math_mode != DQN_MATH_FP32;
+    h->xf_from_gather = f32;
 }
 
 // ---- synthetic fill: states/next_states ~ U{0..255}; actions ~ U{0..A-1};

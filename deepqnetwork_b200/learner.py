@@ -384,10 +384,10 @@ class Learner:
         return ms.value
 
     def debug_timeline(self, mode, M, N, K, a_kcontig=True, b_kcontig=True):
-        out = np.zeros(512, np.uint64)
         m = mode if isinstance(mode, int) else {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
+        out = np.zeros(1024 if m == 20 else 512, np.uint64)  # mode 20: the fused conv tower, 128 rows of marks
         self._c(self._lib.dqn_debug_timeline(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(out)))
-        return out.reshape(64, 8)
+        return out.reshape(-1, 8)
 
     # -- persistence ---------------------------------------------------------------------------
     def save(self, prefix):

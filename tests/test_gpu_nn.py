@@ -427,7 +427,7 @@ def _run_steps(cfg_name, opts, steps=5):
     return out
 
 
-@pytest.mark.parametrize('opts', [dict(prefetch=0), dict(priorities=0), dict(fc_split_streams=0), dict(defer_adam=1), dict(merge_towers=0), dict(pack_in_tail=0), dict(fuse_td=0),
+@pytest.mark.parametrize('opts', [dict(prefetch=0), dict(priorities=0), dict(fc_split_streams=0), dict(defer_adam=1), dict(merge_towers=0), dict(tower_fused=0), dict(tower_fused=0, merge_towers=0), dict(pack_in_tail=0), dict(fuse_td=0),
                                   dict(fc_tma_adam=1), dict(fc_tma_adam=1, fc_tma_ctas=148), dict(fc_tma_adam=1, fc_tma_ctas=61)],
                          ids=lambda o: '+'.join('%s=%d' % kv for kv in o.items()))
 def test_scheduling_options_are_bit_identical(opts):
