@@ -920,7 +920,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
     const int rows_on = h->cfg.use_double ? 2 * n : n;  // double DQN: s and s' share one pass of the online tower
-    if ((fused_tower && towers_conv_forward_fused(h, h->online, states2, rows_on, h->acts_on, states2 + (size_t)n * S, n)) ||
+    if ((fused_tower && towers_conv_forward_fused(h, h->online, states2, rows_on, h->acts_on, states2 + (size_t)n * S, n, train ? n : -1)) ||
         (xf && h->xf_valid && towers_conv_forward_merged(h, xf, rows_on, xf + (size_t)n * S, n))) {
         side_begin(h, saved, 0, 2);
         h->prof_tag = "tg_";
@@ -1503,6 +1503,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
     else if (n == "tower_fused") h->tower_fused = value != 0;  // conv1..conv3 of both towers as one kernel on the uint8 batch (cvtower.cuh)
+    else if (n == "tower_cluster") { DQN_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8, "tower_cluster: 1, 2, 4 or 8"); h->tower_cluster = (int)value; }
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "fuse_td") h->fuse_td = value != 0;
     else if (n == "pack_in_tail") h->pack_in_tail = value != 0;

@@ -23,6 +23,7 @@
 // issues the weight TMA copies.
 #pragma once
 #include "tsgemm.cuh"
+#include "cvpack.cuh"
 
 namespace cv {
 using namespace tc;
@@ -109,56 +110,22 @@ static inline bool dgrad_geom(const ConvGeom& g, ImgGeom& q, Bands& bd) {
     return q.nkb >= 1 && q.nkb <= 64;
 }
 
-// packed weights of one layer: [k-block][hi, lo][tile], tile = cout rows x 32 k in the dense canonical K-major layout
-// (8-row x 16-byte core matrices, LBO 128, SBO 1024): element (n, k) at (n/8)*1024 + (k/4)*128 + (n%8)*16 + (k%4)*4
-constexpr uint32_t PK_LBO = 128, PK_SBO = 1024;
 static inline size_t packed_floats(const ConvGeom& g) { return (size_t)g.k * g.k * g.cin * g.cout * 2; }
 
-// W is HWIO: W[kk][n], kk = (kh*k + kw)*cin + c.  flip: the dgrad operand Wd[(kh',kw',co)][ci] = W[k-1-kh'][k-1-kw'][ci][co]
-__global__ void pack_conv_kernel(const float* __restrict__ W, float* __restrict__ packed, int K, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * N) return;
-    const int kk = i / N, n = i - kk * N;
-    const float v = W[i];
-    const int kb = kk >> 5, kin = kk & 31;
-    const size_t tile = (size_t)N * 32;  // floats per tile
-    const size_t off = (size_t)kb * 2 * tile + ((n >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (n & 7) * 16 + (kin & 3) * 4) / 4;
-    packed[off] = v;
-    packed[off + tile] = lo_part(v);
-}
-
-// dgrad operand of conv g, per stride class (ry, rx): Wd[(th, tw, co)][ci] = W[ry + s (kt-1-th)][rx + s (kt-1-tw)][ci][co],
-// packed like the forward weights (N = cin rows); class c starts at k-block c * kt*kt*cout/32
-__global__ void pack_dgrad_kernel(const float* __restrict__ W, float* __restrict__ packed, int k, int s, int cin, int cout) {
-    const int kt = k / s, Kc = kt * kt * cout;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s * s * Kc * cin) return;
-    const int ci = i % cin;
-    int r = i / cin;
-    const int kk = r % Kc, cls = r / Kc;
-    const int co = kk % cout, tap = kk / cout;
-    const int th = tap / kt, tw = tap - th * kt;
-    const int ry = cls / s, rx = cls - ry * s;
-    const int kh = ry + s * (kt - 1 - th), kw = rx + s * (kt - 1 - tw);
-    const float v = W[((size_t)(kh * k + kw) * cin + ci) * cout + co];
-    const int kb = cls * (Kc / 32) + (kk >> 5), kin = kk & 31;
-    const size_t tile = (size_t)cin * 32;
-    const size_t off = (size_t)kb * 2 * tile + ((ci >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (ci & 7) * 16 + (kin & 3) * 4) / 4;
-    packed[off] = v;
-    packed[off + tile] = lo_part(v);
-}
-
-// all layers of one tower in ONE launch (it runs at the tail of every step): blockIdx.y = job
+// all layers of one tower in ONE launch (it runs after set_param / restore / target sync; every step's re-pack rides in the
+// optimizer tail): blockIdx.y = job.  W is HWIO: W[kk][n], kk = (kh*k + kw)*cin + c.  kind 1: the dgrad operand, per stride
+// class (ry, rx): Wd[(th, tw, co)][ci] = W[ry + s (kt-1-th)][rx + s (kt-1-tw)][ci][co] (N = cin rows), class c starting at
+// k-block c * kt*kt*cout/32.  kind 2: the uint8 form of layer 0 (pk_store_u8).
 struct PackJobs {
     int n;
-    struct J { const float* W; float* out; int K, N, k, s, cin, cout, dgrad; } j[6];
+    struct J { const float* W; float* out; int K, N, k, s, cin, cout, kind; } j[8];
 };
 __global__ void pack_all_kernel(const PackJobs jobs) {
     const PackJobs::J& q = jobs.j[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.K * q.N) return;
     float v; int kb, kin, n, rows;
-    if (!q.dgrad) {
+    if (q.kind != 1) {
         const int kk = i / q.N;
         n = i - kk * q.N; v = q.W[i]; kb = kk >> 5; kin = kk & 31; rows = q.N;
     } else {
@@ -172,10 +139,63 @@ __global__ void pack_all_kernel(const PackJobs jobs) {
         v = q.W[((size_t)(kh * q.k + kw) * q.cin + ci) * q.cout + co];
         kb = cls * (Kc / 32) + (kk >> 5); kin = kk & 31; n = ci; rows = q.cin;
     }
-    const size_t tile = (size_t)rows * 32;
-    const size_t off = (size_t)kb * 2 * tile + ((n >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (n & 7) * 16 + (kin & 3) * 4) / 4;
-    q.out[off] = v;
-    q.out[off + tile] = lo_part(v);
+    uint8_t* blk = reinterpret_cast<uint8_t*>(q.out) + (size_t)kb * rows * 256;
+    if (q.kind == 2) pk_store_u8(blk, rows, n, kin, v); else pk_store(blk, rows, n, kin, v);
+}
+
+// instruction descriptor of the bf16 cross-term MMAs: kind::f16, BF16 x BF16 -> fp32, M = 128, K-major operands
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// A tile of one k-block into its tensor-memory stage (64 columns: hi fp32 | bf16(x) pairs | bf16(lo) pairs), NTERMS == 3
+__device__ __forceinline__ void a_stage_store3(uint32_t ta, const float (&hi)[32]) {
+    ts::tmem_st32(ta, hi);
+    uint32_t x[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        x[j] = bf16_pair(hi[2 * j], hi[2 * j + 1]);
+        x[16 + j] = bf16_pair(lo_part(hi[2 * j]), lo_part(hi[2 * j + 1]));
+    }
+    tmem_st32u(ta + BK, x);
+}
+// the 8 MMAs of one k-block (one elected thread): ta = A stage, sb = B k-block in shared memory (N rows, layout above)
+__device__ __forceinline__ void mma_kblock3(uint32_t tmem_d, uint32_t ta, uint32_t sb, int N, uint32_t idesc, uint32_t idesc16, bool first) {
+    const uint64_t db = make_desc(sb, PK_LBO, PK_SBO);
+    const uint64_t dbh = make_desc(sb + 128u * N, PK_LBO, PK_SBO16);
+    const uint64_t dbl = make_desc(sb + 192u * N, PK_LBO, PK_SBO16);
+    constexpr uint64_t STEP = (uint64_t)(2 * PK_LBO) >> 4;  // two core matrices along K per instruction, either kind
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        mma_bf16_ts(tmem_d, ta + BK + j * 8, dbl + j * STEP, idesc16, !(first && j == 0));   // A_hi * B_lo
+        mma_bf16_ts(tmem_d, ta + BK + 16 + j * 8, dbh + j * STEP, idesc16, 1);                 // A_lo * B_hi
+    }
+#pragma unroll
+    for (int ks = 0; ks < BK / 8; ++ks) ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ks * STEP, idesc, 1);  // A_hi * B_hi
 }
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -342,13 +362,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                  : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + choff[c]));
                 const uint32_t ta = tmem_a(s) + lane_base;
-                ts::tmem_st32(ta, hi);
-                if (NTERMS == 3) {
-                    float lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
-                    ts::tmem_st32(ta + BK, lo);
-                }
+                if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
                 ts::tmem_st_wait();
                 tc_fence_before();
                 CV_STAMP(grp == 0 && lane == 0, step, 1);
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         CV_STAMP(tid == 0, 63, 6);
     } else if (warp == 8) {
         // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(BN, false, false);
+        const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0, step = 0;
@@ -396,24 +410,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
                 // so that the mbarrier round trip overlaps their execution instead of draining the queue
                 const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
                 ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1) && mbar_test(bfull_bar(s1), ph1);
-                const uint64_t db = make_desc(stage_b(s), PK_LBO, PK_SBO);
-                const uint64_t dbl = make_desc(stage_b(s) + P::B_TILE, PK_LBO, PK_SBO);
                 const uint32_t ta = tmem_a(s);
-#pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2 * PK_LBO) >> 4;
-                    const uint32_t acc = (kb | ks) != 0;
-                    if (leader) {
-                        if (NTERMS == 3) {
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, dbl + o, idesc, acc);      // A_hi * B_lo
-                            ts::mma_tf32_ts(tmem_d, ta + BK + ks * 8, db + o, idesc, 1);   // A_lo * B_hi
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, 1);        // A_hi * B_hi
-                        } else {
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, acc);
-                        }
-                    }
-                }
                 if (leader) {
+                    if (NTERMS == 3) mma_kblock3(tmem_d, ta, stage_b(s), BN, idesc, idesc16, kb == 0);
+                    else {
+                        const uint64_t db = make_desc(stage_b(s), PK_LBO, PK_SBO);
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks)
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, (kb | ks) != 0);
+                    }
                     mma_commit(empty_bar(s));
                     if (kb == g.nkb - 1) mma_commit(accum_bar(band));
                 }
@@ -551,9 +556,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
             const int p = p4 * 4 + pq, co = c8 * 8 + cq;
             const float v = p < npix ? __ldg(dimg + (size_t)p * BN + co) : 0.f;
             const int kb = p >> 5, kin = p & 31;
-            const uint32_t a = btiles + (uint32_t)(kb * B_KB + (co >> 3) * PK_SBO + (kin >> 2) * PK_LBO + (co & 7) * 16 + (kin & 3) * 4);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
-            if (NTERMS == 3) asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + B_TILE), "f"(lo_part(v)) : "memory");
+            const uint32_t blk = btiles + (uint32_t)(kb * B_KB);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk + pk_off32(co, kin)), "f"(v) : "memory");
+            if (NTERMS == 3) {  // bf16 copies of the cross-term operands (layout of the packed weights)
+                const uint32_t o = blk + pk_off16(co, kin);
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 128u * BN), "h"(bf16_bits(v)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 192u * BN), "h"(bf16_bits(lo_part(v))) : "memory");
+            }
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -606,13 +615,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                     }
                 }
                 const uint32_t ta = tmem_a(s) + lane_base;
-                ts::tmem_st32(ta, hi);
-                if (NTERMS == 3) {
-                    float lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
-                    ts::tmem_st32(ta + BK, lo);
-                }
+                if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
                 ts::tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
         pdl_launch_dependents();
     } else if (warp == 8) {
         // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(BN, false, false);
+        const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0, step = 0;
@@ -636,24 +639,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                 tc_fence_after();
                 const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
                 ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1);
-                const uint64_t db = make_desc(btiles + kb * B_KB, PK_LBO, PK_SBO);
-                const uint64_t dbl = make_desc(btiles + kb * B_KB + B_TILE, PK_LBO, PK_SBO);
                 const uint32_t ta = tmem_a(s);
-#pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2 * PK_LBO) >> 4;
-                    const uint32_t acc = (kb | ks) != 0;
-                    if (leader) {
-                        if (NTERMS == 3) {
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, dbl + o, idesc, acc);
-                            ts::mma_tf32_ts(tmem_d, ta + BK + ks * 8, db + o, idesc, 1);
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, 1);
-                        } else {
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, acc);
-                        }
-                    }
-                }
                 if (leader) {
+                    if (NTERMS == 3) mma_kblock3(tmem_d, ta, btiles + kb * B_KB, BN, idesc, idesc16, kb == 0);
+                    else {
+                        const uint64_t db = make_desc(btiles + kb * B_KB, PK_LBO, PK_SBO);
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks)
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, (kb | ks) != 0);
+                    }
                     mma_commit(empty_bar(s));
                     if (kb == nkb - 1) mma_commit(accf_bar(ab));
                 }

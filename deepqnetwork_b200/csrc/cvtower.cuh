@@ -12,11 +12,19 @@
 //     trip through L2 between layers;
 //   * the packed weights of the three layers stream through ONE TMA ring whose producer runs ahead across the layer
 //     boundaries; barriers, tensor memory and the converter / MMA / TMA roles are set up once.
-// Operands, roles and the 3-term TF32 split are those of cvconv_kernel (cvgemm.cuh); results are bit-identical to the
-// per-layer kernels (same products, same accumulation order).
+//   * layer 0 multiplies the frame BYTES (exact in bf16) with the three bf16 pieces of w / 255 (cvpack.cuh): 6 MMAs per
+//     k-block, no cast / 255 and no hi / lo split in the converter; layers 1, 2 use the mixed 3-term product (8 MMAs);
+//   * SEVERAL MMA-issuing warps.  One thread issues a tcgen05.mma every ~53 cycles whatever its shape
+//     (scratch/ubench/mma_issue.cu: N = 32 / 64 MMAs from one thread 53 cycles each, from two threads 26.6 / 32.3, from four
+//     16.1 / 32.2 = the tensor pipe's own N / 2), so a single issuer leaves the pipe 40-70 % idle at N <= 64.  Layer 0 (four
+//     bands of 128 output pixels, N = 32): the k-blocks are walked band-interleaved and issuing warp w owns band w (its own
+//     accumulator); layers 1, 2 (one band, N = 64): warp 0 takes the even k-blocks, warp 1 the odd ones, each into its OWN
+//     accumulator (deterministic order inside each), and the epilogue adds the two.
+// Operands and converter roles are those of cvconv_kernel (cvgemm.cuh).
 //
 // Shared memory (C2: 89 x 80 x 4 frames): ring 5 x 16 KB | barriers, tables 8 KB | image A 80.4 KB (conv2 input) |
 // image B 51.9 KB (the uint8 frames, 31.5 KB; re-used as conv3's input once conv1 is done) = 221 KB.
+// Tensor memory: 128 accumulator columns (4 bands x 32 or 2 x 64) + 5 A stages x 64 columns = 448.
 #pragma once
 #include "cvgemm.cuh"
 
@@ -27,6 +35,7 @@ struct TowerSet {  // one tower's operands
     const float* packed[3];  // packed conv weights (pack_all_kernel)
     const float* bias[3];
     float* act[3];           // post-ReLU NHWC outputs
+    int act_rows[3];         // ... written for the first act_rows[l] images only (the backward pass reads the training rows)
     float* pk;               // conv3 output as the dense forward's operand tiles (EpiBiasReluPack layout), or null
     int pk_rows;
 };
@@ -39,14 +48,22 @@ struct TowerArgs {
     int img_zero[3];  // bytes of that image (zero-filled before the previous layer's epilogue writes into it)
     int u8_row;       // bytes per padded row of the layer-0 byte image
     int rt0[3];       // first row-table band of layer l
-    int S;            // ring depth (B tiles in shared memory, A tiles in tensor memory)
 };
 
-constexpr int TW_THREADS = 320;     // warps 0-7 converters / epilogue, warp 8 MMA, warp 9 TMA
-constexpr int TW_STAGE = 16384;     // ring slot: hi + lo tile of a 64-column layer
-constexpr int TW_DCOLS = 128;       // accumulator columns (bands x cout <= 128), A stages follow
+constexpr int TW_THREADS = 544;     // warps 0-7 converters / epilogue, warps 8-11 MMA issuers, warp 12 TMA, warps 13-16 writers
+constexpr int TW_S = 5;             // ring depth (B tiles in shared memory, A tiles in tensor memory)
+constexpr int TW_STAGE = 16384;     // ring slot: one k-block of packed weights of a 64-column layer
+constexpr int TW_DCOLS = 128;       // accumulator columns (4 bands x 32, or 2 k-halves x 64); A stages follow
 constexpr int TW_TAB = 8192;        // barriers 256 | k-block offsets 3 x 256 | bias 3 x 256 | row tables 6 x 128 x 8
 constexpr int TW_MAXBANDS = 6;
+
+__device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 
 template <int NTERMS>
 __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_constant__ TowerArgs t, const float* __restrict__ zeros,
@@ -56,16 +73,24 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
 #define TW_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 128) dbg[(row) * 8 + (col)] = clock64(); } while (0)
     TW_STAMP(threadIdx.x == 0, 127, 0);
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int S = t.S;
+    constexpr int S = TW_S;
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t ring = sbase;
     const uint32_t bars = ring + (uint32_t)S * TW_STAGE;
-    const uint32_t kbtab = bars + 256, bias_s = bars + 1024, rowtab = bars + 2048, imgs = bars + TW_TAB;
-    auto afull_bar = [&](int s) { return bars + 8u * s; };
-    auto bfull_bar = [&](int s) { return bars + 8u * (6 + s); };
-    auto empty_bar = [&](int s) { return bars + 8u * (12 + s); };
-    auto accum_bar = [&](int l, int b) { return bars + 8u * (18 + l * 4 + b); };  // each used once
-    const uint32_t tmem_slot = bars + 248;
+    const uint32_t kbtab = bars + 384, bias_s = bars + 1152, rowtab = bars + 2048, imgs = bars + TW_TAB;
+    auto afull_bar = [&](int s) { return bars + 8u * s; };          // A tile of a step is in tensor memory (4 converter warps)
+    auto aempty_bar = [&](int s) { return bars + 8u * (5 + s); };   // ... and consumed (this CTA's MMAs: tcgen05.commit)
+    auto bfull_bar = [&](int s) { return bars + 8u * (10 + s); };   // weight tile landed (all slices, from every CTA of the cluster)
+    auto bempty_bar = [&](int s) { return bars + 8u * (15 + s); };  // ... and consumed by EVERY CTA of the cluster (multicast commits)
+    auto accum_bar = [&](int l, int b) { return bars + 8u * (20 + l * 4 + b); };  // each used once
+    const uint32_t w0full = bars + 8u * 32;                          // layer 0's weights (all k-blocks) are resident
+    const uint32_t tmem_slot = bars + 8u * 34;
+    auto imgready_bar = [&](int l) { return bars + 8u * (35 + l); };  // layer l's output is complete in shared memory (8 epilogue warps)
+    const uint32_t wdone = bars + 8u * 38;                            // the writers have copied layer 0's output out of image A
+    uint32_t crank, csize;  // thread-block cluster: the CTAs of a cluster (same tower) share one weight stream by TMA multicast
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool set_b = (int)blockIdx.x >= t.images_a;
@@ -75,10 +100,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(afull_bar(s), 4);
+            mbar_init(aempty_bar(s), 1);
             mbar_init(bfull_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(bempty_bar(s), csize);
         }
-        for (int b = 0; b < 12; ++b) mbar_init(accum_bar(0, b), 1);
+        mbar_init(w0full, 1);
+        for (int l = 0; l < 3; ++l) mbar_init(imgready_bar(l), 8);
+        mbar_init(wdone, 4);
+        // a band's accumulator(s) are complete: one issuing warp per band (4 bands), or the two k-halves of a single band
+        for (int l = 0; l < 3; ++l)
+            for (int b = 0; b < 4; ++b) mbar_init(accum_bar(l, b), t.g[l].nbands == 1 ? 2 : 1);
         fence_barrier_init();
     }
     if (tid < 192) {
@@ -118,6 +149,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) {  // every CTA's barriers exist before a peer multicasts into them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -151,7 +186,6 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
                 const int l = tid >> 6, n = tid & 63;
                 if (n < t.g[l].cout) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(ts_.bias[l][n]) : "memory");
             }
-            zero_fill(imgs + t.img_off[1], t.img_zero[1]);  // SAME padding of conv2's input
             asm volatile("cp.async.wait_all;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -168,11 +202,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
             tc_fence_after();
             int opix;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(opix) : "r"(rowtab + 8u * ((t.rt0[l] + band) * 128 + m) + 4u));
+            const bool ksplit = g.nbands == 1;  // two accumulators (even / odd k-blocks) to add
             const uint32_t trow = tmem_base + lane_base + (uint32_t)(band * BN + cg * HC);
-            float* og = ts_.act[l] + ((size_t)image * (g.oh * g.ow) + (opix < 0 ? 0 : opix)) * BN;
+            TW_STAMP(tid == 0, 100 + l * 4 + band, 0);
             uint32_t sdst = 0;
             bool to_smem = false;
-            if (l < 2 && opix >= 0) {
+            if (l == 2) {  // the last layer's output is staged in image A (dead by now) for the writer warps
+                to_smem = opix >= 0;
+                sdst = imgs + t.img_off[1] + (uint32_t)(opix * (BN * 4 + 16));
+            } else if (opix >= 0) {
                 const ImgGeom& n = t.g[l + 1];
                 const int a = opix / g.ow, b = opix - a * g.ow;
                 const int r = a + n.pt, col = b + n.pl;
@@ -183,174 +221,232 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
             for (int c = 0; c < HC; c += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c, v);
+                if (ksplit) {
+                    float v1[16];
+                    tmem_ld16(trow + (uint32_t)(BN + c), v1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v1[j];  // even k-blocks + odd k-blocks
+                }
+                TW_STAMP(tid == 0, 100 + l * 4 + band, 1 + (c >> 4));
                 if (opix < 0) continue;
                 const int n0 = cg * HC + c;
                 const uint32_t sb = bias_s + 4u * (l * 64 + n0);
-                float* pt = nullptr;
-                if (l == 2 && ts_.pk) {
-                    const int k0 = opix * BN + n0;  // flat index (tf.layers.flatten of NHWC) of this run of 16 channels
-                    pt = ts_.pk + (size_t)(k0 >> 5) * (2 * ts_.pk_rows * 32) + (((image >> 3) * 1024 + ((k0 & 31) >> 2) * 128 + (image & 7) * 16) >> 2);
-                }
+                const int k0 = opix * BN + n0;  // flat index (tf.layers.flatten of NHWC) of this run of 16 channels
+                // the dense forward's B operand (fcfwd.cuh): k-block k0 / 32 of pk_rows batch rows, packed layout of cvpack.cuh
+                uint8_t* blk = (l == 2 && ts_.pk) ? reinterpret_cast<uint8_t*>(ts_.pk) + (size_t)(k0 >> 5) * ts_.pk_rows * 256 : nullptr;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 b;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sb + 4u * j));
-                    const float4 r = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f), fmaxf(v[j + 3] + b.w, 0.f));
-                    *reinterpret_cast<float4*>(og + n0 + j) = r;
-                    if (to_smem)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + 4u * (n0 + j)), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
-                    if (pt) {
-                        const float4 lo = make_float4(lo_part(r.x), lo_part(r.y), lo_part(r.z), lo_part(r.w));
-                        *reinterpret_cast<float4*>(pt + (j >> 2) * 32) = r;
-                        *reinterpret_cast<float4*>(pt + (j >> 2) * 32 + ts_.pk_rows * 32) = lo;
+                for (int j = 0; j < 16; j += 8) {
+                    float4 b0, b1;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(sb + 4u * j));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(sb + 4u * j + 16u));
+                    const float4 r0 = make_float4(fmaxf(v[j] + b0.x, 0.f), fmaxf(v[j + 1] + b0.y, 0.f), fmaxf(v[j + 2] + b0.z, 0.f), fmaxf(v[j + 3] + b0.w, 0.f));
+                    const float4 r1 = make_float4(fmaxf(v[j + 4] + b1.x, 0.f), fmaxf(v[j + 5] + b1.y, 0.f), fmaxf(v[j + 6] + b1.z, 0.f), fmaxf(v[j + 7] + b1.w, 0.f));
+                    if (to_smem) {
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + 4u * (n0 + j)), "f"(r0.x), "f"(r0.y), "f"(r0.z), "f"(r0.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + 4u * (n0 + j + 4)), "f"(r1.x), "f"(r1.y), "f"(r1.z), "f"(r1.w) : "memory");
                     }
+                    if (blk) pk_store8(blk, ts_.pk_rows, image, (k0 & 31) + j, r0, r1);
                 }
             }
             tc_fence_before();
+            TW_STAMP(tid == 0, 100 + l * 4 + band, 3);
         };
 
-        int step = cg, s = cg % S, ph = 0, step_end = 0;
-        // the converter loop of one band; U8: layer 0 (byte image, cast / 255 here)
-        auto convert_band = [&](auto u8tag, int l, int band) {
+        int step = cg, step_end = 0;
+        // the converter loop of one layer (its k-blocks band-interleaved: step = kb * nbands + band); U8: layer 0 (byte image)
+        auto convert_layer = [&](auto u8tag, int l) {
             constexpr bool U8 = decltype(u8tag)::value;
             const ImgGeom& g = t.g[l];
-            uint32_t roff;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(roff) : "r"(rowtab + 8u * ((t.rt0[l] + band) * 128 + m)));
-            const uint32_t base = imgs + t.img_off[l] + roff;
+            const int nb = g.nbands;  // 1 or 4
+            const uint32_t ibase = imgs + t.img_off[l];
             const int step0 = step_end;
-            step_end += g.nkb;
+            step_end += g.nkb * nb;
             for (; step < step_end; step += 2) {
-                const int kb = step - step0;
-                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);  // TMEM stage s is free again
-                TW_STAMP(grp == 0 && lane == 0, step, 0);
-                uint32_t koff;
+                const int ls = step - step0;
+                const int kb = nb == 1 ? ls : ls >> 2, band = nb == 1 ? 0 : ls & 3;
+                const int s = step % S, ph = (step / S) & 1;
+                uint32_t roff, koff;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(roff) : "r"(rowtab + 8u * ((t.rt0[l] + band) * 128 + m)));
                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(koff) : "r"(kbtab + 4u * (l * 64 + kb)));
-                const uint32_t src = base + koff;
-                float hi[32];
+                if (step >= S) mbar_wait(aempty_bar(s), ph ^ 1);  // TMEM stage s is free again
+                TW_STAMP(grp == 0 && lane == 0, step, 0);
+                const uint32_t src = ibase + roff + koff;
+                const uint32_t ta = tmem_a(s) + lane_base;
                 if constexpr (U8) {
+                    // the 32 frame bytes of this kernel row as 16 bf16 pairs (integers 0..255 are exact in bf16)
+                    uint32_t x[16];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t w[4];
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src + 16u * c));
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            hi[16 * c + 4 * q] = u8_to_unit(w[q] & 255u);
-                            hi[16 * c + 4 * q + 1] = u8_to_unit((w[q] >> 8) & 255u);
-                            hi[16 * c + 4 * q + 2] = u8_to_unit((w[q] >> 16) & 255u);
-                            hi[16 * c + 4 * q + 3] = u8_to_unit(w[q] >> 24);
+                            // byte b -> float: 0x4B0000bb is 2^23 + b; minus 2^23 leaves b exactly (full-rate ops, no I2F);
+                            // its low 16 bits are zero, so the bf16 is the upper half-word
+                            const float f0 = __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7540)) - 8388608.0f;
+                            const float f1 = __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7541)) - 8388608.0f;
+                            const float f2 = __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7542)) - 8388608.0f;
+                            const float f3 = __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7543)) - 8388608.0f;
+                            x[8 * c + 2 * q] = __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+                            x[8 * c + 2 * q + 1] = __byte_perm(__float_as_uint(f2), __float_as_uint(f3), 0x7632);
                         }
                     }
+                    tmem_st16u(ta, x);
                 } else {
+                    float hi[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + 16u * c));
-                }
-                const uint32_t ta = tmem_a(s) + lane_base;
-                ts::tmem_st32(ta, hi);
-                if (NTERMS == 3) {
-                    float lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) lo[j] = lo_part(hi[j]);
-                    ts::tmem_st32(ta + BK, lo);
+                    if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
                 }
                 ts::tmem_st_wait();
                 tc_fence_before();
                 TW_STAMP(grp == 0 && lane == 0, step, 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull_bar(s));
-                s += 2;
-                if (s >= S) { s -= S; ph ^= 1; }
             }
         };
         for (int l = 0; l < 3; ++l) {
-            const int nb = t.g[l].nbands;
-            for (int band = 0; band < nb; ++band) {
-                if (l == 0) convert_band(std::true_type{}, l, band); else convert_band(std::false_type{}, l, band);
-                if (l == 2 && band == nb - 1) pdl_launch_dependents();
-                // the previous band's accumulator drains while the tensor core works on this one
-                if (band > 0) epilogue(l, band - 1);
-            }
+            if (l == 0) convert_layer(std::true_type{}, l); else convert_layer(std::false_type{}, l);
+            if (l == 2) pdl_launch_dependents();
             if (l == 0) {
-                // all MMAs of layer 0 have completed => every converter has read its last byte of the frame image: its
-                // space becomes conv3's input (zero padding first; conv2's epilogue fills the interior)
-                mbar_wait(accum_bar(0, nb - 1), 0);
+                // all MMAs of layer 0 have completed => its weights (resident in image A) and the frame bytes (image B) are
+                // dead: the two areas become the zero-padded inputs of conv2 / conv3, whose interiors the epilogues fill
+                for (int band = 0; band < t.g[0].nbands; ++band) mbar_wait(accum_bar(0, band), 0);
+                zero_fill(imgs + t.img_off[1], t.img_zero[1]);
                 zero_fill(imgs + t.img_off[2], t.img_zero[2]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            epilogue(l, nb - 1);
+            if (l == 2) mbar_wait(wdone, 0);  // (long since) the writers are done with layer 0's output in image A: it stages layer 2's
+            for (int band = 0; band < t.g[l].nbands; ++band) epilogue(l, band);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(imgready_bar(l));  // the writer warps copy this layer's output to global memory
             TW_STAMP(tid == 0, 120 + l, 0);
             if (l < 2) asm volatile("bar.sync 1, 256;" ::: "memory");  // next layer's image complete, accumulators drained
         }
-    } else if (warp == 8) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp < 12) {
+        // ---------------- MMA issuers (warps 8-11) ----------------
+        // a layer of 4 bands: warp w owns band w (steps kb * 4 + w); a layer of one band: warps 0, 1 own the even / odd
+        // k-blocks, each with its own accumulator; every warp walks ITS steps in order
+        const int w = warp - 8;
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        int nsteps = 0;
-        for (int l = 0; l < 3; ++l) nsteps += t.g[l].nbands * t.g[l].nkb;
-        int s = 0, ph = 0, step = 0;
-        bool ready = false;
+        int step0 = 0, bstep0 = 0;  // first step of the layer; first weight-ring step of the layer (layer 0 does not use the ring)
         for (int l = 0; l < 3; ++l) {
-            const int BN = t.g[l].cout, nkb = t.g[l].nkb;
-            const uint32_t idesc = make_idesc(BN, false, false);
-            const uint32_t b_tile = (uint32_t)BN * 128u;
-            for (int band = 0; band < t.g[l].nbands; ++band) {
-                const uint32_t tmem_d = tmem_base + (uint32_t)(band * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++step) {
-                    if (!ready) {
-                        mbar_wait(afull_bar(s), ph);
-                        mbar_wait(bfull_bar(s), ph);
-                    }
+            const int BN = t.g[l].cout, nkb = t.g[l].nkb, nb = t.g[l].nbands;
+            const int stride = nb == 1 ? 2 : 4;  // distance between this warp's steps
+            if (w < stride) {
+                const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(w * BN);
+                const int last = step0 + nkb * nb;
+                if (l == 0) mbar_wait(w0full, 0);
+                for (int step = step0 + w; step < last; step += stride) {
+                    const int s = step % S, ph = (step / S) & 1;
+                    const int bstep = bstep0 + (step - step0), bs = bstep % S, bph = (bstep / S) & 1;
+                    mbar_wait(afull_bar(s), ph);
+                    if (l > 0) mbar_wait(bfull_bar(bs), bph);
                     TW_STAMP(lane == 0, step, 3);
                     tc_fence_after();
-                    const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
-                    ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1) && mbar_test(bfull_bar(s1), ph1);
-                    const uint64_t db = make_desc(stage_b(s), PK_LBO, PK_SBO);
-                    const uint64_t dbl = make_desc(stage_b(s) + b_tile, PK_LBO, PK_SBO);
                     const uint32_t ta = tmem_a(s);
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t o = (uint64_t)(ks * 2 * PK_LBO) >> 4;
-                        const uint32_t acc = (kb | ks) != 0;
-                        if (leader) {
-                            if (NTERMS == 3) {
-                                ts::mma_tf32_ts(tmem_d, ta + ks * 8, dbl + o, idesc, acc);      // A_hi * B_lo
-                                ts::mma_tf32_ts(tmem_d, ta + BK + ks * 8, db + o, idesc, 1);   // A_lo * B_hi
-                                ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, 1);        // A_hi * B_hi
-                            } else {
-                                ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + o, idesc, acc);
-                            }
-                        }
-                    }
+                    const bool first = step < step0 + stride;
                     if (leader) {
-                        mma_commit(empty_bar(s));
-                        if (kb == nkb - 1) mma_commit(accum_bar(l, band));
+                        if (l == 0) {
+                            // frame bytes (exact bf16) x the bf16 pieces of w / 255, smallest piece first: 2 x NP instructions
+                            constexpr int NP = NTERMS == 3 ? 3 : 2;
+                            const uint32_t wk = imgs + t.img_off[1] + (uint32_t)((step - step0) >> 2) * (192u * BN);  // k-block's weights
+#pragma unroll
+                            for (int p = NP - 1; p >= 0; --p) {
+                                const uint64_t d = make_desc(wk + (uint32_t)(p * 64 * BN), PK_LBO, PK_SBO16);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    mma_bf16_ts(tmem_d, ta + j * 8, d + j * ((uint64_t)(2 * PK_LBO) >> 4), idesc16, !(first && p == NP - 1 && j == 0));
+                            }
+                        } else if (NTERMS == 3) mma_kblock3(tmem_d, ta, stage_b(bs), BN, idesc, idesc16, first);
+                        else {
+                            const uint64_t db = make_desc(stage_b(bs), PK_LBO, PK_SBO);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 8; ++ks)
+                                ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, !(first && ks == 0));
+                        }
+                        mma_commit(aempty_bar(s));
+                        if (l > 0) {  // the weight stage is free once EVERY CTA of the cluster has consumed it
+                            if (csize > 1) mma_commit_mc(bempty_bar(bs), cmask); else mma_commit(bempty_bar(bs));
+                        }
+                        if (step + stride >= last) mma_commit(accum_bar(l, nb == 1 ? 0 : w));
                     }
                     TW_STAMP(lane == 0, step, 4);
                     __syncwarp();
-                    s = s1; ph = ph1;
                 }
             }
+            step0 += nkb * nb;
+            if (l > 0) bstep0 += nkb * nb;
         }
         tc_fence_before();
+    } else if (warp >= 13) {
+        // ---------------- writers (warps 13-16): layer outputs shared memory -> global NHWC, whole 128-byte lines, off the critical
+        // path (layer l's output is layer l+1's resident input image; the last layer's is staged in image A) ----------------
+        const int wt = tid - 13 * 32;
+        for (int l = 0; l < 3; ++l) {
+            const ImgGeom& g = t.g[l];
+            mbar_wait(imgready_bar(l), 0);
+            if (image < ts_.act_rows[l]) {
+                const int cpp = g.cout >> 2, npix = g.oh * g.ow;  // 16-byte chunks per pixel
+                float* og = ts_.act[l] + (size_t)image * npix * g.cout;
+                for (int q = wt; q < npix * cpp; q += 128) {
+                    const int p = q / cpp, c = q - p * cpp;
+                    uint32_t src;
+                    if (l == 2) src = imgs + t.img_off[1] + (uint32_t)(p * (g.cout * 4 + 16));
+                    else {
+                        const ImgGeom& n = t.g[l + 1];
+                        const int a = p / g.ow, b = p - a * g.ow;
+                        const int r = a + n.pt, col = b + n.pl;
+                        if (r >= n.hp || col >= n.wcols) continue;  // (never read by the next layer: not resident) -- cannot happen for SAME
+                        src = imgs + t.img_off[l + 1] + (uint32_t)((r * n.wcols + (col % n.s) * n.wps + col / n.s) * n.pitch);
+                    }
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * c));
+                    *reinterpret_cast<float4*>(og + (size_t)p * g.cout + c * 4) = v;
+                }
+            }
+            if (l == 0) { __syncwarp(); if (lane == 0) mbar_arrive(wdone); }
+        }
     } else {
-        // ---------------- weight TMA producer (warp 9, one lane): runs ahead across the layer boundaries ----------------
+        // ---------------- weight TMA producer (warp 12, one lane): runs ahead across the layer boundaries ----------------
         if (lane == 0) {
             pdl_wait();
-            int s = 0, ph = 0, step = 0;
-            for (int l = 0; l < 3; ++l) {
-                const uint32_t bytes = (uint32_t)t.g[l].cout * 256u;  // hi + lo tile of one k-block
+            {
+                // layer 0: all k-blocks (three bf16 pieces each) become resident in image A; the CTAs of a cluster fetch
+                // alternate k-blocks and multicast them
+                const uint32_t stride = (uint32_t)t.g[0].cout * 256u, bytes = stride / 4 * 3;
+                mbar_expect_tx(w0full, bytes * t.g[0].nkb);
+                for (int kb = crank; kb < t.g[0].nkb; kb += csize) {
+                    const uint32_t dst = imgs + t.img_off[1] + (uint32_t)kb * bytes;
+                    const float* src = ts_.packed[0] + (size_t)kb * (stride / 4);
+                    if (csize > 1) tma_bulk_g2s_mc(dst, src, bytes, w0full, cmask); else tma_bulk_g2s(dst, src, bytes, w0full);
+                }
+            }
+            int s = 0, ph = 0, bstep = 0;
+            for (int l = 1; l < 3; ++l) {
+                const uint32_t bytes = (uint32_t)t.g[l].cout * 256u;  // one k-block of packed weights
+                const uint32_t slice = bytes / csize;                 // this CTA fetches slice `crank` for the whole cluster
                 const float* src = ts_.packed[l];
-                for (int band = 0; band < t.g[l].nbands; ++band)
-                    for (int kb = 0; kb < t.g[l].nkb; ++kb, ++step) {
-                        if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
-                        mbar_expect_tx(bfull_bar(s), bytes);
-                        tma_bulk_g2s(stage_b(s), src + (size_t)kb * (bytes / 4), bytes, bfull_bar(s));
-                        if (++s == S) { s = 0; ph ^= 1; }
-                    }
+                for (int kb = 0; kb < t.g[l].nkb * t.g[l].nbands; ++kb, ++bstep) {
+                    if (bstep >= S) mbar_wait(bempty_bar(s), ph ^ 1);
+                    mbar_expect_tx(bfull_bar(s), bytes);
+                    const uint32_t dst = stage_b(s) + crank * slice;
+                    const float* sp = src + (size_t)(kb / t.g[l].nbands) * (bytes / 4) + (size_t)crank * (slice / 4);
+                    if (csize > 1) tma_bulk_g2s_mc(dst, sp, slice, bfull_bar(s), cmask); else tma_bulk_g2s(dst, sp, slice, bfull_bar(s));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
             }
         }
     }
     __syncthreads();
+    if (csize > 1) {  // no CTA leaves while a peer may still signal its barriers
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -364,7 +460,9 @@ static inline bool tower_plan(const ConvGeom* conv, TowerArgs& t, size_t& smem_b
     int bands = 0;
     for (int l = 0; l < 3; ++l) {
         ImgGeom& q = t.g[l];
-        if (!img_geom(conv[l], q) || q.nbands > 4 || q.nbands * q.cout > TW_DCOLS) return false;
+        // 4 bands: one issuing warp per band; 1 band: two issuing warps, each >= 1 k-block and its own accumulator
+        if (!img_geom(conv[l], q) || (q.nbands != 1 && q.nbands != 4) || q.nbands * q.cout > TW_DCOLS || q.nkb < 2) return false;
+        if (q.nbands == 1 && 2 * q.cout > TW_DCOLS) return false;
         if (l > 0 && (conv[l].cin % 32 != 0 || conv[l].cin != conv[l - 1].cout || conv[l].ih != conv[l - 1].oh || conv[l].iw != conv[l - 1].ow)) return false;
         t.rt0[l] = bands;
         bands += q.nbands;
@@ -378,11 +476,10 @@ static inline bool tower_plan(const ConvGeom* conv, TowerArgs& t, size_t& smem_b
     const int imgA = t.g[1].img_bytes, imgB = img0 > t.g[2].img_bytes ? img0 : t.g[2].img_bytes;
     t.img_off[0] = imgA; t.img_off[1] = 0; t.img_off[2] = imgA;
     t.img_zero[0] = 0; t.img_zero[1] = t.g[1].img_bytes; t.img_zero[2] = t.g[2].img_bytes;
-    for (int S = 6; S >= 3; --S) {
-        const size_t need = (size_t)S * TW_STAGE + TW_TAB + imgA + imgB + 1024;
-        if (need <= 227 * 1024 && TW_DCOLS + S * 64 <= 512) { t.S = S; smem_bytes = need; return true; }
-    }
-    return false;
+    if (t.g[0].nkb * t.g[0].cout * 192 > imgA) return false;  // layer 0's weights are resident in image A during its k-loop
+    smem_bytes = (size_t)TW_S * TW_STAGE + TW_TAB + imgA + imgB + 1024;
+    static_assert(TW_DCOLS + TW_S * 64 <= 512, "tensor memory budget");
+    return smem_bytes <= 227 * 1024;
 }
 
 template <int NTERMS>
@@ -393,7 +490,20 @@ static void launch_tower(dqn_learner* h, const TowerArgs& t, size_t smem_bytes, 
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         configured = smem_bytes;
     }
-    launch_kernel(h->pdl, kern, dim3(images), dim3(TW_THREADS), smem_bytes, h->stream, t, (const float*)h->zeros16, h->tc_dbg);
+    // clusters of up to 4 images of the same tower share the weight stream (TMA multicast): L2 -> SM traffic / 4
+    int csize = 1;
+    const int images_b = images - t.images_a;
+    for (int c = h->tower_cluster; c > 1; c >>= 1)
+        if (t.images_a % c == 0 && images_b % c == 0 && (64 * 256) % c == 0) { csize = c; break; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(images); cfg.blockDim = dim3(TW_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = h->stream;
+    cudaLaunchAttribute at[3];
+    int n = 0;
+    at[n].id = cudaLaunchAttributePriority; at[n].val.priority = g_launch_priority; ++n;
+    if (h->pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = csize; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n;
+    cfg.attrs = at; cfg.numAttrs = n;
+    DQN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t, (const float*)h->zeros16, h->tc_dbg));
     h->launches++;
 }
 

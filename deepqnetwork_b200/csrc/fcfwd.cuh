@@ -105,13 +105,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
 #pragma unroll
             for (int k = 0; k < 32; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[k]) : "r"(src + (uint32_t)k * (BM * 4)));
             const uint32_t ta = tmem_a(s) + lane_base;
-            ts::tmem_st32(ta, hi);
-            if (NTERMS == 3) {
-                float lo[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) lo[k] = lo_part(hi[k]);
-                ts::tmem_st32(ta + BK, lo);
-            }
+            if (NTERMS == 3) cv::a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
             ts::tmem_st_wait();
             tc_fence_before();
             FF_STAMP(tid == 0, j, 2);
@@ -127,7 +121,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         constexpr int PF = 4;             // k-blocks of activation loads in flight per thread (L2 latency ~1 us >> a k-block)
         // chunk q of a thread: 8 consecutive lanes write 8 consecutive 16-byte rows of a core matrix (conflict-free)
         const float* srcp[CH];
-        uint32_t dsto[CH];
+        uint32_t dsto[CH], dsto16[CH];
         bool okr[CH];
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
@@ -137,6 +131,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
             okr[i] = r < rows;
             srcp[i] = act + (size_t)(okr[i] ? r : 0) * flat + (size_t)kb0 * BK + c * 4;
             dsto[i] = (uint32_t)(rg * cv::PK_SBO + c * cv::PK_LBO + r8 * 16);
+            dsto16[i] = cv::pk_off16(r, c * 4);
         }
         float4 pf[PF][CH];
         auto load_blk = [&](int j, float4 (&v)[CH]) {
@@ -162,9 +157,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
             for (int i = 0; i < CH; ++i) {
                 const uint32_t a = stage_b(s) + dsto[i];
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w) : "memory");
-                if (NTERMS == 3)
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + B_TILE), "f"(lo_part(v[i].x)), "f"(lo_part(v[i].y)),
-                                 "f"(lo_part(v[i].z)), "f"(lo_part(v[i].w)) : "memory");
+                if (NTERMS == 3) {  // bf16 copies for the cross terms (cvpack.cuh layout: 8 bytes per four k)
+                    const uint32_t a16 = stage_b(s) + dsto16[i];
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a16 + B_TILE), "r"(cv::bf16_pair(v[i].x, v[i].y)), "r"(cv::bf16_pair(v[i].z, v[i].w)) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a16 + B_TILE + B_TILE / 2), "r"(cv::bf16_pair(lo_part(v[i].x), lo_part(v[i].y))),
+                                 "r"(cv::bf16_pair(lo_part(v[i].z), lo_part(v[i].w))) : "memory");
+                }
             }
             // release-arrive; the generic->async proxy fence runs on the MMA thread after its acquire (a producer-side
             // fence.proxy.async costs ~1000 cycles per k-block here: fftl timeline)
@@ -181,7 +179,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         }
     } else {
         // ---------------- MMA issue (warp 8) ----------------
-        const uint32_t idesc = make_idesc(BN, false, false);
+        const uint32_t idesc = make_idesc(BN, false, false), idesc16 = cv::make_idesc_bf16(BN);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int s = 0, ph = 0;
@@ -200,23 +198,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
                 const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
                 ready = j + 1 < nkb && cv::mbar_test(afull(s1), ph1) && cv::mbar_test(PACKED ? wfull(s1) : bfull(s1), ph1);
             }
-            const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO), dbl = make_desc(stage_b(s) + B_TILE, cv::PK_LBO, cv::PK_SBO);
             const uint32_t ta = tmem_a(s);
-#pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-                const uint64_t o = (uint64_t)(ks * 2 * cv::PK_LBO) >> 4;
-                const uint32_t acc = (j | ks) != 0;
-                if (leader) {
-                    if (NTERMS == 3) {
-                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, dbl + o, idesc, acc);
-                        ts::mma_tf32_ts(tmem_base, ta + BK + ks * 8, db + o, idesc, 1);
-                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, 1);
-                    } else {
-                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + o, idesc, acc);
-                    }
-                }
-            }
             if (leader) {
+                if (NTERMS == 3) cv::mma_kblock3(tmem_base, ta, stage_b(s), BN, idesc, idesc16, j == 0);
+                else {
+                    const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks)
+                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + ((uint64_t)(ks * 2 * cv::PK_LBO) >> 4), idesc, (j | ks) != 0);
+                }
                 mma_commit(empty(s));
                 if (j == nkb - 1) mma_commit(accum);
             }

@@ -6,6 +6,7 @@
 // shared memory, 16-byte global loads along whichever dimension the operand is contiguous in.
 #pragma once
 #include "learner.h"
+#include "cvpack.cuh"
 
 template <int BM_, int BN_, int BK_, int TM_, int TN_>
 struct TileCfg {
@@ -335,20 +336,15 @@ struct EpiBiasReluPack {
         float* o = out + (size_t)m * ldo + n;
         const int img = m / ohw, pix = m - img * ohw;
         const int k0 = pix * ldo + n;  // first flat index of this run of TN channels (TN = 16, n % 16 == 0)
-        float* pt = pk ? pk + (size_t)(k0 >> 5) * (2 * pk_rows * 32) + (((img >> 3) * 1024 + ((k0 & 31) >> 2) * 128 + (img & 7) * 16) >> 2)
-                       : nullptr;
+        // the dense layer's B operand: k-block k0 / 32 of pk_rows batch rows in the packed layout of cvpack.cuh
+        uint8_t* blk = pk ? reinterpret_cast<uint8_t*>(pk) + (size_t)(k0 >> 5) * pk_rows * 256 : nullptr;
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
             float4 b;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sbias + 4u * j));
             const float4 r = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f), fmaxf(v[j + 3] + b.w, 0.f));
             *reinterpret_cast<float4*>(o + j) = r;
-            if (pt) {
-                const float4 l = make_float4(r.x - __uint_as_float(__float_as_uint(r.x) & 0xFFFFE000u), r.y - __uint_as_float(__float_as_uint(r.y) & 0xFFFFE000u),
-                                             r.z - __uint_as_float(__float_as_uint(r.z) & 0xFFFFE000u), r.w - __uint_as_float(__float_as_uint(r.w) & 0xFFFFE000u));
-                *reinterpret_cast<float4*>(pt + (j >> 2) * 32) = r;                    // chunk (k0 % 32) / 4 + j / 4: 128 bytes apart
-                *reinterpret_cast<float4*>(pt + (j >> 2) * 32 + pk_rows * 32) = l;     // lo tile follows the hi tile
-            }
+            if (blk) cv::pk_store4(blk, pk_rows, img, (k0 & 31) + j, r);
         }
     }
 };

@@ -209,7 +209,7 @@ struct dqn_learner {
     // image-resident conv kernels (cvgemm.cuh): pre-split, pre-tiled conv weights per tower ([0]=online, [1]=target),
     // kept in sync with the parameter slabs by launch_pack_conv (after every optimizer step / copy / set_param)
     float* packed[2] = {nullptr, nullptr};
-    int64_t pk_off[3] = {0, 0, 0};
+    int64_t pk_off[4] = {0, 0, 0, 0};  // [3]: layer 0 in the uint8 form of the fused tower (cvgemm.cuh pk_store_u8)
     float* packed_dg = nullptr;            // online tower, dgrad operands (flipped / transposed, per stride class) of conv2, conv3
     int64_t pkd_off[3] = {0, 0, 0};
     int64_t pk_floats = 0;
@@ -220,6 +220,7 @@ struct dqn_learner {
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool tower_fused = true;    // option: the conv stack of both towers as one fused kernel on the uint8 batch (cvtower.cuh)
+    int tower_cluster = 4;      // option: CTAs (images) per thread-block cluster of the fused tower sharing one multicast weight stream (1, 2, 4, 8)
     bool xf_valid = false;      // x_f32 holds the f32 copy of the batch the current step trains on
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
     // staging
@@ -307,7 +308,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
 bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, const float* x_tg, int rows_tg);
 bool tower_fused_ready(const dqn_learner* h);
 bool towers_conv_forward_fused(dqn_learner* h, const float* P_on, const uint8_t* s_on, int rows_on, TowerActs& acts_on,
-                               const uint8_t* s_tg, int rows_tg);
+                               const uint8_t* s_tg, int rows_tg, int act_keep_rows = -1);  // -1: activations of every image are stored
 void tower_fc_forward(dqn_learner* h, const float* params, int rows, TowerActs& acts);  // dense + heads after the conv stack
 void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of the packed conv weights
 void launch_pack_conv(dqn_learner* h, int tower);

@@ -223,6 +223,7 @@ static int fc_kchunk() { return 256; }
 void alloc_packed_conv(dqn_learner* h) {
     int64_t off = 0;
     for (int l = 0; l < 3; ++l) { h->pk_off[l] = off; off += (int64_t)cv::packed_floats(h->net.conv[l]); }
+    h->pk_off[3] = off; off += (int64_t)cv::packed_floats(h->net.conv[0]);
     h->pk_floats = off;
     for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->packed[t], (size_t)off * sizeof(float)));
     for (int t = 0; t < 2; ++t) DQN_CUDA_OK(cudaMalloc(&h->act3_pk[t], (size_t)(t == 0 ? 64 : 32) * h->net.flat * 2 * sizeof(float)));
@@ -246,6 +247,7 @@ void launch_pack_conv(dqn_learner* h, int tower) {
         const int K = g.k * g.k * g.cin, N = g.cout;
         if (K % 32 != 0) continue;
         jobs.j[jobs.n++] = {P + h->net.off_cw[l], h->packed[tower] + h->pk_off[l], K, N, g.k, g.s, g.cin, g.cout, 0};
+        if (l == 0) jobs.j[jobs.n++] = {P + h->net.off_cw[l], h->packed[tower] + h->pk_off[3], K, N, g.k, g.s, g.cin, g.cout, 2};
         most = std::max(most, K * N);
         cv::ImgGeom q; cv::Bands bd;
         if (tower == 0 && l > 0 && cv::dgrad_geom(g, q, bd))
@@ -320,7 +322,7 @@ bool tower_fused_ready(const dqn_learner* h) {
 }
 
 bool towers_conv_forward_fused(dqn_learner* h, const float* P_on, const uint8_t* s_on, int rows_on, TowerActs& acts_on,
-                               const uint8_t* s_tg, int rows_tg) {
+                               const uint8_t* s_tg, int rows_tg, int act_keep_rows) {
     const NetDesc& net = h->net;
     if (!tower_fused_ready(h)) return false;
     if (P_on != h->online && P_on != h->target) return false;  // packed weights exist for the handle's two towers only
@@ -331,8 +333,16 @@ bool towers_conv_forward_fused(dqn_learner* h, const float* P_on, const uint8_t*
     const int tw = P_on == h->online ? 0 : 1;
     t.a.in = s_on; t.b.in = s_tg; t.images_a = rows_on;
     for (int l = 0; l < 3; ++l) {
-        t.a.packed[l] = h->packed[tw] + h->pk_off[l]; t.a.bias[l] = P_on + net.off_cb[l]; t.a.act[l] = acts_on.act[l];
-        t.b.packed[l] = h->packed[1] + h->pk_off[l]; t.b.bias[l] = h->target + net.off_cb[l]; t.b.act[l] = h->acts_tg.act[l];
+        const int64_t po = h->pk_off[l == 0 ? 3 : l];  // layer 0: the uint8 form (frame bytes x bf16 pieces of w / 255)
+        t.a.packed[l] = h->packed[tw] + po; t.a.bias[l] = P_on + net.off_cb[l]; t.a.act[l] = acts_on.act[l];
+        t.b.packed[l] = h->packed[1] + po; t.b.bias[l] = h->target + net.off_cb[l]; t.b.act[l] = h->acts_tg.act[l];
+    }
+    // activations to global memory: a training step reads those of the online tower's s rows only (weight gradients, ReLU
+    // gates); act3 of every row is needed where the dense forward does not take the packed tiles
+    const int keep = act_keep_rows < 0 ? rows_on : act_keep_rows;
+    for (int l = 0; l < 3; ++l) {
+        t.a.act_rows[l] = (l == 2 && !pack) ? rows_on : keep;
+        t.b.act_rows[l] = (l == 2 && !pack) ? rows_tg : (act_keep_rows < 0 ? rows_tg : 0);
     }
     t.a.pk = pack ? h->act3_pk[0] : nullptr; t.a.pk_rows = rows_on;
     t.b.pk = pack ? h->act3_pk[1] : nullptr; t.b.pk_rows = rows_tg;
@@ -421,7 +431,10 @@ void debug_conv_layer(dqn_learner* h, int layer, int rows) {
         return;
     }
     if (layer == 4) {
-        DQN_REQUIRE(towers_conv_forward_fused(h, h->online, h->b_states, rows, h->acts_on, nullptr, 0), "fused conv tower not available");
+        // rows % 3 == 0: both towers as in a training step (2/3 online images, 1/3 target images)
+        const int r_on = rows % 3 == 0 ? rows / 3 * 2 : rows, r_tg = rows - r_on;
+        DQN_REQUIRE(towers_conv_forward_fused(h, h->online, h->b_states, r_on, h->acts_on, r_tg ? h->b_states + (size_t)(r_on / 2) * h->state_bytes : nullptr, r_tg),
+                    "fused conv tower not available");
         return;
     }
     const ConvGeom& g = net.conv[layer];

@@ -8,6 +8,7 @@
 // var -= m*lr_t/(sqrt(v)+eps).  ApplyMomentum(nesterov): acc = acc*mom + g; var -= g*lr + acc*mom*lr.
 // All parameters live in one slab, so "multi-tensor apply" is a single elementwise pass.
 #include "learner.h"
+#include "cvpack.cuh"
 #include <algorithm>
 
 // Streaming Adam over one slab range, one-wave grid-stride grid (8 CTAs per SM).  Launch shapes measured inside the
@@ -209,19 +210,20 @@ struct OptRanges { long long beg4[3], n4[3]; int count; };
 // which saves the separate pack launch at the very end of every step.
 struct TailPack {
     int n;
-    struct L { long long w0; int KN, N, k, s, cin, cout; float* fwd; float* dg; } l[3];
+    struct L { long long w0; int KN, N, k, s, cin, cout; float* fwd; float* dg; float* u8; } l[3];
 };
 __device__ __forceinline__ void tail_pack4(const TailPack::L& q, int e, const float4& w) {
     const float v[4] = {w.x, w.y, w.z, w.w};
     const int kk = e / q.N, n = e - kk * q.N;  // HWIO: e = kk * cout + n, the four values are n .. n+3 of one kk
     {
         const int kb = kk >> 5, kin = kk & 31;
-        const size_t tile = (size_t)q.N * 32;
-        float* o = q.fwd + (size_t)kb * 2 * tile + (((n >> 3) * 1024 + (kin >> 2) * 128 + (n & 7) * 16 + (kin & 3) * 4) >> 2);
+        uint8_t* blk = reinterpret_cast<uint8_t*>(q.fwd) + (size_t)kb * q.N * 256;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            o[4 * j] = v[j];
-            o[4 * j + tile] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+        for (int j = 0; j < 4; ++j) cv::pk_store(blk, q.N, n + j, kin, v[j]);
+        if (q.u8) {
+            uint8_t* b8 = reinterpret_cast<uint8_t*>(q.u8) + (size_t)kb * q.N * 256;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cv::pk_store_u8(b8, q.N, n + j, kin, v[j]);
         }
     }
     if (q.dg) {
@@ -232,13 +234,8 @@ __device__ __forceinline__ void tail_pack4(const TailPack::L& q, int e, const fl
         const int th = kt - 1 - kh / q.s, tw = kt - 1 - kw / q.s;
         const int k2 = (th * kt + tw) * q.cout + n;  // co = n .. n+3 -> four consecutive k of the dgrad operand
         const int kb = cls * (Kc >> 5) + (k2 >> 5), kin = k2 & 31;
-        const size_t tile = (size_t)q.cin * 32;
-        float* o = q.dg + (size_t)kb * 2 * tile + (((ci >> 3) * 1024 + (kin >> 2) * 128 + (ci & 7) * 16) >> 2);
-        *reinterpret_cast<float4*>(o) = w;
-        *reinterpret_cast<float4*>(o + tile) = make_float4(v[0] - __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u),
-                                                           v[1] - __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u),
-                                                           v[2] - __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u),
-                                                           v[3] - __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u));
+        uint8_t* blk = reinterpret_cast<uint8_t*>(q.dg) + (size_t)kb * q.cin * 256;
+        cv::pk_store4(blk, q.cin, ci, kin, w);
     }
 }
 
@@ -317,7 +314,8 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
             const int K = g.k * g.k * g.cin, N = g.cout;
             if (K % 32 != 0 || N % 4 != 0) { tp.n = 0; break; }
             tp.l[tp.n++] = {net.off_cw[l], K * N, N, g.k, g.s, g.cin, g.cout, h->packed[0] + h->pk_off[l],
-                            (l > 0 && h->packed_dg && dgrad_pack_ok(h, l)) ? h->packed_dg + h->pkd_off[l] : nullptr};
+                            (l > 0 && h->packed_dg && dgrad_pack_ok(h, l)) ? h->packed_dg + h->pkd_off[l] : nullptr,
+                            l == 0 ? h->packed[0] + h->pk_off[3] : nullptr};
         }
     }
     long long most = 1;

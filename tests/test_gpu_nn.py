@@ -427,7 +427,7 @@ def _run_steps(cfg_name, opts, steps=5):
     return out
 
 
-@pytest.mark.parametrize('opts', [dict(prefetch=0), dict(priorities=0), dict(fc_split_streams=0), dict(defer_adam=1), dict(merge_towers=0), dict(tower_fused=0), dict(tower_fused=0, merge_towers=0), dict(pack_in_tail=0), dict(fuse_td=0),
+@pytest.mark.parametrize('opts', [dict(prefetch=0), dict(priorities=0), dict(fc_split_streams=0), dict(defer_adam=1), dict(merge_towers=0), dict(tower_cluster=1), dict(tower_cluster=2), dict(pack_in_tail=0), dict(fuse_td=0),
                                   dict(fc_tma_adam=1), dict(fc_tma_adam=1, fc_tma_ctas=148), dict(fc_tma_adam=1, fc_tma_ctas=61)],
                          ids=lambda o: '+'.join('%s=%d' % kv for kv in o.items()))
 def test_scheduling_options_are_bit_identical(opts):
@@ -469,12 +469,13 @@ def test_fused_row_kernel_matches_split_path(ctas):
             assert np.array_equal(got[slot][k], got2[slot][k]), (slot, k)
 
 
-@pytest.mark.parametrize('opts', [dict(img_conv=0), dict(img_dgrad=0), dict(fc_tma_fwd=1)],
+@pytest.mark.parametrize('opts', [dict(img_conv=0), dict(img_dgrad=0), dict(fc_tma_fwd=1), dict(tower_fused=0), dict(tower_fused=0, merge_towers=0)],
                          ids=lambda o: '+'.join('%s=%d' % kv for kv in o.items()))
 @pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c3_mspacman_ddp', 'nature84_ddp'])
 def test_kernel_variants_agree(name, opts):
-    """Image-resident conv kernels (forward / dgrad / wgrad) and the TMA-streamed dense forward against the generic
-    implicit-GEMM kernels: a different tiling and summation order of the same 3xTF32 products -- weights after 3 fused
+    """Image-resident conv kernels (forward / dgrad / wgrad), the fused conv tower (layer 0 on the frame bytes x bf16 pieces of
+    w / 255, two accumulators per band) and the TMA-streamed dense forward against the per-layer / generic implicit-GEMM
+    kernels: a different tiling and summation order of fp32-grade products -- weights after 3 fused
     steps agree to 1e-5 of the tensor's scale for >= 95 % of the elements, and to that plus the Adam steps taken (2.5 lr each)
     for the elements whose gradient is within rounding of 0."""
     ref = _run_steps(name, {}, steps=3)
