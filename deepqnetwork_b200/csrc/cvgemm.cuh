@@ -214,11 +214,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 
 template <int BN, int NTERMS>
 struct CvPlan {
-    static constexpr int S = 6;                                   // ring depth: B tiles in smem, A tiles in TMEM
-    static constexpr int B_TILE = BN * 128;                       // bytes of one hi (or lo) tile
-    static constexpr int B_STAGE = B_TILE * 2;                    // hi + lo travel together
+    static constexpr int B_TILE = BN * 128;                       // bytes of the fp32 tile of a k-block (the two bf16 tiles: half each)
+    static constexpr int B_STAGE = B_TILE * 2;                    // one k-block of packed weights (cvpack.cuh)
     static constexpr int ACOLS = BK * (NTERMS == 3 ? 2 : 1);
-    static constexpr int MAXB = 4;                                // bands (accumulators) per image
+    static constexpr int MAXB = 4;                                // bands per CTA; also the number of accumulators / issuing warps
+    static constexpr int DCOLS = MAXB * BN;                       // accumulator a at column a * BN
+    static constexpr int S0 = (512 - DCOLS) / ACOLS;              // ring depth: B tiles in smem, A tiles in TMEM
+    static constexpr int S = S0 > 6 ? 6 : S0;
     static constexpr int BAR_BYTES = 1024 + 4 * 128 * 8;          // barriers, tmem slot, k-block offsets, bias; row tables of 4 bands
 };
 
@@ -237,8 +239,13 @@ __device__ __forceinline__ void load_image_async(uint32_t img, const float* __re
     }
 }
 
-constexpr int CV_THREADS = 320;
+constexpr int CV_THREADS = 416;  // warps 0-7 converters / epilogue, warps 8-11 MMA issuers, warp 12 TMA
 
+// Several MMA-issuing warps: one thread issues a tcgen05.mma every ~53 cycles whatever its shape, the tensor pipe needs N / 2
+// (scratch/ubench/mma_issue.cu), so a single issuer leaves it 40-70 % idle at N <= 64.  The k-blocks of the CTA's bands are
+// walked band-interleaved (step = kb * nb + band) and issuing warp i takes the steps with step % NI == i into ITS OWN
+// accumulator (deterministic order inside each): 4 bands -> one accumulator per band, 2 bands -> two per band (even / odd
+// k-blocks), 1 band -> four; the epilogue adds the accumulators of a band in index order.
 template <int BN, int NTERMS, class Epi>
 __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __restrict__ in_a, const float* __restrict__ packed_a,
                                                                const Epi epi_a, int images_a, const float* __restrict__ in_b,
@@ -276,8 +283,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
     const int band0 = blockIdx.y * bands_per_cta;
     const int nb = min(bd.n - band0, bands_per_cta);
     const int nsteps = nb * g.nkb;
-    constexpr int DCOLS_MIN = 32;
-    const int dcols = nb * BN < DCOLS_MIN ? DCOLS_MIN : nb * BN;  // accumulators: band b at column b*BN
+    // issuing warps == accumulators; accumulator a belongs to band a % nb (nb = 1, 2 or 4).  Warp i's steps all have the parity
+    // of i, i.e. they and every step that shares a stage with them (S is even) come from the SAME converter group, in order:
+    // when the warp waits for a phase of a stage barrier, the phases it skipped (other warps' steps) are complete
+    constexpr int NI = 4;
+    const int per_band = NI / nb;      // accumulators (issuing warps) per band
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
             mbar_init(bfull_bar(s), 1);   // the TMA thread's expect_tx arrival (+ the bytes)
             mbar_init(empty_bar(s), 1);   // tcgen05.commit
         }
-        for (int b = 0; b < P::MAXB; ++b) mbar_init(accum_bar(b), 1);
+        for (int b = 0; b < P::MAXB; ++b) mbar_init(accum_bar(b), per_band);  // the last commit of every issuing warp of the band
         fence_barrier_init();
     }
     if (tid < g.nkb) {
@@ -319,8 +329,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     CV_STAMP(threadIdx.x == 0, 63, 1);
-    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(dcols + s * P::ACOLS); };
+    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(P::DCOLS + s * P::ACOLS); };
     auto stage_b = [&](int s) { return ring + s * P::B_STAGE; };
+    auto step_kb = [&](int step) { return nb == 1 ? step : nb == 2 ? step >> 1 : step >> 2; };
 
     if (warp < 8) {
         pdl_wait();  // the input image is the stream predecessor's output
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         CV_STAMP(tid == 0, 63, 3);
-        // ---------------- A converters ----------------
+        // ---------------- A converters (two groups of 4 warps take alternate steps) ----------------
         const int grp = warp & 3, cg = warp >> 2;  // TMEM lane quarter, converter group
         const int m = grp * 32 + lane;             // row of the band tile
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
@@ -342,33 +353,27 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
         uint32_t choff[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) choff[j] = g.cin >= 32 ? 16u * j : (uint32_t)(((j % g.s) * g.wps + j / g.s) * g.pitch);
-        int step = cg;
-        for (int band = 0; band < nb; ++band) {
-            uint32_t roff;
+        for (int step = cg; step < nsteps; step += 2) {
+            const int kb = step_kb(step), band = step - kb * nb;
+            const int s = step % S, ph = (step / S) & 1;
+            uint32_t roff, koff;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(roff) : "r"(rowtab + 8u * (band * 128 + m)));
-            const uint32_t base = img + roff;
-            const int step_end = (band + 1) * g.nkb;
-            for (; step < step_end; step += 2) {
-                const int kb = step - band * g.nkb;
-                const int s = step % S, ph = (step / S) & 1;
-                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);  // TMEM stage s is free again
-                CV_STAMP(grp == 0 && lane == 0, step, 0);
-                uint32_t koff;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(koff) : "r"(kbtab + 4u * kb));
-                const uint32_t src = base + koff;
-                float hi[32];
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(koff) : "r"(kbtab + 4u * kb));
+            if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);  // TMEM stage s is free again
+            CV_STAMP(grp == 0 && lane == 0, step, 0);
+            const uint32_t src = img + roff + koff;
+            float hi[32];
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + choff[c]));
-                const uint32_t ta = tmem_a(s) + lane_base;
-                if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
-                ts::tmem_st_wait();
-                tc_fence_before();
-                CV_STAMP(grp == 0 && lane == 0, step, 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(afull_bar(s));
-            }
+            for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(hi[4 * c]), "=f"(hi[4 * c + 1]), "=f"(hi[4 * c + 2]), "=f"(hi[4 * c + 3]) : "r"(src + choff[c]));
+            const uint32_t ta = tmem_a(s) + lane_base;
+            if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
+            ts::tmem_st_wait();
+            tc_fence_before();
+            CV_STAMP(grp == 0 && lane == 0, step, 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull_bar(s));
         }
         CV_STAMP(tid == 0, 63, 4);
         pdl_launch_dependents();
@@ -385,63 +390,62 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
             for (int c = 0; c < HC; c += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c, v);
+                for (int a = 1; a < per_band; ++a) {  // the band's other accumulators, in index order
+                    float v1[16];
+                    tmem_ld16(trow + (uint32_t)(a * nb * BN + c), v1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v1[j];
+                }
                 if (mg >= 0) epi.template store_b<16>(mg, cg * HC + c, v, bias_s + 4u * (cg * HC + c));
             }
         }
         tc_fence_before();
         CV_STAMP(tid == 0, 63, 6);
-    } else if (warp == 8) {
-        // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
-        uint32_t leader;
-        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        int s = 0, ph = 0, step = 0;
-        bool ready = false;  // barriers of the current step already seen complete (tested during the previous step)
-        for (int band = 0; band < nb; ++band) {
-            const uint32_t tmem_d = tmem_base + (uint32_t)(band * BN);
-            for (int kb = 0; kb < g.nkb; ++kb, ++step) {
-                if (!ready) {
-                    mbar_wait(afull_bar(s), ph);   // A tile of this step is in tensor memory
-                    mbar_wait(bfull_bar(s), ph);   // B tile has landed (TMA, async proxy: no proxy fence needed)
-                }
+    } else if (warp < 12) {
+        // ---------------- MMA issuers (warps 8-11): warp i takes the steps i, i + NI, ... into accumulator i ----------------
+        const int wi = warp - 8;
+        if (wi < NI) {
+            const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
+            uint32_t leader;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(wi * BN);
+            for (int step = wi; step < nsteps; step += NI) {
+                const int s = step % S, ph = (step / S) & 1;
+                mbar_wait(afull_bar(s), ph);   // A tile of this step is in tensor memory
+                mbar_wait(bfull_bar(s), ph);   // B tile has landed (TMA, async proxy: no proxy fence needed)
                 CV_STAMP(lane == 0, step, 3);
                 tc_fence_after();
-                // the tensor pipe queues only a few MMAs: look at the NEXT step's barriers before issuing this step's,
-                // so that the mbarrier round trip overlaps their execution instead of draining the queue
-                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
-                ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1) && mbar_test(bfull_bar(s1), ph1);
                 const uint32_t ta = tmem_a(s);
+                const bool first = step == wi;
                 if (leader) {
-                    if (NTERMS == 3) mma_kblock3(tmem_d, ta, stage_b(s), BN, idesc, idesc16, kb == 0);
+                    if (NTERMS == 3) mma_kblock3(tmem_d, ta, stage_b(s), BN, idesc, idesc16, first);
                     else {
                         const uint64_t db = make_desc(stage_b(s), PK_LBO, PK_SBO);
 #pragma unroll
                         for (int ks = 0; ks < BK / 8; ++ks)
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, (kb | ks) != 0);
+                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, !(first && ks == 0));
                     }
                     mma_commit(empty_bar(s));
-                    if (kb == g.nkb - 1) mma_commit(accum_bar(band));
+                    if (step + NI >= nsteps) mma_commit(accum_bar(wi % nb));
                 }
                 CV_STAMP(lane == 0, step, 4);
                 __syncwarp();
-                s = s1; ph = ph1;
             }
+            tc_fence_before();
         }
-        tc_fence_before();
     } else {
-        // ---------------- weight TMA producer (warp 9, one lane) ----------------
+        // ---------------- weight TMA producer (warp 12, one lane): band-interleaved like the converters ----------------
         if (lane == 0) {
             pdl_wait();
-            int s = 0, ph = 0, step = 0;
-            for (int band = 0; band < nb; ++band) {
-                const float* src = packed + (size_t)bd.c[band0 + band].pk_kb0 * (P::B_STAGE / 4);
-                for (int kb = 0; kb < g.nkb; ++kb, ++step) {
-                    if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
-                    CV_STAMP(true, step, 5);
-                    mbar_expect_tx(bfull_bar(s), P::B_STAGE);
-                    tma_bulk_g2s(stage_b(s), src + (size_t)kb * (P::B_STAGE / 4), P::B_STAGE, bfull_bar(s));
-                    if (++s == S) { s = 0; ph ^= 1; }
-                }
+            int s = 0, ph = 0;
+            for (int step = 0; step < nsteps; ++step) {
+                const int kb = step_kb(step), band = step - kb * nb;
+                const float* src = packed + (size_t)(bd.c[band0 + band].pk_kb0 + kb) * (P::B_STAGE / 4);
+                if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
+                CV_STAMP(true, step, 5);
+                mbar_expect_tx(bfull_bar(s), P::B_STAGE);
+                tma_bulk_g2s(stage_b(s), src, P::B_STAGE, bfull_bar(s));
+                if (++s == S) { s = 0; ph ^= 1; }
             }
         }
     }
@@ -460,7 +464,9 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
     auto kern = cvconv_kernel<BN, NTERMS, Epi>;
     const size_t bytes = (size_t)P::S * P::B_STAGE + P::BAR_BYTES + g.img_bytes + 1024;
     DQN_REQUIRE(bytes <= 227 * 1024, "image-resident conv: shared memory budget");
-    DQN_REQUIRE(bd.n <= P::MAXB && bd.n * BN + P::S * P::ACOLS <= 512, "image-resident conv: tensor memory budget");
+    static_assert(P::S >= 3 && P::S % 2 == 0 && P::DCOLS + P::S * P::ACOLS <= 512, "image-resident conv: tensor memory budget");
+    DQN_REQUIRE(bd.n <= P::MAXB && g.nkb >= 4, "image-resident conv: bands / k-blocks (every issuing warp needs a step)");
+    DQN_REQUIRE(std::min(bd.n, bands_per_cta) != 3, "image-resident conv: 1, 2 or 4 bands per CTA");
     static size_t configured = 0;  // one per template instantiation
     if (bytes > configured) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -484,16 +490,41 @@ static void launch_conv(dqn_learner* h, const float* in, const float* packed, co
 //   B (smem, rows n = co, k = pixel): dY of the image, transposed once into the dense K-major hi/lo tiles, resident.
 // Accumulators are double-buffered (2 x 64 TMEM columns): a dedicated epilogue warpgroup drains M tile i while the
 // converters and the MMA thread work on tile i+1.
-constexpr int WG_THREADS = 512;  // warps 0-7 converters, 8 MMA, 9 bias row, 10-11 idle, 12-15 epilogue
+// Several MMA-issuing warps (see cvconv_kernel): issuing warp i takes the k-blocks kb % NI == i of every M tile into its own
+// accumulator (two issuing warps: the tensor pipe needs N / 2 cycles per MMA, one thread issues one every ~53).
+constexpr int WG_THREADS = 544;  // warps 0-7 converters, 8-11 MMA issuers (8 allocates TMEM), 12-15 epilogue, 16 bias row
 
 // U8IN (conv1): the layer input is the uint8 frame stack itself.  The image is staged as bytes (one pixel = 4 bytes, rows
 // zero-padded, NOT phase-split: the 32 lanes of a warp are the (kw, ci) of one kernel row and read 32 consecutive bytes)
 // and the converter applies cast / 255 (deep_q_model.py:226-227, exactly rounded) before the hi/lo split.
+// bias row of one image's partial: db[co] = sum over pixels of dY (ascending pixel order), read from the resident fp32 B tiles
+template <int BN>
+__device__ __forceinline__ void wgrad_bias_row(float* __restrict__ part, uint32_t btiles, int b_kb, int image, int mreal, int npix, int lane, bool active) {
+    if (!active) return;
+    float* prow = part + ((size_t)image * (mreal + 4) + mreal) * BN;
+    for (int co = lane; co < BN; co += 32) {
+        float sacc = 0.f;
+        for (int p = 0; p < npix; ++p) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(btiles + (uint32_t)((p >> 5) * b_kb) + pk_off32(co, p & 31)));
+            sacc += v;
+        }
+        prow[co] = sacc;
+    }
+}
+
 template <int BN, int NTERMS, bool U8IN>
 __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __restrict__ xin, const float* __restrict__ dy,
                                                                 float* __restrict__ part, const ImgGeom g, int mreal,
                                                                 int mtiles_per_cta, const float* __restrict__ zeros) {
-    constexpr int S = 6, ACOLS = BK * (NTERMS == 3 ? 2 : 1), B_TILE = BN * 128, B_KB = B_TILE * 2;
+    // issuing warps (8 ..): warp i takes the steps with step % NI == i (step = tile * nkb + kb), so that it waits on the barriers of
+    // the stages s % NI == i only and sees EVERY phase of them (S is a multiple of NI).  A waiter that skips phases of an
+    // mbarrier can find it one phase behind and mistake the preceding phase of the same parity for the one it wants.
+    constexpr int NI = BN == 32 ? 4 : 2;
+    constexpr int DCOLS = 2 * NI * BN;               // double-buffered accumulators: buffer ab, issuer i at column (ab * NI + i) * BN
+    constexpr int ACOLS = BK * (NTERMS == 3 ? 2 : 1), S0 = (512 - DCOLS) / ACOLS, S = (S0 > 6 ? 6 : S0) / NI * NI;
+    constexpr int B_TILE = BN * 128, B_KB = B_TILE * 2;
+    static_assert(S >= 3 && S % NI == 0, "tensor memory budget / stage ownership");
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const int npix = g.oh * g.ow, nkb = (npix + 31) / 32;
@@ -514,7 +545,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(afull_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), NI); mbar_init(acce_bar(b), 4); }
         fence_barrier_init();
     }
     if (warp == 8) {
@@ -572,8 +603,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(2 * BN + s * ACOLS); };
-    const int nsteps = (mt1 - mt0) * nkb;
+    auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(DCOLS + s * ACOLS); };
 
     if (warp < 8) {
         // ---------------- A converters: thread == row m = (tap, ci) of the current M tile ----------------
@@ -623,56 +653,44 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
             }
         }
         pdl_launch_dependents();
-    } else if (warp == 8) {
-        // ---------------- MMA issuer ----------------
-        const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
-        uint32_t leader;
-        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        int s = 0, ph = 0, step = 0;
-        bool ready = false;
-        for (int mt = mt0; mt < mt1; ++mt) {
-            const int ab = (mt - mt0) & 1, use = (mt - mt0) >> 1;
-            if (use >= 1) { mbar_wait(acce_bar(ab), (use - 1) & 1); tc_fence_after(); }  // epilogue has drained this accumulator
-            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
-            for (int kb = 0; kb < nkb; ++kb, ++step) {
-                if (!ready) mbar_wait(afull_bar(s), ph);
-                tc_fence_after();
-                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
-                ready = step + 1 < nsteps && mbar_test(afull_bar(s1), ph1);
-                const uint32_t ta = tmem_a(s);
-                if (leader) {
-                    if (NTERMS == 3) mma_kblock3(tmem_d, ta, btiles + kb * B_KB, BN, idesc, idesc16, kb == 0);
-                    else {
-                        const uint64_t db = make_desc(btiles + kb * B_KB, PK_LBO, PK_SBO);
+    } else if (warp < 12) {
+        // ---------------- MMA issuers (warps 8 .. 8 + NI - 1) ----------------
+        const int wi = warp - 8;
+        if (wi < NI) {
+            const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
+            uint32_t leader;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+            for (int mt = mt0; mt < mt1; ++mt) {
+                const int ab = (mt - mt0) & 1, use = (mt - mt0) >> 1;
+                if (use >= 1) { mbar_wait(acce_bar(ab), (use - 1) & 1); tc_fence_after(); }  // epilogue has drained this buffer
+                const uint32_t tmem_d = tmem_base + (uint32_t)((ab * NI + wi) * BN);
+                const int t0 = (mt - mt0) * nkb, t1 = t0 + nkb;
+                for (int step = t0 + (wi - t0 % NI + NI) % NI; step < t1; step += NI) {  // this warp's steps of the tile (nkb >= NI: at least one)
+                    const int kb = step - t0, s = step % S, ph = (step / S) & 1;
+                    const bool first = step - NI < t0;
+                    mbar_wait(afull_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_a(s);
+                    if (leader) {
+                        if (NTERMS == 3) mma_kblock3(tmem_d, ta, btiles + kb * B_KB, BN, idesc, idesc16, first);
+                        else {
+                            const uint64_t db = make_desc(btiles + kb * B_KB, PK_LBO, PK_SBO);
 #pragma unroll
-                        for (int ks = 0; ks < BK / 8; ++ks)
-                            ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, (kb | ks) != 0);
+                            for (int ks = 0; ks < BK / 8; ++ks)
+                                ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * PK_LBO) >> 4), idesc, !(first && ks == 0));
+                        }
+                        mma_commit(empty_bar(s));
+                        if (step + NI >= t1) mma_commit(accf_bar(ab));
                     }
-                    mma_commit(empty_bar(s));
-                    if (kb == nkb - 1) mma_commit(accf_bar(ab));
+                    __syncwarp();
                 }
-                __syncwarp();
-                s = s1; ph = ph1;
             }
+            tc_fence_before();
         }
-        tc_fence_before();
-    } else if (warp == 9) {
-        // ---------------- bias row: db[co] = sum over pixels of dY (ascending pixel order) ----------------
-        if (blockIdx.y == 0) {
-            float* prow = part + ((size_t)image * (mreal + 4) + mreal) * BN;
-            for (int co = lane; co < BN; co += 32) {
-                float sacc = 0.f;
-                for (int p = 0; p < npix; ++p) {
-                    float v;
-                    const uint32_t a = btiles + (uint32_t)((p >> 5) * B_KB + (co >> 3) * PK_SBO + ((p & 31) >> 2) * PK_LBO + (co & 7) * 16 + (p & 3) * 4);
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-                    sacc += v;
-                }
-                prow[co] = sacc;
-            }
-        }
-    } else if (warp >= 12) {
-        // ---------------- epilogue warpgroup: accumulator of M tile i -> part[image][m][co] ----------------
+    } else if (warp == 16) {
+        wgrad_bias_row<BN>(part, btiles, B_KB, image, mreal, npix, lane, blockIdx.y == 0);
+    } else {
+        // ---------------- epilogue warpgroup (warps 12-15): accumulator of M tile i -> part[image][m][co] ----------------
         const int grp = warp & 3;
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
         for (int mt = mt0; mt < mt1; ++mt) {
@@ -684,8 +702,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
 #pragma unroll
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * BN + c), v);
-                if (c + 16 >= BN) {  // all columns of this accumulator are in registers: hand it back to the MMA thread
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * NI * BN + c), v);
+#pragma unroll
+                for (int i = 1; i < NI; ++i) {  // the other issuing warps' accumulators, in index order
+                    float v1[16];
+                    tmem_ld16(tmem_base + lane_base + (uint32_t)((ab * NI + i) * BN + c), v1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v1[j];
+                }
+                if (c + 16 >= BN) {  // all columns of this buffer are in registers: hand it back to the MMA warps
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(ab));
@@ -723,7 +748,7 @@ static bool launch_wgrad(dqn_learner* h, const void* x, bool u8_states, const fl
         img_bytes = g.img_bytes;
     }
     const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + img_bytes + 1024 + 128;
-    if (bytes > 227 * 1024) return false;
+    if (bytes > 227 * 1024 || nkb < (BN == 32 ? 4 : 2)) return false;  // (every issuing warp needs a k-block in every M tile)
     const int mtiles = (mreal + BM - 1) / BM;
     const int per_cta = mtiles >= 8 ? mtiles / 2 : mtiles;  // two CTAs per image once an image carries >= 8 M tiles
     auto go = [&](auto kern) {

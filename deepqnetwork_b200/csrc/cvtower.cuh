@@ -22,9 +22,9 @@
 //     accumulator (deterministic order inside each), and the epilogue adds the two.
 // Operands and converter roles are those of cvconv_kernel (cvgemm.cuh).
 //
-// Shared memory (C2: 89 x 80 x 4 frames): ring 5 x 16 KB | barriers, tables 8 KB | image A 80.4 KB (conv2 input) |
-// image B 51.9 KB (the uint8 frames, 31.5 KB; re-used as conv3's input once conv1 is done) = 221 KB.
-// Tensor memory: 128 accumulator columns (4 bands x 32 or 2 x 64) + 5 A stages x 64 columns = 448.
+// Shared memory (C2: 89 x 80 x 4 frames): ring 4 x 16 KB | barriers, tables 8 KB | image A 80.4 KB (conv2 input) |
+// image B 51.9 KB (the uint8 frames, 31.5 KB; re-used as conv3's input once conv1 is done) = 205 KB.
+// Tensor memory: 128 accumulator columns (4 bands x 32 or 2 x 64) + 4 A stages x 64 columns = 384.
 #pragma once
 #include "cvgemm.cuh"
 
@@ -51,7 +51,10 @@ struct TowerArgs {
 };
 
 constexpr int TW_THREADS = 544;     // warps 0-7 converters / epilogue, warps 8-11 MMA issuers, warp 12 TMA, warps 13-16 writers
-constexpr int TW_S = 5;             // ring depth (B tiles in shared memory, A tiles in tensor memory)
+constexpr int TW_S = 4;             // ring depth (B tiles in shared memory, A tiles in tensor memory).  == the number of issuing warps:
+                                    // warp i (layer 0) / warp i % 2 (layers 1, 2) waits on the stages s % 4 == i / s % 2 == i only and so
+                                    // sees every phase of their barriers (a waiter that skips phases can mistake an older phase of the
+                                    // same parity for the one it wants)
 constexpr int TW_STAGE = 16384;     // ring slot: one k-block of packed weights of a 64-column layer
 constexpr int TW_DCOLS = 128;       // accumulator columns (4 bands x 32, or 2 k-halves x 64); A stages follow
 constexpr int TW_TAB = 8192;        // barriers 256 | k-block offsets 3 x 256 | bias 3 x 256 | row tables 6 x 128 x 8

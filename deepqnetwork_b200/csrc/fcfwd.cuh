@@ -24,7 +24,7 @@ namespace ff {
 using namespace tc;
 
 struct WMaps { CUtensorMap w[2]; };  // per hidden stream: [flat][hid] f32, box 128 (n) x 32 (k), no swizzle
-constexpr int FF_S = 6, FF_THREADS = 320;
+constexpr int FF_S = 6, FF_THREADS = 416;  // warps 0-7 converters / B producers / epilogue, 8-11 MMA issuers, 12 TMA
 
 // PACKED: the B tiles arrive ready-made (EpiBiasReluPack wrote them), one bulk copy per k-block; warps 4-7 become a second
 // converter group instead of B producers
@@ -32,6 +32,9 @@ template <int BN, int NTERMS, bool PACKED>
 __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __restrict__ act, const float* __restrict__ act_pk, int rows, int flat, int NH, int hid,
                                                               const __grid_constant__ WMaps maps, float* __restrict__ part, int w_policy,
                                                               int kb_per_split, unsigned long long* __restrict__ dbg) {
+    // several MMA-issuing warps (cvgemm.cuh, cvconv_kernel): warp i takes the k-blocks j % NI == i into its own accumulator,
+    // the epilogue adds them in index order
+    constexpr int NI = BN == 32 ? 4 : 2;
     constexpr int S = FF_S, ACOLS = BK * (NTERMS == 3 ? 2 : 1);
     const bool cta0 = dbg && blockIdx.x == 0 && blockIdx.y == 0;
 #define FF_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 64) dbg[(row) * 8 + (col)] = clock64(); } while (0)
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(wfull(s), 1); mbar_init(afull(s), 4); mbar_init(bfull(s), 4); mbar_init(empty(s), 1); }
-        mbar_init(accum, 1);
+        mbar_init(accum, nkb < NI ? (nkb > 0 ? nkb : 1) : NI);  // the last commit of every issuing warp that has a k-block
         fence_barrier_init();
     }
     if (warp == 8) {
@@ -69,10 +72,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     FF_STAMP(threadIdx.x == 0, 63, 1);
-    constexpr int DCOLS = BN < 32 ? 32 : BN;
+    constexpr int DCOLS = NI * BN;
+    static_assert(DCOLS + S * ACOLS <= 512, "tensor memory budget");
     auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(DCOLS + s * ACOLS); };
 
-    if (warp == 9) {
+    if (warp == 12) {
         // ---------------- W boxes by TMA (weights were written by an earlier step: no dependency on the predecessor) ----------------
         if (lane == 0) {
             if (PACKED) pdl_wait();  // the packed activation tiles are the stream predecessor's output
@@ -177,42 +181,36 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
             for (int p = 0; p < PF; ++p)
                 if (j + p < nkb) put_blk(j + p, pf[p]);
         }
-    } else {
-        // ---------------- MMA issue (warp 8) ----------------
+    } else if (warp - 8 < NI) {
+        // ---------------- MMA issuers (warps 8 .. 8 + NI - 1) ----------------
+        const int wi = warp - 8;
         const uint32_t idesc = make_idesc(BN, false, false), idesc16 = cv::make_idesc_bf16(BN);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        int s = 0, ph = 0;
-        bool ready = false;  // this block's barriers were already seen complete while the previous block's MMAs were issued
-        for (int j = 0; j < nkb; ++j) {
-            if (!ready) {
-                mbar_wait(afull(s), ph);
-                if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
-                else mbar_wait(bfull(s), ph);
-            }
+        const uint32_t tmem_d = tmem_base + (uint32_t)(wi * BN);
+        for (int j = wi; j < nkb; j += NI) {
+            const int s = j % S, ph = (j / S) & 1;
+            mbar_wait(afull(s), ph);
+            if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
+            else mbar_wait(bfull(s), ph);
             FF_STAMP(lane == 0, j, 5);
             if (!PACKED) fence_proxy_async();  // B tile: generic -> async proxy
             FF_STAMP(lane == 0, j, 6);
             tc_fence_after();
-            {
-                const int s1 = s + 1 == S ? 0 : s + 1, ph1 = s + 1 == S ? ph ^ 1 : ph;
-                ready = j + 1 < nkb && cv::mbar_test(afull(s1), ph1) && cv::mbar_test(PACKED ? wfull(s1) : bfull(s1), ph1);
-            }
             const uint32_t ta = tmem_a(s);
             if (leader) {
-                if (NTERMS == 3) cv::mma_kblock3(tmem_base, ta, stage_b(s), BN, idesc, idesc16, j == 0);
+                if (NTERMS == 3) cv::mma_kblock3(tmem_d, ta, stage_b(s), BN, idesc, idesc16, j == wi);
                 else {
                     const uint64_t db = make_desc(stage_b(s), cv::PK_LBO, cv::PK_SBO);
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks)
-                        ts::mma_tf32_ts(tmem_base, ta + ks * 8, db + ((uint64_t)(ks * 2 * cv::PK_LBO) >> 4), idesc, (j | ks) != 0);
+                        ts::mma_tf32_ts(tmem_d, ta + ks * 8, db + ((uint64_t)(ks * 2 * cv::PK_LBO) >> 4), idesc, !(j == wi && ks == 0));
                 }
                 mma_commit(empty(s));
-                if (j == nkb - 1) mma_commit(accum);
+                if (j + NI >= nkb) mma_commit(accum);
             }
             FF_STAMP(lane == 0, j, 7);
             __syncwarp();
-            if (++s == S) { s = 0; ph ^= 1; }
         }
         tc_fence_before();
     }
@@ -227,8 +225,17 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
 #pragma unroll
         for (int c = 0; c < HC; c += 16) {
             float v[16];
-            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * HC + c), v);
-            else {
+            if (nkb > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * HC + c), v);
+#pragma unroll
+                for (int i = 1; i < NI; ++i)
+                    if (i < nkb) {  // the other issuing warps' accumulators, in index order
+                        float v1[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * BN + half * HC + c), v1);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] += v1[k];
+                    }
+            } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }

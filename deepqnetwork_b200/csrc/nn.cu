@@ -261,7 +261,7 @@ void launch_pack_conv(dqn_learner* h, int tower) {
 template <class Epi>
 static bool conv_image_resident(dqn_learner* h, const float* in, const float* packed, const Epi& e, const ConvGeom& g, int images) {
     cv::ImgGeom q; cv::Bands bd;
-    if (!h->img_conv || !cv::img_geom(g, q) || q.nbands > 4) return false;
+    if (!h->img_conv || !cv::img_geom(g, q) || q.nbands > 4 || q.nbands == 3 || q.nkb < 4) return false;
     cv::forward_bands(q, bd);
     const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
     if (g.cout == 64) { if (x3) cv::launch_conv<64, 3>(h, in, packed, e, q, bd, images); else cv::launch_conv<64, 1>(h, in, packed, e, q, bd, images); }
@@ -283,7 +283,7 @@ bool towers_conv_forward_merged(dqn_learner* h, const float* x_on, int rows_on, 
     if (h->cfg.math_mode == DQN_MATH_FP32 || !h->img_conv || !h->merge_towers) return false;
     cv::ImgGeom q[3]; cv::Bands bd[3];
     for (int l = 0; l < 3; ++l) {
-        if (!cv::img_geom(net.conv[l], q[l]) || q[l].nbands > 4) return false;
+        if (!cv::img_geom(net.conv[l], q[l]) || q[l].nbands > 4 || q[l].nbands == 3 || q[l].nkb < 4) return false;
         cv::forward_bands(q[l], bd[l]);
     }
     const bool x3 = h->cfg.math_mode == DQN_MATH_TC3X;
@@ -716,7 +716,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             const int Kd = (g.k / g.s) * (g.k / g.s) * g.cout;
             const int ctas = ceil_div(Mc, tc::BM) * ceil_div(g.cin, 32) * Zc;
             cv::ImgGeom q; cv::Bands bd;
-            if (tcm && h->img_conv && h->img_dgrad && cv::dgrad_geom(g, q, bd)) {
+            if (tcm && h->img_conv && h->img_dgrad && cv::dgrad_geom(g, q, bd) && q.nkb >= 4) {
                 // image-resident: one CTA per image holds dY, the stride-parity classes are its accumulators
                 EpiGatePix e{h->d_act[l - 1], acts.act[l - 1], g.cin};
                 const float* pk = h->packed_dg + h->pkd_off[l];
