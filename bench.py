@@ -522,21 +522,44 @@ def main():
                 return L.train_step(uniforms=u_np)
             return L.train_step(rows=draw_rows())
 
-        for i in range(10):
-            agent_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            agent_step(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tm = torch.tensor([dt], device='cuda', dtype=torch.float64)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
-        e2e = dict(value=world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=BATCH * 8, d2h_bytes_per_step=BATCH * 4 + 8 + 4,
-                   steps=e2e_steps, path='DeepQAgent._train_run_train as the drop-in agent runs it: dqn_train_step(h_u = B host draws) -> '
-                   '(step, losses[B], loss) on the host every step; replay, sum tree and batch stay in HBM',
+        def agent_step_async(i):
+            # the same step through dqn_train_step_async / dqn_train_step_result (DeepQAgent with pipeline_train): step i is queued,
+            # then step i-1's (step, losses[B], loss) are read -- every step's draws go in and every step's results come out
+            if cfg['per']:
+                for k in range(BATCH):
+                    u_np[k] = pyrandom.random()
+                L.train_step_async(uniforms=u_np)
+            else:
+                L.train_step_async(rows=draw_rows())
+            return L.train_step_result() if i > 0 else None
+
+        def timed(fn, n, drain=None):
+            for i in range(10):
+                fn(i)
+            if drain:
+                drain()
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n):
+                fn(i)
+            if drain:
+                drain()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tm = torch.tensor([dt], device='cuda', dtype=torch.float64)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dt = float(tm.item())
+            return world * n / dt
+
+        v_sync = timed(agent_step, e2e_steps)
+        v_async = timed(agent_step_async, e2e_steps, drain=lambda: L.train_step_result())
+        e2e = dict(value=v_async, unit=UNIT, h2d_bytes_per_step=BATCH * 8, d2h_bytes_per_step=BATCH * 4 + 8 + 4,
+                   steps=e2e_steps, path='DeepQAgent._train_run_train as the drop-in agent runs it with pipeline_train: '
+                   'dqn_train_step_async(h_u = B host draws from pinned memory) queues step i, dqn_train_step_result returns '
+                   '(step, losses[B], loss) of step i-1 to the host -- every step, in order; replay, sum tree and batch stay in HBM',
+                   synchronous=dict(value=v_sync, unit=UNIT, path='dqn_train_step(h_u) -> (step, losses[B], loss): the host waits for '
+                                    'the step it has just launched'),
                    excluded='replay append (actor side, once per environment step, not per train step)')
 
         # the other integration: seams 3 + 2 + 3 with a HOST replay -- the sampled rows are gathered on the host from a pinned

@@ -71,6 +71,8 @@ _SIGS = {
     'dqn_get_losses': [_P, C.c_int32, _P, _P, _P, _P, _P, _P],
     'dqn_debug_read': [_P, C.c_char_p, _P, C.c_int64],
     'dqn_train_step': [_P, _P, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_float)],
+    'dqn_train_step_async': [_P, _P, _P],
+    'dqn_train_step_result': [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_float)],
     'dqn_train_steps': [_P, C.c_int64],
     'dqn_train_step_phase': [_P, C.c_int32, C.c_double],
     'dqn_phase_wait': [_P, C.c_char_p, _P],

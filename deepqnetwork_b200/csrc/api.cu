@@ -131,6 +131,8 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         DQN_CUDA_OK(cudaMemsetAsync(h->d_sc, 0, sizeof(dqn_learner::Scalars), h->stream));
         DQN_CUDA_OK(cudaMemsetAsync(h->d_dev, 0, sizeof(dqn_learner::DevSizes), h->stream));
         DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc, SC_BLOCK + 4 * (size_t)h->max_rows, cudaHostAllocMapped));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_sc_alt, SC_BLOCK + 4 * (size_t)h->max_rows, cudaHostAllocMapped));
+        for (int k = 0; k < 2; ++k) DQN_CUDA_OK(cudaEventCreateWithFlags(&h->ustep_ev[k], cudaEventDisableTiming));
         set_f2_kernel<<<1, 1, 0, h->stream>>>(&h->d_sc->b1p, 0.9f, &h->d_sc->b2p, 0.999f);
 
         // replay ring + tree
@@ -178,6 +180,7 @@ extern "C" int dqn_create(const dqn_config* cfg, dqn_learner** out) {
         h->b_prio = h->sets[0].prio; h->b_isw64 = h->sets[0].isw64; h->b_u = h->sets[0].u;
         dmalloc(h->b_isw, R);
         DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2, 64 * R, cudaHostAllocMapped));
+        DQN_CUDA_OK(cudaHostAlloc((void**)&h->h_stage2_alt, 64 * R, cudaHostAllocMapped));
         DQN_CUDA_OK(cudaEventCreateWithFlags(&h->stage2_ev, cudaEventDisableTiming));
         dmalloc(h->b_y, R); dmalloc(h->b_maxq, R); dmalloc(h->b_dq, R); dmalloc(h->b_newprio, R);
         dmalloc(h->b_rows, R);
@@ -254,6 +257,10 @@ extern "C" int dqn_destroy(dqn_learner* h) {
     if (h->fa_row_maps) free(h->fa_row_maps);
     for (int t = 0; t < 2; ++t) if (h->ff_maps[t]) free(h->ff_maps[t]);
     if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_sc_alt) cudaFreeHost(h->h_sc_alt);
+    if (h->h_stage2_alt) cudaFreeHost(h->h_stage2_alt);
+    for (int k = 0; k < 2; ++k) if (h->ustep_ev[k]) cudaEventDestroy(h->ustep_ev[k]);
+    if (h->ustep_graph_alt) cudaGraphExecDestroy(h->ustep_graph_alt);
     if (h->h_in_small) cudaFreeHost(h->h_in_small);
     if (h->h_stage2) cudaFreeHost(h->h_stage2);
     if (h->stage2_ev) cudaEventDestroy(h->stage2_ev);
@@ -292,7 +299,7 @@ extern "C" int dqn_set_stream(dqn_learner* h, void* s) {
     API_BEGIN(h)
     DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
     h->stream = s ? (cudaStream_t)s : h->own_stream;
-    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false;
+    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false; h->graph_valid_u_alt = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }
@@ -917,6 +924,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         side_begin(h, sv, 2, 0); launch_optimizer_fc_stream(h, 0, true); side_end(h, sv);
         side_begin(h, sv, 5, 0); launch_optimizer_fc_stream(h, 1, true); side_end(h, sv);
     }
+    if (fused_tower) launch_dense_prefetch(h, true);  // dense kernels -> L2 while the conv towers run
     // the two towers are independent until the TD epilogue: target tower on the side stream
     cudaStream_t saved;
     const int rows_on = h->cfg.use_double ? 2 * n : n;  // double DQN: s and s' share one pass of the online tower
@@ -938,6 +946,7 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
         tower_forward(h, h->online, states2, xf, rows_on, h->acts_on);
     }
     main_wait_side(h);
+    if (fused_tower && h->fc_prefetch) main_wait_side(h, 6);  // (join of the prefetch branch; it ended long ago)
     const bool fuse_td = train && h->fuse_td;
     TdFuse tf{h->acts_on.q, h->acts_on.q + (size_t)n * A, h->acts_tg.q, rewards, cont, isw, grad_scale};
     if (fuse_td) {
@@ -1071,6 +1080,53 @@ static void after_step_host(dqn_learner* h) {
     if (h->cfg.copy_network_steps > 0 && h->host_step % h->cfg.copy_network_steps == 0) launch_copy_network(h);
 }
 
+
+// The drop-in agent's call (DeepQAgent._train_run_train) with HOST draws: ~35 launches replayed as ONE graph.  The draws are
+// copied into a pinned staging block with a fixed address (first node of the graph: H2D of that block); scalars and per-sample
+// losses are written into their pinned mirror by the step's last kernel, so a caller that wants them pays one event wait and no
+// copy operation.  Two slots (staging block, mirror, graph, event each): dqn_train_step_async alternates them, so that the host
+// can queue step i+1 while step i runs and read step i's results afterwards (dqn_train_step_result).
+static void launch_ustep(dqn_learner* h, int slot, const double* u, const int64_t* rows) {
+    const size_t readback = SC_BLOCK + (size_t)h->B * 4;
+    uint8_t* stage = slot ? h->h_stage2_alt : h->h_stage2;
+    dqn_learner::Scalars* mirror = slot ? h->h_sc_alt : h->h_sc;
+    cudaGraphExec_t& gx = slot ? h->ustep_graph_alt : h->ustep_graph;
+    bool& valid = slot ? h->graph_valid_u_alt : h->graph_valid_u;
+    DQN_CUDA_OK(cudaEventSynchronize(h->ustep_ev[slot]));  // the slot's previous launch is complete: block and mirror are free
+    memcpy(stage, u ? (const void*)u : (const void*)rows, (size_t)h->B * 8);
+    select_set(h, 0);
+    if (!gx || !valid) {
+        cudaGraph_t g = nullptr;
+        const int64_t l0 = h->launches, s0 = h->host_step;
+        DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->tail_mirror = reinterpret_cast<float*>(mirror); h->tail_mirror_words = (int)(readback / 4);
+        try {
+            fused_step_launches(h, u ? reinterpret_cast<const double*>(stage) : nullptr,
+                                rows ? reinterpret_cast<const int64_t*>(stage) : nullptr, 1.0, 3);
+            h->tail_mirror = nullptr; h->tail_mirror_words = 0;
+        } catch (...) {
+            h->tail_mirror = nullptr; h->tail_mirror_words = 0;
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+        h->ustep_graph_launches = h->launches - l0;
+        h->launches = l0; h->host_step = s0;
+        if (gx) { cudaGraphExecDestroy(gx); gx = nullptr; }
+        DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&gx, g, cudaGraphInstantiateFlagUseNodePriority));
+        DQN_CUDA_OK(cudaGraphDestroy(g));
+        valid = true;
+    }
+    DQN_CUDA_OK(cudaGraphLaunch(gx, h->stream));
+    DQN_CUDA_OK(cudaEventRecord(h->ustep_ev[slot], h->stream));
+    h->launches += h->ustep_graph_launches;
+    h->host_step++;
+    after_step_host(h);
+}
+
+static void drain_ustep(dqn_learner* h) { h->ustep_pending = 0; h->ustep_slot = 0; h->ustep_read = 0; }
+
 extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* rows, int64_t* step, float* losses, float* loss) {
     API_BEGIN(h)
     DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
@@ -1083,44 +1139,10 @@ extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* ro
     maybe_refresh_stats(h);
     const bool host_draws = u != nullptr || rows != nullptr;
     if (host_draws && !h->profile && h->batch_graph_enabled) {
-        // The drop-in agent's call (DeepQAgent._train_run_train): ~35 launches replayed as ONE graph.  The draws are copied
-        // into a pinned staging block with a fixed address (first node of the graph: H2D of that block); scalars and
-        // per-sample losses are written into their pinned mirror by the step's last kernel, so a caller that wants them
-        // pays one stream synchronisation and no copy operation.
-        const size_t readback = SC_BLOCK + (size_t)h->B * 4;
-        DQN_CUDA_OK(cudaEventSynchronize(h->stage2_ev));  // the previous launch has consumed the staging block
-        memcpy(h->h_stage2, u ? (const void*)u : (const void*)rows, (size_t)h->B * 8);
-        select_set(h, 0);
-        if (!h->ustep_graph || !h->graph_valid_u) {
-            cudaGraph_t g = nullptr;
-            const int64_t l0 = h->launches, s0 = h->host_step;
-            DQN_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            h->tail_mirror = reinterpret_cast<float*>(h->h_sc); h->tail_mirror_words = (int)(readback / 4);
-            try {
-                fused_step_launches(h, u ? reinterpret_cast<const double*>(h->h_stage2) : nullptr,
-                                    rows ? reinterpret_cast<const int64_t*>(h->h_stage2) : nullptr, 1.0, 3);
-                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
-            } catch (...) {
-                h->tail_mirror = nullptr; h->tail_mirror_words = 0;
-                cudaStreamEndCapture(h->stream, &g);
-                if (g) cudaGraphDestroy(g);
-                throw;
-            }
-            DQN_CUDA_OK(cudaStreamEndCapture(h->stream, &g));
-            h->ustep_graph_launches = h->launches - l0;
-            h->launches = l0; h->host_step = s0;
-            if (h->ustep_graph) { cudaGraphExecDestroy(h->ustep_graph); h->ustep_graph = nullptr; }
-            DQN_CUDA_OK(cudaGraphInstantiateWithFlags(&h->ustep_graph, g, cudaGraphInstantiateFlagUseNodePriority));
-            DQN_CUDA_OK(cudaGraphDestroy(g));
-            h->graph_valid_u = true;
-        }
-        DQN_CUDA_OK(cudaGraphLaunch(h->ustep_graph, h->stream));
-        DQN_CUDA_OK(cudaEventRecord(h->stage2_ev, h->stream));
-        h->launches += h->ustep_graph_launches;
-        h->host_step++;
-        after_step_host(h);
+        drain_ustep(h);  // (results of asynchronous steps nobody read are dropped)
+        launch_ustep(h, 0, u, rows);
         if (step || losses || loss) {
-            DQN_CUDA_OK(cudaStreamSynchronize(h->stream));
+            DQN_CUDA_OK(cudaEventSynchronize(h->ustep_ev[0]));
             if (losses) memcpy(losses, reinterpret_cast<const char*>(h->h_sc) + SC_BLOCK, (size_t)h->B * 4);
             if (step) *step = h->h_sc->step;
             if (loss) *loss = h->h_sc->loss;
@@ -1135,6 +1157,35 @@ extern "C" int dqn_train_step(dqn_learner* h, const double* u, const int64_t* ro
         if (step) *step = h->h_sc->step;
         if (loss) *loss = h->h_sc->loss;
     }
+    API_END(h)
+}
+
+extern "C" int dqn_train_step_async(dqn_learner* h, const double* u, const int64_t* rows) {
+    API_BEGIN(h)
+    DQN_REQUIRE(h->ring_size >= 1, "replay is empty");
+    DQN_REQUIRE((u != nullptr) != (rows != nullptr), "dqn_train_step_async: host draws -- uniforms (PER) or rows (uniform sampler)");
+    DQN_REQUIRE((u != nullptr) == (h->cfg.use_per != 0), "dqn_train_step_async: uniforms with use_per, rows without");
+    DQN_REQUIRE(!h->profile && h->batch_graph_enabled, "dqn_train_step_async needs the graph path (no profile mode)");
+    DQN_REQUIRE(h->ustep_pending < 2, "dqn_train_step_async: two steps are in flight, read a result first");
+    if (rows) for (int i = 0; i < h->B; ++i) DQN_REQUIRE(rows[i] >= 0 && rows[i] < h->ring_size, "row index out of range");
+    maybe_refresh_stats(h);
+    launch_ustep(h, h->ustep_slot, u, rows);
+    h->ustep_slot ^= 1;
+    h->ustep_pending++;
+    API_END(h)
+}
+
+extern "C" int dqn_train_step_result(dqn_learner* h, int64_t* step, float* losses, float* loss) {
+    API_BEGIN_KEEP(h)
+    DQN_REQUIRE(h->ustep_pending > 0, "dqn_train_step_result: no asynchronous step in flight");
+    const int slot = h->ustep_read;
+    DQN_CUDA_OK(cudaEventSynchronize(h->ustep_ev[slot]));
+    const dqn_learner::Scalars* mirror = slot ? h->h_sc_alt : h->h_sc;
+    if (losses) memcpy(losses, reinterpret_cast<const char*>(mirror) + SC_BLOCK, (size_t)h->B * 4);
+    if (step) *step = mirror->step;
+    if (loss) *loss = mirror->loss;
+    h->ustep_read ^= 1;
+    h->ustep_pending--;
     API_END(h)
 }
 
@@ -1503,6 +1554,8 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
     else if (n == "tower_fused") h->tower_fused = value != 0;  // conv1..conv3 of both towers as one kernel on the uint8 batch (cvtower.cuh)
+    else if (n == "fc_prefetch") h->fc_prefetch = value != 0;
+    else if (n == "fc_rows_pf") { DQN_REQUIRE(value >= 0 && value <= 16, "fc_rows_pf: 0..16 tiles per CTA ahead"); h->fc_rows_pf = (int)value; }
     else if (n == "tower_cluster") { DQN_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8, "tower_cluster: 1, 2, 4 or 8"); h->tower_cluster = (int)value; }
     else if (n == "img_dgrad") h->img_dgrad = value != 0;
     else if (n == "fuse_td") h->fuse_td = value != 0;
@@ -1513,7 +1566,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "defer_adam") h->defer_adam = value != 0;  // dense-kernel optimizer pass of step i under the conv forward of step i+1
     else if (n == "priorities") h->use_prio = value != 0; // critical-chain kernels dispatch ahead of the multi-wave side kernels
     else throw std::string("unknown option: ") + n;
-    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false;
+    h->graph_valid = false; h->graph_valid_batch = false; h->graph_valid_u = false; h->graph_valid_u_alt = false;
     if (h->prof_graph) { cudaGraphExecDestroy(h->prof_graph); h->prof_graph = nullptr; }
     API_END(h)
 }

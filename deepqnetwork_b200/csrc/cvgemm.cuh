@@ -582,17 +582,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
         const float* dimg = dy + (size_t)image * npix * BN;
         const int pq = lane & 3, cq = lane >> 2;
         const int groups = (nkb * 8) * (BN / 8);  // (pixel quad, channel octet) pairs
-        for (int gi = warp; gi < groups; gi += WG_THREADS / 32) {
-            const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
-            const int p = p4 * 4 + pq, co = c8 * 8 + cq;
-            const float v = p < npix ? __ldg(dimg + (size_t)p * BN + co) : 0.f;
-            const int kb = p >> 5, kin = p & 31;
-            const uint32_t blk = btiles + (uint32_t)(kb * B_KB);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk + pk_off32(co, kin)), "f"(v) : "memory");
-            if (NTERMS == 3) {  // bf16 copies of the cross-term operands (layout of the packed weights)
-                const uint32_t o = blk + pk_off16(co, kin);
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 128u * BN), "h"(bf16_bits(v)) : "memory");
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 192u * BN), "h"(bf16_bits(lo_part(v))) : "memory");
+        // eight passes of loads in flight per thread: issued one at a time (the shared stores are volatile asm, the compiler keeps a
+        // load in front of its store) every pass paid a full L2 round trip -- 15-28 of them were most of this kernel's time
+        constexpr int U = 8, NW = WG_THREADS / 32;
+        for (int g0 = warp; g0 < groups; g0 += NW * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int gi = g0 + u * NW;
+                const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
+                const int p = p4 * 4 + pq, co = c8 * 8 + cq;
+                v[u] = (gi < groups && p < npix) ? __ldg(dimg + (size_t)p * BN + co) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int gi = g0 + u * NW;
+                if (gi >= groups) break;
+                const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
+                const int p = p4 * 4 + pq, co = c8 * 8 + cq;
+                const int kb = p >> 5, kin = p & 31;
+                const uint32_t blk = btiles + (uint32_t)(kb * B_KB);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk + pk_off32(co, kin)), "f"(v[u]) : "memory");
+                if (NTERMS == 3) {  // bf16 copies of the cross-term operands (layout of the packed weights)
+                    const uint32_t o = blk + pk_off16(co, kin);
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 128u * BN), "h"(bf16_bits(v[u])) : "memory");
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 192u * BN), "h"(bf16_bits(lo_part(v[u]))) : "memory");
+                }
             }
         }
     }

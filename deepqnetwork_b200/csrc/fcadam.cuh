@@ -28,6 +28,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+// the box into L2 only (no shared-memory destination, no barrier): a way to have more bytes in flight than the stages hold
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                                                                        const __grid_constant__ RowMaps maps,
                                                                        float lr, float mom, int use_momentum,
                                                                        const dqn_learner::Scalars* __restrict__ sc,
-                                                                       unsigned int* __restrict__ tile_ctr, int l2_keep) {
+                                                                       unsigned int* __restrict__ tile_ctr, int l2_keep, int pf_dist) {
     // Tiles are claimed DYNAMICALLY (atomic counter, stream-major order, so a CTA sees at most one switch of stream): the CTAs of this low-priority
     // kernel get their SMs at different times -- whenever the conv chain of the backward pass leaves some free -- and
     // with a static partition the late starters, each still holding a full share, ended the kernel ~15 us late.
@@ -516,6 +520,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                 const int tt = t < ntotal ? t : -1;
                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_ids + 4u * s), "r"(tt) : "memory");
                 mbar_arrive(id_full(s));  // release: the B producer and the MMA warp may look at the id now
+                // The pass is bound by bytes in flight per SM (3 stages x 48 KB against the loaded HBM latency), not by HBM
+                // bandwidth.  Tiles are claimed in order by the whole grid, so the tile `pf_dist` claims ahead will be wanted by
+                // some CTA a few tile times from now: pull it into L2 (no stage needed), its loads then see L2 latency.
+                if (pf_dist > 0 && t + pf_dist < ntotal) {
+                    const int tp = t + pf_dist, sp = tp / per_stream, rp = tp - sp * per_stream;
+                    const int rowp = (rp / halves) * RT_ROWS, nhp = rp % halves;
+                    tma_prefetch_2d(&maps.w[sp], nhp * RT_N, rowp);
+                    tma_prefetch_2d(&maps.m[sp], nhp * RT_N, rowp);
+                    if (!use_momentum) tma_prefetch_2d(&maps.v[sp], nhp * RT_N, rowp);
+                }
                 if (tt < 0) { mbar_arrive(st_full(s)); return; }
                 const int strm = tt / per_stream, r = tt - strm * per_stream;
                 const int row0 = (r / halves) * RT_ROWS, nh = r % halves;
@@ -742,7 +756,7 @@ static void launch_rows(dqn_learner* h, int rows, int ctas) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(ctas), dim3(RT_THREADS), bytes, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid,
                       rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum,
-                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr, h->l2_keep);
+                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr, h->l2_keep, h->fc_rows_pf * ctas);
     };
     if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_rows_kernel<3>); else go(fcwg_adam_rows_kernel<1>);
     h->launches++;

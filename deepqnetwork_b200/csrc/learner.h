@@ -220,6 +220,8 @@ struct dqn_learner {
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool tower_fused = true;    // option: the conv stack of both towers as one fused kernel on the uint8 batch (cvtower.cuh)
+    int fc_rows_pf = 0;         // option: the fused dense kernel prefetches the tile fc_rows_pf x CTAs claims ahead into L2 (0 = off; measured: 6550-6630 vs 6650-6670 steps/s without -- the pass is not latency-bound in situ)
+    bool fc_prefetch = true;    // option: the dense hidden kernels are prefetched into L2 under the conv towers (nn.cu launch_dense_prefetch)
     int tower_cluster = 4;      // option: CTAs (images) per thread-block cluster of the fused tower sharing one multicast weight stream (1, 2, 4, 8)
     bool xf_valid = false;      // x_f32 holds the f32 copy of the batch the current step trains on
     bool xf_from_gather = false;  // the gather that filled b_states also wrote x_f32 (consumed by the next step_core)
@@ -245,8 +247,13 @@ struct dqn_learner {
     bool graph_valid_batch = false, batch_graph_enabled = true;
     // graph of one fused step fed HOST draws (dqn_train_step with h_u / h_rows: the drop-in agent's call): the draws ride a
     // pinned staging block (fixed address -> memcpy node), scalars + losses come back through the optimizer tail's mirror
-    cudaGraphExec_t ustep_graph = nullptr;
-    bool graph_valid_u = false;
+    cudaGraphExec_t ustep_graph = nullptr, ustep_graph_alt = nullptr;
+    bool graph_valid_u = false, graph_valid_u_alt = false;
+    // asynchronous form (dqn_train_step_async / dqn_train_step_result): two slots {pinned draws, pinned result mirror, graph, event}
+    uint8_t* h_stage2_alt = nullptr;
+    Scalars* h_sc_alt = nullptr;
+    cudaEvent_t ustep_ev[2] = {nullptr, nullptr};
+    int ustep_slot = 0, ustep_read = 0, ustep_pending = 0;
     int64_t ustep_graph_launches = 0;
     int64_t batch_graph_launches = 0;
     int64_t graph_launches = 0;
@@ -314,6 +321,7 @@ void alloc_packed_conv(dqn_learner* h);          // sizes + device buffers of th
 void launch_pack_conv(dqn_learner* h, int tower);
 bool dgrad_pack_ok(const dqn_learner* h, int layer);  // nn.cu: layer has a packed dgrad operand (cv::dgrad_geom)  // re-pack one tower's conv weights from its parameter slab
 void launch_u8_to_f32(dqn_learner* h, const uint8_t* src, float* dst, size_t n);
+void launch_dense_prefetch(dqn_learner* h, bool with_target);
 int selftest_gemm(dqn_learner* h, int mode, int M, int N, int K, int a_kcontig, int b_kcontig, const float* dA, const float* dB, float* dC);
 
 // heads.cu

@@ -219,6 +219,34 @@ static void launch_fc_reduce_heads(dqn_learner* h, const float* P, int splits, i
 
 static int fc_kchunk() { return 256; }
 
+// Pull the dense hidden kernels (2 towers x 31.5 MB at C2) into L2 while the conv towers run: HBM is idle then, a third of the
+// SMs too, and the dense forward / dgrad that follow are streams of exactly these bytes.  One bulk prefetch per 16 KB.
+__global__ void l2_prefetch_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, const float* __restrict__ d,
+                                   unsigned chunks_each) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * chunks_each) return;
+    const unsigned w = i / chunks_each, k = i - w * chunks_each;
+    const float* base = w == 0 ? a : w == 1 ? b : w == 2 ? c : d;
+    if (!base) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (size_t)k * 4096), "r"(16384) : "memory");
+}
+
+// forked at the start of a step (own branch, lowest priority); nothing waits for it
+void launch_dense_prefetch(dqn_learner* h, bool with_target) {
+    const NetDesc& net = h->net;
+    const size_t fcw = (size_t)net.flat * net.hidden;
+    if (!h->fc_prefetch || fcw % 4096 != 0) return;
+    const unsigned chunks = (unsigned)(fcw / 4096);
+    const float* t0 = with_target ? h->target + net.off_fc_w[0] : nullptr;
+    const float* t1 = with_target && net.dueling ? h->target + net.off_fc_w[1] : nullptr;
+    cudaStream_t sv;
+    side_begin(h, sv, 6, 0);
+    launch_kernel(false, l2_prefetch_kernel, dim3(ceil_div(4 * (int)chunks, 128)), dim3(128), 0, h->stream, (const float*)(h->online + net.off_fc_w[0]),
+                  net.dueling ? (const float*)(h->online + net.off_fc_w[1]) : (const float*)nullptr, t0, t1, chunks);
+    h->launches++;
+    side_end(h, sv);
+}
+
 // ---- image-resident conv path (cvgemm.cuh) -------------------------------------------------------------------------
 void alloc_packed_conv(dqn_learner* h) {
     int64_t off = 0;

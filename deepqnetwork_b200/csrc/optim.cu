@@ -247,9 +247,13 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-    for (int q = 0; q < rg.count; ++q) {
-        const size_t o = (size_t)rg.beg4[q], n4 = (size_t)rg.n4[q];
-        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    // the (up to three) parameter ranges as ONE index space: a thread that is active in several ranges would otherwise walk
+    // their load -> update -> store latency chains one after the other (the lowest-numbered CTAs set the kernel's duration)
+    const size_t n0 = rg.count > 0 ? (size_t)rg.n4[0] : 0, n1 = rg.count > 1 ? (size_t)rg.n4[1] : 0, n2 = rg.count > 2 ? (size_t)rg.n4[2] : 0;
+    {
+        for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n0 + n1 + n2; j += (size_t)gridDim.x * blockDim.x) {
+            const int q = j < n0 ? 0 : j < n0 + n1 ? 1 : 2;
+            const size_t o = (size_t)rg.beg4[q], i = j - (q == 0 ? 0 : q == 1 ? n0 : n0 + n1);
             const float4 gg = g[o + i];
             float4 mm = m[o + i], pp = p[o + i];
             if (use_momentum) {

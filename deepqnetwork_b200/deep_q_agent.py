@@ -142,6 +142,7 @@ class DeepQAgent(GameAgent):
         self.memories = ReplayMemory(m.INPUT_HEIGHT, m.INPUT_WIDTH, m.INPUT_CHANNELS, max_size=self.replay_max_memory_length,
                                      state_type=m.STATE_TYPE, learner=learner)
         self.train_batch = None  # the B-row batch is device resident (learner.batch_read() for inspection)
+        self._train_inflight = False  # pipeline_train: a queued step whose result has not been collected yet
         if self.use_per:
             self.per_memory_batch = ReplayMemory(m.INPUT_HEIGHT, m.INPUT_WIDTH, m.INPUT_CHANNELS,
                                                  max_size=self.MAX_MEMORY_BATCH_SIZE, state_type=m.STATE_TYPE, host=True)
@@ -215,14 +216,27 @@ class DeepQAgent(GameAgent):
             u, rows = np.array([random.random() for _ in range(self.batch_size)]), None  # replay_sampler_priority.py:33
         else:
             u, rows = None, self.replay_sampler.draw_rows(self.batch_size)                # replay_sampler.py:30
-        self.step, losses, loss = learner.train_step(uniforms=u, rows=rows)
-        if self.use_per:
-            st = learner.get_stats()
-            self.per_b = st['per_b'] if not self.conf['use_per_annealing'] else self._annealed_beta(self.step)
-            self.last_avg_loss, self.last_max_weight = st['avg'], st['last_max_weight']
-            self.last_min_loss = max(st['min'], self.MIN_ERROR_PRIORITY)
-            self.last_max_loss = min(st['max'], self.MAX_ERROR_PRIORITY)
-        self.total_losses.append(loss)
+        if self.conf.get('pipeline_train'):
+            # queue this step and collect the previous one's loss (it finished while the environment was stepping): the host never
+            # waits for the step it has just launched.  One optimizer step per call, so the step counter is known without a read-back
+            learner.train_step_async(uniforms=u, rows=rows)
+            if self._train_inflight:
+                _, losses, loss = learner.train_step_result()
+                self.total_losses.append(loss)
+            self._train_inflight = True
+            self.step += 1
+        else:
+            self.step, losses, loss = learner.train_step(uniforms=u, rows=rows)
+            self.total_losses.append(loss)
+
+    def _refresh_per_stats(self):
+        """The PER statistics of the report line (deep_q_agent.py:505-510 keeps them on the host; here they live on the device and
+        are read back when a line is printed, not every step)."""
+        st = self.model.learner.get_stats()
+        self.per_b = st['per_b'] if not self.conf['use_per_annealing'] else self._annealed_beta(self.step)
+        self.last_avg_loss, self.last_max_weight = st['avg'], st['last_max_weight']
+        self.last_min_loss = max(st['min'], self.MIN_ERROR_PRIORITY)
+        self.last_max_loss = min(st['max'], self.MAX_ERROR_PRIORITY)
 
     def _annealed_beta(self, step):
         return min(self.per_b_end, self.per_b_start + step * ((self.per_b_end - self.per_b_start) / self.per_anneal_steps))
@@ -245,6 +259,7 @@ class DeepQAgent(GameAgent):
         self.total_losses.clear()
         per_str = ''
         if self.use_per:
+            self._refresh_per_stats()
             per_str = ('per_ab: {:0.2f}/{:0.2f}'.format(self.per_a, self.per_b) +
                        ' avg/min/max loss: {:0.3f}/{:0.3f}/{:0.3f}'.format(self.last_avg_loss, self.last_min_loss, self.last_max_loss) +
                        ' max_weight: {:0.3f} sum total: {:0.1f} '.format(self.last_max_weight, self.replay_sampler.total))
@@ -254,6 +269,9 @@ class DeepQAgent(GameAgent):
 
     def _train_finish(self):
         log('train finish')
+        if self._train_inflight:  # pipeline_train: the last queued step
+            self.total_losses.append(self.model.learner.train_step_result()[2])
+            self._train_inflight = False
         if self.conf.get('use_memory', True):
             # deep_q_agent.py:416-432: the replay goes to disk at exit (own container instead of HDF5, same contents)
             log('saving', len(self.memories), 'memories to disk')

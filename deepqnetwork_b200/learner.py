@@ -337,6 +337,18 @@ class Learner:
         self._c(self._lib.dqn_train_step(self._h, ptr(u), ptr(r), C.byref(step), ptr(losses), C.byref(loss)))
         return step.value, losses, np.float32(loss.value)
 
+    def train_step_async(self, uniforms=None, rows=None):
+        """Queue one step with host draws (copied before the call returns); at most two in flight."""
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        self._c(self._lib.dqn_train_step_async(self._h, ptr(u), ptr(r)))
+
+    def train_step_result(self):
+        """(step, losses[B], loss) of the oldest queued step that has not been read yet; blocks until it has finished."""
+        step = C.c_int64(); loss = C.c_float(); losses = np.empty(self.batch_size, np.float32)
+        self._c(self._lib.dqn_train_step_result(self._h, C.byref(step), ptr(losses), C.byref(loss)))
+        return step.value, losses, np.float32(loss.value)
+
     def train_steps(self, n):
         self._c(self._lib.dqn_train_steps(self._h, int(n)))
 

@@ -183,6 +183,12 @@ int dqn_debug_read(dqn_learner* h, const char* what, float* h_out, int64_t count
  * Parity runs hand in the reference's draws: h_u = B random.random() values (PER) or h_rows = B randint rows
  * (uniform sampler); both NULL -> device Philox. Outputs may be NULL (then there is no D2H and no sync). */
 int dqn_train_step(dqn_learner* h, const double* h_u, const int64_t* h_rows, int64_t* step, float* h_losses, float* loss);
+/* The same step, asynchronous: _train_run_train returns nothing (rl/deep_q_agent.py:326-349; the losses only feed the log line
+ * of _train_report_stats :220-236), so the caller may queue step i+1 -- its B host draws are copied from h_u / h_rows before the
+ * call returns -- while step i runs, and collect (step, losses[B], loss) afterwards.  At most two steps in flight; results come
+ * back in launch order.  dqn_train_step_result blocks until the oldest unread step has finished. */
+int dqn_train_step_async(dqn_learner* h, const double* h_u, const int64_t* h_rows);
+int dqn_train_step_result(dqn_learner* h, int64_t* step, float* h_losses, float* loss);
 /* n back-to-back fused steps (device RNG), target sync every copy_network_steps and PER stats
  * refresh every per_calculate_steps included; returns after enqueueing (call dqn_sync). */
 int dqn_train_steps(dqn_learner* h, int64_t n);

@@ -320,6 +320,40 @@ def test_per_stats_getters_match_numpy():
     L.close()
 
 
+@pytest.mark.parametrize('name', ['c2_breakout_ddp', 'c1_vanilla'])
+def test_async_steps_equal_synchronous_steps(name):
+    """dqn_train_step_async / dqn_train_step_result (two steps in flight, results read one step late) give bit-identical step
+    numbers, losses and weights to the same host draws handed to the synchronous dqn_train_step."""
+    cfg = CONFIGS[name]
+    rng = np.random.RandomState(11)
+    draws = [rng.random_sample(32) if cfg.get('per') else None for _ in range(7)]
+    rows = [None if cfg.get('per') else rng.randint(0, 4096, 32) for _ in range(7)]
+    out = []
+    for mode in ('sync', 'async'):
+        L, spec, shapes, on, tg = make(cfg, capacity=4096, math_mode='tc3x')
+        L.replay_fill_synthetic(4096, seed=5)
+        res = []
+        if mode == 'sync':
+            for u, r in zip(draws, rows):
+                res.append(L.train_step(uniforms=u, rows=r))
+        else:
+            for i, (u, r) in enumerate(zip(draws, rows)):
+                L.train_step_async(uniforms=u, rows=r)
+                if i >= 1:
+                    res.append(L.train_step_result())
+            res.append(L.train_step_result())
+            with pytest.raises(RuntimeError):
+                L.train_step_result()  # nothing in flight any more
+        L.sync()
+        out.append((res, L.get_tower(0), L.tree_read()[0]))
+        L.close()
+    for a, b in zip(out[0][0], out[1][0]):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    assert np.array_equal(out[0][2], out[1][2])
+
+
 @pytest.mark.parametrize('math_mode', MODES)
 def test_graph_replay_equals_eager_steps(math_mode):
     """dqn_train_steps (CUDA-graph replay, device Philox) == the same steps launched one by one."""
@@ -476,16 +510,20 @@ def test_kernel_variants_agree(name, opts):
     """Image-resident conv kernels (forward / dgrad / wgrad), the fused conv tower (layer 0 on the frame bytes x bf16 pieces of
     w / 255, two accumulators per band) and the TMA-streamed dense forward against the per-layer / generic implicit-GEMM
     kernels: a different tiling and summation order of fp32-grade products -- weights after 3 fused
-    steps agree to 1e-5 of the tensor's scale for >= 95 % of the elements, and to that plus the Adam steps taken (2.5 lr each)
-    for the elements whose gradient is within rounding of 0."""
+    steps agree to 1e-5 of the tensor's scale (+ 0.2 % of the Adam steps taken) for >= 95 % of the elements, and to that plus the
+    Adam steps taken (2.5 lr each) for the elements whose gradient is within rounding of 0."""
     ref = _run_steps(name, {}, steps=3)
     got = _run_steps(name, opts, steps=3)
-    assert np.allclose(ref[3], got[3], rtol=1e-4, atol=1e-6)  # sum tree (priorities from the TD errors)
+    # sum tree (priorities from the TD errors): the paths differ by ~1e-6 |q|, which is 1e-3 of a TD error of 1e-3
+    assert np.allclose(ref[3], got[3], rtol=2e-3, atol=1e-5)
     for k in ref[0]:
         scale = float(np.abs(ref[0][k]).max()) + 1e-12
         err = np.abs(ref[0][k] - got[0][k])
         assert float(np.mean(err > 1e-5 * scale + 2.5 * 0.00025 * 3)) == 0.0, k
-        assert float(np.mean(err > 1e-5 * scale)) < 5e-2, k  # Adam turns a gradient within rounding of 0 into +-lr (DESIGN.md D16)
+        # Adam normalises every element by the root of its own second moment: an element whose gradient is 1e-3 of the tensor's
+        # largest and differs by 1e-6 of it between the two kernels moves 1e-3 of an Adam step differently; a gradient within
+        # rounding of 0 becomes +-lr (DESIGN.md D16).  >= 95 % of the elements within 1e-5 of the scale + 0.2 % of the steps taken
+        assert float(np.mean(err > 1e-5 * scale + 2e-3 * 0.00025 * 3)) < 5e-2, k
 
 
 def test_train_batch_default_path_uses_fused_dense_kernel_and_agrees():
