@@ -18,13 +18,13 @@
 //     (scratch/ubench/mma_issue.cu: N = 32 / 64 MMAs from one thread 53 cycles each, from two threads 26.6 / 32.3, from four
 //     16.1 / 32.2 = the tensor pipe's own N / 2), so a single issuer leaves the pipe 40-70 % idle at N <= 64.  Layer 0 (four
 //     bands of 128 output pixels, N = 32): the k-blocks are walked band-interleaved and issuing warp w owns band w (its own
-//     accumulator); layers 1, 2 (one band, N = 64): warp 0 takes the even k-blocks, warp 1 the odd ones, each into its OWN
-//     accumulator (deterministic order inside each), and the epilogue adds the two.
+//     accumulator); layers 1, 2 (one band, N = 64): warp w takes the k-blocks kb % 4 == w, each into its OWN accumulator
+//     (deterministic order inside each), and the epilogue adds the four in index order.
 // Operands and converter roles are those of cvconv_kernel (cvgemm.cuh).
 //
 // Shared memory (C2: 89 x 80 x 4 frames): ring 4 x 16 KB | barriers, tables 8 KB | image A 80.4 KB (conv2 input) |
 // image B 51.9 KB (the uint8 frames, 31.5 KB; re-used as conv3's input once conv1 is done) = 205 KB.
-// Tensor memory: 128 accumulator columns (4 bands x 32 or 2 x 64) + 4 A stages x 64 columns = 384.
+// Tensor memory: 256 accumulator columns (4 bands x 32 or 4 k-quarters x 64) + 4 A stages x 64 columns = 512.
 #pragma once
 #include "cvgemm.cuh"
 
@@ -56,7 +56,7 @@ constexpr int TW_S = 4;             // ring depth (B tiles in shared memory, A t
                                     // sees every phase of their barriers (a waiter that skips phases can mistake an older phase of the
                                     // same parity for the one it wants)
 constexpr int TW_STAGE = 16384;     // ring slot: one k-block of packed weights of a 64-column layer
-constexpr int TW_DCOLS = 128;       // accumulator columns (4 bands x 32, or 2 k-halves x 64); A stages follow
+constexpr int TW_DCOLS = 256;       // accumulator columns (4 bands x 32, or 4 k-quarters x 64); A stages follow
 constexpr int TW_TAB = 8192;        // barriers 256 | k-block offsets 3 x 256 | bias 3 x 256 | row tables 6 x 128 x 8
 constexpr int TW_MAXBANDS = 6;
 
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
         mbar_init(wdone, 4);
         // a band's accumulator(s) are complete: one issuing warp per band (4 bands), or the two k-halves of a single band
         for (int l = 0; l < 3; ++l)
-            for (int b = 0; b < 4; ++b) mbar_init(accum_bar(l, b), t.g[l].nbands == 1 ? 2 : 1);
+            for (int b = 0; b < 4; ++b) mbar_init(accum_bar(l, b), t.g[l].nbands == 1 ? 4 : 1);
         fence_barrier_init();
     }
     if (tid < 192) {
@@ -137,13 +137,20 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
             const int band = e >> 7, m = e & 127;
             const int a0 = band * g.th, na = min(g.th, g.oh - a0);
             const int ai = m / g.ow, bi = m - ai * g.ow;
-            int off = 0, opix = -1;  // rows past the band: any finite data, never stored
+            // {byte offset of the row's input pixel, where its output goes}: layers 0, 1 -> byte offset of the pixel in the next
+            // layer's resident image; layer 2 -> output pixel index; -1: rows past the band (any finite data, never stored)
+            int off = 0, dst = -1;
             if (ai < na) {
                 const int a = a0 + ai;
                 off = l == 0 ? a * g.s * t.u8_row + bi * g.s * g.cin : (a * g.s * g.wcols + bi) * g.pitch;
-                opix = a * g.ow + bi;
+                dst = a * g.ow + bi;
+                if (l < 2) {
+                    const ImgGeom& n = t.g[l + 1];
+                    const int r = a + n.pt, col = bi + n.pl;
+                    dst = (r * n.wcols + (col % n.s) * n.wps + col / n.s) * n.pitch;
+                }
             }
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowtab + 8u * ((t.rt0[l] + band) * 128 + m)), "r"(off), "r"(opix) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowtab + 8u * ((t.rt0[l] + band) * 128 + m)), "r"(off), "r"(dst) : "memory");
         }
     }
     if (warp == 8) {
@@ -208,27 +215,21 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
             const bool ksplit = g.nbands == 1;  // two accumulators (even / odd k-blocks) to add
             const uint32_t trow = tmem_base + lane_base + (uint32_t)(band * BN + cg * HC);
             TW_STAMP(tid == 0, 100 + l * 4 + band, 0);
-            uint32_t sdst = 0;
-            bool to_smem = false;
-            if (l == 2) {  // the last layer's output is staged in image A (dead by now) for the writer warps
-                to_smem = opix >= 0;
-                sdst = imgs + t.img_off[1] + (uint32_t)(opix * (BN * 4 + 16));
-            } else if (opix >= 0) {
-                const ImgGeom& n = t.g[l + 1];
-                const int a = opix / g.ow, b = opix - a * g.ow;
-                const int r = a + n.pt, col = b + n.pl;
-                to_smem = r < n.hp && col < n.wcols;
-                const int phase = col % n.s, j = col / n.s;
-                sdst = imgs + t.img_off[l + 1] + (uint32_t)((r * n.wcols + phase * n.wps + j) * n.pitch);
-            }
+            // layers 0, 1: the row table holds the pixel's place in the next layer's image; the last layer's output is staged in
+            // image A (dead by now) for the writer warps, one pixel every cout * 4 + 16 bytes
+            const bool to_smem = opix >= 0;
+            const uint32_t sdst = l == 2 ? imgs + t.img_off[1] + (uint32_t)(opix * (BN * 4 + 16)) : imgs + t.img_off[l + 1] + (uint32_t)opix;
             for (int c = 0; c < HC; c += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c, v);
                 if (ksplit) {
-                    float v1[16];
-                    tmem_ld16(trow + (uint32_t)(BN + c), v1);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += v1[j];  // even k-blocks + odd k-blocks
+                    for (int a = 1; a < 4; ++a) {  // the other issuing warps' accumulators (k-blocks kb % 4 == a), in index order
+                        float v1[16];
+                        tmem_ld16(trow + (uint32_t)(a * BN + c), v1);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += v1[j];
+                    }
                 }
                 TW_STAMP(tid == 0, 100 + l * 4 + band, 1 + (c >> 4));
                 if (opix < 0) continue;
@@ -330,16 +331,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
         }
     } else if (warp < 12) {
         // ---------------- MMA issuers (warps 8-11) ----------------
-        // a layer of 4 bands: warp w owns band w (steps kb * 4 + w); a layer of one band: warps 0, 1 own the even / odd
-        // k-blocks, each with its own accumulator; every warp walks ITS steps in order
+        // a layer of 4 bands: warp w owns band w (steps kb * 4 + w); a layer of one band: warp w owns the k-blocks kb % 4 == w,
+        // each with its own accumulator; every warp walks ITS steps in order (per issuing warp a step costs ~8 x 53 cycles of
+        // issue + ~500 of barrier waits and commits: four of them keep the tensor pipe, 8 x 32 cycles per step, busy)
         const int w = warp - 8;
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         int step0 = 0, bstep0 = 0;  // first step of the layer; first weight-ring step of the layer (layer 0 does not use the ring)
         for (int l = 0; l < 3; ++l) {
             const int BN = t.g[l].cout, nkb = t.g[l].nkb, nb = t.g[l].nbands;
-            const int stride = nb == 1 ? 2 : 4;  // distance between this warp's steps
-            if (w < stride) {
+            constexpr int stride = 4;  // distance between this warp's steps (== TW_S: the warp owns stage w)
+            {
                 const uint32_t idesc = make_idesc(BN, false, false), idesc16 = make_idesc_bf16(BN);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(w * BN);
                 const int last = step0 + nkb * nb;
@@ -465,12 +467,15 @@ static inline bool tower_plan(const ConvGeom* conv, TowerArgs& t, size_t& smem_b
         ImgGeom& q = t.g[l];
         // 4 bands: one issuing warp per band; 1 band: two issuing warps, each >= 1 k-block and its own accumulator
         if (!img_geom(conv[l], q) || (q.nbands != 1 && q.nbands != 4) || q.nbands * q.cout > TW_DCOLS || q.nkb < 2) return false;
-        if (q.nbands == 1 && 2 * q.cout > TW_DCOLS) return false;
+        if (q.nbands == 1 && (4 * q.cout > TW_DCOLS || q.nkb < 4)) return false;
         if (l > 0 && (conv[l].cin % 32 != 0 || conv[l].cin != conv[l - 1].cout || conv[l].ih != conv[l - 1].oh || conv[l].iw != conv[l - 1].ow)) return false;
         t.rt0[l] = bands;
         bands += q.nbands;
     }
     if (bands > TW_MAXBANDS) return false;
+    for (int l = 1; l < 3; ++l)  // layer l-1's whole output is resident as layer l's image (the writer warps copy it from there)
+        if (t.g[l].hp < conv[l].ih + conv[l].pt || t.g[l].wcols < conv[l].iw + conv[l].pl) return false;
+    if ((t.g[0].nbands * t.g[0].nkb) % TW_S != 0 || (t.g[1].nbands * t.g[1].nkb) % TW_S != 0) return false;  // issuing warp w keeps stage w
     const ConvGeom& g0 = conv[0];
     if (g0.cin != 4 || g0.k != 8 || g0.s * g0.cin != 16) return false;  // a k-block = one kernel row = 32 bytes, pixels 16 bytes apart
     t.u8_row = ((g0.ow - 1) * g0.s + g0.k) * g0.cin;
