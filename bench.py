@@ -85,6 +85,9 @@ def kernel_bytes(name, cfg, nn):
     acts = [g['oh'] * g['ow'] * g['cout'] for g in geo]
     wts = [g['k'] * g['k'] * g['cin'] * g['cout'] for g in geo]
     ins = [nn['S'] // 4 * 1, acts[0], acts[1]]  # elements per sample feeding conv l (conv1 input counted as bytes below)
+    if base == 'conv_tower_fwd':   # fused conv tower, both towers: frames in (uint8), fp32 weights of both towers once, the
+        # training rows' activations out (the backward pass reads them) + conv3's output of every row (the dense layer's operand)
+        return (rows_on + B) * nn['S'] + 2 * sum(wts) * 4 + B * (acts[0] + acts[1]) * 4 + (rows_on + B) * acts[2] * 4
     if base.startswith('conv') and base.endswith('_fwd'):
         l = int(base[4]) - 1
         in_b = rows * nn['S'] if l == 0 else rows * acts[l - 1] * 4
