@@ -1870,8 +1870,9 @@ extern "C" int dqn_debug_timeline(dqn_learner* h, int32_t mode, int32_t M, int32
     unsigned long long* dT = nullptr;
     if (mode >= 16) {  // conv layer (mode - 16) of the online tower over M images, in place on the tower's buffers
         // mode 20: the fused conv tower (cvtower.cuh) of the online tower over M images of the sampled batch; 1024 marks
-        DQN_REQUIRE(mode - 16 <= 4 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
-        const int marks = mode == 20 ? 1024 : 512;
+        // modes 21-23: the image-resident weight gradient of conv layer 1-3 (1024 marks as well)
+        DQN_REQUIRE(mode - 16 <= 7 && M >= 1 && M <= 2 * h->max_rows, "debug conv layer / rows");
+        const int marks = mode >= 20 ? 1024 : 512;
         dmalloc(dT, 1024);
         DQN_CUDA_OK(cudaMemsetAsync(dT, 0, 1024 * 8, h->stream));
         debug_conv_layer(h, mode - 16, M);

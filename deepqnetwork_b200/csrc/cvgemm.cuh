@@ -516,7 +516,11 @@ __device__ __forceinline__ void wgrad_bias_row(float* __restrict__ part, uint32_
 template <int BN, int NTERMS, bool U8IN>
 __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __restrict__ xin, const float* __restrict__ dy,
                                                                 float* __restrict__ part, const ImgGeom g, int mreal,
-                                                                int mtiles_per_cta, const float* __restrict__ zeros) {
+                                                                int mtiles_per_cta, const float* __restrict__ zeros,
+                                                                unsigned long long* __restrict__ dbg, int smem_bytes) {
+    const bool cta0 = dbg && blockIdx.x == 0 && blockIdx.y == 0;  // in-kernel timeline (dqn_debug_timeline, modes 21-23)
+#define WG_STAMP(cond, row, col) do { if (cta0 && (cond) && (row) < 128) dbg[(row) * 8 + (col)] = clock64(); } while (0)
+    WG_STAMP(threadIdx.x == 0, 127, 0);
     // issuing warps (8 ..): warp i takes the steps with step % NI == i (step = tile * nkb + kb), so that it waits on the barriers of
     // the stages s % NI == i only and sees EVERY phase of them (S is a multiple of NI).  A waiter that skips phases of an
     // mbarrier can find it one phase behind and mistake the preceding phase of the same parity for the one it wants.
@@ -532,6 +536,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
     const uint32_t bars = btiles + nkb * B_KB;             // afull[S], empty[S], acc_full[2], acc_empty[2], tmem slot
     const uint32_t pixtab = bars + 256;                    // int pixoff[nkb * 32]
     const uint32_t img = pixtab + 4u * nkb * 32;
+    const uint32_t stg = (sbase + (uint32_t)smem_bytes - (uint32_t)(BM * BN * 4) - 1024u) & ~127u;  // epilogue staging tile (end of the block)
     auto afull_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
     auto accf_bar = [&](int b) { return bars + 8u * (2 * S + b); };
@@ -559,7 +564,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
         const int off = p >= npix ? 0 : U8IN ? oy * g.s * u8_row + ox * g.s * g.cin : (oy * g.s * g.wcols + ox) * g.pitch;
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(pixtab + 4u * p), "r"(off) : "memory");
     }
+    WG_STAMP(threadIdx.x == 0, 127, 1);
     pdl_wait();
+    WG_STAMP(threadIdx.x == 0, 127, 2);
     // ---- stage the image and dY (all threads) ----
     if constexpr (U8IN) {
         // 8-byte cp.async chunks: a padded row = [pl pixels of zeros][iw pixels][zeros]; pl * cin and iw * cin are multiples of 8
@@ -577,45 +584,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
         load_image_async(img, static_cast<const float*>(xin) + (size_t)image * g.ih * g.iw * g.cin, g, tid, WG_THREADS, zeros);
     }
     {
-        // dY[p][co] -> B(co, p): a warp covers 4 pixels x 8 channels per pass, lane = (p % 4) + 4 * (co % 8), so the
-        // 32 scalar stores of a pass fall into 32 consecutive words of one core matrix (conflict-free)
+        // dY[p][co] -> B(co, p): a thread takes 4 consecutive pixels (k) of one channel -- four scalar loads, coalesced over the
+        // warp's 32 consecutive channels -- and writes them as one 16-byte (fp32 tile) and two 8-byte (bf16 tiles) shared stores.
+        // (One element per thread and pass, three scalar stores each, was ~60 instructions per element: 7 k cycles of issue for
+        // conv1's 460 x 32 gradient, a third of that kernel's time -- tools/wgrad_timeline.py.)
         const float* dimg = dy + (size_t)image * npix * BN;
-        const int pq = lane & 3, cq = lane >> 2;
-        const int groups = (nkb * 8) * (BN / 8);  // (pixel quad, channel octet) pairs
-        // eight passes of loads in flight per thread: issued one at a time (the shared stores are volatile asm, the compiler keeps a
-        // load in front of its store) every pass paid a full L2 round trip -- 15-28 of them were most of this kernel's time
-        constexpr int U = 8, NW = WG_THREADS / 32;
-        for (int g0 = warp; g0 < groups; g0 += NW * U) {
-            float v[U];
+        constexpr int CG = BN / 32, NW = WG_THREADS / 32;
+        for (int it = warp; it < nkb * 8 * CG; it += NW) {
+            const int p4 = it / CG, co = (it - p4 * CG) * 32 + lane, p0 = p4 * 4;
+            float v[4];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int gi = g0 + u * NW;
-                const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
-                const int p = p4 * 4 + pq, co = c8 * 8 + cq;
-                v[u] = (gi < groups && p < npix) ? __ldg(dimg + (size_t)p * BN + co) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int gi = g0 + u * NW;
-                if (gi >= groups) break;
-                const int p4 = gi / (BN / 8), c8 = gi - p4 * (BN / 8);
-                const int p = p4 * 4 + pq, co = c8 * 8 + cq;
-                const int kb = p >> 5, kin = p & 31;
-                const uint32_t blk = btiles + (uint32_t)(kb * B_KB);
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk + pk_off32(co, kin)), "f"(v[u]) : "memory");
-                if (NTERMS == 3) {  // bf16 copies of the cross-term operands (layout of the packed weights)
-                    const uint32_t o = blk + pk_off16(co, kin);
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 128u * BN), "h"(bf16_bits(v[u])) : "memory");
-                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(o + 192u * BN), "h"(bf16_bits(lo_part(v[u]))) : "memory");
-                }
+            for (int j = 0; j < 4; ++j) v[j] = p0 + j < npix ? __ldg(dimg + (size_t)(p0 + j) * BN + co) : 0.f;
+            const int kb = p0 >> 5, kin = p0 & 31;
+            const uint32_t blk = btiles + (uint32_t)(kb * B_KB);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + pk_off32(co, kin)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+            if (NTERMS == 3) {  // bf16 copies of the cross-term operands (layout of the packed weights)
+                const uint32_t o = blk + pk_off16(co, kin);
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o + 128u * BN), "r"(bf16_pair(v[0], v[1])), "r"(bf16_pair(v[2], v[3])) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o + 192u * BN), "r"(bf16_pair(lo_part(v[0]), lo_part(v[1]))),
+                             "r"(bf16_pair(lo_part(v[2]), lo_part(v[3]))) : "memory");
             }
         }
     }
+    WG_STAMP(threadIdx.x == 0, 127, 3);
     asm volatile("cp.async.wait_all;" ::: "memory");
     fence_proxy_async();  // the B tiles were written through the generic proxy and are read by the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    WG_STAMP(threadIdx.x == 0, 127, 4);
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(DCOLS + s * ACOLS); };
@@ -639,6 +636,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                 const int kb = step - (mt - mt0) * nkb;
                 const int s = step % S, ph = (step / S) & 1;
                 if (step >= S) mbar_wait(empty_bar(s), ph ^ 1);
+                WG_STAMP(grp == 0 && lane == 0, step, 0);
                 float hi[32];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -663,6 +661,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                 if (NTERMS == 3) a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
                 ts::tmem_st_wait();
                 tc_fence_before();
+                WG_STAMP(grp == 0 && lane == 0, step, 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull_bar(s));
             }
@@ -684,6 +683,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                     const int kb = step - t0, s = step % S, ph = (step / S) & 1;
                     const bool first = step - NI < t0;
                     mbar_wait(afull_bar(s), ph);
+                    WG_STAMP(lane == 0, step, 3);
                     tc_fence_after();
                     const uint32_t ta = tmem_a(s);
                     if (leader) {
@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                         mma_commit(empty_bar(s));
                         if (step + NI >= t1) mma_commit(accf_bar(ab));
                     }
+                    WG_STAMP(lane == 0, step, 4);
                     __syncwarp();
                 }
             }
@@ -708,12 +709,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
         // ---------------- epilogue warpgroup (warps 12-15): accumulator of M tile i -> part[image][m][co] ----------------
         const int grp = warp & 3;
         const uint32_t lane_base = (uint32_t)(grp * 32) << 16;
+        // The tile goes to global memory through a staging copy in shared memory and leaves it as whole 128-byte lines (a warp
+        // instruction = 512 contiguous bytes of part[image][m][:]).  Stored row by row from registers -- 32 lanes x 16 bytes at a
+        // 256-byte pitch, 32 lines per instruction -- the epilogue held the LSU for ~2000 cycles per tile and stalled the converters'
+        // shared-memory loads of the next tile for as long (tools/wgrad_timeline.py).  A warp stages and reads back its own 32 rows.
+        const int r = grp * 32 + lane;
+        constexpr int NCH = BN / 4, RPI = 32 / NCH;  // 16-byte chunks per row; rows per read-back instruction
         for (int mt = mt0; mt < mt1; ++mt) {
             const int ab = (mt - mt0) & 1, use = (mt - mt0) >> 1;
             mbar_wait(accf_bar(ab), use & 1);
             tc_fence_after();
-            const int m = mt * BM + grp * 32 + lane;
-            float* o = part + ((size_t)image * (mreal + 4) + m) * BN;
+            WG_STAMP(warp == 12 && lane == 0, 100 + (mt - mt0), 0);
 #pragma unroll
             for (int c = 0; c < BN; c += 16) {
                 float v[16];
@@ -730,19 +736,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(ab));
                 }
-                if (m < mreal) {
+                // the four 16-byte chunks of this column group, each lane starting at a different one: rows are 128 / 256 bytes
+                // apart (the same banks), so the same chunk from 8 lanes would be an 8-way conflict; rotated it is 2-way
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int jq = 0; jq < 4; ++jq) {
+                    const int q = (jq + r) & 3;
+                    const float x0 = q == 0 ? v[0] : q == 1 ? v[4] : q == 2 ? v[8] : v[12];
+                    const float x1 = q == 0 ? v[1] : q == 1 ? v[5] : q == 2 ? v[9] : v[13];
+                    const float x2 = q == 0 ? v[2] : q == 1 ? v[6] : q == 2 ? v[10] : v[14];
+                    const float x3 = q == 0 ? v[3] : q == 1 ? v[7] : q == 2 ? v[11] : v[15];
+                    const uint32_t a = stg + (uint32_t)(r * BN * 4 + (c + 4 * q) * 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
                 }
             }
+            __syncwarp();
+            float* o = part + ((size_t)image * (mreal + 4) + (size_t)mt * BM + grp * 32) * BN;
+            const int rows_valid = mreal - mt * BM - grp * 32;  // rows of this warp's 32 that exist (all of them but in a ragged last tile)
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int row = i * RPI + lane / NCH, ch = lane % NCH;
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                             : "r"(stg + (uint32_t)((grp * 32 + row) * BN * 4 + ch * 16)));
+                if (row < rows_valid) *reinterpret_cast<float4*>(o + (size_t)row * BN + ch * 4) = x;
+            }
+            __syncwarp();  // the staging rows are free again
         }
         tc_fence_before();
+        WG_STAMP(warp == 12 && lane == 0, 127, 5);
     }
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    WG_STAMP(threadIdx.x == 0, 127, 6);
+#undef WG_STAMP
 }
 
 // true if launched: part[image][mreal + 4][N] holds the per-image partial sums (bias row at m = mreal).  u8_states: the
@@ -762,14 +791,14 @@ static bool launch_wgrad(dqn_learner* h, const void* x, bool u8_states, const fl
         if (g.cin % 32 != 0 || npix > 128) return false;
         img_bytes = g.img_bytes;
     }
-    const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + img_bytes + 1024 + 128;
+    const size_t bytes = (size_t)nkb * BN * 256 + 256 + 4 * nkb * 32 + img_bytes + 1024 + 128 + (size_t)BM * BN * 4 + 1024 + 128;  // .. + staging tile
     if (bytes > 227 * 1024 || nkb < (BN == 32 ? 4 : 2)) return false;  // (every issuing warp needs a k-block in every M tile)
     const int mtiles = (mreal + BM - 1) / BM;
     const int per_cta = mtiles >= 8 ? mtiles / 2 : mtiles;  // two CTAs per image once an image carries >= 8 M tiles
     auto go = [&](auto kern) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(images, (mtiles + per_cta - 1) / per_cta), dim3(WG_THREADS), bytes, h->stream, x, dy, part, g, mreal,
-                      per_cta, (const float*)h->zeros16);
+                      per_cta, (const float*)h->zeros16, h->tc_dbg, (int)bytes);
     };
     if (u8_states) go(cvwgrad_kernel<BN, NTERMS, true>); else go(cvwgrad_kernel<BN, NTERMS, false>);
     h->launches++;

@@ -458,6 +458,17 @@ void debug_conv_layer(dqn_learner* h, int layer, int rows) {
         tower_fc_heads(h, h->online, rows, h->acts_on, false);
         return;
     }
+    if (layer >= 5 && layer <= 7) {  // image-resident weight gradient of conv layer (layer - 5) on the buffers of the last training step
+        const int l = layer - 5;
+        const ConvGeom& g = net.conv[l];
+        cv::ImgGeom q;
+        DQN_REQUIRE(cv::img_geom(g, q), "debug wgrad geometry");
+        const void* xin = l == 0 ? (const void*)h->b_states : (const void*)h->acts_on.act[l - 1];
+        float* part = h->wg_part + h->wg_off[l];
+        const bool ok = g.cout == 64 ? cv::launch_wgrad<64, 3>(h, xin, l == 0, h->d_act[l], part, q, rows) : cv::launch_wgrad<32, 3>(h, xin, l == 0, h->d_act[l], part, q, rows);
+        DQN_REQUIRE(ok, "debug wgrad launch");
+        return;
+    }
     if (layer == 4) {
         // rows % 3 == 0: both towers as in a training step (2/3 online images, 1/3 target images)
         const int r_on = rows % 3 == 0 ? rows / 3 * 2 : rows, r_tg = rows - r_on;

@@ -397,7 +397,7 @@ class Learner:
 
     def debug_timeline(self, mode, M, N, K, a_kcontig=True, b_kcontig=True):
         m = mode if isinstance(mode, int) else {'fp32': 0, 'tc3x': 1, 'tc1x': 2}[mode]
-        out = np.zeros(1024 if m == 20 else 512, np.uint64)  # mode 20: the fused conv tower, 128 rows of marks
+        out = np.zeros(1024 if m >= 20 else 512, np.uint64)  # modes 20-23: fused conv tower / conv weight gradients, 128 rows of marks
         self._c(self._lib.dqn_debug_timeline(self._h, m, M, N, K, int(a_kcontig), int(b_kcontig), ptr(out)))
         return out.reshape(-1, 8)
 
