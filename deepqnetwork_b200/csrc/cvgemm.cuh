@@ -388,14 +388,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) cvconv_kernel(const float* __re
             const uint32_t trow = tmem_base + lane_base + (uint32_t)(band * BN + cg * HC);
 #pragma unroll
             for (int c = 0; c < HC; c += 16) {
-                float v[16];
-                tmem_ld16(trow + (uint32_t)c, v);
-                for (int a = 1; a < per_band; ++a) {  // the band's other accumulators, in index order
-                    float v1[16];
-                    tmem_ld16(trow + (uint32_t)(a * nb * BN + c), v1);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += v1[j];
-                }
+                float v[16];  // the band's accumulators (index order), one wait for all of them
+                const uint32_t t0 = trow + (uint32_t)c, ts_ = (uint32_t)(nb * BN);
+                if (per_band == 4) tmem_ld16_sum4(t0, t0 + ts_, t0 + 2 * ts_, t0 + 3 * ts_, v);
+                else if (per_band == 2) tmem_ld16_sum2(t0, t0 + ts_, v);
+                else tmem_ld16(t0, v);
                 if (mg >= 0) epi.template store_b<16>(mg, cg * HC + c, v, bias_s + 4u * (cg * HC + c));
             }
         }
@@ -722,15 +719,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) cvwgrad_kernel(const void* __re
             WG_STAMP(warp == 12 && lane == 0, 100 + (mt - mt0), 0);
 #pragma unroll
             for (int c = 0; c < BN; c += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * NI * BN + c), v);
-#pragma unroll
-                for (int i = 1; i < NI; ++i) {  // the other issuing warps' accumulators, in index order
-                    float v1[16];
-                    tmem_ld16(tmem_base + lane_base + (uint32_t)((ab * NI + i) * BN + c), v1);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += v1[j];
-                }
+                float v[16];  // the issuing warps' accumulators of this buffer (index order), one wait for all of them
+                const uint32_t t0 = tmem_base + lane_base + (uint32_t)(ab * NI * BN + c);
+                if (NI == 4) tmem_ld16_sum4(t0, t0 + BN, t0 + 2 * BN, t0 + 3 * BN, v);
+                else tmem_ld16_sum2(t0, t0 + BN, v);
                 if (c + 16 >= BN) {  // all columns of this buffer are in registers: hand it back to the MMA warps
                     tc_fence_before();
                     __syncwarp();

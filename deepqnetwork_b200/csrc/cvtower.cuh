@@ -221,16 +221,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
             const uint32_t sdst = l == 2 ? imgs + t.img_off[1] + (uint32_t)(opix * (BN * 4 + 16)) : imgs + t.img_off[l + 1] + (uint32_t)opix;
             for (int c = 0; c < HC; c += 16) {
                 float v[16];
-                tmem_ld16(trow + (uint32_t)c, v);
-                if (ksplit) {
-#pragma unroll
-                    for (int a = 1; a < 4; ++a) {  // the other issuing warps' accumulators (k-blocks kb % 4 == a), in index order
-                        float v1[16];
-                        tmem_ld16(trow + (uint32_t)(a * BN + c), v1);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += v1[j];
-                    }
-                }
+                const uint32_t t0 = trow + (uint32_t)c;
+                if (ksplit) tmem_ld16_sum4(t0, t0 + BN, t0 + 2 * BN, t0 + 3 * BN, v);  // the four issuing warps' accumulators (k-blocks kb % 4 == a), index order
+                else tmem_ld16(t0, v);
                 TW_STAMP(tid == 0, 100 + l * 4 + band, 1 + (c >> 4));
                 if (opix < 0) continue;
                 const int n0 = cg * HC + c;

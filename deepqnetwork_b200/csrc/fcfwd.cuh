@@ -226,15 +226,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         for (int c = 0; c < HC; c += 16) {
             float v[16];
             if (nkb > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * HC + c), v);
+                const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * HC + c);
+                if (nkb >= NI) {  // every issuing warp has written its accumulator: all of them in index order, one wait
+                    if (NI == 4) tmem_ld16_sum4(t0, t0 + BN, t0 + 2 * BN, t0 + 3 * BN, v);
+                    else tmem_ld16_sum2(t0, t0 + BN, v);
+                } else {
+                    tmem_ld16(t0, v);
 #pragma unroll
-                for (int i = 1; i < NI; ++i)
-                    if (i < nkb) {  // the other issuing warps' accumulators, in index order
-                        float v1[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * BN + half * HC + c), v1);
+                    for (int i = 1; i < NI; ++i)
+                        if (i < nkb) {
+                            float v1[16];
+                            tmem_ld16(t0 + (uint32_t)(i * BN), v1);
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] += v1[k];
-                    }
+                            for (int k = 0; k < 16; ++k) v[k] += v1[k];
+                        }
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
