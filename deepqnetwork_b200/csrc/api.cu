@@ -1554,6 +1554,7 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
     else if (n == "repack") { launch_pack_conv(h, 0); launch_pack_conv(h, 1); }  // after writing weights through dqn_device_ptr
     else if (n == "img_conv") h->img_conv = value != 0;   // conv layers through the image-resident kernel (cvgemm.cuh)
     else if (n == "tower_fused") h->tower_fused = value != 0;  // conv1..conv3 of both towers as one kernel on the uint8 batch (cvtower.cuh)
+    else if (n == "tower_ext2") h->tower_ext2 = value != 0;
     else if (n == "fc_prefetch") h->fc_prefetch = value != 0;
     else if (n == "fc_rows_pf") { DQN_REQUIRE(value >= 0 && value <= 16, "fc_rows_pf: 0..16 tiles per CTA ahead"); h->fc_rows_pf = (int)value; }
     else if (n == "tower_cluster") { DQN_REQUIRE(value == 1 || value == 2 || value == 4 || value == 8, "tower_cluster: 1, 2, 4 or 8"); h->tower_cluster = (int)value; }

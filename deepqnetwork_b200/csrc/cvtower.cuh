@@ -48,6 +48,7 @@ struct TowerArgs {
     int img_zero[3];  // bytes of that image (zero-filled before the previous layer's epilogue writes into it)
     int u8_row;       // bytes per padded row of the layer-0 byte image
     int rt0[3];       // first row-table band of layer l
+    int ext2;         // layer 2 streams its weights through 4 extra stages in image A (free during its k-loop)
 };
 
 constexpr int TW_THREADS = 544;     // warps 0-7 converters / epilogue, warps 8-11 MMA issuers, warp 12 TMA, warps 13-16 writers
@@ -57,7 +58,7 @@ constexpr int TW_S = 4;             // ring depth (B tiles in shared memory, A t
                                     // same parity for the one it wants)
 constexpr int TW_STAGE = 16384;     // ring slot: one k-block of packed weights of a 64-column layer
 constexpr int TW_DCOLS = 256;       // accumulator columns (4 bands x 32, or 4 k-quarters x 64); A stages follow
-constexpr int TW_TAB = 8192;        // barriers 256 | k-block offsets 3 x 256 | bias 3 x 256 | row tables 6 x 128 x 8
+constexpr int TW_TAB = 8192;        // barriers 512 | k-block offsets 3 x 256 | bias 3 x 256 | row tables 6 x 128 x 8
 constexpr int TW_MAXBANDS = 6;
 
 __device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
@@ -80,11 +81,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
     const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t ring = sbase;
     const uint32_t bars = ring + (uint32_t)S * TW_STAGE;
-    const uint32_t kbtab = bars + 384, bias_s = bars + 1152, rowtab = bars + 2048, imgs = bars + TW_TAB;
+    const uint32_t kbtab = bars + 512, bias_s = bars + 1280, rowtab = bars + 2048, imgs = bars + TW_TAB;
     auto afull_bar = [&](int s) { return bars + 8u * s; };          // A tile of a step is in tensor memory (4 converter warps)
     auto aempty_bar = [&](int s) { return bars + 8u * (5 + s); };   // ... and consumed (this CTA's MMAs: tcgen05.commit)
-    auto bfull_bar = [&](int s) { return bars + 8u * (10 + s); };   // weight tile landed (all slices, from every CTA of the cluster)
-    auto bempty_bar = [&](int s) { return bars + 8u * (15 + s); };  // ... and consumed by EVERY CTA of the cluster (multicast commits)
+    // weight ring of layers 1, 2: slots 0-3 = the ring, slots 4-7 (layer 2 only, t.ext2) = 4 more stages in image A, which is free
+    // during layer 2's k-loop.  One numbering of uses per slot across the two layers: parity of use u is u & 1.
+    auto bfull_bar = [&](int s) { return bars + 8u * (40 + s); };   // weight tile landed (all slices, from every CTA of the cluster)
+    auto bempty_bar = [&](int s) { return bars + 8u * (48 + s); };  // ... and consumed by EVERY CTA of the cluster (multicast commits)
     auto accum_bar = [&](int l, int b) { return bars + 8u * (20 + l * 4 + b); };  // each used once
     const uint32_t w0full = bars + 8u * 32;                          // layer 0's weights (all k-blocks) are resident
     const uint32_t tmem_slot = bars + 8u * 34;
@@ -104,6 +107,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
         for (int s = 0; s < S; ++s) {
             mbar_init(afull_bar(s), 4);
             mbar_init(aempty_bar(s), 1);
+        }
+        for (int s = 0; s < 8; ++s) {
             mbar_init(bfull_bar(s), 1);
             mbar_init(bempty_bar(s), csize);
         }
@@ -167,7 +172,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(TW_DCOLS + s * ACOLS); };
-    auto stage_b = [&](int s) { return ring + (uint32_t)s * TW_STAGE; };
+    auto stage_b = [&](int s) { return s < S ? ring + (uint32_t)s * TW_STAGE : imgs + t.img_off[1] + (uint32_t)(s - S) * TW_STAGE; };
+    // weight-ring slot and use number of step j (layer-local) of layer l (1 or 2)
+    const int n1 = t.g[1].nkb * t.g[1].nbands, nst2 = t.ext2 ? 2 * S : S;
+    auto b_slot = [&](int l, int j) { return l == 1 ? j % S : j % nst2; };
+    auto b_use = [&](int l, int j) { return l == 1 ? j / S : (j % nst2 < S ? n1 / S : 0) + j / nst2; };
     TW_STAMP(tid == 0, 127, 1);
 
     if (warp < 8) {
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
         const int w = warp - 8;
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        int step0 = 0, bstep0 = 0;  // first step of the layer; first weight-ring step of the layer (layer 0 does not use the ring)
+        int step0 = 0;  // first step of the layer
         for (int l = 0; l < 3; ++l) {
             const int BN = t.g[l].cout, nkb = t.g[l].nkb, nb = t.g[l].nbands;
             constexpr int stride = 4;  // distance between this warp's steps (== TW_S: the warp owns stage w)
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
                 if (l == 0) mbar_wait(w0full, 0);
                 for (int step = step0 + w; step < last; step += stride) {
                     const int s = step % S, ph = (step / S) & 1;
-                    const int bstep = bstep0 + (step - step0), bs = bstep % S, bph = (bstep / S) & 1;
+                    const int bs = l > 0 ? b_slot(l, step - step0) : 0, bph = l > 0 ? b_use(l, step - step0) & 1 : 0;
                     mbar_wait(afull_bar(s), ph);
                     if (l > 0) mbar_wait(bfull_bar(bs), bph);
                     TW_STAMP(lane == 0, step, 3);
@@ -378,7 +387,6 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
                 }
             }
             step0 += nkb * nb;
-            if (l > 0) bstep0 += nkb * nb;
         }
         tc_fence_before();
     } else if (warp >= 13) {
@@ -424,18 +432,23 @@ __global__ void __launch_bounds__(TW_THREADS, 1) cvtower_kernel(const __grid_con
                     if (csize > 1) tma_bulk_g2s_mc(dst, src, bytes, w0full, cmask); else tma_bulk_g2s(dst, src, bytes, w0full);
                 }
             }
-            int s = 0, ph = 0, bstep = 0;
             for (int l = 1; l < 3; ++l) {
                 const uint32_t bytes = (uint32_t)t.g[l].cout * 256u;  // one k-block of packed weights
                 const uint32_t slice = bytes / csize;                 // this CTA fetches slice `crank` for the whole cluster
                 const float* src = ts_.packed[l];
-                for (int kb = 0; kb < t.g[l].nkb * t.g[l].nbands; ++kb, ++bstep) {
-                    if (bstep >= S) mbar_wait(bempty_bar(s), ph ^ 1);
+                for (int j = 0; j < t.g[l].nkb * t.g[l].nbands; ++j) {
+                    const int s = b_slot(l, j), u = b_use(l, j);
+                    if (u >= 1) mbar_wait(bempty_bar(s), (u - 1) & 1);
+                    else if (s >= S) {
+                        // first use of an extra stage: image A is free once every MMA of layer 1 has completed (its converters have
+                        // read their last pixel) and the writer warps have copied layer 0's output out of it
+                        mbar_wait(accum_bar(1, 0), 0);
+                        mbar_wait(wdone, 0);
+                    }
                     mbar_expect_tx(bfull_bar(s), bytes);
                     const uint32_t dst = stage_b(s) + crank * slice;
-                    const float* sp = src + (size_t)(kb / t.g[l].nbands) * (bytes / 4) + (size_t)crank * (slice / 4);
+                    const float* sp = src + (size_t)(j / t.g[l].nbands) * (bytes / 4) + (size_t)crank * (slice / 4);
                     if (csize > 1) tma_bulk_g2s_mc(dst, sp, slice, bfull_bar(s), cmask); else tma_bulk_g2s(dst, sp, slice, bfull_bar(s));
-                    if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -478,6 +491,7 @@ static inline bool tower_plan(const ConvGeom* conv, TowerArgs& t, size_t& smem_b
     t.img_off[0] = imgA; t.img_off[1] = 0; t.img_off[2] = imgA;
     t.img_zero[0] = 0; t.img_zero[1] = t.g[1].img_bytes; t.img_zero[2] = t.g[2].img_bytes;
     if (t.g[0].nkb * t.g[0].cout * 192 > imgA) return false;  // layer 0's weights are resident in image A during its k-loop
+    t.ext2 = imgA >= TW_S * TW_STAGE && t.g[2].nbands == 1 && t.g[1].nbands == 1;  // (launch_tower clears it for clusters)
     smem_bytes = (size_t)TW_S * TW_STAGE + TW_TAB + imgA + imgB + 1024;
     static_assert(TW_DCOLS + TW_S * 64 <= 512, "tensor memory budget");
     return smem_bytes <= 227 * 1024;
@@ -496,6 +510,8 @@ static void launch_tower(dqn_learner* h, const TowerArgs& t, size_t smem_bytes, 
     const int images_b = images - t.images_a;
     for (int c = h->tower_cluster; c > 1; c >>= 1)
         if (t.images_a % c == 0 && images_b % c == 0 && (64 * 256) % c == 0) { csize = c; break; }
+    TowerArgs ta = t;
+    if (csize > 1 || !h->tower_ext2) ta.ext2 = 0;  // a peer's image A is not known to be free when this CTA's is
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(images); cfg.blockDim = dim3(TW_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = h->stream;
     cudaLaunchAttribute at[3];
@@ -504,7 +520,7 @@ static void launch_tower(dqn_learner* h, const TowerArgs& t, size_t smem_bytes, 
     if (h->pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
     at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = csize; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n;
     cfg.attrs = at; cfg.numAttrs = n;
-    DQN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, t, (const float*)h->zeros16, h->tc_dbg));
+    DQN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, (const float*)h->zeros16, h->tc_dbg));
     h->launches++;
 }
 

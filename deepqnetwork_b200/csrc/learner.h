@@ -222,6 +222,10 @@ struct dqn_learner {
     bool tower_fused = true;    // option: the conv stack of both towers as one fused kernel on the uint8 batch (cvtower.cuh)
     int fc_rows_pf = 0;         // option: the fused dense kernel prefetches the tile fc_rows_pf x CTAs claims ahead into L2 (0 = off; measured: 6550-6630 vs 6650-6670 steps/s without -- the pass is not latency-bound in situ)
     bool fc_prefetch = true;    // option: the dense hidden kernels are prefetched into L2 under the conv towers (nn.cu launch_dense_prefetch)
+    bool tower_ext2 = false;    // option: conv3 of the fused tower streams its weights through 8 stages (4 of them in image A, free by then).
+                                // Measured SLOWER (6537-6567 vs 6637-6651 steps/s): the layer's k-loop is not bound by the depth of the weight
+                                // ring but by shared-memory bandwidth -- per k-block 16 KB of TMA writes + 16 KB of converter reads + 16 KB of
+                                // MMA operand reads = 384 cycles at 128 B/clk, against 256 cycles of tensor time
     int tower_cluster = 1;      // option: CTAs (images) per thread-block cluster of the fused tower sharing one multicast weight stream (1, 2, 4, 8).
                                 // Measured 6605-6633 steps/s without clusters, 6515-6589 with 4, 6549 with 8: the weight stream of a CTA is bound by the
                                 // round trip of its 4 stages, not by L2 bandwidth, and a cluster adds the skew of its slowest CTA to every stage

@@ -87,12 +87,17 @@ struct Plan {
     static constexpr int A_STAGE = BM * A_PITCH;  // K-contiguous: [128 rows][144]; M-contiguous: [32 k][512] fits too
     static constexpr int B_BYTES = Tile<BN>::BYTES;
     static constexpr int STAGE = A_STAGE + B_BYTES * (NTERMS == 3 ? 2 : 1);
-    static constexpr int DCOLS = BN < 32 ? 32 : BN;
+    // Two MMA-issuing warps for N <= 64 (one thread issues a tcgen05.mma every ~53 cycles, the tensor pipe needs N / 2: DESIGN.md D19):
+    // warp i takes the k-blocks kb % NI == i into its own accumulator (column i * DC1), the epilogue adds them in index order.  The ring
+    // depth is a multiple of NI, so that a warp waits on the barriers of "its" stages only and sees every phase of them (D20).
+    static constexpr int NI = BN <= 64 ? 2 : 1;
+    static constexpr int DC1 = BN < 32 ? 32 : BN;
+    static constexpr int DCOLS = NI * DC1;
     static constexpr int ACOLS = BK * (NTERMS == 3 ? 2 : 1);
     static constexpr int S_TMEM = (512 - DCOLS) / ACOLS;
     static constexpr int S_SMEM = (196 * 1024) / STAGE;
     static constexpr int S0 = S_TMEM < S_SMEM ? S_TMEM : S_SMEM;
-    static constexpr int STAGES = S0 > 6 ? 6 : S0;
+    static constexpr int STAGES = (S0 > 6 ? 6 : S0) / NI * NI;
     static_assert(STAGES >= 3, "pipeline too shallow");
     static constexpr int NG = 2;                                // converter groups (take k-blocks round-robin)
     static constexpr int EPI_BYTES = BM * (BN + 4) * 4;         // coalesced-epilogue transpose tile
@@ -103,7 +108,7 @@ struct Plan {
 };
 
 template <int BN, int NTERMS, bool SPLIT, class AOp, class BOp, class Epi>
-__global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
+__global__ void __launch_bounds__(((is_heavy<AOp>::value ? 20 : 16) + Plan<BN, NTERMS>::NI) * 32, 1) tsgemm_kernel(const AOp a, const BOp b, const Epi epi, int M, int N, int K,
                                                             int kchunk, int nclass, const float* __restrict__ zeros,
                                                             unsigned long long* __restrict__ dbg) {
     constexpr bool A_MC = !AOp::KCONTIG;  // A contiguous along M: staged as [k][m], converters read a column
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
             mbar_init(empty_bar(s), 1);
             mbar_init(afull_bar(s), 32 * NLA);  // one pre-counted cp.async arrival per A-loader thread
         }
-        mbar_init(accum_bar, 1);
+        mbar_init(accum_bar, nkb >= P::NI ? P::NI : nkb > 0 ? nkb : 1);  // the last commit of every issuing warp that has a k-block
         fence_barrier_init();
     }
     if (warp == MMA_WARP) {
@@ -355,6 +360,22 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
         const int m = m0 + sub * 32 + lane;
         constexpr int QCOLS = BN / 4;  // columns per warp: 8, 16 or 32
         const uint32_t trow = tmem_base + ((uint32_t)(sub * 32) << 16);
+        // columns [col, col + 8 / 16) of the tile: sum of the issuing warps' accumulators, in index order
+        auto ld8s = [&](int col, float (&v)[8]) {
+            tmem_ld8(trow + (uint32_t)col, v);
+#pragma unroll
+            for (int i = 1; i < P::NI; ++i)
+                if (i < nkb) {
+                    float v1[8];
+                    tmem_ld8(trow + (uint32_t)(i * P::DC1 + col), v1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += v1[j];
+                }
+        };
+        auto ld16s = [&](int col, float (&v)[16]) {
+            if (P::NI == 2 && nkb >= 2) { tmem_ld16_sum2(trow + (uint32_t)col, trow + (uint32_t)(P::DC1 + col), v); return; }
+            tmem_ld16(trow + (uint32_t)col, v);
+        };
         if constexpr (wants_coalesce<Epi>::value) {
             // accumulators -> smem tile [128][BN+4] (the pipeline buffers are idle now) -> rows handed to whole warps
             constexpr int PITCH = BN + 4;
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
             const int row = sub * 32 + lane;
             if (QCOLS == 8) {
                 float v[8];
-                if (nkb > 0) tmem_ld8(trow + (uint32_t)(quarter * 8), v);
+                if (nkb > 0) ld8s(quarter * 8, v);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -374,7 +395,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
 #pragma unroll
                 for (int c = 0; c < QCOLS; c += 16) {
                     float v[16];
-                    if (nkb > 0) tmem_ld16(trow + (uint32_t)(quarter * QCOLS + c), v);
+                    if (nkb > 0) ld16s(quarter * QCOLS + c, v);
                     else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
         } else if (QCOLS == 8) {
             const int col = quarter * 8;
             float v[8];
-            if (nkb > 0) tmem_ld8(trow + (uint32_t)col, v);
+            if (nkb > 0) ld8s(col, v);
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -418,7 +439,7 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
             for (int c = 0; c < QCOLS; c += 16) {
                 const int col = quarter * QCOLS + c;
                 float v[16];
-                if (nkb > 0) tmem_ld16(trow + (uint32_t)col, v);
+                if (nkb > 0) ld16s(col, v);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -435,8 +456,10 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         const uint64_t db0 = TB::desc(stage_b(0), 0), dbl0 = TB::desc(stage_blo(0), 0);
         constexpr uint64_t STAGE16 = P::STAGE >> 4, KS16 = (2 * LBO) >> 4;  // descriptor address units (16 bytes)
-        int s = 0, ph = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int wi = warp - MMA_WARP;  // issuing warp: k-blocks kb % NI == wi, accumulator wi
+        const uint32_t tmem_d = tmem_base + (uint32_t)(wi * P::DC1);
+        for (int kb = wi; kb < nkb; kb += P::NI) {
+            const int s = kb % S, ph = (kb / S) & 1;
             mbar_wait(full_bar(s), ph);             // acquire: B tile stores and A TMEM stores of this block
             TS_STAMP(lane == 0, kb, 6);
             fence_proxy_async();                      // B tile: generic -> async proxy
@@ -446,24 +469,23 @@ __global__ void __launch_bounds__((is_heavy<AOp>::value ? 21 : 17) * 32, 1) tsge
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
                 const uint64_t o = so + ks * KS16;
-                const uint32_t acc = (kb | ks) != 0;
+                const uint32_t acc = (kb != wi) || ks != 0;
                 if (leader) {
                     if (NTERMS == 3) {
-                        mma_tf32_ts(tmem_base, ta + ks * 8, dbl0 + o, idesc, acc);       // A_hi * B_lo
-                        mma_tf32_ts(tmem_base, ta + BK + ks * 8, db0 + o, idesc, 1);    // A_lo * B_hi
-                        mma_tf32_ts(tmem_base, ta + ks * 8, db0 + o, idesc, 1);         // A_hi * B_hi
+                        mma_tf32_ts(tmem_d, ta + ks * 8, dbl0 + o, idesc, acc);       // A_hi * B_lo
+                        mma_tf32_ts(tmem_d, ta + BK + ks * 8, db0 + o, idesc, 1);    // A_lo * B_hi
+                        mma_tf32_ts(tmem_d, ta + ks * 8, db0 + o, idesc, 1);         // A_hi * B_hi
                     } else {
-                        mma_tf32_ts(tmem_base, ta + ks * 8, db0 + o, idesc, acc);
+                        mma_tf32_ts(tmem_d, ta + ks * 8, db0 + o, idesc, acc);
                     }
                 }
             }
             if (leader) {
-                mma_commit(empty_bar(s));                    // frees the stage (smem B, staging A, TMEM A) when these retire
-                if (kb == nkb - 1) mma_commit(accum_bar);    // accumulator complete
+                mma_commit(empty_bar(s));                         // frees the stage (smem B, staging A, TMEM A) when these retire
+                if (kb + P::NI >= nkb) mma_commit(accum_bar);     // this warp's accumulator is complete
             }
             TS_STAMP(lane == 0, kb, 7);
             __syncwarp();
-            if (++s == S) { s = 0; ph ^= 1; }
         }
         tc_fence_before();
     }
@@ -484,7 +506,7 @@ static void launch(dqn_learner* h, const AOp& a, const BOp& b, const Epi& e, int
         configured = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), Z);
-    launch_kernel(h->pdl, kern, grid, dim3((is_heavy<AOp>::value ? 21 : 17) * 32), (size_t)P::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk, nclass,
+    launch_kernel(h->pdl, kern, grid, dim3(((is_heavy<AOp>::value ? 20 : 16) + P::NI) * 32), (size_t)P::BYTES + 1024, h->stream, a, b, e, M, N, K, kchunk, nclass,
                   (const float*)h->zeros16, h->tc_dbg);
     h->launches++;
 }
