@@ -13,6 +13,6 @@ t0 = t[63,0]
 r = np.where(t>0, t-t0, -1)
 print('special: start prologue pdl accum epi_done', r[63,:5])
 print('j: TMA:issue | CV:wfull CV:done | B:start B:arrive | MMA:afull MMA:bfull MMA:issued')
-for st in range(0, 16):
+for st in range(0, 30):
     if (t[st]>0).any(): print('%2d '%st + ' '.join('%7d'%x for x in r[st,:8]))
 L.close()
