@@ -189,8 +189,13 @@ class ClockSampler:
 # capture committed as profiles/r01c_top_kernels_raw.csv (adam_kernel: 62.9 MB read + 1.0-2.4 MB written per launch;
 # the stores are still dirty in L2 when the kernel ends)
 NCU_TRAFFIC = {'optimizer_fc': 62.92e6 + 0.92e6, 'optimizer_fc1': 62.92e6 + 2.35e6,
-               # fcwg_adam_rows_kernel (profiles/r01d_fused_dense_kernel_raw.csv): 95.8 MB read + 36.7 MB written per launch
-               'fc_wgrad_adam': 95.77e6 + 36.72e6}
+               # fcwg_adam_rows_kernel (profiles/r02_top_kernels_raw.csv): 95.55 MB read + 37.71 MB written per launch (C2 shapes)
+               'fc_wgrad_adam': 95.55e6 + 37.71e6,
+               # cvtower_kernel, 96 images (same capture): 3.54 MB read, stores still in L2
+               'conv_tower_fwd': 3.54e6}
+# dominant kernels that are not bandwidth-bound: what bounds them instead
+KERNEL_NOTES = {'conv_tower_fwd': 'tensor-issue / shared-memory-bandwidth / latency bound (one CTA per image through three conv layers): '
+                                  'its few MB of algorithmic bytes make the HBM fraction meaningless; in-kernel timeline in profiles/README.md'}
 
 
 def measured_peak_hbm():
@@ -488,7 +493,7 @@ def main():
         roofline = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s',
                         frac=(achieved / peak) if achieved else None, traffic=NCU_TRAFFIC.get(dom), peak_source=how,
                         algorithmic_bytes_per_launch=kb, us_per_launch=per_kernel[dom],
-                        kernel_share_of_step=per_kernel[dom] / total_us,
+                        kernel_share_of_step=per_kernel[dom] / total_us, note=KERNEL_NOTES.get(dom),
                         step_frac_of_hbm_roofline=(nn['step_bytes'] / (ms / args.steps * 1e-3) / 1e9) / peak,
                         per_kernel_us={k: round(v, 2) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])})
     elif rank == 0:

@@ -1479,7 +1479,7 @@ extern "C" int dqn_predict(dqn_learner* h, int32_t n, const uint8_t* st, int32_t
         DQN_CUDA_OK(cudaMemcpyAsync(h->in_states, st + (size_t)done * S, m * S, cudaMemcpyHostToDevice, h->stream));
         TowerActs& acts = use_target ? h->acts_tg : h->acts_on;
         const float* xf = nullptr;
-        if (h->cfg.math_mode != DQN_MATH_FP32) { launch_u8_to_f32(h, h->in_states, h->x_f32, (size_t)m * S); xf = h->x_f32; }
+        if (h->cfg.math_mode != DQN_MATH_FP32 && !tower_fused_ready(h)) { launch_u8_to_f32(h, h->in_states, h->x_f32, (size_t)m * S); xf = h->x_f32; }
         tower_forward(h, use_target ? h->target : h->online, h->in_states, xf, m, acts);
         DQN_CUDA_OK(cudaMemcpyAsync(q + (size_t)done * A, acts.q, (size_t)m * A * 4, cudaMemcpyDeviceToHost, h->stream));
         done += m;

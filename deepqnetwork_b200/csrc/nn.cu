@@ -388,9 +388,14 @@ void tower_fc_forward(dqn_learner* h, const float* P, int rows, TowerActs& acts)
 void tower_forward(dqn_learner* h, const float* P, const uint8_t* d_states, const float* x_f32, int rows, TowerActs& acts) {
     const NetDesc& net = h->net;
     const bool tcm = h->cfg.math_mode != DQN_MATH_FP32;
+    const bool tg = h->prof_tag[0] == 't';
+    // one tower (dqn_predict: the actor's get_action / get_actions): the fused conv tower on the uint8 rows, no f32 copy
+    if (tcm && (P == h->online || P == h->target) && towers_conv_forward_fused(h, P, d_states, rows, acts, nullptr, 0)) {
+        tower_fc_heads(h, P, rows, acts, tg);
+        return;
+    }
     DQN_REQUIRE(!tcm || x_f32 != nullptr, "tensor-core path needs the f32 input batch");
     const void* in = tcm ? (const void*)x_f32 : (const void*)d_states;
-    const bool tg = h->prof_tag[0] == 't';
     static const char* kConvName[2][3] = {{"on_conv1_fwd", "on_conv2_fwd", "on_conv3_fwd"}, {"tg_conv1_fwd", "tg_conv2_fwd", "tg_conv3_fwd"}};
     for (int l = 0; l < 3; ++l) {
         const ConvGeom& g = net.conv[l];
