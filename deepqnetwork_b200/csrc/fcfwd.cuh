@@ -24,7 +24,7 @@ namespace ff {
 using namespace tc;
 
 struct WMaps { CUtensorMap w[2]; };  // per hidden stream: [flat][hid] f32, box 128 (n) x 32 (k), no swizzle
-constexpr int FF_S = 6, FF_THREADS = 416;  // warps 0-7 converters / B producers / epilogue, 8-11 MMA issuers, 12 TMA
+constexpr int FF_S = 6, FF_THREADS = 448;  // warps 0-7 converters / B producers / epilogue, 8-11 MMA issuers, 12 W TMA, 13 B TMA (PACKED)
 
 // PACKED: the B tiles arrive ready-made (EpiBiasReluPack wrote them), one bulk copy per k-block; warps 4-7 become a second
 // converter group instead of B producers
@@ -48,6 +48,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
     auto bfull = [&](int s) { return bars + 8u * (2 * S + s); };
     auto empty = [&](int s) { return bars + 8u * (3 * S + s); };
     const uint32_t accum = bars + 8u * (4 * S), tmem_slot = bars + 8u * (4 * S + 1);
+    // The W half of a stage is released by the converters that have read it (wfree), not by the MMAs of the block (empty): the weight
+    // stream -- the long pole, 16 KB per k-block from L2 / HBM -- turns a stage around in TMA latency + one conversion instead of
+    // waiting for the block's MMAs to retire as well (2500 -> ~1300 cycles per stage, tools/dense_fwd_timeline.py); and, needing
+    // nothing from the stream predecessor, it starts under the predecessor's tail (PDL).
+    auto wfree = [&](int s) { return bars + 8u * (4 * S + 2 + s); };
     auto stage_w = [&](int s) { return sbase + s * STAGE; };
     auto stage_b = [&](int s) { return sbase + s * STAGE + W_TILE; };
 
@@ -58,7 +63,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
     const int kb0 = z * kb_per_split, kb1 = min(nkb_total, kb0 + kb_per_split), nkb = kb1 - kb0;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(wfull(s), 1); mbar_init(afull(s), 4); mbar_init(bfull(s), 4); mbar_init(empty(s), 1); }
+        for (int s = 0; s < S; ++s) {
+            mbar_init(wfull(s), 1); mbar_init(afull(s), 4); mbar_init(bfull(s), PACKED ? 1 : 4); mbar_init(empty(s), 1); mbar_init(wfree(s), 4);
+        }
         mbar_init(accum, nkb < NI ? (nkb > 0 ? nkb : 1) : NI);  // the last commit of every issuing warp that has a k-block
         fence_barrier_init();
     }
@@ -79,18 +86,28 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
     if (warp == 12) {
         // ---------------- W boxes by TMA (weights were written by an earlier step: no dependency on the predecessor) ----------------
         if (lane == 0) {
-            if (PACKED) pdl_wait();  // the packed activation tiles are the stream predecessor's output
             int s = 0, ph = 0;
             // w_policy: 1 = evict_last (online weights: re-read by the dgrad and the optimizer pass), 2 = evict_first (target
             // weights: read once per step), 0 = no hint
             const uint64_t pol = w_policy == 1 ? fa::l2_policy_evict_last() : fa::l2_policy_evict_first();
             for (int j = 0; j < nkb; ++j) {
-                if (j >= S) mbar_wait(empty(s), ph ^ 1);
+                if (j >= S) mbar_wait(wfree(s), ph ^ 1);  // the converters of block j - S have read the box
                 FF_STAMP(true, j, 0);
-                cv::mbar_expect_tx(wfull(s), PACKED ? W_TILE + 2 * B_TILE : W_TILE);
+                cv::mbar_expect_tx(wfull(s), W_TILE);
                 if (w_policy) fa::tma_load_2d_hint(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s), pol);
                 else fa::tma_load_2d(stage_w(s), &maps.w[strm], ncol, (kb0 + j) * BK, wfull(s));
-                if (PACKED) cv::tma_bulk_g2s(stage_b(s), act_pk + (size_t)(kb0 + j) * (2 * BN * 32), 2 * B_TILE, wfull(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 13) {
+        // ---------------- packed activation tiles by TMA (PACKED): one bulk copy per k-block ----------------
+        if (PACKED && lane == 0) {
+            pdl_wait();  // the tiles are the stream predecessor's output
+            int s = 0, ph = 0;
+            for (int j = 0; j < nkb; ++j) {
+                if (j >= S) mbar_wait(empty(s), ph ^ 1);  // the MMAs of block j - S have retired
+                cv::mbar_expect_tx(bfull(s), 2 * B_TILE);
+                cv::tma_bulk_g2s(stage_b(s), act_pk + (size_t)(kb0 + j) * (2 * BN * 32), 2 * B_TILE, bfull(s));
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
@@ -102,19 +119,20 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         const uint32_t col = (uint32_t)(q4 * 32 + lane) * 4u;
         for (int j = grp; j < nkb; j += NG) {
             const int s = j % S, ph = (j / S) & 1;
-            mbar_wait(wfull(s), ph);  // (the stage's TMEM half was released together with its smem half: empty(s))
+            mbar_wait(wfull(s), ph);
             FF_STAMP(tid == 0, j, 1);
             float hi[32];
             const uint32_t src = stage_w(s) + col;
 #pragma unroll
             for (int k = 0; k < 32; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hi[k]) : "r"(src + (uint32_t)k * (BM * 4)));
+            if (j >= S) { mbar_wait(empty(s), ph ^ 1); tc_fence_after(); }  // the stage's tensor-memory half: block j - S's MMAs have retired
             const uint32_t ta = tmem_a(s) + lane_base;
             if (NTERMS == 3) cv::a_stage_store3(ta, hi); else ts::tmem_st32(ta, hi);
             ts::tmem_st_wait();
             tc_fence_before();
             FF_STAMP(tid == 0, j, 2);
             __syncwarp();
-            if (lane == 0) mbar_arrive(afull(s));
+            if (lane == 0) { mbar_arrive(wfree(s)); mbar_arrive(afull(s)); }  // (the box's values went through registers into the store above)
         }
     } else if (warp < 8) {
         // ---------------- B producers: act[b][k0 .. k0+31] -> dense K-major hi/lo tiles ----------------
@@ -191,8 +209,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fcfwd_kernel(const float* __res
         for (int j = wi; j < nkb; j += NI) {
             const int s = j % S, ph = (j / S) & 1;
             mbar_wait(afull(s), ph);
-            if (PACKED) mbar_wait(wfull(s), ph);  // B tile came with the W box (TMA, async proxy)
-            else mbar_wait(bfull(s), ph);
+            mbar_wait(bfull(s), ph);  // B tile: by TMA (PACKED, async proxy) or from the producer warps
             FF_STAMP(lane == 0, j, 5);
             if (!PACKED) fence_proxy_async();  // B tile: generic -> async proxy
             FF_STAMP(lane == 0, j, 6);
