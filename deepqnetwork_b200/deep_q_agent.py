@@ -15,6 +15,7 @@ import numpy as np
 
 from .agent.game_agent import GameAgent
 from .data.replay_memory import ReplayMemory
+from .data.replay_memory_disk import ReplayMemoryDisk
 from .data.replay_sampler import ReplaySampler
 from .data.replay_sampler_priority import ReplaySamplerPriority
 from .utils.config import get_conf
@@ -134,13 +135,33 @@ class DeepQAgent(GameAgent):
         learner = m.learner
         # the replay ring lives in the model's device learner (HBM); the reference's RAM/HDF5 choice (--memory /
         # --disk) only decides where the *reference* keeps it, so both map to the HBM ring here
-        if c.get('use_memory', True) and os.path.exists(self._get_replay_memory_path()):
-            # deep_q_agent.py:218-222: reload the replay written at the last exit (before the sampler is built: under PER its
-            # tree is rebuilt from the stored float16 losses, as ReplaySamplerPriority.add_losses does)
-            log('loading old memories from', self._get_replay_memory_path())
+        native_replay = '{}_replay_memory.dqnb200'.format(self.save_path_prefix)
+        old_memories = None
+        if c.get('use_memory', True) and os.path.exists(self._get_replay_memory_path(reference=True)):
+            # deep_q_agent.py:216-221: the HDF5 replay written at the last exit (by the reference or by this build)
+            log('loading old memories from', self._get_replay_memory_path(reference=True))
+            old_memories = ReplayMemoryDisk(self._get_replay_memory_path(reference=True))
+            log('found', len(old_memories))
+        elif c.get('use_memory', True) and os.path.exists(native_replay):
+            # own container (persist_format 'native'); before the sampler is built: under PER its tree is rebuilt from the
+            # stored float16 losses, as ReplaySamplerPriority.add_losses does
+            log('loading old memories from', native_replay)
             log('found', learner.restore_replay(self.save_path_prefix))
         self.memories = ReplayMemory(m.INPUT_HEIGHT, m.INPUT_WIDTH, m.INPUT_CHANNELS, max_size=self.replay_max_memory_length,
                                      state_type=m.STATE_TYPE, learner=learner)
+        if old_memories is not None:
+            # self.memories.extend(old_memories) (:221), a block of rows at a time; under PER every row also enters the sum
+            # tree with its stored float16 loss as priority, which is what ReplaySamplerPriority.add_losses rebuilds (:57-59)
+            n = len(old_memories)
+            if n > self.replay_max_memory_length:
+                raise ValueError('replay file holds %d rows, replay_max_memory_length is %d' % (n, self.replay_max_memory_length))
+            for s0 in range(0, n, 1024):
+                r = slice(s0, min(n, s0 + 1024))
+                self.memories.append_rows(np.asarray(old_memories.states[r]), np.asarray(old_memories.actions[r]),
+                                          np.asarray(old_memories.rewards[r]), np.asarray(old_memories.next_states[r]),
+                                          np.asarray(old_memories.continues[r]),
+                                          np.asarray(old_memories.losses[r], dtype=np.float32) if self.use_per else None)
+            old_memories.close()
         self.train_batch = None  # the B-row batch is device resident (learner.batch_read() for inspection)
         self._train_inflight = False  # pipeline_train: a queued step whose result has not been collected yet
         if self.use_per:
@@ -273,9 +294,18 @@ class DeepQAgent(GameAgent):
             self.total_losses.append(self.model.learner.train_step_result()[2])
             self._train_inflight = False
         if self.conf.get('use_memory', True):
-            # deep_q_agent.py:416-432: the replay goes to disk at exit (own container instead of HDF5, same contents)
             log('saving', len(self.memories), 'memories to disk')
-            self.model.learner.save_replay(self.save_path_prefix)
+            if self.conf.get('persist_format', 'reference') == 'native':
+                self.model.learner.save_replay(self.save_path_prefix)
+            else:
+                # deep_q_agent.py:416-429 as written: the file is opened (created with this run's geometry when missing) and
+                # the ring is appended at the file's own cur_idx
+                m = self.model
+                old_memories = ReplayMemoryDisk(self._get_replay_memory_path(reference=True), m.INPUT_HEIGHT, m.INPUT_WIDTH,
+                                                m.INPUT_CHANNELS, state_type=m.STATE_TYPE,
+                                                max_size=self.replay_max_memory_length, cache_size=0)
+                old_memories.extend(self.memories)
+                old_memories.close()
             log('saved memory to disk')
         self.model.save(self.save_path_prefix)
         elapsed = time.time() - self.train_start_time
@@ -298,8 +328,11 @@ class DeepQAgent(GameAgent):
     def _make_priority(self, losses):
         return make_priority(losses, self.per_a)
 
-    def _get_replay_memory_path(self):
-        return '{}_replay_memory.dqnb200'.format(self.save_path_prefix)
+    def _get_replay_memory_path(self, reference=None):
+        """deep_q_agent.py:537-541: <prefix>_replay_memory.hdf5; the own container of persist_format 'native' sits beside it."""
+        if reference is None:
+            reference = self.conf.get('persist_format', 'reference') != 'native'
+        return '{}_replay_memory.{}'.format(self.save_path_prefix, 'hdf5' if reference else 'dqnb200')
 
     # -- epsilon-greedy -----------------------------------------------------------------------------------------------
     def _get_epsilon(self, step):

@@ -156,16 +156,31 @@ class DeepQModel:
         self.close(ty, value, tb)
 
     def save(self, save_path_prefix):
+        """rl/model/model.py:60-67.  conf['persist_format'] = 'reference' (default) writes what `tf.train.Saver().save` leaves
+        behind -- <prefix>.index, <prefix>.data-00000-of-00001 and the directory's `checkpoint` file, with the reference
+        graph's variable names (formats/tf_bundle.py) -- so a save-dir moves between the reference and this build in both
+        directions; 'native' writes the <prefix>.dqnb200 container (adds the device RNG counter of device_rng runs)."""
         log('saving model: ', save_path_prefix)
-        self.learner.save(save_path_prefix)
+        if self.conf.get('persist_format', 'reference') == 'native':
+            self.learner.save(save_path_prefix)
+        else:
+            self.learner.save(save_path_prefix, fmt='reference', shapes=self.param_shapes(),
+                              use_momentum=bool(self.conf.get('use_momentum')))
         log('saved model')
 
     def restore(self, save_path_prefix):
-        if not os.path.exists(save_path_prefix + '.dqnb200'):
+        """rl/model/model.py:70-83: False when there is no checkpoint.  A TensorFlow checkpoint (<prefix>.index) is read
+        whatever wrote it; a <prefix>.dqnb200 container is used when only that exists."""
+        if os.path.exists(save_path_prefix + '.index'):
+            log('  restoring model: ', save_path_prefix)
+            ok = self.learner.restore(save_path_prefix, fmt='reference', shapes=self.param_shapes(),
+                                      use_momentum=bool(self.conf.get('use_momentum')))
+        elif os.path.exists(save_path_prefix + '.dqnb200'):
+            log('  restoring model: ', save_path_prefix + '.dqnb200')
+            ok = self.learner.restore(save_path_prefix)
+        else:
             log('  model does not exist:', save_path_prefix)
             return False
-        log('  restoring model: ', save_path_prefix)
-        ok = self.learner.restore(save_path_prefix)
         log('  restored model')
         return ok
 

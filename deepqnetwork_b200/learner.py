@@ -6,6 +6,8 @@ that a training step never leaves the GPU.  The mirror classes in deep_q_model.p
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _capi
@@ -133,6 +135,10 @@ class Learner:
         a = C.c_float(); b = C.c_float()
         self._c(self._lib.dqn_get_beta_powers(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def set_beta_powers(self, b1p, b2p):
+        """train/beta1_power, train/beta2_power of tf.train.AdamOptimizer (checkpoint restore)."""
+        self._c(self._lib.dqn_set_beta_powers(self._h, float(b1p), float(b2p)))
 
     def copy_network(self):
         self._c(self._lib.dqn_copy_network(self._h))
@@ -402,10 +408,22 @@ class Learner:
         return out.reshape(-1, 8)
 
     # -- persistence ---------------------------------------------------------------------------
-    def save(self, prefix):
+    def save(self, prefix, fmt='native', shapes=None, use_momentum=False):
+        """fmt 'native': <prefix>.dqnb200 (dqn_save).  fmt 'reference': the files tf.train.Saver().save leaves behind
+        (<prefix>.index, <prefix>.data-00000-of-00001, `checkpoint`; formats/tf_bundle.py), which needs the tower's
+        `shapes` ({variable name: shape}, deep_q_model.tower_param_shapes)."""
+        if fmt == 'reference':
+            from .formats import tf_bundle
+            tf_bundle.save_model(self, str(prefix), shapes, use_momentum)
+            return
         self._c(self._lib.dqn_save(self._h, str(prefix).encode()))
 
-    def restore(self, prefix):
+    def restore(self, prefix, fmt='native', shapes=None, use_momentum=False):
+        if fmt == 'reference':
+            from .formats import tf_bundle
+            if not os.path.exists(str(prefix) + '.index'):
+                return False
+            return tf_bundle.restore_model(self, str(prefix), shapes, use_momentum)
         rc = self._lib.dqn_restore(self._h, str(prefix).encode())
         if rc == 3:
             return False

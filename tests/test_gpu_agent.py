@@ -133,9 +133,9 @@ class CheckingLearner:
         for k in self.shapes:
             assert np.array_equal(self._r.get_param(k, tower=1), self._r.get_param(k, tower=0))
 
-    def save(self, prefix):
+    def save(self, prefix, **kw):
         self.events.append(('save', self._r.get_step()))
-        self._r.save(prefix)
+        self._r.save(prefix, **kw)
 
 
 def expected_events(calls, conf, per):
@@ -277,7 +277,11 @@ def test_agent_seam_drives_the_device_like_the_reference(tmp_path, per, caplog):
     assert any('copying online to target dqn' in l for l in lines)
     # save-dir layout (deep_q_agent.py:126-133): <save_dir>/<environment>.conf + the checkpoint at the same prefix
     prefix = os.path.join(conf['save_dir'], conf['environment'])
-    assert os.path.exists(prefix + '.conf') and os.path.exists(prefix + '.dqnb200')
+    # (persist_format 'reference', the default: what tf.train.Saver and ReplayMemoryDisk leave behind, model.py:60-67 and
+    # deep_q_agent.py:416-432,537-541)
+    for suffix in ('.conf', '.index', '.data-00000-of-00001', '_replay_memory.hdf5'):
+        assert os.path.exists(prefix + suffix), suffix
+    assert os.path.exists(os.path.join(conf['save_dir'], 'checkpoint')) and not os.path.exists(prefix + '.dqnb200')
 
 
 def test_uniform_sampler_draw_rows_matches_reference_execution():
