@@ -866,6 +866,24 @@ void side_begin(dqn_learner* h, cudaStream_t& saved, int which, int prio_class) 
 
 void side_end(dqn_learner* h, cudaStream_t saved) { h->stream = saved; g_launch_priority = h->saved_prio; }
 
+cudaEvent_t fork_event_here(dqn_learner* h) {
+    if (!overlap_enabled(h)) return nullptr;
+    cudaEvent_t e = next_fork_event(h);
+    DQN_CUDA_OK(cudaEventRecord(e, h->stream));
+    return e;
+}
+
+void side_begin_at(dqn_learner* h, cudaStream_t& saved, int which, int prio_class, cudaEvent_t after) {
+    if (!after) { side_begin(h, saved, which, prio_class); return; }
+    saved = h->stream;
+    h->saved_prio = g_launch_priority;
+    if (!overlap_enabled(h)) return;
+    g_launch_priority = prio_of(h, prio_class);
+    cudaStream_t side = side_of(h, which);
+    DQN_CUDA_OK(cudaStreamWaitEvent(side, after, 0));
+    h->stream = side;
+}
+
 void main_wait_side(dqn_learner* h, int which) {
     if (!overlap_enabled(h)) return;
     cudaEvent_t e = next_fork_event(h);
@@ -992,8 +1010,10 @@ static void step_core(dqn_learner* h, int n, const uint8_t* states2, const uint8
 
 static void finish_step(dqn_learner* h, int per_update) {
     prof_mark(h, "optimizer");
+    const bool joined = h->rows_joined;  // (tail_join) the fused dense kernel is still running on side stream 0: the tail starts beside it ...
     launch_optimizer(h, h->fuse_fc_adam || h->fc_adam_done);
     h->fc_adam_done = false;
+    if (joined) main_wait_side(h, 0);    // ... and the step ends when both are done
     prof_mark(h, "post_step");
     launch_post_step(h, per_update);
     prof_mark(h, "end");
@@ -1546,6 +1566,8 @@ extern "C" int dqn_set_option(dqn_learner* h, const char* name, int32_t value) {
         fprintf(stderr, "[dqn_b200] persisting L2: max %d MB, set %zu MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
     }
     else if (n == "wg1_fit") h->wg1_fit = value != 0;
+    else if (n == "tail_join") h->tail_join = value != 0;
+    else if (n == "fc_after_dgrad") h->fc_after_dgrad = value != 0;
     else if (n == "keep_grads") h->keep_grads = value != 0;  // dqn_train_batch: dense-kernel gradients stay readable (slot 3)
     else if (n == "fc_tma_adam") h->fc_tma_adam = value != 0;    // dense wgrad (tcgen05) + optimizer, TMA-staged state
     else if (n == "fc_ffma_adam") h->fc_ffma_adam = value != 0;  // dense wgrad+optimizer as one fp32 pass

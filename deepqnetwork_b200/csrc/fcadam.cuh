@@ -456,8 +456,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
                                                                        int Bn, int flat, int NH, int hid,
                                                                        const __grid_constant__ RowMaps maps,
                                                                        float lr, float mom, int use_momentum,
-                                                                       const dqn_learner::Scalars* __restrict__ sc,
-                                                                       unsigned int* __restrict__ tile_ctr, int l2_keep, int pf_dist) {
+                                                                       const dqn_learner::Scalars* sc,
+                                                                       unsigned int* __restrict__ tile_ctr, int l2_keep, int pf_dist,
+                                                                       unsigned int* join_ticket, float* host_mirror, int mirror_words) {
     // Tiles are claimed DYNAMICALLY (atomic counter, stream-major order, so a CTA sees at most one switch of stream): the CTAs of this low-priority
     // kernel get their SMs at different times -- whenever the conv chain of the backward pass leaves some free -- and
     // with a static partition the late starters, each still holding a full share, ended the kernel ~15 us late.
@@ -710,6 +711,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) fcwg_adam_rows_kernel(const flo
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    // (option tail_join) the optimizer tail runs beside this kernel: the last CTA here arrives at the end-of-step join (learner.h);
+    // every CTA has made its last tile claim by now, so the bookkeeping may reset the tile counter
+    if (join_ticket != nullptr && tid == 0) {
+        __threadfence();
+        if (atomicAdd(join_ticket + 2, 1u) == gridDim.x - 1)
+            if (step_join_arrive(join_ticket, 2u))
+                step_bookkeeping(const_cast<dqn_learner::Scalars*>(sc), join_ticket, use_momentum, host_mirror, mirror_words);
+    }
 }
 
 static void encode_row_maps(dqn_learner* h, RowMaps& out, float* wout_base) {
@@ -743,7 +752,7 @@ static inline bool rows_supported(const dqn_learner* h, int rows) {
     return rows <= 32 && net.hidden == 2 * RT_N && net.flat % RT_ROWS == 0 && net.dueling && (net.off_fc_w[0] % 4) == 0 && (net.off_fc_w[1] % 4) == 0;
 }
 
-static void launch_rows(dqn_learner* h, int rows, int ctas) {
+static void launch_rows(dqn_learner* h, int rows, int ctas, bool join = false) {
     const NetDesc& net = h->net;
     if (!h->fa_row_maps) {
         h->fa_row_maps = aligned_alloc(64, sizeof(RowMaps));
@@ -756,7 +765,8 @@ static void launch_rows(dqn_learner* h, int rows, int ctas) {
         DQN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         launch_kernel(h->pdl, kern, dim3(ctas), dim3(RT_THREADS), bytes, h->stream, (const float*)h->acts_on.act[2], (const float*)h->d_hid,
                       rows, net.flat, net.NH, net.hidden, maps, (float)h->cfg.learning_rate, (float)h->cfg.momentum, h->cfg.use_momentum,
-                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr, h->l2_keep, h->fc_rows_pf * ctas);
+                      (const dqn_learner::Scalars*)h->d_sc, h->fa_tile_ctr, h->l2_keep, h->fc_rows_pf * ctas,
+                      join ? h->opt_ticket : (unsigned int*)nullptr, join ? h->tail_mirror : (float*)nullptr, join ? h->tail_mirror_words : 0);
     };
     if (h->cfg.math_mode == DQN_MATH_TC3X) go(fcwg_adam_rows_kernel<3>); else go(fcwg_adam_rows_kernel<1>);
     h->launches++;

@@ -220,6 +220,12 @@ struct dqn_learner {
     bool img_dgrad = true;      // option: conv dgrads through the image-resident kernel as well
     bool img_conv = true;       // option: conv forward through the image-resident kernel where the geometry allows
     bool tower_fused = true;    // option: the conv stack of both towers as one fused kernel on the uint8 batch (cvtower.cuh)
+    int tail_join = 1;          // option: the optimizer tail does not wait for the fused dense wgrad+optimizer kernel; the two run side by side and
+                                // the end-of-step bookkeeping (step counter, beta powers, counters, host mirror) is done by the last CTA of whichever
+                                // finishes second (step_join_arrive / step_bookkeeping below).  Pure rescheduling: bit-identical results
+    int fc_after_dgrad = 0;     // option (measured: +0.3 % alone, -4 % together with tail_join -- the persistent grid then takes its SMs before conv3's dgrad and wgrad get theirs): the fused dense kernel's branch forks behind the dense dgrad GEMM (the last reader of the old dense
+                                // weights), not behind the sum+gate kernel that follows it on the main stream
+    bool rows_joined = false;   // set per launch sequence: the fused dense kernel takes part in the end-of-step join
     int fc_rows_pf = 0;         // option: the fused dense kernel prefetches the tile fc_rows_pf x CTAs claims ahead into L2 (0 = off; measured: 6550-6630 vs 6650-6670 steps/s without -- the pass is not latency-bound in situ)
     bool fc_prefetch = true;    // option: the dense hidden kernels are prefetched into L2 under the conv towers (nn.cu launch_dense_prefetch)
     bool tower_ext2 = false;    // option: conv3 of the fused tower streams its weights through 8 stages (4 of them in image A, free by then).
@@ -285,6 +291,8 @@ bool overlap_enabled(const dqn_learner* h);
 // 1 = needed soon (conv wgrads, look-ahead sampling), 2 = critical path (same as the main stream)
 void side_begin(dqn_learner* h, cudaStream_t& saved, int which = 0, int prio_class = 0);
 void side_end(dqn_learner* h, cudaStream_t saved);
+cudaEvent_t fork_event_here(dqn_learner* h);  // an event recorded on the current stream at this point of the launch sequence (nullptr: no overlap)
+void side_begin_at(dqn_learner* h, cudaStream_t& saved, int which, int prio_class, cudaEvent_t after);  // side_begin forking at `after` (nullptr: here)
 void main_wait_side(dqn_learner* h, int which = 0);
 void launch_optimizer_fc(dqn_learner* h);
 void launch_optimizer_fc_stream(dqn_learner* h, int st, bool prev_betas = false);  // one hidden stream's dense kernel
@@ -342,3 +350,31 @@ void launch_head_backward(dqn_learner* h, int n, const uint8_t* actions, const T
 void launch_optimizer(dqn_learner* h, bool skip_fc);
 void launch_post_step(dqn_learner* h, int per_update);
 void launch_copy_network(dqn_learner* h);
+
+#ifdef __CUDACC__
+// End-of-step bookkeeping, run by exactly ONE thread per step.  opt_ticket layout: [0] CTAs of the optimizer tail that are done,
+// [1] tile counter of the fused dense wgrad+optimizer kernel, [2] CTAs of that kernel that are done, [3] kernels that are done.
+// The last CTA of the optimizer tail and (option tail_join) the last CTA of the fused dense kernel arrive at [3]; the arrival that
+// completes `expected` runs step_bookkeeping.  Both kernels read the beta powers when they start, and nothing else reads the
+// scalars before the step's graph has ended, so it does not matter which of the two it is.
+__device__ __forceinline__ bool step_join_arrive(unsigned int* ticket, unsigned int expected) {
+    __threadfence();
+    return atomicAdd(ticket + 3, 1u) == expected - 1u;
+}
+__device__ __forceinline__ void step_bookkeeping(dqn_learner::Scalars* sc, unsigned int* ticket, int use_momentum, float* host_mirror,
+                                                 int mirror_words) {
+    ticket[0] = 0; ticket[1] = 0; ticket[2] = 0; ticket[3] = 0;  // ready for the next step (no memset nodes in the graph)
+    sc->step += 1;
+    sc->b1p_prev = sc->b1p; sc->b2p_prev = sc->b2p;
+    if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
+    sc->rng_counter += 1;
+    // host-fed step (dqn_train_batch / dqn_train_step with host draws): the scalar block and the per-sample losses behind it go
+    // straight into their pinned, device-mapped mirror -- the step needs no read-back copy operation after its last kernel
+    if (host_mirror) {
+        __threadfence();
+        const volatile float* src = reinterpret_cast<const volatile float*>(sc);
+        for (int i = 0; i < mirror_words; ++i) host_mirror[i] = src[i];
+        __threadfence_system();
+    }
+}
+#endif

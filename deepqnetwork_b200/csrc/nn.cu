@@ -567,6 +567,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     const float* P = h->online;
     float* G = h->grads;
     TowerActs& acts = h->acts_on;
+    h->rows_joined = false;
     // Weight gradients do not feed anything before the optimizer, so each one is forked onto the side stream as soon
     // as its dY exists, while the main stream continues down the dgrad chain.
     cudaStream_t saved;
@@ -618,6 +619,7 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     cudaStream_t early_saved = nullptr;
     if (rows_early) { side_begin(h, early_saved, 0); side_end(h, early_saved); }
     // dense hidden dgrad, gated by conv3's ReLU: d_act[2] = (dH W^T) * (act3 > 0)
+    cudaEvent_t dgrad_read_w = nullptr;
     {
         prof_mark(h, "fc_dgrad");
         if (tcm && rows % 32 == 0) {
@@ -630,6 +632,9 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             OpRowMajorK b{h->d_hid, net.NH};
             EpiPartialT e{acts.fc_part, rows, net.flat};  // the forward split-K workspace is idle during backward
             gemm_auto<true>(h, a, b, e, net.flat, rows, net.NH, Z, kchunk, 32);
+            // the GEMM above is the last reader of the old dense weights: the in-place fused dense wgrad+optimizer kernel may start
+            // behind it, next to the sum+gate kernel
+            if (h->fc_after_dgrad && rows_adam && !rows_early && !h->profile) dgrad_read_w = fork_event_here(h);
             prof_mark(h, "fc_dgrad_reduce");
             const int total4 = rows * net.flat / 4;
             launch_kernel(false, sum_gate_kernel, dim3(ceil_div(total4, 256)), dim3(256), 0, h->stream, acts.fc_part, Z, total4,
@@ -673,11 +678,14 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
     } else if (h->early_fc_adam && !h->fuse_fc_adam) {
         // the dense kernels hold 98.6% of the parameters: update them now on the first side stream (after their wgrad,
         // and after the dgrad above has read the old W) while the main stream walks the conv dgrad chain
-        side_begin(h, saved, 0);
+        side_begin_at(h, saved, 0, 0, dgrad_read_w);
         if (tma_adam) {
             prof_mark(h, "fc_wgrad_adam");
             if (rows_adam) {
-                fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count));
+                // (tail_join) the optimizer tail will not wait for this kernel: they share the end-of-step join
+                const bool join = h->tail_join && !(h->w_scratch_on && h->w_scratch);
+                fa::launch_rows(h, rows, std::min(h->fc_rows_ctas, h->sm_count), join);
+                h->rows_joined = join;
                 if (h->w_scratch_on && h->w_scratch) {  // (not forked early: single-stream / profile mode) the copy follows at once
                     const size_t fcw = (size_t)net.flat * net.hidden * sizeof(float);
                     for (int st = 0; st < 2; ++st)
@@ -786,8 +794,8 @@ void tower_backward(dqn_learner* h, const uint8_t* d_states, const float* x_f32,
             }
         }
     }
-    main_wait_side(h, 0);  // all weight gradients are in the slab (and the dense kernels updated) before the
-    main_wait_side(h, 1);  // optimizer pass over the remaining tensors runs
+    if (!h->rows_joined) main_wait_side(h, 0);  // all weight gradients are in the slab (and the dense kernels updated) before the
+    main_wait_side(h, 1);                       // optimizer pass over the remaining tensors runs (rows_joined: finish_step joins stream 0)
     main_wait_side(h, 3);
     main_wait_side(h, 4);
     if (split_fc) main_wait_side(h, 5);

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
                                                              const float4* __restrict__ g, OptRanges rg, float lr, float mom,
                                                              int use_momentum, dqn_learner::Scalars* sc,
                                                              unsigned int* __restrict__ ticket, const TailPack tp,
-                                                             float* host_mirror, int mirror_words) {
+                                                             float* host_mirror, int mirror_words, unsigned int join_expected) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float lr_t = use_momentum ? lr : lr * sqrtf(1.0f - sc->b2p) / (1.0f - sc->b1p);
     const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -278,20 +278,8 @@ __global__ void __launch_bounds__(256) optimizer_tail_kernel(float4* __restrict_
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-            *ticket = 0;
-            ticket[1] = 0;  // tile counter of the fused dense wgrad+optimizer kernel (fcadam.cuh): ready for the next step
-            sc->step += 1;
-            sc->b1p_prev = sc->b1p; sc->b2p_prev = sc->b2p;
-            if (!use_momentum) { sc->b1p *= 0.9f; sc->b2p *= 0.999f; }
-            sc->rng_counter += 1;
-            // host-fed step (dqn_train_batch): the scalar block and the per-sample losses behind it go straight into their
-            // pinned, device-mapped mirror -- the step needs no read-back copy operation after its last kernel
-            if (host_mirror) {
-                __threadfence();
-                const volatile float* src = reinterpret_cast<const volatile float*>(sc);
-                for (int i = 0; i < mirror_words; ++i) host_mirror[i] = src[i];
-                __threadfence_system();
-            }
+            // this kernel is done; join_expected = 2 when the fused dense kernel runs beside it (learner.h)
+            if (step_join_arrive(ticket, join_expected)) step_bookkeeping(sc, ticket, use_momentum, host_mirror, mirror_words);
         }
     }
 }
@@ -327,7 +315,8 @@ void launch_optimizer(dqn_learner* h, bool skip_fc) {
     const int blocks = (int)std::min<long long>((most + 255) / 256, (long long)h->sm_count * 8);
     launch_kernel(false, optimizer_tail_kernel, dim3(blocks), dim3(256), 0, h->stream, (float4*)h->online, (float4*)h->slot_m,
                   (float4*)h->slot_v, (const float4*)h->grads, rg, (float)h->cfg.learning_rate, (float)h->cfg.momentum,
-                  h->cfg.use_momentum, h->d_sc, h->opt_ticket, tp, h->tail_mirror, h->tail_mirror_words);
+                  h->cfg.use_momentum, h->d_sc, h->opt_ticket, tp, h->tail_mirror, h->tail_mirror_words, h->rows_joined ? 2u : 1u);
+    h->rows_joined = false;
     h->launches++;
     if (!tp.n) launch_pack_conv(h, 0);  // (option off: separate pack launch) the conv kernels read the weights pre-split and pre-tiled
 }

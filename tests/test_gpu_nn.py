@@ -477,6 +477,20 @@ def test_scheduling_options_are_bit_identical(opts):
     assert np.array_equal(ref[3], got[3])
 
 
+@pytest.mark.parametrize('opts', [dict(tail_join=0), dict(fc_after_dgrad=0), dict(tail_join=0, fc_after_dgrad=0)],
+                         ids=lambda o: '+'.join('%s=%d' % kv for kv in o.items()))
+def test_end_of_step_join_is_bit_identical(opts):
+    """Default path (fused dense wgrad+optimizer kernel): letting the optimizer tail run beside that kernel, with the end-of-step
+    bookkeeping done by whichever finishes second, and forking the kernel's branch behind the dense dgrad GEMM instead of behind
+    the sum+gate kernel, only reschedule: weights, slots and tree after 5 fused steps are bit-identical to the serial arrangement."""
+    ref = _run_steps('c2_breakout_ddp', dict(opts))
+    got = _run_steps('c2_breakout_ddp', {})
+    for slot in range(3):
+        for k in ref[slot]:
+            assert np.array_equal(ref[slot][k], got[slot][k]), (slot, k)
+    assert np.array_equal(ref[3], got[3])
+
+
 def test_fused_row_kernel_momentum_matches_split_path():
     """Same comparison for the Nesterov-momentum optimizer (MomentumOptimizer, deep_q_model.py:385): no division, so the two
     paths differ only by the summation order of the gradient."""
