@@ -367,7 +367,7 @@ def main():
     from deepqnetwork_b200.learner import Learner
     from deepqnetwork_b200.deep_q_model import init_tower_params, tower_param_shapes
 
-    dp = args.config == 'c5'
+    dp = dp_mode = args.config == 'c5'
     batch = cfg['global_batch'] // world if dp else BATCH
     capacity = args.capacity // world if dp else args.capacity
     L = Learner(cfg['h'], cfg['w'], 4, num_actions=cfg['a'], use_dueling=cfg['dueling'], use_double=cfg['double'],
@@ -375,9 +375,20 @@ def main():
                 math_mode=args.math, seed=7 + rank, device=local_rank, max_rows=max(batch, 256), frame_dedup=args.layout == 'frames')
     # a real (non-default) stream: stream capture is illegal on the legacy stream; high priority, because the learner's
     # own side streams (weight gradients, optimizer, look-ahead sampling) only carry work with slack
-    stream = torch.cuda.Stream(priority=-1)
+    # Replicas are timed on the learner's OWN stream (the configuration a user of the handle gets), wrapped for torch so that
+    # torch.cuda.Event brackets exactly the learner's work.  Measured at the end of round 2: handing the learner a torch pool
+    # stream (torch.cuda.Stream(priority=-1) + dqn_set_stream) costs 5 % of the step rate (6630 vs 6960 steps/s, same build).
+    stream = None
+    if not dp_mode:
+        try:
+            stream = torch.cuda.ExternalStream(int(L.device_ptr('stream')[0]), device=torch.device('cuda', local_rank))
+        except Exception as e:  # (library without the "stream" query)
+            sys.stderr.write('bench: own-stream timing unavailable (%s); using a torch stream\n' % (e,))
+            stream = None
+    if stream is None:
+        stream = torch.cuda.Stream(priority=-1)
+        L.set_stream(stream.cuda_stream)
     torch.cuda.set_stream(stream)
-    L.set_stream(stream.cuda_stream)  # so that torch.cuda.Event brackets exactly the learner's work
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
     if args.no_fuse:
         L.set_option('fuse_fc_adam', 0)

@@ -371,6 +371,7 @@ extern "C" int dqn_device_ptr(dqn_learner* h, const char* what, void** ptr, int6
     else if (w == "replay_next_states") { p = h->r_next; b = h->cap * (int64_t)h->state_bytes; }
     else if (w == "batch_states") { p = h->b_states; b = 2 * (int64_t)h->max_rows * h->state_bytes; }
     else if (w == "scalars") { p = h->d_sc; b = sizeof(dqn_learner::Scalars); }
+    else if (w == "stream") { p = (void*)h->stream; b = 0; }  // the cudaStream_t the handle issues its work on (CUDA-event timing by the caller)
     else throw std::string("unknown device buffer: ") + w;
     if (ptr) *ptr = p;
     if (bytes) *bytes = b;
