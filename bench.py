@@ -643,6 +643,8 @@ def main():
                    sample='%d consecutive train steps (%.0f s) on %d threads, %d steps on 1 thread; 20000-row host replay; NumPy/Python '
                           'replay+PER as in rl/data/*.py, torch-CPU fp32 network (stand-in for TF 1.x CPU)' % (done, args.cpu_seconds, threads, done1))
 
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())  # the learner's own stream dies with the handle: nothing of torch's may refer to it
     L.close()
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
