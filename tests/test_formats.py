@@ -477,3 +477,21 @@ def test_replay_memory_disk_ring_semantics_match_the_reference_class(tmp_path, m
         for m in [m for m in sys.modules if m == 'rl' or m.startswith('rl.')]:
             sys.modules.pop(m, None)
         _FakeH5File.store.clear()
+
+
+def test_inspection_tool_lists_a_save_dir_and_flags_damage(tmp_path):
+    import io
+    from deepqnetwork_b200.data.replay_memory_disk import ReplayMemoryDisk
+    from deepqnetwork_b200.formats.__main__ import describe
+    prefix = str(tmp_path / 'rl.game_environment.BreakoutEnvironment')
+    tb.write_bundle(prefix, {'q_networks/online/dense/kernel': np.ones((6, 4), np.float32), 'train/step': np.int32(5)})
+    ReplayMemoryDisk(prefix + '_replay_memory.hdf5', 4, 4, 4, 'uint8', max_size=8).close()
+    out = io.StringIO()
+    assert describe(prefix, out) is True
+    text = out.getvalue()
+    assert 'q_networks/online/dense/kernel' in text and 'crc ok  = 5' in text and "attr state_type       = 'uint8'" in text
+    assert 'dataset next_states  uint8    (8, 4, 4, 4)' in text
+    with open(tb.data_path(prefix), 'r+b') as f:
+        f.seek(10); f.write(b'\xff')
+    out = io.StringIO()
+    assert describe(prefix, out) is False and 'UNREADABLE' in out.getvalue()
