@@ -385,9 +385,11 @@ def main():
         except Exception as e:  # (library without the "stream" query)
             sys.stderr.write('bench: own-stream timing unavailable (%s); using a torch stream\n' % (e,))
             stream = None
+    config['stream'] = "the learner's own stream (torch.cuda.ExternalStream around dqn_device_ptr('stream'))"
     if stream is None:
         stream = torch.cuda.Stream(priority=-1)
         L.set_stream(stream.cuda_stream)
+        config['stream'] = 'torch.cuda.Stream(priority=-1) handed to the learner (dqn_set_stream)'
     torch.cuda.set_stream(stream)
     shapes = tower_param_shapes(cfg['h'], cfg['w'], 4, cfg['a'], 512, cfg['dueling'], cfg['variant'])
     if args.no_fuse:
